@@ -1,0 +1,118 @@
+/* surfnet_b200.h -- C ABI of libsurfnet_b200.so
+ *
+ * B200 (sm_100a) operator-application kernels for SurfaceNetworks' LapResNet2 / DirResNet2 blocks.
+ * This is the drop-in boundary that replaces the reference's only native seam:
+ *
+ *   reference                                              replaced by
+ *   -----------------------------------------------------  ------------------------------------------
+ *   src/utils/cuda/batch_csr.cu:13-47  (+ batch_csr.py:28-59)   sn_coo_to_csr32, sn_csr32_to_bsr4_*
+ *   src/utils/cuda/sparse_bmm.cu:16-61 (+ sparse_bmm.py:28-61)  sn_csr_spmm_f32, sn_bsr4_spmm_f32
+ *   torch.mm(sparse_coo, dense) at src/utils/utils_pt.py:167,176   sn_csr_spmm_f32   (Laplacian)
+ *   torch.mm(sparse_coo, dense) at src/utils/utils_pt.py:202,214   sn_bsr4_spmm_f32  (Dirac / adjoint)
+ *   src/utils/cuda/sparse_bmm_func.py:53-72 (backward = A^T grad)  same SpMM entry points on a
+ *                                                                  transposed structure built once
+ *   GraphConv1x1 "pre" BN + Linear, utils_pt.py:91-104             sn_colstats_*, sn_bn_fold_f32,
+ *                                                                  sn_linear_* (fused stage)
+ *
+ * Conventions (same as the reference's cupy launch seam, sparse_bmm.py:49-59, made explicit):
+ *   - every pointer is a DEVICE pointer unless its name starts with host_;
+ *   - the library never allocates, never synchronises and keeps no mutable global state:
+ *     the caller owns every buffer (outputs and workspaces included) and passes the stream;
+ *   - work is enqueued on `stream` (a cudaStream_t; pass torch's current stream) and the call returns;
+ *   - shapes are run-time arguments (the reference re-JITs a kernel per shape, sparse_bmm.py:29-47);
+ *   - return value: SN_OK, a negative SN_ERR_* argument error, or a positive cudaError_t.
+ *   - dense matrices are row-major fp32 with an explicit leading dimension (in floats).
+ */
+#ifndef SURFNET_B200_H
+#define SURFNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* sn_stream_t; /* cudaStream_t */
+
+#define SN_VERSION 100 /* 0.1.0 */
+
+#define SN_OK 0
+#define SN_ERR_ARG (-1)          /* null pointer / negative size / inconsistent arguments        */
+#define SN_ERR_UNSUPPORTED (-2)  /* shape or alignment not supported by this entry point          */
+#define SN_ERR_WORKSPACE (-3)    /* workspace smaller than the matching *_ws_bytes() query        */
+#define SN_ERR_OVERFLOW (-4)     /* nnz / rows / cols do not fit the 32-bit index format          */
+
+/* flags for sn_coo_to_csr32 */
+#define SN_COO_SORTED 1 /* input is coalesced: sorted by (batch,row,col), as torch .coalesce() returns */
+
+/* flags for the SpMM entry points */
+#define SN_SPMM_ELU_INPUT 1 /* apply ELU(alpha=1) to the gathered dense operand: Y = S * elu(X)      */
+
+int sn_version(void);
+const char* sn_status_string(int status);
+
+/* ------------------------------------------------------------------------------------------------
+ * Format layer.  COO (int64 indices, as torch.sparse / sparse_cat / sparse_diag_cat produce,
+ * src/utils/utils_pt.py:21-69) -> CSR32 (int32 row pointers / column indices, fp32 values).
+ *
+ * batch == NULL : 2-D operator, indices are (row, col)                      [sparse_diag_cat layout]
+ * batch != NULL : 3-D operator [B, rows_per_batch, cols_per_batch]          [sparse_cat layout, the
+ *                 input of the reference's batch_csr kernel]; it is flattened to the block-diagonal
+ *                 2-D operator: row' = b*rows_per_batch + row, col' = b*cols_per_batch + col.
+ * n_rows is the total (flattened) row count; rowptr has n_rows+1 entries.  Unlike the reference
+ * kernel (batch_csr.cu:36-42, which leaves interior empty rows pointing at 0) empty rows anywhere are
+ * handled.  Without SN_COO_SORTED entries may come in any order; duplicates are kept (not summed) in
+ * (col, input position) order, so results are deterministic.  Passing (col,row) swapped without
+ * SN_COO_SORTED builds the transpose.
+ * ---------------------------------------------------------------------------------------------- */
+size_t sn_coo_to_csr32_ws_bytes(int64_t nnz, int64_t n_rows);
+int sn_coo_to_csr32(const int64_t* batch, const int64_t* row, const int64_t* col, const float* val,
+                    int64_t nnz, int64_t rows_per_batch, int64_t cols_per_batch, int64_t n_rows,
+                    int64_t n_cols, int flags, int32_t* rowptr, int32_t* colind, float* out_val,
+                    void* ws, size_t ws_bytes, sn_stream_t stream);
+
+/* CSR32 -> BSR4 (4x4 blocks; n_rows % 4 == 0).  Two steps because the block count is data dependent:
+ *   count : browptr[0..n_rows/4] <- exclusive scan of blocks per block-row; browptr[n_rows/4] = #blocks
+ *           (read it back, allocate bcolind[#blocks], bval[16*#blocks]), then
+ *   fill  : bcolind ascending per block-row; bval holds each block COLUMN-major:
+ *           bval[16*k + 4*q + p] = block_k[p][q]  (p = row in block, q = column in block).
+ * The Dirac view of utils_pt.py:201-203 makes q index the q-th quarter of the channel vector. */
+size_t sn_csr32_to_bsr4_ws_bytes(int64_t n_rows);
+int sn_csr32_to_bsr4_count(const int32_t* rowptr, const int32_t* colind, int64_t n_rows,
+                           int32_t* browptr, void* ws, size_t ws_bytes, sn_stream_t stream);
+int sn_csr32_to_bsr4_fill(const int32_t* rowptr, const int32_t* colind, const float* val, int64_t n_rows,
+                          const int32_t* browptr, int32_t* bcolind, float* bval, sn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Operator application.
+ *
+ * sn_csr_spmm_f32 :  Y[n_rows x C] = S * X            (scalar Laplacian, utils_pt.py:167,176)
+ * sn_bsr4_spmm_f32:  Y[n_brows x C] = S * X with the quaternion view of utils_pt.py:201-203,213-215:
+ *                    Y[r, p*C/4 + c] = sum_{blocks (r,j)} sum_q block[p][q] * X[j, q*C/4 + c],  C % 4 == 0
+ * X rows are addressed through colind, so X must have at least n_cols rows.  Accumulation is fp32 FMA
+ * in ascending storage order (bit-reproducible run to run).  X and Y must not alias.
+ * ---------------------------------------------------------------------------------------------- */
+int sn_csr_spmm_f32(const int32_t* rowptr, const int32_t* colind, const float* val,
+                    const float* X, int64_t ldx, float* Y, int64_t ldy,
+                    int64_t n_rows, int64_t C, int flags, sn_stream_t stream);
+int sn_bsr4_spmm_f32(const int32_t* browptr, const int32_t* bcolind, const float* bval,
+                     const float* X, int64_t ldx, float* Y, int64_t ldy,
+                     int64_t n_brows, int64_t C, int flags, sn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Activation pass in front of each operator application (F.elu at utils_pt.py:161,172,195,208).
+ * sn_elu_f32     : Y = elu(X), strided in/out so the result lands in the left half of the stage's
+ *                  concat buffer [rows x 2C] (replaces elu + torch.cat, utils_pt.py:168,177,204,216).
+ * sn_elu_bwd_f32 : Y = (G + G2) * elu'(x); G2 may be NULL.  a_is_raw = 0: A holds the activated value
+ *                  elu(x) (elu' = 1 if A > 0 else A + 1); a_is_raw = 1: A holds x (elu' = 1 if x > 0
+ *                  else exp(x)).  Y may alias G or G2.
+ * ---------------------------------------------------------------------------------------------- */
+int sn_elu_f32(const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t rows, int64_t C, sn_stream_t stream);
+int sn_elu_bwd_f32(const float* A, int64_t lda, int a_is_raw, const float* G, int64_t ldg, const float* G2,
+                   int64_t ldg2, float* Y, int64_t ldy, int64_t rows, int64_t C, sn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SURFNET_B200_H */

@@ -1,0 +1,70 @@
+"""ctypes binding of libsurfnet_b200.so (C ABI in include/surfnet_b200.h).
+
+The library is the product: there is no Python / CPU fallback.  If the shared object is missing or a
+symbol cannot be resolved, importing this module raises -- the layers must fail loudly rather than run
+on something else (the reference's seam had no error handling at all, src/utils/cuda/sparse_bmm.py:57-59;
+here every call's status code is checked).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("SURFNET_B200_LIB", os.path.join(_HERE, "libsurfnet_b200.so"))
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "libsurfnet_b200.so not found at %s -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "or `make -C surfacenetworks_b200/csrc` (nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+
+lib = ctypes.CDLL(LIB_PATH)
+
+_i64, _i32, _f32, _ptr, _sz, _int = c_int64, c_int32, c_float, c_void_p, c_size_t, c_int
+
+# name -> (restype, argtypes).  Pointers are passed as raw addresses (tensor.data_ptr()).
+SIGNATURES = {
+    "sn_version": (_int, []),
+    "sn_status_string": (c_char_p, [_int]),
+    "sn_coo_to_csr32_ws_bytes": (_sz, [_i64, _i64]),
+    "sn_coo_to_csr32": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _int, _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),
+    "sn_csr32_to_bsr4_ws_bytes": (_sz, [_i64]),
+    "sn_csr32_to_bsr4_count": (_int, [_ptr, _ptr, _i64, _ptr, _ptr, _sz, _ptr]),
+    "sn_csr32_to_bsr4_fill": (_int, [_ptr, _ptr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr]),
+    "sn_csr_spmm_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _int, _ptr]),
+    "sn_bsr4_spmm_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _int, _ptr]),
+    "sn_elu_f32": (_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _ptr]),
+    "sn_elu_bwd_f32": (_int, [_ptr, _i64, _int, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)  # AttributeError here == broken build; do not swallow it
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+SN_OK = 0
+SN_ERR_ARG, SN_ERR_UNSUPPORTED, SN_ERR_WORKSPACE, SN_ERR_OVERFLOW = -1, -2, -3, -4
+SN_COO_SORTED = 1
+SN_SPMM_ELU_INPUT = 1
+
+
+class SurfnetError(RuntimeError):
+    def __init__(self, fn, status):
+        self.status = status
+        msg = lib.sn_status_string(status)
+        super().__init__("%s failed: status %d (%s)" % (fn, status, msg.decode() if msg else "?"))
+
+
+def check(fn, status):
+    if status != SN_OK:
+        raise SurfnetError(fn, status)
+
+
+def call(name, *args):
+    """Call an int-returning entry point and raise SurfnetError on a non-zero status."""
+    check(name, getattr(lib, name)(*args))
+
+
+def version():
+    return lib.sn_version()

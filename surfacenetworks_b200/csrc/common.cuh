@@ -1,0 +1,66 @@
+// common.cuh -- shared helpers for libsurfnet_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/surfnet_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libsurfnet_b200 targets sm_100a (B200) only"
+#endif
+
+#define SN_API extern "C" __attribute__((visibility("default")))
+
+namespace sn {
+
+constexpr int kWarp = 32;
+
+__host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+inline int launch_status() {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();  // clear the sticky-less launch error so the next call starts clean
+    return (int)e;
+  }
+  return SN_OK;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ELU(alpha = 1), the activation in front of every operator application (utils_pt.py:161,172,195,208).
+// torch's CPU kernel evaluates the negative branch with expm1; expm1f keeps us within 1 ulp of it.
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+__device__ __forceinline__ float4 elu4(float4 v) {
+  return make_float4(elu1(v.x), elu1(v.y), elu1(v.z), elu1(v.w));
+}
+
+// Read-only 128-bit gather of a dense feature row segment.  Rows are re-read by neighbouring sparse
+// rows (mesh valence ~6), so they are allowed to allocate in L1.
+__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// Streaming 128-bit store of an output row segment: written once, never re-read by this kernel.
+__device__ __forceinline__ void st_stream_f4(float* p, float4 v) {
+  __stcs(reinterpret_cast<float4*>(p), v);
+}
+
+__device__ __forceinline__ float4 fma4(float a, float4 x, float4 acc) {
+  acc.x = fmaf(a, x.x, acc.x);
+  acc.y = fmaf(a, x.y, acc.y);
+  acc.z = fmaf(a, x.z, acc.z);
+  acc.w = fmaf(a, x.w, acc.w);
+  return acc;
+}
+__device__ __forceinline__ float4 add4(float4 a, float4 b) {
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ float4 sel4(bool c, float4 a, float4 b) { return c ? a : b; }
+__device__ __forceinline__ float4 shfl_xor4(float4 v, int m) {
+  v.x = __shfl_xor_sync(0xffffffffu, v.x, m);
+  v.y = __shfl_xor_sync(0xffffffffu, v.y, m);
+  v.z = __shfl_xor_sync(0xffffffffu, v.z, m);
+  v.w = __shfl_xor_sync(0xffffffffu, v.w, m);
+  return v;
+}
+
+}  // namespace sn

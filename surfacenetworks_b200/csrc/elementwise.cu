@@ -1,0 +1,80 @@
+// elementwise.cu -- the activation pass in front of each operator application.
+//
+// Every LapResNet2 / DirResNet2 stage starts with F.elu (reference src/utils/utils_pt.py:161,172,195,208)
+// and concatenates the activated features with S * activated features (:168,177,204,216).  These kernels
+// write the activated rows straight into the left half of the concat buffer [rows x 2C] (strided
+// output), so torch.cat never runs and the SpMM gathers from / writes into the same buffer.
+#include "common.cuh"
+
+namespace sn {
+
+// grid-stride over float4 elements of a [rows x C] matrix with arbitrary (16 B aligned) leading dims
+__global__ void __launch_bounds__(256)
+elu_vec4_kernel(const float* __restrict__ X, int64_t ldx, float* __restrict__ Y, int64_t ldy, int64_t rows, int C4) {
+  const int64_t total = rows * C4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / C4;
+    const int c = (int)(i - r * C4) * 4;
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(X + r * ldx + c));
+    *reinterpret_cast<float4*>(Y + r * ldy + c) = elu4(v);
+  }
+}
+__global__ void __launch_bounds__(256)
+elu_scalar_kernel(const float* __restrict__ X, int64_t ldx, float* __restrict__ Y, int64_t ldy, int64_t rows, int C) {
+  const int64_t total = rows * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / C;
+    const int c = (int)(i - r * C);
+    Y[r * ldy + c] = elu1(X[r * ldx + c]);
+  }
+}
+// Y[r,c] = (G[r,c] + G2[r,c]) * elu'(x).  RAW: A holds x itself (elu' = x > 0 ? 1 : exp(x));
+// otherwise A holds the activated value a = elu(x) (elu' = a > 0 ? 1 : a + 1).  G2 may be null.
+template <bool RAW>
+__global__ void __launch_bounds__(256)
+elu_bwd_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ G, int64_t ldg,
+               const float* __restrict__ G2, int64_t ldg2, float* __restrict__ Y, int64_t ldy, int64_t rows, int C) {
+  const int64_t total = rows * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / C;
+    const int c = (int)(i - r * C);
+    const float a = A[r * lda + c];
+    float g = G[r * ldg + c];
+    if (G2) g += G2[r * ldg2 + c];
+    const float d = a > 0.f ? 1.f : (RAW ? expf(a) : a + 1.f);
+    Y[r * ldy + c] = g * d;
+  }
+}
+
+}  // namespace sn
+
+SN_API int sn_elu_f32(const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t rows, int64_t C,
+                      sn_stream_t stream) {
+  using namespace sn;
+  if (rows < 0 || C < 0 || C > 0x7fffffffLL) return SN_ERR_ARG;
+  if (rows == 0 || C == 0) return SN_OK;
+  if (!X || !Y || ldx < C || ldy < C) return SN_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (C % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && aligned16(X) && aligned16(Y);
+  const int64_t work = vec ? rows * (C / 4) : rows * C;
+  const unsigned grid = (unsigned)(ceil_div(work, 256) < 148 * 16 ? ceil_div(work, 256) : 148 * 16);
+  if (vec)
+    elu_vec4_kernel<<<grid, 256, 0, st>>>(X, ldx, Y, ldy, rows, (int)(C / 4));
+  else
+    elu_scalar_kernel<<<grid, 256, 0, st>>>(X, ldx, Y, ldy, rows, (int)C);
+  return launch_status();
+}
+
+SN_API int sn_elu_bwd_f32(const float* A, int64_t lda, int a_is_raw, const float* G, int64_t ldg, const float* G2,
+                          int64_t ldg2, float* Y, int64_t ldy, int64_t rows, int64_t C, sn_stream_t stream) {
+  using namespace sn;
+  if (rows < 0 || C < 0 || C > 0x7fffffffLL) return SN_ERR_ARG;
+  if (rows == 0 || C == 0) return SN_OK;
+  if (!A || !G || !Y || lda < C || ldg < C || ldy < C || (G2 && ldg2 < C)) return SN_ERR_ARG;
+  const unsigned grid = (unsigned)(ceil_div(rows * C, 256) < 148 * 16 ? ceil_div(rows * C, 256) : 148 * 16);
+  if (a_is_raw)
+    elu_bwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(A, lda, G, ldg, G2, ldg2, Y, ldy, rows, (int)C);
+  else
+    elu_bwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(A, lda, G, ldg, G2, ldg2, Y, ldy, rows, (int)C);
+  return launch_status();
+}

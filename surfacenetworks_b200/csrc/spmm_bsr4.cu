@@ -1,0 +1,159 @@
+// spmm_bsr4.cu -- 4x4-block CSR SpMM for the quaternion Dirac operator D (faces x vertices) and its
+// adjoint D* (vertices x faces).
+//
+// Replaces torch.mm(Di, v.view(B*V*4, C/4)) / torch.mm(DiA, f.view(B*F*4, C/4)) at reference
+// src/utils/utils_pt.py:201-203,213-215 (and the dead SparseBMMFunc branch :197-199,209-211).
+// The reference's `view` makes quaternion component q of node n the q-th QUARTER of its channel vector:
+//
+//     Y[r, p*C4 + c] = sum_{blocks (r,j)} sum_q  B[p][q] * X[j, q*C4 + c],      C4 = C/4
+//
+// Mapping (C4 % 4 == 0 path):  G = 4*LPQ lanes own one block-row; lane (q, t) loads the float4
+// X[j, q*C4 + 4t .. +3] -- so a warp instruction still reads whole contiguous 128 B lines of the dense
+// row -- multiplies it by the four entries of block column q (one 128-bit load thanks to the
+// column-major block storage chosen by sn_csr32_to_bsr4_fill) and keeps four float4 partial sums, one
+// per output component p.  After the row's blocks are consumed a 2-step shuffle reduce-scatter
+// across the four q-lanes leaves lane q holding output component p = q, which it stores as one
+// coalesced float4.  No shared memory, no atomics, deterministic summation order.
+//
+// Bound: HBM.  Algorithmic bytes per launch = 4(Rb+1) + 68 nb + 4 Cb C + 4 Rb C.
+#include "common.cuh"
+
+namespace sn {
+
+template <int LPQ, bool ELU>
+__global__ void __launch_bounds__(256)
+bsr4_spmm_vec4_kernel(const int32_t* __restrict__ browptr, const int32_t* __restrict__ bcolind,
+                      const float* __restrict__ bval, const float* __restrict__ X, int64_t ldx,
+                      float* __restrict__ Y, int64_t ldy, int64_t n_brows, int C4) {
+  constexpr int G = 4 * LPQ;        // lanes per block-row
+  constexpr int RPW = kWarp / G;    // block-rows per warp
+  constexpr int U = 3;              // blocks in flight (a face row of D has exactly 3 blocks)
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G;
+  const int q = gl / LPQ;           // quaternion component (block column) this lane reads
+  const int t = gl % LPQ;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t row = warp * RPW + lane / G;
+  const bool row_ok = row < n_brows;
+
+  int start = 0, end = 0;
+  if (row_ok) {
+    start = __ldg(browptr + row);
+    end = __ldg(browptr + row + 1);
+  }
+  int maxlen = end - start;
+  if (RPW > 1) {
+#pragma unroll
+    for (int m = G; m < kWarp; m <<= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, m));
+  }
+  const bool b1 = (q & 2) != 0, b0 = (q & 1) != 0;
+
+  for (int cb0 = 0; cb0 < C4; cb0 += 4 * LPQ) {  // chunks of the quarter-width (one for C <= 128)
+    const int cb = cb0 + 4 * t;
+    const bool col_ok = cb < C4;
+    const int xoff = q * C4 + cb;
+    float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0, acc2 = acc0, acc3 = acc0;
+    for (int k0 = 0; k0 < maxlen; k0 += U) {
+      float4 xv[U], wv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int k = start + k0 + u;
+        xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        wv[u] = xv[u];
+        if (k < end && col_ok) {
+          const int j = __ldg(bcolind + k);
+          wv[u] = ldg_f4(bval + (int64_t)k * 16 + 4 * q);  // B[0..3][q]
+          xv[u] = ldg_f4(X + (int64_t)j * ldx + xoff);
+          if (ELU) xv[u] = elu4(xv[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        acc0 = fma4(wv[u].x, xv[u], acc0);
+        acc1 = fma4(wv[u].y, xv[u], acc1);
+        acc2 = fma4(wv[u].z, xv[u], acc2);
+        acc3 = fma4(wv[u].w, xv[u], acc3);
+      }
+    }
+    // reduce-scatter over the four q-lanes: lane q ends up with sum over q' of acc_{p=q}
+    float4 keep0 = sel4(b1, acc2, acc0), keep1 = sel4(b1, acc3, acc1);
+    float4 send0 = sel4(b1, acc0, acc2), send1 = sel4(b1, acc1, acc3);
+    keep0 = add4(keep0, shfl_xor4(send0, 2 * LPQ));
+    keep1 = add4(keep1, shfl_xor4(send1, 2 * LPQ));
+    float4 keep = sel4(b0, keep1, keep0), send = sel4(b0, keep0, keep1);
+    keep = add4(keep, shfl_xor4(send, LPQ));
+    if (row_ok && col_ok) st_stream_f4(Y + row * ldy + xoff, keep);
+  }
+}
+
+// Any C % 4 == 0 / any alignment: one thread per (block-row, quarter column).
+template <bool ELU>
+__global__ void __launch_bounds__(256)
+bsr4_spmm_scalar_kernel(const int32_t* __restrict__ browptr, const int32_t* __restrict__ bcolind,
+                        const float* __restrict__ bval, const float* __restrict__ X, int64_t ldx,
+                        float* __restrict__ Y, int64_t ldy, int64_t n_brows, int C4) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = idx / C4;
+  const int c = (int)(idx % C4);
+  if (row >= n_brows) return;
+  const int start = __ldg(browptr + row), end = __ldg(browptr + row + 1);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k = start; k < end; ++k) {
+    const float* xr = X + (int64_t)__ldg(bcolind + k) * ldx + c;
+    const float* b = bval + (int64_t)k * 16;
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) {
+      float x = __ldg(xr + (int64_t)qq * C4);
+      if (ELU) x = elu1(x);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) acc[p] = fmaf(__ldg(b + 4 * qq + p), x, acc[p]);
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < 4; ++p) Y[row * ldy + (int64_t)p * C4 + c] = acc[p];
+}
+
+template <int LPQ>
+static int launch_vec4(const int32_t* browptr, const int32_t* bcolind, const float* bval, const float* X,
+                       int64_t ldx, float* Y, int64_t ldy, int64_t n_brows, int C4, bool elu, cudaStream_t st) {
+  constexpr int RPW = kWarp / (4 * LPQ);
+  constexpr int kThreads = 256;
+  const int64_t grid = ceil_div(n_brows, (int64_t)RPW * (kThreads / 32));
+  if (grid > 0x7fffffffLL) return SN_ERR_OVERFLOW;
+  if (elu)
+    bsr4_spmm_vec4_kernel<LPQ, true><<<(unsigned)grid, kThreads, 0, st>>>(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C4);
+  else
+    bsr4_spmm_vec4_kernel<LPQ, false><<<(unsigned)grid, kThreads, 0, st>>>(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C4);
+  return launch_status();
+}
+
+}  // namespace sn
+
+SN_API int sn_bsr4_spmm_f32(const int32_t* browptr, const int32_t* bcolind, const float* bval, const float* X,
+                            int64_t ldx, float* Y, int64_t ldy, int64_t n_brows, int64_t C, int flags,
+                            sn_stream_t stream) {
+  using namespace sn;
+  if (n_brows < 0 || C < 0 || C > 0x7fffffffLL) return SN_ERR_ARG;
+  if (C % 4 != 0) return SN_ERR_UNSUPPORTED;  // the reference's view(.., C/4) needs it too
+  if (n_brows == 0 || C == 0) return SN_OK;
+  if (!browptr || !bcolind || !bval || !X || !Y || ldx < C || ldy < C) return SN_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool elu = (flags & SN_SPMM_ELU_INPUT) != 0;
+  const int C4 = (int)(C / 4);
+  const bool vec_ok = (C4 % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && aligned16(X) && aligned16(Y) &&
+                      aligned16(bval);
+  if (!vec_ok) {
+    const int64_t grid = ceil_div(n_brows * C4, 256);
+    if (grid > 0x7fffffffLL) return SN_ERR_OVERFLOW;
+    if (elu)
+      bsr4_spmm_scalar_kernel<true><<<(unsigned)grid, 256, 0, st>>>(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C4);
+    else
+      bsr4_spmm_scalar_kernel<false><<<(unsigned)grid, 256, 0, st>>>(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C4);
+    return launch_status();
+  }
+  const int v = C4 / 4;  // float4 columns per quaternion component
+  if (v <= 1) return launch_vec4<1>(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C4, elu, st);
+  if (v <= 2) return launch_vec4<2>(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C4, elu, st);
+  if (v <= 4) return launch_vec4<4>(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C4, elu, st);
+  return launch_vec4<8>(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C4, elu, st);
+}

@@ -1,0 +1,299 @@
+"""Device-resident sparse operators (CSR32 / BSR4) and their construction from torch COO tensors.
+
+The reference hands its layers a torch sparse COO tensor built on the CPU every step
+(``sparse_diag_cat`` / ``sparse_cat``, src/utils/utils_pt.py:21-53) and re-derives a CSR from it on
+every forward AND backward (src/utils/cuda/sparse_bmm_func.py:39,66-67; caching is stubbed out with
+``if False`` at :36,63).  Here an operator is converted ONCE on the GPU into
+
+  * ``CsrOperator``  -- int32 rowptr / colind + fp32 values         (scalar cotangent Laplacian)
+  * ``Bsr4Operator`` -- int32 block rowptr / colind + 16 fp32/block (quaternion Dirac D and adjoint D*)
+
+together with (lazily) the transposed structure the backward pass needs, and cached on the torch tensor
+it came from, so the per-step hot path never touches COO again.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _native as N
+
+__all__ = ["CsrOperator", "Bsr4Operator", "as_csr", "as_bsr4", "clear_cache"]
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(
+            "surfacenetworks_b200 runs on CUDA (sm_100a) only; %s is on %s. There is no CPU fallback -- "
+            "use the reference implementation for CPU runs." % (what, t.device))
+
+
+def _check_dense(X, name):
+    _require_cuda(X, name)
+    if X.dtype != torch.float32:
+        raise TypeError("%s must be float32, got %s" % (name, X.dtype))
+    if X.dim() != 2 or (X.shape[1] > 1 and X.stride(1) != 1):
+        raise ValueError("%s must be a 2-D row-major matrix (stride(1) == 1); got shape %s strides %s"
+                         % (name, tuple(X.shape), X.stride()))
+
+
+def _coo_to_csr32(batch, row, col, val, rows_per_batch, cols_per_batch, n_rows, n_cols, is_sorted):
+    """COO (int64, device) -> (rowptr, colind, val) via sn_coo_to_csr32 (replaces batch_csr.cu:13-47)."""
+    dev = val.device
+    nnz = int(val.numel())
+    rowptr = torch.empty(n_rows + 1, dtype=torch.int32, device=dev)
+    colind = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+    out_val = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)
+    ws_bytes = 0 if is_sorted else N.lib.sn_coo_to_csr32_ws_bytes(nnz, n_rows)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        N.call("sn_coo_to_csr32", _ptr(batch), _ptr(row), _ptr(col), _ptr(val), nnz, rows_per_batch, cols_per_batch,
+               n_rows, n_cols, N.SN_COO_SORTED if is_sorted else 0, _ptr(rowptr), _ptr(colind), _ptr(out_val),
+               _ptr(ws), ws_bytes, _stream())
+    return rowptr, colind[:nnz], out_val[:nnz]
+
+
+class _CooSource:
+    """The COO arrays an operator was built from -- kept only to build the transpose lazily."""
+
+    def __init__(self, batch, row, col, val, rows_per_batch, cols_per_batch, n_rows, n_cols, is_sorted):
+        self.batch, self.row, self.col, self.val = batch, row, col, val
+        self.rows_per_batch, self.cols_per_batch = rows_per_batch, cols_per_batch
+        self.n_rows, self.n_cols, self.is_sorted = n_rows, n_cols, is_sorted
+
+    def transposed(self):
+        return _CooSource(self.batch, self.col, self.row, self.val, self.cols_per_batch, self.rows_per_batch,
+                          self.n_cols, self.n_rows, False)
+
+    def to_csr(self):
+        return _coo_to_csr32(self.batch, self.row, self.col, self.val, self.rows_per_batch, self.cols_per_batch,
+                             self.n_rows, self.n_cols, self.is_sorted)
+
+    @staticmethod
+    def from_torch(S):
+        """Accepts the reference's two sparse layouts: 2-D block-diagonal (sparse_diag_cat) or 3-D
+        [B, R, C] (sparse_cat, the layout of the reference's dead SparseBMMFunc path)."""
+        _require_cuda(S, "sparse operator")
+        if S.layout != torch.sparse_coo:
+            raise TypeError("expected a torch sparse COO tensor, got layout %s" % S.layout)
+        idx, val = S._indices(), S._values()
+        if val.dtype != torch.float32:
+            raise TypeError("operator values must be float32 (the reference stores float32, "
+                            "add_laplacian.py:61-65); got %s" % val.dtype)
+        idx = idx.contiguous()
+        val = val.contiguous()
+        if S.dim() == 2:
+            return _CooSource(None, idx[0], idx[1], val, 0, 0, S.shape[0], S.shape[1], S.is_coalesced())
+        if S.dim() == 3:
+            B, R, C = S.shape
+            return _CooSource(idx[0], idx[1], idx[2], val, R, C, B * R, B * C, S.is_coalesced())
+        raise ValueError("sparse operator must be 2-D or 3-D, got %d-D" % S.dim())
+
+
+class CsrOperator:
+    """Scalar CSR32 operator ``S`` [n_rows x n_cols]; ``apply`` computes ``Y = S @ X`` on the GPU."""
+
+    kind = "csr"
+
+    def __init__(self, rowptr, colind, val, n_rows, n_cols, source=None):
+        self.rowptr, self.colind, self.val = rowptr, colind, val
+        self.n_rows, self.n_cols = int(n_rows), int(n_cols)
+        self._source = source
+        self._T = None
+
+    @property
+    def shape(self):
+        return (self.n_rows, self.n_cols)
+
+    @property
+    def nnz(self):
+        return int(self.val.numel())
+
+    @property
+    def device(self):
+        return self.rowptr.device
+
+    @classmethod
+    def from_source(cls, src):
+        rowptr, colind, val = src.to_csr()
+        return cls(rowptr, colind, val, src.n_rows, src.n_cols, src)
+
+    @classmethod
+    def from_torch_coo(cls, S):
+        return cls.from_source(_CooSource.from_torch(S))
+
+    @property
+    def T(self):
+        """Transposed operator (what backward applies, sparse_bmm_func.py:66-70) -- built once."""
+        if self._T is None:
+            if self._source is None:
+                raise RuntimeError("transpose unavailable: operator was built without its COO source")
+            self._T = CsrOperator.from_source(self._source.transposed())
+            self._T._T = self
+        return self._T
+
+    def release_source(self):
+        self._source = None
+
+    def algorithmic_bytes(self, C):
+        """Canonical HBM bytes of one application at feature width C."""
+        return 4 * (self.n_rows + 1) + 8 * self.nnz + 4 * self.n_cols * C + 4 * self.n_rows * C
+
+    def flops(self, C):
+        return 2 * self.nnz * C
+
+    def apply(self, X, out=None, elu_input=False):
+        """``out[n_rows, C] = S @ (elu(X) if elu_input else X)``; X: [>= n_cols, C] (row stride free)."""
+        _check_dense(X, "X")
+        if X.shape[0] < self.n_cols:
+            raise ValueError("X has %d rows, operator has %d columns" % (X.shape[0], self.n_cols))
+        C = X.shape[1]
+        if out is None:
+            out = torch.empty(self.n_rows, C, dtype=torch.float32, device=X.device)
+        _check_dense(out, "out")
+        if out.shape[0] != self.n_rows or out.shape[1] != C:
+            raise ValueError("out must be [%d, %d], got %s" % (self.n_rows, C, tuple(out.shape)))
+        with torch.cuda.device(X.device):
+            N.call("sn_csr_spmm_f32", _ptr(self.rowptr), _ptr(self.colind), _ptr(self.val), _ptr(X), X.stride(0),
+                   _ptr(out), out.stride(0), self.n_rows, C, N.SN_SPMM_ELU_INPUT if elu_input else 0, _stream())
+        return out
+
+
+class Bsr4Operator:
+    """4x4-block CSR operator for the quaternion Dirac operators; scalar shape [4*n_brows x 4*n_bcols].
+
+    ``apply`` implements the reference's ``view`` semantics (utils_pt.py:201-203): X is [n_bcols, C] node
+    features, the q-th quarter of the channel vector is quaternion component q.
+    """
+
+    kind = "bsr4"
+
+    def __init__(self, browptr, bcolind, bval, n_brows, n_bcols, source=None):
+        self.browptr, self.bcolind, self.bval = browptr, bcolind, bval
+        self.n_brows, self.n_bcols = int(n_brows), int(n_bcols)
+        self._source = source
+        self._T = None
+
+    @property
+    def shape(self):
+        return (4 * self.n_brows, 4 * self.n_bcols)
+
+    @property
+    def n_blocks(self):
+        return int(self.bcolind.numel())
+
+    @property
+    def device(self):
+        return self.browptr.device
+
+    @classmethod
+    def from_source(cls, src):
+        if src.n_rows % 4 or src.n_cols % 4:
+            raise ValueError("Dirac operator shape must be a multiple of 4 in both dims, got %dx%d"
+                             % (src.n_rows, src.n_cols))
+        rowptr, colind, val = src.to_csr()
+        dev = val.device
+        n_brows = src.n_rows // 4
+        browptr = torch.empty(n_brows + 1, dtype=torch.int32, device=dev)
+        ws_bytes = N.lib.sn_csr32_to_bsr4_ws_bytes(src.n_rows)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            N.call("sn_csr32_to_bsr4_count", _ptr(rowptr), _ptr(colind), src.n_rows, _ptr(browptr), _ptr(ws),
+                   ws_bytes, _stream())
+            nb = int(browptr[-1].item())  # one 4-byte read-back per operator conversion (not per step)
+            bcolind = torch.empty(max(nb, 1), dtype=torch.int32, device=dev)
+            bval = torch.empty(max(nb, 1) * 16, dtype=torch.float32, device=dev)
+            N.call("sn_csr32_to_bsr4_fill", _ptr(rowptr), _ptr(colind), _ptr(val), src.n_rows, _ptr(browptr),
+                   _ptr(bcolind), _ptr(bval), _stream())
+        return cls(browptr, bcolind[:nb], bval[:nb * 16], n_brows, src.n_cols // 4, src)
+
+    @classmethod
+    def from_torch_coo(cls, S):
+        return cls.from_source(_CooSource.from_torch(S))
+
+    @property
+    def T(self):
+        if self._T is None:
+            if self._source is None:
+                raise RuntimeError("transpose unavailable: operator was built without its COO source")
+            self._T = Bsr4Operator.from_source(self._source.transposed())
+            self._T._T = self
+        return self._T
+
+    def release_source(self):
+        self._source = None
+
+    def algorithmic_bytes(self, C):
+        return 4 * (self.n_brows + 1) + 68 * self.n_blocks + 4 * self.n_bcols * C + 4 * self.n_brows * C
+
+    def flops(self, C, stored_nnz_per_block=12):
+        """Reference-stored nnz count (12 per Dirac block) by default; pass 16 for dense-block FLOPs."""
+        return 2 * stored_nnz_per_block * self.n_blocks * (C // 4)
+
+    def apply(self, X, out=None, elu_input=False):
+        _check_dense(X, "X")
+        if X.shape[0] < self.n_bcols:
+            raise ValueError("X has %d rows, operator has %d block columns" % (X.shape[0], self.n_bcols))
+        C = X.shape[1]
+        if C % 4:
+            raise ValueError("feature width must be divisible by 4 for the quaternion view, got %d" % C)
+        if out is None:
+            out = torch.empty(self.n_brows, C, dtype=torch.float32, device=X.device)
+        _check_dense(out, "out")
+        if out.shape[0] != self.n_brows or out.shape[1] != C:
+            raise ValueError("out must be [%d, %d], got %s" % (self.n_brows, C, tuple(out.shape)))
+        with torch.cuda.device(X.device):
+            N.call("sn_bsr4_spmm_f32", _ptr(self.browptr), _ptr(self.bcolind), _ptr(self.bval), _ptr(X), X.stride(0),
+                   _ptr(out), out.stride(0), self.n_brows, C, N.SN_SPMM_ELU_INPUT if elu_input else 0, _stream())
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# Cache: converted operators live on the torch tensor object they came from (``S._sn_ops``).
+_ATTR = "_sn_ops"
+
+
+def _cached(S, kind, builder):
+    cache = getattr(S, _ATTR, None)
+    if cache is None:
+        cache = {}
+        try:
+            setattr(S, _ATTR, cache)
+        except Exception:  # pragma: no cover - exotic tensor subclasses
+            return builder(S)
+    key = (kind, S._values().data_ptr(), S._values()._version, S._nnz())
+    op = cache.get(key)
+    if op is None:
+        cache.clear()
+        op = cache[key] = builder(S)
+    return op
+
+
+def clear_cache(S):
+    if hasattr(S, _ATTR):
+        getattr(S, _ATTR).clear()
+
+
+def as_csr(S):
+    """torch sparse COO (2-D block-diagonal or 3-D batched) or CsrOperator -> CsrOperator (cached)."""
+    if isinstance(S, CsrOperator):
+        return S
+    if isinstance(S, Bsr4Operator):
+        raise TypeError("expected a scalar (Laplacian) operator, got a Bsr4Operator")
+    return _cached(S, "csr", CsrOperator.from_torch_coo)
+
+
+def as_bsr4(S):
+    """torch sparse COO (2-D block-diagonal or 3-D batched) or Bsr4Operator -> Bsr4Operator (cached)."""
+    if isinstance(S, Bsr4Operator):
+        return S
+    if isinstance(S, CsrOperator):
+        raise TypeError("expected a Dirac (4x4-block) operator, got a CsrOperator")
+    return _cached(S, "bsr4", Bsr4Operator.from_torch_coo)

@@ -1,0 +1,110 @@
+"""Autograd seam of the operator-application path.
+
+Mirrors the reference's ``SparseBMMFunc`` (src/utils/cuda/sparse_bmm_func.py:23-72): forward applies the
+sparse operator to a dense matrix, backward applies the TRANSPOSED operator to the incoming gradient and
+returns no gradient for the operator itself (:60,72).  Differences: static new-style Functions, the CSR /
+BSR structures (and their transposes) are built once per operator instead of on every call (:39,66-67),
+and the ELU in front of the product and the ``torch.cat`` behind it (utils_pt.py:161-168 etc.) are folded
+into the same Function so the concat buffer is written in place.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _native as N
+from .operators import Bsr4Operator, CsrOperator, _check_dense, _ptr, _stream
+
+__all__ = ["spmm", "stage_concat", "elu_into"]
+
+
+def _as2d(x):
+    """[B, n, C] contiguous -> [B*n, C] view (what ``x.view(-1, feat)`` does at utils_pt.py:167)."""
+    if x.dim() == 3:
+        return x.reshape(-1, x.shape[-1])
+    return x
+
+
+def elu_into(X, out):
+    """out[:, :] = elu(X) through sn_elu_f32 (strided destination, e.g. the left half of a concat buffer)."""
+    _check_dense(X, "X")
+    _check_dense(out, "out")
+    with torch.cuda.device(X.device):
+        N.call("sn_elu_f32", _ptr(X), X.stride(0), _ptr(out), out.stride(0), X.shape[0], X.shape[1], _stream())
+    return out
+
+
+def _elu_bwd(A, a_is_raw, G, G2, out):
+    with torch.cuda.device(G.device):
+        N.call("sn_elu_bwd_f32", _ptr(A), A.stride(0), 1 if a_is_raw else 0, _ptr(G), G.stride(0),
+               _ptr(G2), 0 if G2 is None else G2.stride(0), _ptr(out), out.stride(0), G.shape[0], G.shape[1], _stream())
+    return out
+
+
+class _Spmm(torch.autograd.Function):
+    """Y = S @ X  (grad only w.r.t. X, as sparse_bmm_func.py:53-72)."""
+
+    @staticmethod
+    def forward(ctx, X, op):
+        ctx.op = op
+        return op.apply(X.contiguous())
+
+    @staticmethod
+    def backward(ctx, gY):
+        return ctx.op.T.apply(gY.contiguous()), None
+
+
+def spmm(op, X):
+    """Differentiable ``op @ X`` for a CsrOperator / Bsr4Operator and a 2-D dense X."""
+    if not isinstance(op, (CsrOperator, Bsr4Operator)):
+        raise TypeError("op must be a CsrOperator or Bsr4Operator")
+    return _Spmm.apply(X, op)
+
+
+class _StageConcat(torch.autograd.Function):
+    """Z[rows_out, 2C] = [ elu(x_self) | S @ elu(x_gather) ]  -- one stage's operator application.
+
+    Covers utils_pt.py:161-168 / 172-177 (Laplacian, x_self is x_gather) and :195-204 / :208-216 (Dirac D with
+    x_self = f, x_gather = v; adjoint D* with x_self = v, x_gather = f_out).
+    """
+
+    @staticmethod
+    def forward(ctx, x_self, x_gather, op, same):
+        xs = x_self.contiguous()
+        rows_out, C = xs.shape
+        Z = torch.empty(rows_out, 2 * C, dtype=torch.float32, device=xs.device)
+        left, right = Z[:, :C], Z[:, C:]
+        elu_into(xs, left)
+        if same:
+            # gather from the already-activated left half (row stride 2C): no ELU recompute
+            op.apply(left, out=right)
+            ctx.save_for_backward(Z)
+        else:
+            xg = x_gather.contiguous()
+            op.apply(xg, out=right, elu_input=True)
+            ctx.save_for_backward(Z, xg)
+        ctx.op, ctx.same, ctx.C = op, same, C
+        return Z
+
+    @staticmethod
+    def backward(ctx, gZ):
+        op, C = ctx.op, ctx.C
+        gZ = gZ.contiguous()
+        g_left, g_right = gZ[:, :C], gZ[:, C:]
+        if ctx.same:
+            (Z,) = ctx.saved_tensors
+            t = op.T.apply(g_right)                       # S^T g
+            gx = torch.empty_like(t)
+            _elu_bwd(Z[:, :C], False, g_left, t, gx)      # (g_left + S^T g) * elu'(x)
+            return gx, None, None, None
+        Z, xg = ctx.saved_tensors
+        g_self = torch.empty(gZ.shape[0], C, dtype=torch.float32, device=gZ.device)
+        _elu_bwd(Z[:, :C], False, g_left, None, g_self)
+        t = op.T.apply(g_right)
+        _elu_bwd(xg, True, t, None, t)
+        return g_self, t, None, None
+
+
+def stage_concat(op, x_self, x_gather=None):
+    """``[elu(x_self) | op @ elu(x_gather)]`` as one [rows, 2C] buffer; ``x_gather=None`` means x_self."""
+    same = x_gather is None
+    return _StageConcat.apply(x_self, x_self if same else x_gather, op, same)

@@ -1,0 +1,60 @@
+"""Closed-form deterministic tensors / parameter fills shared by make_golden.py and the tests.
+
+Integer hashing only (splitmix64-style finaliser), so the same values come out on any platform and do
+not depend on torch's RNG stream or on nn.Module init code.
+"""
+import numpy as np
+import torch
+
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _mix(z):
+    z = z.astype(np.uint64)
+    with np.errstate(over="ignore"):
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return z
+
+
+def det_uniform(n, seed, stream=0):
+    """n values in [0,1) with 24-bit resolution (exact in float32)."""
+    with np.errstate(over="ignore"):
+        idx = np.arange(n, dtype=np.uint64) * np.uint64(4) + np.uint64(stream)
+        base = np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15)
+        h = _mix(idx * np.uint64(0xD1B54A32D192ED03) + base)
+    return ((h >> np.uint64(40)).astype(np.float64)) / float(1 << 24)
+
+
+def det_array(shape, seed):
+    """Roughly N(0,1) float32 array (Irwin-Hall of 4 uniforms, rescaled)."""
+    n = int(np.prod(shape))
+    s = sum(det_uniform(n, seed, k) for k in range(4))
+    return ((s - 2.0) * np.sqrt(3.0)).astype(np.float32).reshape(shape)
+
+
+def det_tensor(shape, seed):
+    return torch.from_numpy(det_array(tuple(shape), seed))
+
+
+def det_fill(module, seed):
+    """Overwrite every parameter and BatchNorm buffer of ``module`` with closed-form values."""
+    with torch.no_grad():
+        for k, (name, p) in enumerate(module.named_parameters()):
+            s = seed * 1000 + k
+            if name.endswith("bn.weight"):
+                p.copy_(1.0 + 0.3 * det_tensor(p.shape, s))
+            elif name.endswith("bn.bias"):
+                p.copy_(0.2 * det_tensor(p.shape, s))
+            elif p.dim() == 2:
+                p.copy_(det_tensor(p.shape, s) / float(np.sqrt(p.shape[1])))
+            else:
+                p.copy_(0.1 * det_tensor(p.shape, s))
+        for k, (name, b) in enumerate(module.named_buffers()):
+            s = seed * 1000 + 500 + k
+            if name.endswith("running_mean"):
+                b.copy_(0.1 * det_tensor(b.shape, s))
+            elif name.endswith("running_var"):
+                b.copy_(1.0 + 0.5 * torch.from_numpy(det_uniform(b.numel(), s).astype(np.float32)).reshape(b.shape))
+    return module
