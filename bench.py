@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the operator-application hot path on the as_rigid_as_possible workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...)
+
+Workload (BASELINE.json configs[2], "cfg3" in SURVEY.md 8(d)): per GPU a batch of 64 synthetic meshes x 2000
+vertices (~3970 faces), the reference's DirModel (src/as_rigid_as_possible/models.py:108-152: 8 DirResNet2 +
+7 AvgResNet2 blocks, 128 features).  One STEP = the training step of src/as_rigid_as_possible/main.py:219-230 on
+one batch: forward, masked smooth-L1 loss, backward, (N > 1: one flat NCCL gradient all-reduce), Adam update.
+Every Dirac application D v / D* f (16 forward + 16 backward per step) runs through sn_bsr4_spmm_f32.
+Weak scaling: 64 meshes per GPU.  metric = meshes/s over all ranks.
+
+  value     : device-timed, batch resident in HBM (operators already converted to BSR4)
+  e2e       : same step through the public module API starting from HOST (pinned) buffers every step: inputs,
+              targets, mask AND the two COO batch operators (int64 indices, as the reference's sample_batch
+              hands them over, main.py:172-183) are copied H2D, converted on the GPU, and the loss is read back
+  roofline  : the Dirac BSR4 SpMM kernel -- the kernel BASELINE.json's metric / north_star name -- timed live with
+              CUDA events around every launch inside the timed region; achieved = canonical algorithmic bytes
+               / time; peak = MEASURED_PEAKS.json hbm_gbs.  "kernels" lists the share of the step
+              each of our kernels takes, so the dominant one is visible.
+  cpu_baseline : the oracle port (torch-CPU restatement of the reference modules, oracle/layers.py -- the
+              reference itself is Python and does not travel to the GPU box) on a bounded sample, host cores.
+  --impl reference : that CPU path alone (rank 0), same metric/config, bounded sample per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "arap_dirmodel_train_meshes_per_sec"
+UNIT = "meshes/s"
+MESHES_PER_GPU = 64
+NUM_VERTICES = 2000
+WIDTH = 128
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--meshes-per-gpu", type=int, default=MESHES_PER_GPU)
+    ap.add_argument("--num-vertices", type=int, default=NUM_VERTICES)
+    ap.add_argument("--cpu-sample-meshes", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-spmm-sweep", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus):
+    return {"workload": "as_rigid_as_possible DirModel (8 DirResNet2 + 7 AvgResNet2, 128 features) training step; "
+                        "%d synthetic meshes x %d vertices per GPU (BASELINE configs[2]/[3])"
+                        % (args.meshes_per_gpu, args.num_vertices),
+            "meshes_per_gpu": args.meshes_per_gpu, "num_vertices": args.num_vertices, "features": WIDTH,
+            "global_batch": args.meshes_per_gpu * n_gpus, "parallelism": "dp%d (one flat grad all-reduce)" % n_gpus,
+            "optimizer": "Adam lr 1e-3 wd 1e-5", "l2": "working set per step >> 126 MB L2 (inputs larger than L2)"}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
+def cpu_step_fn(meshes, seed):
+    """Training step of the oracle port on the host; returns (step_fn, n_meshes)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from oracle import layers as O
+    from surfacenetworks_b200 import models as M, workloads as W
+
+    batch = W.arap_batch(meshes, seed)
+    torch.manual_seed(0)
+    model = M.ArapDirModel()
+    P = {}
+    for k, v in model.state_dict().items():
+        v = v.clone()
+        if v.is_floating_point() and not k.endswith(("running_mean", "running_var")):
+            v.requires_grad_(True)
+        P[k] = v
+    params = [v for v in P.values() if v.requires_grad]
+    opt = torch.optim.Adam(params, 1e-3, weight_decay=1e-5)
+    Di, DiA = batch["Di"], batch["DiA"]
+
+    def step():
+        opt.zero_grad()
+        out = O.arap_dir_model(P, Di, DiA, batch["mask"], batch["inputs"])
+        loss = O.arap_loss(out, batch["targets"], batch["mask"], len(meshes))
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+
+    return step, len(meshes)
+
+
+def time_cpu(args, steps, warmup):
+    from surfacenetworks_b200 import workloads as W
+    torch.set_num_threads(os.cpu_count() or 1)
+    n = args.cpu_sample_meshes
+    meshes = W.make_mesh_ops(args.num_vertices, range(n))
+    step, n = cpu_step_fn(meshes, 0)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d meshes x %d vertices per step, %d timed steps after %d warm-up (oracle/layers.py, torch %s CPU)"
+                      % (n, args.num_vertices, steps, warmup, torch.__version__),
+            "ms_per_step": dt * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = time_cpu(args, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, args.gpus),
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc, self.lines, self.idx = None, [], gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return float(p["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy; kernel timed per launch)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
+def spmm_sweep(dev):
+    """Operator-only numbers named by BASELINE.json's metric: GB/s (canonical bytes) and GFLOP/s per SpMM family."""
+    from surfacenetworks_b200 import operators as OP, workloads as W
+    out = {}
+
+    def time_op(op, X, reps=30):
+        Y = op.apply(X)
+        for _ in range(3):
+            op.apply(X, out=Y)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        total = 0.0
+        for _ in range(reps):
+            flush.zero_()                      # evict L2 (126 MB) between timed launches
+            e0.record()
+            op.apply(X, out=Y)
+            e1.record()
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+        return total / reps
+
+    def entry(op, X, C):
+        ms = time_op(op, X)
+        return {"us": ms * 1e3, "GBps": op.algorithmic_bytes(C) / ms / 1e6, "GFLOPs": op.flops(C) / ms / 1e6,
+                "alg_MB": op.algorithmic_bytes(C) / 1e6}
+
+    # cfg2: mesh_mnist Laplacian, 32 meshes x 500 V, C=128
+    meshes = W.make_mesh_ops(500, range(32))
+    L = OP.as_csr(W.lap_batch(meshes)["L"].to(dev))
+    out["lap_cfg2_B32_V500_C128"] = entry(L, torch.randn(L.n_cols, 128, device=dev), 128)
+    # cfg5: FAUST-size single mesh, Dirac sweep over feature width
+    m = W.make_mesh_ops(7000, [0])
+    b = W.arap_batch(m, 0)
+    D, DA = OP.as_bsr4(b["Di"].to(dev)), OP.as_bsr4(b["DiA"].to(dev))
+    for C in (16, 32, 64, 128, 256, 512):
+        out["dirac_D_cfg5_V7000_C%d" % C] = entry(D, torch.randn(D.n_bcols, C, device=dev), C)
+        out["dirac_Dstar_cfg5_V7000_C%d" % C] = entry(DA, torch.randn(DA.n_bcols, C, device=dev), C)
+    return out
+
+
+def run_b200(args):
+    from surfacenetworks_b200 import _native as N
+    from surfacenetworks_b200 import dist as D
+    from surfacenetworks_b200 import models as M
+    from surfacenetworks_b200 import operators as OP
+    from surfacenetworks_b200 import workloads as W
+    import torch.distributed as tdist
+
+    rank, local_rank, world = D.init_from_env()
+    if world != args.gpus:
+        if rank == 0:
+            print("warning: --gpus %d but WORLD_SIZE %d; using WORLD_SIZE" % (args.gpus, world), file=sys.stderr)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B, K, Wu = args.meshes_per_gpu, args.steps, max(args.warmup, 3)
+
+    # ---- this rank's shard: B distinct meshes (seeds disjoint across ranks), host batch in pinned memory
+    meshes = W.make_mesh_ops(args.num_vertices, range(rank * B, rank * B + B))
+    host = W.arap_batch(meshes, seed=rank)
+    nv, nf = host["num_vertices"], host["num_faces"]
+    pinned = {k: host[k].pin_memory() for k in ("inputs", "targets", "mask")}
+    for k in ("Di", "DiA"):
+        pinned[k + "_idx"] = host[k]._indices().pin_memory()
+        pinned[k + "_val"] = host[k]._values().pin_memory()
+    shapes = {k: tuple(host[k].shape) for k in ("Di", "DiA")}
+    h2d_bytes = sum(t.numel() * t.element_size() for t in pinned.values())
+
+    torch.manual_seed(0)
+    model = M.ArapDirModel().to(dev).train()
+    D.broadcast_module(model)
+    grads = D.FlatGradAllReduce(model)
+    opt = torch.optim.Adam(model.parameters(), 1e-3, weight_decay=1e-5, fused=True)
+
+    def upload():
+        d = {k: pinned[k].to(dev, non_blocking=True) for k in ("inputs", "targets", "mask")}
+        for k in ("Di", "DiA"):
+            d[k] = torch.sparse_coo_tensor(pinned[k + "_idx"].to(dev, non_blocking=True),
+                                           pinned[k + "_val"].to(dev, non_blocking=True), shapes[k], is_coalesced=True)
+        return d
+
+    def train_step(d, Dop, DAop):
+        grads.zero()
+        out = model(Dop, DAop, d["mask"], d["inputs"])
+        loss = M.arap_loss(out, d["targets"], d["mask"], B)
+        loss.backward()
+        grads.allreduce()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- resident run: batch + converted operators (and their transposes) already in HBM
+    res = upload()
+    Dop, DAop = OP.as_bsr4(res["Di"]), OP.as_bsr4(res["DiA"])
+    Dop.T, DAop.T  # build the backward structures once, outside the timed region
+    for _ in range(Wu):
+        train_step(res, Dop, DAop)
+    clocks = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    N.TIMER = N.KernelTimer(["sn_bsr4_spmm_f32", "sn_csr_spmm_f32", "sn_elu_f32", "sn_elu_bwd_f32"])
+    counts0 = dict(N.CALL_COUNTS)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        loss = train_step(res, Dop, DAop)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    timer, N.TIMER = N.TIMER, None
+    launches = sum(v - counts0.get(k, 0) for k, v in N.CALL_COUNTS.items())
+    clock_info = clocks.stop() if rank == 0 else None
+    ms_step = ms_total / K
+    value = B * world / (ms_step / 1e3)
+    final_loss = float(loss)
+
+    # ---- live roofline of the Dirac SpMM + per-kernel shares
+    ksum = timer.summary()
+    peak, peak_src = measured_peaks()
+    bsr = [v for (name, _), v in ksum.items() if name == "sn_bsr4_spmm_f32"]
+    bsr_ms = sum(v["ms"] for v in bsr)
+    bsr_bytes = sum(v["bytes"] for v in bsr)
+    bsr_launches = sum(v["launches"] for v in bsr)
+    achieved = bsr_bytes / (bsr_ms / 1e3) / 1e9 if bsr_ms > 0 else 0.0
+    roofline = {"kernel": "bsr4_spmm_vec4_kernel (sn_bsr4_spmm_f32: D, D*, D^T, D*^T at C=128)", "bound": "hbm",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "launches_timed": bsr_launches,
+                "avg_launch_us": bsr_ms / max(bsr_launches, 1) * 1e3,
+                "alg_bytes_per_launch": bsr_bytes / max(bsr_launches, 1),
+                "share_of_step": bsr_ms / ms_total if ms_total > 0 else None}
+    kernels = {}
+    for (name, tag), v in sorted(ksum.items()):
+        kernels["%s [%s]" % (name, tag)] = {"launches_per_step": v["launches"] / K, "us_per_launch": v["ms"] / v["launches"] * 1e3,
+                                           "share_of_step": v["ms"] / ms_total,
+                                           "GBps": (v["bytes"] / (v["ms"] / 1e3) / 1e9) if v["bytes"] else None}
+
+    # ---- end-to-end: every step starts from pinned host buffers (inputs + COO operators) and reads the loss back
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step():
+            d = upload()
+            Dn, DAn = OP.Bsr4Operator.from_torch_coo(d["Di"]), OP.Bsr4Operator.from_torch_coo(d["DiA"])
+            return float(train_step(d, Dn, DAn))          # .item(): D2H read of the loss
+        for _ in range(Wu):
+            e2e_step()
+        barrier()
+        e0.record()
+        for _ in range(K):
+            e2e_step()
+        e1.record()
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / K
+        e2e = {"value": B * world / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+               "d2h_bytes_per_step": 4 + 8, "ms_per_step": ms_e2e,
+               "path": "pinned host inputs/targets/mask + int64 COO Di, DiA -> H2D -> sn_coo_to_csr32 / sn_csr32_to_bsr4 "
+                       "(+ transposes) -> ArapDirModel step -> loss.item()"}
+
+    if rank != 0:
+        return
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wu,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args, world), "clocks": clock_info, "e2e": e2e,
+            "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "final_loss": final_loss,
+            "padded": {"num_vertices": nv, "num_faces": nf, "dirac_blocks": Dop.n_blocks},
+            "grad_allreduce_bytes": grads.nbytes}
+    if not args.no_spmm_sweep and world == 1:
+        line["spmm"] = spmm_sweep(dev)
+    if not args.no_cpu_baseline and world == 1:
+        cb = time_cpu(args, 3, 1)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback); "
+                         "use --impl reference for the CPU arm")
+    run_b200(args)
+    import torch.distributed as tdist
+    if tdist.is_available() and tdist.is_initialized():
+        tdist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -61,9 +61,52 @@ def check(fn, status):
         raise SurfnetError(fn, status)
 
 
+# Launch accounting: every successful call of a kernel-launching entry point is counted here (bench.py reports
+# the total inside its timed region as "gpu_launches"); TIMER, when set, brackets selected calls with CUDA events
+# on the launching stream (bench.py's live roofline measurement).
+CALL_COUNTS = {}
+TIMER = None
+
+
+class KernelTimer:
+    """Collects (name, tag, bytes, flops, start_event, end_event) for calls whose name is in ``names``."""
+
+    def __init__(self, names):
+        self.names = set(names)
+        self.records = []
+        self._meta = None
+
+    def annotate(self, tag, nbytes, flops):
+        self._meta = (tag, nbytes, flops)
+
+    def summary(self):
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, tag, nbytes, flops, e0, e1 in self.records:
+            s = out.setdefault((name, tag), {"launches": 0, "ms": 0.0, "bytes": 0, "flops": 0})
+            s["launches"] += 1
+            s["ms"] += e0.elapsed_time(e1)
+            s["bytes"] += nbytes
+            s["flops"] += flops
+        return out
+
+
 def call(name, *args):
     """Call an int-returning entry point and raise SurfnetError on a non-zero status."""
-    check(name, getattr(lib, name)(*args))
+    t = TIMER
+    if t is not None and name in t.names:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(name, getattr(lib, name)(*args))
+        e1.record()
+        tag, nbytes, flops = t._meta or ("", 0, 0)
+        t._meta = None
+        t.records.append((name, tag, nbytes, flops, e0, e1))
+    else:
+        check(name, getattr(lib, name)(*args))
+    CALL_COUNTS[name] = CALL_COUNTS.get(name, 0) + 1
 
 
 def version():

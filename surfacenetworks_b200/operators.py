@@ -57,7 +57,8 @@ def _coo_to_csr32(batch, row, col, val, rows_per_batch, cols_per_batch, n_rows, 
         N.call("sn_coo_to_csr32", _ptr(batch), _ptr(row), _ptr(col), _ptr(val), nnz, rows_per_batch, cols_per_batch,
                n_rows, n_cols, N.SN_COO_SORTED if is_sorted else 0, _ptr(rowptr), _ptr(colind), _ptr(out_val),
                _ptr(ws), ws_bytes, _stream())
-    return rowptr, colind[:nnz], out_val[:nnz]
+    # nnz == 0 keeps the 1-element allocations so the C ABI never sees a null pointer
+    return rowptr, (colind[:nnz] if nnz else colind), (out_val[:nnz] if nnz else out_val), nnz
 
 
 class _CooSource:
@@ -102,9 +103,10 @@ class CsrOperator:
 
     kind = "csr"
 
-    def __init__(self, rowptr, colind, val, n_rows, n_cols, source=None):
+    def __init__(self, rowptr, colind, val, n_rows, n_cols, source=None, nnz=None):
         self.rowptr, self.colind, self.val = rowptr, colind, val
         self.n_rows, self.n_cols = int(n_rows), int(n_cols)
+        self._nnz = int(val.numel()) if nnz is None else int(nnz)
         self._source = source
         self._T = None
 
@@ -114,7 +116,7 @@ class CsrOperator:
 
     @property
     def nnz(self):
-        return int(self.val.numel())
+        return self._nnz
 
     @property
     def device(self):
@@ -122,8 +124,8 @@ class CsrOperator:
 
     @classmethod
     def from_source(cls, src):
-        rowptr, colind, val = src.to_csr()
-        return cls(rowptr, colind, val, src.n_rows, src.n_cols, src)
+        rowptr, colind, val, nnz = src.to_csr()
+        return cls(rowptr, colind, val, src.n_rows, src.n_cols, src, nnz)
 
     @classmethod
     def from_torch_coo(cls, S):
@@ -160,6 +162,8 @@ class CsrOperator:
         _check_dense(out, "out")
         if out.shape[0] != self.n_rows or out.shape[1] != C:
             raise ValueError("out must be [%d, %d], got %s" % (self.n_rows, C, tuple(out.shape)))
+        if N.TIMER is not None:
+            N.TIMER.annotate("csr %dx%d C=%d" % (self.n_rows, self.n_cols, C), self.algorithmic_bytes(C), self.flops(C))
         with torch.cuda.device(X.device):
             N.call("sn_csr_spmm_f32", _ptr(self.rowptr), _ptr(self.colind), _ptr(self.val), _ptr(X), X.stride(0),
                    _ptr(out), out.stride(0), self.n_rows, C, N.SN_SPMM_ELU_INPUT if elu_input else 0, _stream())
@@ -175,9 +179,10 @@ class Bsr4Operator:
 
     kind = "bsr4"
 
-    def __init__(self, browptr, bcolind, bval, n_brows, n_bcols, source=None):
+    def __init__(self, browptr, bcolind, bval, n_brows, n_bcols, source=None, n_blocks=None):
         self.browptr, self.bcolind, self.bval = browptr, bcolind, bval
         self.n_brows, self.n_bcols = int(n_brows), int(n_bcols)
+        self._n_blocks = int(bcolind.numel()) if n_blocks is None else int(n_blocks)
         self._source = source
         self._T = None
 
@@ -187,7 +192,7 @@ class Bsr4Operator:
 
     @property
     def n_blocks(self):
-        return int(self.bcolind.numel())
+        return self._n_blocks
 
     @property
     def device(self):
@@ -198,7 +203,7 @@ class Bsr4Operator:
         if src.n_rows % 4 or src.n_cols % 4:
             raise ValueError("Dirac operator shape must be a multiple of 4 in both dims, got %dx%d"
                              % (src.n_rows, src.n_cols))
-        rowptr, colind, val = src.to_csr()
+        rowptr, colind, val, _ = src.to_csr()
         dev = val.device
         n_brows = src.n_rows // 4
         browptr = torch.empty(n_brows + 1, dtype=torch.int32, device=dev)
@@ -212,7 +217,9 @@ class Bsr4Operator:
             bval = torch.empty(max(nb, 1) * 16, dtype=torch.float32, device=dev)
             N.call("sn_csr32_to_bsr4_fill", _ptr(rowptr), _ptr(colind), _ptr(val), src.n_rows, _ptr(browptr),
                    _ptr(bcolind), _ptr(bval), _stream())
-        return cls(browptr, bcolind[:nb], bval[:nb * 16], n_brows, src.n_cols // 4, src)
+        if nb:
+            bcolind, bval = bcolind[:nb], bval[:nb * 16]
+        return cls(browptr, bcolind, bval, n_brows, src.n_cols // 4, src, nb)
 
     @classmethod
     def from_torch_coo(cls, S):
@@ -249,6 +256,8 @@ class Bsr4Operator:
         _check_dense(out, "out")
         if out.shape[0] != self.n_brows or out.shape[1] != C:
             raise ValueError("out must be [%d, %d], got %s" % (self.n_brows, C, tuple(out.shape)))
+        if N.TIMER is not None:
+            N.TIMER.annotate("bsr4 %dx%d C=%d" % (self.n_brows, self.n_bcols, C), self.algorithmic_bytes(C), self.flops(C))
         with torch.cuda.device(X.device):
             N.call("sn_bsr4_spmm_f32", _ptr(self.browptr), _ptr(self.bcolind), _ptr(self.bval), _ptr(X), X.stride(0),
                    _ptr(out), out.stride(0), self.n_brows, C, N.SN_SPMM_ELU_INPUT if elu_input else 0, _stream())

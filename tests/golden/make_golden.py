@@ -227,8 +227,9 @@ def main():
     targets = det_tensor((B, nv, 120), 52) * mask
     arrays["inputs"] = inputs.numpy()
     arrays["targets"] = targets.numpy()
-    for tag, model, args in (("dir", det_fill(arap_models.DirModel(), 9), (Dib, DiAb, mask, inputs)),
-                             ("lap", det_fill(arap_models.Model(15), 10), (Lb, mask, inputs))):
+    for tag, make, seed, args in (("dir", arap_models.DirModel, 9, (Dib, DiAb, mask, inputs)),
+                                  ("lap", lambda: arap_models.Model(15), 10, (Lb, mask, inputs))):
+        model = det_fill(make(), seed, gain=0.25)
         model.train()
         out = model(*args)
         outm = out * mask.expand_as(out)
@@ -241,6 +242,18 @@ def main():
         for k in ("conv1.fc.weight", "rn0.bn_fc0.fc.weight", "rn0.bn_fc0.bn.weight", "rn0.bn_fc1.fc.bias",
                   "rn7.bn_fc0.fc.bias", "rn14.bn_fc1.bn.bias", "conv2.fc.weight"):
             arrays[tag + "/g." + k] = named[k].grad.numpy().copy()
+        # the same reference modules in double precision: how far the reference's own fp32 result is from exact
+        model64 = det_fill(make(), seed, gain=0.25).double().train()
+        args64 = tuple(a.double() if torch.is_tensor(a) else a for a in args)
+        out64 = model64(*args64)
+        loss64 = torch.nn.functional.smooth_l1_loss(out64 * mask.double().expand_as(out64), targets.double(),
+                                                    reduction="sum") / B
+        loss64.backward()
+        arrays[tag + "/out64"] = out64.detach().numpy()
+        arrays[tag + "/loss64"] = loss64.detach().numpy()
+        named64 = dict(model64.named_parameters())
+        for k in [k for k in list(arrays) if k.startswith(tag + "/g.")]:
+            arrays[k.replace("/g.", "/g64.")] = named64[k[len(tag) + 3:]].grad.numpy().copy()
     save("arap_models.npz", **arrays)
 
 

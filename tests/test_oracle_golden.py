@@ -12,9 +12,9 @@ from surfacenetworks_b200 import utils_pt as U
 EPS32 = float(np.finfo(np.float32).eps)
 
 
-def params_of(module, seed):
+def params_of(module, seed, gain=1.0):
     """Deterministic parameters in the reference's state_dict layout (keys shared by both implementations)."""
-    det_fill(module, seed)
+    det_fill(module, seed, gain)
     P = {}
     for k, v in module.state_dict().items():
         v = v.clone()
@@ -207,10 +207,10 @@ def test_arap_models(golden, batch, tag):
     B, d = batch, golden("arap_models")
     inputs, targets = torch.from_numpy(d["inputs"]), torch.from_numpy(d["targets"])
     if tag == "dir":
-        P = params_of(M.ArapDirModel(), 9)
+        P = params_of(M.ArapDirModel(), 9, 0.25)
         out = O.arap_dir_model(P, B["Di"], B["DiA"], B["mask"], inputs)
     else:
-        P = params_of(M.ArapLapModel(15), 10)
+        P = params_of(M.ArapLapModel(15), 10, 0.25)
         out = O.arap_lap_model(P, B["L"], B["mask"], inputs)
     loss = O.arap_loss(out, targets, B["mask"], 2)
     loss.backward()
