@@ -47,7 +47,8 @@ typedef void* sn_stream_t; /* cudaStream_t */
 #define SN_COO_SORTED 1 /* input is coalesced: sorted by (batch,row,col), as torch .coalesce() returns */
 
 /* flags for the SpMM entry points */
-#define SN_SPMM_ELU_INPUT 1 /* apply ELU(alpha=1) to the gathered dense operand: Y = S * elu(X)      */
+#define SN_SPMM_ELU_INPUT 1     /* apply ELU(alpha=1) to the gathered dense operand: Y = S * elu(X)  */
+#define SN_SPMM_DIRECT_GATHER 2 /* sn_bsr4_spmm_f32: force the direct-gather kernel (no smem streaming) */
 
 int sn_version(void);
 const char* sn_status_string(int status);
@@ -75,8 +76,11 @@ int sn_coo_to_csr32(const int64_t* batch, const int64_t* row, const int64_t* col
 /* CSR32 -> BSR4 (4x4 blocks; n_rows % 4 == 0).  Two steps because the block count is data dependent:
  *   count : browptr[0..n_rows/4] <- exclusive scan of blocks per block-row; browptr[n_rows/4] = #blocks
  *           (read it back, allocate bcolind[#blocks], bval[16*#blocks]), then
- *   fill  : bcolind ascending per block-row; bval holds each block COLUMN-major:
- *           bval[16*k + 4*q + p] = block_k[p][q]  (p = row in block, q = column in block).
+ *   fill  : bcolind ascending per block-row; bval holds each block column-major with every column rotated so
+ *           that its diagonal entry comes first:
+ *           bval[16*k + 4*q + s] = block_k[(q + s) mod 4][q]   (q = column in block, s = 0..3).
+ *           (Lane q of the SpMM kernels then accumulates output component (q + s) mod 4 in slot s, and the
+ *           cross-lane reduction needs no per-lane register selection.)
  * The Dirac view of utils_pt.py:201-203 makes q index the q-th quarter of the channel vector. */
 size_t sn_csr32_to_bsr4_ws_bytes(int64_t n_rows);
 int sn_csr32_to_bsr4_count(const int32_t* rowptr, const int32_t* colind, int64_t n_rows,
@@ -92,6 +96,8 @@ int sn_csr32_to_bsr4_fill(const int32_t* rowptr, const int32_t* colind, const fl
  *                    Y[r, p*C/4 + c] = sum_{blocks (r,j)} sum_q block[p][q] * X[j, q*C/4 + c],  C % 4 == 0
  * X rows are addressed through colind, so X must have at least n_cols rows.  Accumulation is fp32 FMA
  * in ascending storage order (bit-reproducible run to run).  X and Y must not alias.
+ * sn_bsr4_spmm_f32 runs the streaming kernel (persistent CTAs, cp.async gathers through a shared-memory double
+ * buffer, prefetched indices) for C = 128 / 256 / 512 and the direct-gather kernel for other widths.
  * ---------------------------------------------------------------------------------------------- */
 int sn_csr_spmm_f32(const int32_t* rowptr, const int32_t* colind, const float* val,
                     const float* X, int64_t ldx, float* Y, int64_t ldy,

@@ -47,6 +47,7 @@ SN_OK = 0
 SN_ERR_ARG, SN_ERR_UNSUPPORTED, SN_ERR_WORKSPACE, SN_ERR_OVERFLOW = -1, -2, -3, -4
 SN_COO_SORTED = 1
 SN_SPMM_ELU_INPUT = 1
+SN_SPMM_DIRECT_GATHER = 2
 
 
 class SurfnetError(RuntimeError):

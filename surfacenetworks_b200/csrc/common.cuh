@@ -63,4 +63,12 @@ __device__ __forceinline__ float4 shfl_xor4(float4 v, int m) {
   return v;
 }
 
+__device__ __forceinline__ float4 shfl_idx4(float4 v, int src_lane) {
+  v.x = __shfl_sync(0xffffffffu, v.x, src_lane);
+  v.y = __shfl_sync(0xffffffffu, v.y, src_lane);
+  v.z = __shfl_sync(0xffffffffu, v.z, src_lane);
+  v.w = __shfl_sync(0xffffffffu, v.w, src_lane);
+  return v;
+}
+
 }  // namespace sn

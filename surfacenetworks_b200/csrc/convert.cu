@@ -239,7 +239,7 @@ csr_to_bsr4_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict
           const float v = val[p[i]];
 #pragma unroll
           for (int s = 0; s < 4; ++s)  // static indexing keeps blk[] in registers
-            if (s == qq) blk[4 * s + i] += v;  // column-major: [q][p]
+            if (s == qq) blk[4 * s + ((i - s) & 3)] += v;  // column q, slot (p - q) mod 4
         }
         ++p[i];
       }

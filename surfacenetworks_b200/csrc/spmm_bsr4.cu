@@ -9,11 +9,12 @@
 //
 // Mapping (C4 % 4 == 0 path):  G = 4*LPQ lanes own one block-row; lane (q, t) loads the float4
 // X[j, q*C4 + 4t .. +3] -- so a warp instruction still reads whole contiguous 128 B lines of the dense
-// row -- multiplies it by the four entries of block column q (one 128-bit load thanks to the
-// column-major block storage chosen by sn_csr32_to_bsr4_fill) and keeps four float4 partial sums, one
-// per output component p.  After the row's blocks are consumed a 2-step shuffle reduce-scatter
-// across the four q-lanes leaves lane q holding output component p = q, which it stores as one
-// coalesced float4.  No shared memory, no atomics, deterministic summation order.
+// row -- multiplies it by the four entries of block column q (one 128-bit load thanks to the rotated
+// column-major block storage chosen by sn_csr32_to_bsr4_fill: slot s holds B[(q+s)%4][q]) and keeps four
+// float4 partial sums, slot s feeding output component (q+s)%4.  After the row's blocks are consumed, lane q
+// adds slot (4-d)%4 of the lane d quaternion-components further on (three rotating shuffles, no per-lane
+// register selection) and holds output component p = q, which it stores as one coalesced float4.
+// No shared memory, no atomics, deterministic summation order.
 //
 // Bound: HBM.  Algorithmic bytes per launch = 4(Rb+1) + 68 nb + 4 Cb C + 4 Rb C.
 #include "common.cuh"
@@ -46,7 +47,7 @@ bsr4_spmm_vec4_kernel(const int32_t* __restrict__ browptr, const int32_t* __rest
 #pragma unroll
     for (int m = G; m < kWarp; m <<= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, m));
   }
-  const bool b1 = (q & 2) != 0, b0 = (q & 1) != 0;
+  const int grp = lane - gl;  // first lane of this block-row's lane group
 
   for (int cb0 = 0; cb0 < C4; cb0 += 4 * LPQ) {  // chunks of the quarter-width (one for C <= 128)
     const int cb = cb0 + 4 * t;
@@ -62,7 +63,7 @@ bsr4_spmm_vec4_kernel(const int32_t* __restrict__ browptr, const int32_t* __rest
         wv[u] = xv[u];
         if (k < end && col_ok) {
           const int j = __ldg(bcolind + k);
-          wv[u] = ldg_f4(bval + (int64_t)k * 16 + 4 * q);  // B[0..3][q]
+          wv[u] = ldg_f4(bval + (int64_t)k * 16 + 4 * q);  // B[(q+s)%4][q], s = 0..3
           xv[u] = ldg_f4(X + (int64_t)j * ldx + xoff);
           if (ELU) xv[u] = elu4(xv[u]);
         }
@@ -75,14 +76,12 @@ bsr4_spmm_vec4_kernel(const int32_t* __restrict__ browptr, const int32_t* __rest
         acc3 = fma4(wv[u].w, xv[u], acc3);
       }
     }
-    // reduce-scatter over the four q-lanes: lane q ends up with sum over q' of acc_{p=q}
-    float4 keep0 = sel4(b1, acc2, acc0), keep1 = sel4(b1, acc3, acc1);
-    float4 send0 = sel4(b1, acc0, acc2), send1 = sel4(b1, acc1, acc3);
-    keep0 = add4(keep0, shfl_xor4(send0, 2 * LPQ));
-    keep1 = add4(keep1, shfl_xor4(send1, 2 * LPQ));
-    float4 keep = sel4(b0, keep1, keep0), send = sel4(b0, keep0, keep1);
-    keep = add4(keep, shfl_xor4(send, LPQ));
-    if (row_ok && col_ok) st_stream_f4(Y + row * ldy + xoff, keep);
+    // lane q: out_{p=q} = slot0(q) + slot3(q+1) + slot2(q+2) + slot1(q+3)   (lane indices mod 4 groups of LPQ)
+    float4 out = acc0;
+    out = add4(out, shfl_idx4(acc3, grp + (gl + LPQ) % G));
+    out = add4(out, shfl_idx4(acc2, grp + (gl + 2 * LPQ) % G));
+    out = add4(out, shfl_idx4(acc1, grp + (gl + 3 * LPQ) % G));
+    if (row_ok && col_ok) st_stream_f4(Y + row * ldy + xoff, out);
   }
 }
 
@@ -106,7 +105,7 @@ bsr4_spmm_scalar_kernel(const int32_t* __restrict__ browptr, const int32_t* __re
       float x = __ldg(xr + (int64_t)qq * C4);
       if (ELU) x = elu1(x);
 #pragma unroll
-      for (int p = 0; p < 4; ++p) acc[p] = fmaf(__ldg(b + 4 * qq + p), x, acc[p]);
+      for (int p = 0; p < 4; ++p) acc[p] = fmaf(__ldg(b + 4 * qq + ((p - qq) & 3)), x, acc[p]);
     }
   }
 #pragma unroll
@@ -127,10 +126,13 @@ static int launch_vec4(const int32_t* browptr, const int32_t* bcolind, const flo
   return launch_status();
 }
 
+int launch_bsr4_stream(const int32_t* browptr, const int32_t* bcolind, const float* bval, const float* X, int64_t ldx,
+                       float* Y, int64_t ldy, int64_t n_brows, int64_t C, bool elu, cudaStream_t st);
+
 }  // namespace sn
 
-SN_API int sn_bsr4_spmm_f32(const int32_t* browptr, const int32_t* bcolind, const float* bval, const float* X,
-                            int64_t ldx, float* Y, int64_t ldy, int64_t n_brows, int64_t C, int flags,
+SN_API int sn_bsr4_spmm_f32(const int32_t* browptr, const int32_t* bcolind, const float* bval,
+                            const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t n_brows, int64_t C, int flags,
                             sn_stream_t stream) {
   using namespace sn;
   if (n_brows < 0 || C < 0 || C > 0x7fffffffLL) return SN_ERR_ARG;
@@ -150,6 +152,10 @@ SN_API int sn_bsr4_spmm_f32(const int32_t* browptr, const int32_t* bcolind, cons
     else
       bsr4_spmm_scalar_kernel<false><<<(unsigned)grid, 256, 0, st>>>(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C4);
     return launch_status();
+  }
+  if (!(flags & SN_SPMM_DIRECT_GATHER)) {  // streaming kernel: C = 128 / 256 / 512
+    const int rc = launch_bsr4_stream(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C, elu, st);
+    if (rc != SN_ERR_UNSUPPORTED) return rc;
   }
   const int v = C4 / 4;  // float4 columns per quaternion component
   if (v <= 1) return launch_vec4<1>(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C4, elu, st);

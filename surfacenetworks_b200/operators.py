@@ -179,10 +179,12 @@ class Bsr4Operator:
 
     kind = "bsr4"
 
-    def __init__(self, browptr, bcolind, bval, n_brows, n_bcols, source=None, n_blocks=None):
+    def __init__(self, browptr, bcolind, bval, n_brows, n_bcols, source=None, n_blocks=None, max_row_blocks=0):
         self.browptr, self.bcolind, self.bval = browptr, bcolind, bval
         self.n_brows, self.n_bcols = int(n_brows), int(n_bcols)
         self._n_blocks = int(bcolind.numel()) if n_blocks is None else int(n_blocks)
+        # largest number of blocks in a block-row (3 for D, the largest vertex valence for D*); informational
+        self.max_row_blocks = int(max_row_blocks)
         self._source = source
         self._T = None
 
@@ -212,14 +214,16 @@ class Bsr4Operator:
         with torch.cuda.device(dev):
             N.call("sn_csr32_to_bsr4_count", _ptr(rowptr), _ptr(colind), src.n_rows, _ptr(browptr), _ptr(ws),
                    ws_bytes, _stream())
-            nb = int(browptr[-1].item())  # one 4-byte read-back per operator conversion (not per step)
+            # one small read-back per operator conversion (not per step): block count + densest block-row
+            stats = torch.stack([browptr[-1], (browptr[1:] - browptr[:-1]).max() if n_brows else browptr[-1]]).tolist()
+            nb, max_row_blocks = int(stats[0]), int(stats[1])
             bcolind = torch.empty(max(nb, 1), dtype=torch.int32, device=dev)
             bval = torch.empty(max(nb, 1) * 16, dtype=torch.float32, device=dev)
             N.call("sn_csr32_to_bsr4_fill", _ptr(rowptr), _ptr(colind), _ptr(val), src.n_rows, _ptr(browptr),
                    _ptr(bcolind), _ptr(bval), _stream())
         if nb:
             bcolind, bval = bcolind[:nb], bval[:nb * 16]
-        return cls(browptr, bcolind, bval, n_brows, src.n_cols // 4, src, nb)
+        return cls(browptr, bcolind, bval, n_brows, src.n_cols // 4, src, nb, max_row_blocks)
 
     @classmethod
     def from_torch_coo(cls, S):
@@ -244,7 +248,7 @@ class Bsr4Operator:
         """Reference-stored nnz count (12 per Dirac block) by default; pass 16 for dense-block FLOPs."""
         return 2 * stored_nnz_per_block * self.n_blocks * (C // 4)
 
-    def apply(self, X, out=None, elu_input=False):
+    def apply(self, X, out=None, elu_input=False, direct_gather=False):
         _check_dense(X, "X")
         if X.shape[0] < self.n_bcols:
             raise ValueError("X has %d rows, operator has %d block columns" % (X.shape[0], self.n_bcols))
@@ -259,8 +263,9 @@ class Bsr4Operator:
         if N.TIMER is not None:
             N.TIMER.annotate("bsr4 %dx%d C=%d" % (self.n_brows, self.n_bcols, C), self.algorithmic_bytes(C), self.flops(C))
         with torch.cuda.device(X.device):
-            N.call("sn_bsr4_spmm_f32", _ptr(self.browptr), _ptr(self.bcolind), _ptr(self.bval), _ptr(X), X.stride(0),
-                   _ptr(out), out.stride(0), self.n_brows, C, N.SN_SPMM_ELU_INPUT if elu_input else 0, _stream())
+            flags = (N.SN_SPMM_ELU_INPUT if elu_input else 0) | (N.SN_SPMM_DIRECT_GATHER if direct_gather else 0)
+            N.call("sn_bsr4_spmm_f32", _ptr(self.browptr), _ptr(self.bcolind), _ptr(self.bval),
+                   _ptr(X), X.stride(0), _ptr(out), out.stride(0), self.n_brows, C, flags, _stream())
         return out
 
 

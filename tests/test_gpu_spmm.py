@@ -208,7 +208,10 @@ def test_bsr4_feature_widths_and_strides(golden, C):
     x = det_array((2 * nv, C), 200 + C)
     xg = torch.from_numpy(x).to(DEV)
     y64, bound = c_oracle.dirac_view_mm_f64(idx[0], idx[1], val, 2 * nf, x)
-    within_bound(Di.apply(xg).cpu().numpy(), y64, bound, "contiguous")
+    y = Di.apply(xg)
+    within_bound(y.cpu().numpy(), y64, bound, "contiguous")
+    # streaming kernel (C = 128/256/512) and direct-gather kernel use the same summation order: bit-identical
+    assert torch.equal(y, Di.apply(xg, direct_gather=True))
     Xs = torch.zeros(2 * nv, 2 * C, device=DEV)
     Xs[:, :C] = xg
     Z = torch.zeros(2 * nf, 2 * C, device=DEV)
@@ -269,6 +272,10 @@ def test_mesh_operators_vs_oracle(V, B, C):
         worst = within_bound(y.cpu().numpy(), y64, bound, kind)
         assert worst < 32
         assert torch.equal(y, op.apply(ing)), "run-to-run bit reproducibility"
+        if kind == "bsr4":
+            assert op.max_row_blocks >= 3
+            assert torch.equal(y, op.apply(ing, direct_gather=True)), "streaming vs direct-gather kernel"
+            within_bound(op.T.apply(y).cpu().numpy(), *c_oracle.dirac_view_mm_f64(idx[1], idx[0], val, S.shape[1] // 4, y.cpu().numpy()), "bsr4^T")
         # the reference's own path on the same inputs (CPU torch.mm) obeys the same bound
         ref = torch.mm(S, torch.from_numpy(inp).view(S.shape[1], -1)).view(rows, C).numpy()
         within_bound(ref, y64, bound, "reference torch.mm")
