@@ -42,6 +42,12 @@ __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// base + a * b with 32-bit a, b and a 64-bit base: one IMAD.WIDE.U32
+__device__ __forceinline__ const char* ptr_mad(const char* base, uint32_t a, uint32_t b) {
+  uint64_t r;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(reinterpret_cast<uint64_t>(base)));
+  return reinterpret_cast<const char*>(r);
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
@@ -68,10 +74,14 @@ bsr4_spmm_stream_kernel(const int32_t* __restrict__ browptr, const int32_t* __re
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = lane >> 3, tl = lane & 7;
-  unsigned char* my_slots = slots + (size_t)warp * kSlots * kSlotBytes;
-  const float* Xlane = X + lane * 4;                      // this lane's 16-byte unit of every gathered row
   const int lane_xoff = q * C4 + 4 * tl;                  // float offset of this lane's float4 inside a row
   const int src1 = (lane + 8) & 31, src2 = (lane + 16) & 31, src3 = (lane + 24) & 31;
+  // 32-bit strides (bytes) keep the per-block address arithmetic to one IMAD.WIDE
+  const uint32_t ldxb = (uint32_t)ldx * 4u, ldyb = (uint32_t)ldy * 4u;
+  const char* Xl = reinterpret_cast<const char*>(X) + lane * 16;       // this lane's 16-byte unit of every row
+  char* Yl = reinterpret_cast<char*>(Y + lane_xoff);
+  const unsigned char* my_slots = slots + (size_t)warp * kSlots * kSlotBytes;
+  const uint32_t slot_u32 = smem_u32(my_slots) + lane * 16;            // shared-memory destination of that unit
 
   // ---- index staging helpers (all threads of the CTA)
   auto prefetch_bp = [&](int tile, int buf) {   // row pointers of `tile` -> bp_buf[buf]
@@ -112,32 +122,53 @@ bsr4_spmm_stream_kernel(const int32_t* __restrict__ browptr, const int32_t* __re
     prefetch_bp(tile + 2 * gridDim.x, (it + 2) % 3);
     cp_async_commit();
 
-    const int r0 = tile * kTileRows;
     const int k0 = bp[0];
     const int rw0 = warp * kRowsPerWarp;                       // this warp's rows inside the tile
+    const int grow0 = tile * kTileRows + rw0;                  // ... their global index
     const int kb = bp[rw0], ke = bp[rw0 + kRowsPerWarp];       // ... and its contiguous run of blocks
     const int nchunks = (ke - kb + GB - 1) / GB;
+    // lane l < 16 keeps the end pointer of the warp's row l: row boundaries inside a chunk become a bit mask,
+    // and so do empty rows (end pointer equal to the previous row's)
+    const int my_re = lane < kRowsPerWarp ? bp[rw0 + lane + 1] : -1;
+    const int up_re = __shfl_up_sync(0xffffffffu, my_re, 1);   // every lane takes part in the shuffle
+    const int prev_re = lane == 0 ? kb : up_re;
+    const unsigned emptymask = __ballot_sync(0xffffffffu, lane < kRowsPerWarp && my_re == prev_re);
+    const char* vsrc_lane = reinterpret_cast<const char*>(bval) + lane * 16;
 
-    const int kbase = kb - k0;
-    auto issue = [&](int c) {  // gather chunk c (blocks [kb + c*GB, ...)) into slot c & 1
+    auto issue_n = [&](int c, const int nn) {  // gather chunk c (nn blocks from kb + c*GB) into slot c & 1
       const int kc = kb + c * GB;
-      const int n = min(GB, ke - kc);
-      unsigned char* xs = my_slots + (c & 1) * kSlotBytes;
+      const uint32_t dst = slot_u32 + (c & 1) * kSlotBytes;
+      const int kk = kc - k0;
+      int j[GB];
+      if (kk + GB <= kBcCap) {                 // staged indices (the normal case)
+#pragma unroll
+        for (int b = 0; b < GB; ++b) j[b] = bc[kk + b];
+      } else {
+#pragma unroll
+        for (int b = 0; b < GB; ++b) j[b] = b < nn ? __ldg(bcolind + kc + b) : 0;
+      }
 #pragma unroll
       for (int b = 0; b < GB; ++b) {
-        if (b < n) {
-          const int kk = kbase + c * GB + b;
-          const int j = kk < kBcCap ? bc[kk] : __ldg(bcolind + kc + b);
-          const float* src = Xlane + (int64_t)j * ldx;
+        if (b < nn) {
+          const char* src = ptr_mad(Xl, (uint32_t)j[b], ldxb);
 #pragma unroll
-          for (int ch = 0; ch < NCH; ++ch) cp_async16(xs + b * kRowBytes + ch * 512 + lane * 16, src + ch * 128);
+          for (int ch = 0; ch < NCH; ++ch)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + b * kRowBytes + ch * 512),
+                         "l"(src + ch * 512)
+                         : "memory");
         }
       }
-      if (lane < n * 4) cp_async16(xs + GB * kRowBytes + lane * 16, bval + (int64_t)kc * 16 + lane * 4);
+      if (lane < nn * 4)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + GB * kRowBytes),
+                     "l"(ptr_mad(vsrc_lane, (uint32_t)kc, 64u))
+                     : "memory");
+    };
+    auto issue = [&](int c) {
+      const int n = ke - (kb + c * GB);
+      if (n >= GB) issue_n(c, GB); else issue_n(c, n);   // full chunks compile without per-block checks
     };
 
-    int row = rw0;                 // current row (tile-local) and the end of its run of blocks
-    int row_end = bp[row + 1];
+    int row = 0;                   // warp-local index of the row being accumulated
     float4 acc[NCH][4];
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch)
@@ -145,36 +176,40 @@ bsr4_spmm_stream_kernel(const int32_t* __restrict__ browptr, const int32_t* __re
       for (int p = 0; p < 4; ++p) acc[ch][p] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     auto finish_row = [&]() {      // lane q: out_q = slot0(q) + slot3(q+1) + slot2(q+2) + slot1(q+3); store; reset
-      const int grow = r0 + row;
+      const int grow = grow0 + row;
+      char* yrow = const_cast<char*>(ptr_mad(Yl, (uint32_t)grow, ldyb));
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
         float4 out = acc[ch][0];
         out = add4(out, shfl_idx4(acc[ch][3], src1));
         out = add4(out, shfl_idx4(acc[ch][2], src2));
         out = add4(out, shfl_idx4(acc[ch][1], src3));
-        if (grow < n_brows) st_stream_f4(Y + (int64_t)grow * ldy + lane_xoff + ch * 32, out);
+        if (grow < n_brows) st_stream_f4(reinterpret_cast<float*>(yrow) + ch * 32, out);
 #pragma unroll
         for (int p = 0; p < 4; ++p) acc[ch][p] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      ++row;
+    };
+    // finish the current row, then any empty rows that follow it (they store zeros)
+    auto finish_rows = [&]() {
+      finish_row();
+      while (row < kRowsPerWarp && ((emptymask >> row) & 1u)) finish_row();
     };
 
-    if (nchunks > 0) issue(0);
-    cp_async_commit();
-    for (int c = 0; c < nchunks; ++c) {
-      if (c + 1 < nchunks) issue(c + 1);
-      cp_async_commit();
-      cp_async_wait<1>();          // chunk c (and everything older) has landed
-      __syncwarp();
+    if (emptymask & 1u) {                             // leading empty rows
+      do finish_row(); while (row < kRowsPerWarp && ((emptymask >> row) & 1u));
+    }
+    auto compute_n = [&](int c, const int nn) {
       const int kc = kb + c * GB;
-      const int n = min(GB, ke - kc);
       const unsigned char* xs = my_slots + (c & 1) * kSlotBytes;
       const float* xp = reinterpret_cast<const float*>(xs) + lane_xoff;
       const float* wp = reinterpret_cast<const float*>(xs + GB * kRowBytes) + 4 * q;
-      int b = 0;
-      while (b < n) {
-        const int stop = min(n, row_end - kc);   // blocks of the current row that live in this chunk
-#pragma unroll 3
-        for (; b < stop; ++b) {
+      // bit b set <=> block kc + b is the last block of its row
+      const unsigned rel = (unsigned)(my_re - kc - 1);
+      const unsigned endmask = __reduce_or_sync(0xffffffffu, rel < (unsigned)nn ? 1u << rel : 0u);
+#pragma unroll
+      for (int b = 0; b < GB; ++b) {             // fully unrolled: shared-memory offsets become immediates
+        if (b < nn) {
           const float4 w = *reinterpret_cast<const float4*>(wp + b * 16);  // B[(q+s)%4][q], s = 0..3
 #pragma unroll
           for (int ch = 0; ch < NCH; ++ch) {
@@ -185,17 +220,22 @@ bsr4_spmm_stream_kernel(const int32_t* __restrict__ browptr, const int32_t* __re
             acc[ch][2] = fma4(w.z, x, acc[ch][2]);
             acc[ch][3] = fma4(w.w, x, acc[ch][3]);
           }
-        }
-        if (b < n) {                             // the row's run ended inside the chunk (or the row is empty)
-          finish_row();
-          ++row;
-          row_end = bp[row + 1];
+          if (endmask & (1u << b)) finish_rows();
         }
       }
+    };
+
+    if (nchunks > 0) issue(0);
+    cp_async_commit();
+    for (int c = 0; c < nchunks; ++c) {
+      if (c + 1 < nchunks) issue(c + 1);
+      cp_async_commit();
+      cp_async_wait<1>();          // chunk c (and everything older) has landed
+      __syncwarp();
+      const int n = ke - (kb + c * GB);
+      if (n >= GB) compute_n(c, GB); else compute_n(c, n);
       __syncwarp();                // all lanes done with slot c & 1 before chunk c + 2 overwrites it
     }
-    // remaining rows of this warp (the last non-empty one and any trailing empty rows)
-    for (; row < rw0 + kRowsPerWarp; ++row) finish_row();
 
     cp_async_wait<0>();            // this thread's share of the index prefetch has landed
     __syncthreads();               // ... and everyone else's; also: all warps are done with bp / bc of this tile
@@ -225,7 +265,7 @@ static int launch_stream(const int32_t* browptr, const int32_t* bcolind, const f
 // Returns SN_ERR_UNSUPPORTED when the streaming kernel does not apply (caller falls back to direct gather).
 int launch_bsr4_stream(const int32_t* browptr, const int32_t* bcolind, const float* bval, const float* X, int64_t ldx,
                        float* Y, int64_t ldy, int64_t n_brows, int64_t C, bool elu, cudaStream_t st) {
-  if (n_brows >= 0x7fffffffLL - kTileRows) return SN_ERR_UNSUPPORTED;
+  if (n_brows >= 0x7fffffffLL - kTileRows || ldx >= (1LL << 30) || ldy >= (1LL << 30)) return SN_ERR_UNSUPPORTED;
   switch (C) {
     case 128: return launch_stream<1, 6>(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, elu, st);
     case 256: return launch_stream<2, 4>(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, elu, st);
