@@ -64,7 +64,10 @@ class _StageConcat(torch.autograd.Function):
     """Z[rows_out, 2C] = [ elu(x_self) | S @ elu(x_gather) ]  -- one stage's operator application.
 
     Covers utils_pt.py:161-168 / 172-177 (Laplacian, x_self is x_gather) and :195-204 / :208-216 (Dirac D with
-    x_self = f, x_gather = v; adjoint D* with x_self = v, x_gather = f_out).
+    x_self = f, x_gather = v; adjoint D* with x_self = v, x_gather = f_out).  The activation is materialised once
+    per operand (sn_elu_f32) instead of being recomputed for every gathered copy of a row: each row is gathered
+    ~3-7 times, and expm1 on the gather path costs more than the extra pass (measured: +60..100 us per SpMM at
+    the ARAP size).  For the Laplacian the activated rows ARE the left half of Z and the SpMM gathers from there.
     """
 
     @staticmethod
@@ -75,13 +78,14 @@ class _StageConcat(torch.autograd.Function):
         left, right = Z[:, :C], Z[:, C:]
         elu_into(xs, left)
         if same:
-            # gather from the already-activated left half (row stride 2C): no ELU recompute
-            op.apply(left, out=right)
+            op.apply(left, out=right)                     # gather from the activated left half (row stride 2C)
             ctx.save_for_backward(Z)
         else:
             xg = x_gather.contiguous()
-            op.apply(xg, out=right, elu_input=True)
-            ctx.save_for_backward(Z, xg)
+            act = torch.empty_like(xg)
+            elu_into(xg, act)
+            op.apply(act, out=right)
+            ctx.save_for_backward(Z, act)
         ctx.op, ctx.same, ctx.C = op, same, C
         return Z
 
@@ -93,14 +97,13 @@ class _StageConcat(torch.autograd.Function):
         if ctx.same:
             (Z,) = ctx.saved_tensors
             t = op.T.apply(g_right)                       # S^T g
-            gx = torch.empty_like(t)
-            _elu_bwd(Z[:, :C], False, g_left, t, gx)      # (g_left + S^T g) * elu'(x)
-            return gx, None, None, None
-        Z, xg = ctx.saved_tensors
+            _elu_bwd(Z[:, :C], False, g_left, t, t)       # (g_left + S^T g) * elu'(x), in place
+            return t, None, None, None
+        Z, act = ctx.saved_tensors
         g_self = torch.empty(gZ.shape[0], C, dtype=torch.float32, device=gZ.device)
         _elu_bwd(Z[:, :C], False, g_left, None, g_self)
         t = op.T.apply(g_right)
-        _elu_bwd(xg, True, t, None, t)
+        _elu_bwd(act, False, t, None, t)
         return g_self, t, None, None
 
 

@@ -1,0 +1,140 @@
+"""Host-side checks that need no GPU: the C ABI library loads and exports every symbol the header declares,
+argument validation, batching helpers vs the reference's outputs, module surface / state_dict layout."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import REPO
+
+HEADER = os.path.join(REPO, "include", "surfnet_b200.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sn_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from surfacenetworks_b200 import _native as N
+    syms = declared_symbols()
+    assert len(syms) >= 10
+    lib = ctypes.CDLL(N.LIB_PATH)
+    for s in syms:
+        assert hasattr(lib, s), "libsurfnet_b200.so does not export %s" % s
+    assert set(N.SIGNATURES) == set(syms), "ctypes signature table and header disagree"
+    assert N.version() == 100
+    assert b"workspace" in N.lib.sn_status_string(N.SN_ERR_WORKSPACE)
+
+
+def test_argument_validation_without_a_gpu():
+    """Argument errors are detected on the host before any CUDA call."""
+    from surfacenetworks_b200 import _native as N
+    L = N.lib
+    assert L.sn_csr_spmm_f32(0, 0, 0, 0, 4, 0, 4, 8, 4, 0, 0) == N.SN_ERR_ARG          # null pointers
+    assert L.sn_csr_spmm_f32(0, 0, 0, 0, 4, 0, 4, -1, 4, 0, 0) == N.SN_ERR_ARG         # negative size
+    assert L.sn_csr_spmm_f32(0, 0, 0, 0, 4, 0, 4, 0, 4, 0, 0) == N.SN_OK               # empty problem
+    assert L.sn_bsr4_spmm_f32(1, 1, 1, 1, 6, 1, 6, 2, 6, 0, 0) == N.SN_ERR_UNSUPPORTED  # C % 4 != 0
+    assert L.sn_bsr4_spmm_f32(1, 1, 1, 1, 4, 1, 8, 2, 8, 0, 0) == N.SN_ERR_ARG          # ldx < C
+    assert L.sn_csr32_to_bsr4_count(1, 1, 6, 1, 1, 1 << 20, 0) == N.SN_ERR_UNSUPPORTED  # rows % 4 != 0
+    assert L.sn_coo_to_csr32(0, 1, 1, 1, 5, 0, 0, 4, 4, 0, 1, 1, 1, 0, 0, 0) == N.SN_ERR_WORKSPACE
+    assert L.sn_coo_to_csr32(0, 1, 1, 1, 1 << 33, 0, 0, 4, 4, 0, 1, 1, 1, 0, 0, 0) == N.SN_ERR_OVERFLOW
+    assert L.sn_elu_f32(0, 4, 0, 4, 3, 4, 0) == N.SN_ERR_ARG
+    assert L.sn_coo_to_csr32_ws_bytes(1000, 100) >= 4 * 1000 + 4 * 101
+    with pytest.raises(N.SurfnetError) as e:
+        N.call("sn_csr_spmm_f32", 0, 0, 0, 0, 4, 0, 4, 8, 4, 0, 0)
+    assert e.value.status == N.SN_ERR_ARG and "invalid argument" in str(e.value)
+
+
+def test_batching_helpers_match_reference(golden):
+    """sparse_diag_cat / sparse_cat / sp_sparse_to_pt_sparse: identical indices and values to utils_pt.py:21-69."""
+    import scipy.sparse as sp
+    from surfacenetworks_b200 import utils_pt as U
+    b = golden("batching")
+    nv, nf = int(b["nv"]), int(b["nf"])
+
+    def scipy_op(mesh, name):
+        r, c, v, shape = golden.coo("operators", "%s_%s" % (mesh, name))
+        return sp.coo_matrix((v, (r, c)), shape=shape)
+
+    t = U.sp_sparse_to_pt_sparse(scipy_op("s45", "L"))
+    assert np.array_equal(t._indices().numpy(), b["pt_L1_idx"]) and np.array_equal(t._values().numpy(), b["pt_L1_val"])
+    assert t._values().dtype == torch.float32 and t._indices().dtype == torch.int64
+    for name, s0, s1 in (("L", nv, nv), ("Di", 4 * nf, 4 * nv), ("DiA", 4 * nv, 4 * nf)):
+        parts = [U.sp_sparse_to_pt_sparse(scipy_op(m, name)) for m in ("s60", "s45")]
+        d = U.sparse_diag_cat(parts, s0, s1)
+        assert d.is_coalesced() and tuple(d.shape) == (2 * s0, 2 * s1)
+        assert np.array_equal(d._indices().numpy(), b["diag_%s_idx" % name])
+        assert np.array_equal(d._values().numpy(), b["diag_%s_val" % name])
+    for name, s0, s1 in (("L", nv, nv), ("Di", 4 * nf, 4 * nv)):
+        parts = [U.sp_sparse_to_pt_sparse(scipy_op(m, name)) for m in ("s60", "s45")]
+        c3 = U.sparse_cat(parts, s0, s1)
+        assert tuple(c3.shape) == (2, s0, s1)
+        assert np.array_equal(c3._indices().numpy(), b["cat_%s_idx" % name])
+        assert np.array_equal(c3._values().numpy(), b["cat_%s_val" % name])
+    dense = U.to_dense_batched(U.sp_sparse_to_pt_sparse(scipy_op("s45", "L")), 3)
+    assert dense.shape == (3, 45, 45)
+
+
+def test_workload_block_diag_equals_sparse_diag_cat():
+    """bench.py's sort-free batch assembly gives exactly what sparse_diag_cat(...).coalesce() gives."""
+    from surfacenetworks_b200 import utils_pt as U, workloads as W
+    meshes = W.make_mesh_ops(40, [0, 1, 2])
+    nv = max(m.num_vertices for m in meshes)
+    nf = max(m.num_faces for m in meshes)
+    batch = W.arap_batch(meshes, 0)
+    ref = U.sparse_diag_cat([U.sp_sparse_to_pt_sparse(m.Di) for m in meshes], 4 * nf, 4 * nv)
+    assert torch.equal(batch["Di"]._indices(), ref._indices()) and torch.equal(batch["Di"]._values(), ref._values())
+    ref = U.sparse_diag_cat([U.sp_sparse_to_pt_sparse(m.DiA) for m in meshes], 4 * nv, 4 * nf)
+    assert torch.equal(batch["DiA"]._indices(), ref._indices()) and torch.equal(batch["DiA"]._values(), ref._values())
+    lb = W.lap_batch(meshes)
+    ref = U.sparse_diag_cat([U.sp_sparse_to_pt_sparse(m.L) for m in meshes], nv, nv)
+    assert torch.equal(lb["L"]._indices(), ref._indices()) and torch.equal(lb["L"]._values(), ref._values())
+    assert batch["inputs"].shape == (3, nv, 6) and batch["targets"].shape == (3, nv, 120)
+
+
+def test_module_surface_and_state_dict_layout():
+    """Same constructor arguments and state_dict keys as the reference modules."""
+    from surfacenetworks_b200 import models as M, utils_pt as U
+    blk = U.DirResNet2(32, res_f=True)
+    assert blk.res_f is True and blk.num_outputs == 32
+    expect = ["bn_fc%d.bn.%s" % (i, k) for i in (0, 1)
+              for k in ("weight", "bias", "running_mean", "running_var", "num_batches_tracked")]
+    expect += ["bn_fc%d.fc.%s" % (i, k) for i in (0, 1) for k in ("weight", "bias")]
+    for cls in (U.LapResNet2, U.DirResNet2, U.AvgResNet2, U.DenseLapResNet2):
+        sd = cls(32).state_dict()
+        assert sorted(sd) == sorted(expect)
+        assert sd["bn_fc0.fc.weight"].shape == (32, 64) and sd["bn_fc1.bn.weight"].shape == (64,)
+    assert sorted(U.MlpResNet2(8).state_dict())[:2] == ["bn0.bn.bias", "bn0.bn.num_batches_tracked"]
+    assert U.GraphConv1x1(4, 5, batch_norm=None).state_dict().keys() == {"fc.weight", "fc.bias"}
+    for model, n in ((M.ArapDirModel(), 1018872), (M.ArapLapModel(15), 1018872)):
+        assert sum(p.numel() for p in model.parameters()) == n
+        assert "rn14.bn_fc1.fc.weight" in model.state_dict() and "conv2.bn.running_var" in model.state_dict()
+    g = M.LapResNet2General(16, 32, inner_layers=3)
+    assert g.state_dict()["bn_fc0.fc.weight"].shape == (32, 32) and g.state_dict()["bn_fc2.fc.weight"].shape == (32, 64)
+
+
+def test_cpu_tensors_are_refused_loudly():
+    """There is no CPU fallback in the product path."""
+    from surfacenetworks_b200 import operators, ops, utils_pt as U
+    S = torch.sparse_coo_tensor(torch.tensor([[0, 1], [1, 0]]), torch.tensor([1.0, 2.0]), (2, 2))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        operators.as_csr(S)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.elu_into(torch.zeros(2, 4), torch.zeros(2, 4))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        U.LapResNet2(4)(S, None, torch.zeros(1, 2, 4))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(REPO, "surfacenetworks_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "sn_oracle" not in text, f
