@@ -118,6 +118,24 @@ int sn_elu_f32(const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t rows,
 int sn_elu_bwd_f32(const float* A, int64_t lda, int a_is_raw, const float* G, int64_t ldg, const float* G2,
                    int64_t ldg2, float* Y, int64_t ldy, int64_t rows, int64_t C, sn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Dense half of a stage on the tensor cores (tcgen05, kind::tf32, accumulators in TMEM):
+ *
+ *   C[M x N] = A[M x K] * B[N x K]^T + bias[N] + rscale[N] .* R[M x N]
+ *
+ * bias, R, rscale may be NULL (rscale NULL with R given means R is added unscaled).  A is the stage's concat
+ * buffer Z, B the Linear weight of GraphConv1x1 (utils_pt.py:89,99) with the training-mode BatchNorm of
+ * utils_pt.py:84,98 folded in by the caller; R carries the block residual (utils_pt.py:180,220).  The same
+ * entry point serves the backward product dZ = dY * W_s + p .* Z + q.
+ * Default precision is 3xTF32 (hi/lo operand split in shared memory, three MMAs per k-step): results agree
+ * with an fp32 GEMM to ~1e-6 relative to |A||B|.  SN_GEMM_SINGLE_PASS issues one TF32 MMA (~1e-3).
+ * Supported: N in {64, 128, 256}, K % 32 == 0, 16-byte aligned pointers, leading dimensions % 4 == 0.
+ * ---------------------------------------------------------------------------------------------- */
+#define SN_GEMM_SINGLE_PASS 1
+int sn_gemm_tf32_f32(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, const float* R,
+                     int64_t ldr, const float* rscale, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                     int flags, sn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,7 @@ SIGNATURES = {
     "sn_csr_spmm_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _int, _ptr]),
     "sn_bsr4_spmm_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _int, _ptr]),
     "sn_elu_f32": (_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _ptr]),
+    "sn_gemm_tf32_f32": (_int, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _i64, _i64, _i64, _int, _ptr]),
     "sn_elu_bwd_f32": (_int, [_ptr, _i64, _int, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr]),
 }
 
@@ -48,6 +49,7 @@ SN_ERR_ARG, SN_ERR_UNSUPPORTED, SN_ERR_WORKSPACE, SN_ERR_OVERFLOW = -1, -2, -3, 
 SN_COO_SORTED = 1
 SN_SPMM_ELU_INPUT = 1
 SN_SPMM_DIRECT_GATHER = 2
+SN_GEMM_SINGLE_PASS = 1
 
 
 class SurfnetError(RuntimeError):

@@ -1,0 +1,351 @@
+// gemm_tf32.cu -- the dense half of a ResNet stage on the 5th-generation tensor cores.
+//
+//   C[M x N] = A[M x K] * B[N x K]^T + bias[N] (+ rscale[N] .* R[M x N])        fp32 in, fp32 out
+//
+// Replaces nn.Linear inside GraphConv1x1 (reference src/utils/utils_pt.py:89,99) with the training-mode
+// BatchNorm of :84,98 folded into B / bias by the caller (W' = W diag(gamma*rstd), b' = b + W (beta - gamma*mu*rstd)),
+// and serves the backward product dZ = dY W_s + p .* Z + q through the same epilogue.  M is B*V or B*F
+// (1e5..1e6 rows), N and K are feature widths (128 / 256).
+//
+// Precision: the reference Linear is true fp32.  tcgen05 `kind::tf32` keeps 10 mantissa bits, so every
+// operand tile is split in shared memory into hi = tf32(x) and lo = x - hi and three MMAs are issued per
+// k-step (hi*hi + hi*lo + lo*hi; the dropped lo*lo term is ~2^-22 relative): fp32-grade results at 3 MMAs.
+//
+// Structure (one CTA per SM, persistent over 128-row tiles; 12 warps):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D loads of the A tile [128 x 32] and B tile [N x 32]
+//               (128-byte swizzle) into a STAGES-deep ring, completion on `full` mbarriers
+//   warps 4-7   split: hi written back in place, lo into the twin tile, fence.proxy.async, `ready` mbarrier
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N, K=8) x 12 per
+//               k-block; tcgen05.commit frees the smem stage (`empty`) and publishes the accumulator (`tmem_full`)
+//   warp 2      TMEM allocation (2 accumulator buffers of N columns)
+//   warps 8-11  epilogue: tcgen05.ld 32 lanes x 32 columns, bias / residual / scaled-residual, streaming stores;
+//               overlaps the next tile's MMAs through the second TMEM buffer
+// Bound: the fused stage is HBM-bound once on tensor cores (A read once, C written once; B stays in L2).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace sn {
+namespace gemm {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 32;            // 32 fp32 = 128 bytes = one swizzle row
+constexpr int kUmmaK = 8;              // tf32: 32 bytes per MMA k-step
+constexpr int kThreads = 384;
+constexpr int kMaxStages = 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// K-major, 128-byte-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), version 1
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffff) >> 4);       // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                        // layout type: SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+struct Params {
+  const float* bias;     // [N] or null
+  const float* R;        // [M x N] or null: out += rscale .* R
+  const float* rscale;   // [N] or null (= 1)
+  float* C;
+  int64_t ldr, ldc;
+  int M, N, K;
+  int stages;
+  int split;             // 1: 3xTF32 (hi/lo split), 0: single-pass TF32
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // 1024-byte alignment is required by the 128-byte swizzle (TMA and UMMA agree on address bits [7,10))
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int N = p.N;
+  const uint32_t a_bytes = kBlockM * kBlockK * 4;           // 16 KB
+  const uint32_t b_bytes = (uint32_t)N * kBlockK * 4;       // 16 / 32 KB
+  const uint32_t stage_bytes = 2 * (a_bytes + b_bytes);     // A, A_lo, B, B_lo
+  __shared__ uint64_t full_bar[kMaxStages], ready_bar[kMaxStages], empty_bar[kMaxStages], tmem_full[2], tmem_empty[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (p.M + kBlockM - 1) / kBlockM;
+  const int n_kb = p.K / kBlockK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(ready_bar + s, 4);      // one arrival per split warp
+      mbar_init(empty_bar + s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tmem_full + b, 1);
+      mbar_init(tmem_empty + b, 4);     // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {                       // TMEM: 2 accumulator buffers of N fp32 columns (power of two >= 32)
+    const uint32_t cols = 2u * (uint32_t)N;
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(empty_bar + stage, phase ^ 1u);
+          unsigned char* sa = smem + (size_t)stage * stage_bytes;
+          unsigned char* sb = sa + 2 * a_bytes;
+          mbar_arrive_expect_tx(full_bar + stage, a_bytes + b_bytes);
+          tma_load_2d(sa, &map_a, kb * kBlockK, tile * kBlockM, full_bar + stage);
+          tma_load_2d(sb, &map_b, kb * kBlockK, 0, full_bar + stage);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(tmem_empty + buf, ((it >> 1) & 1) ^ 1u);       // epilogue drained this accumulator
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * N);
+      for (int kb = 0; kb < n_kb; ++kb) {
+        mbar_wait(ready_bar + stage, phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t sal = sa + a_bytes, sb = sa + 2 * a_bytes, sbl = sb + b_bytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint32_t off = k * kUmmaK * 4;               // 32 bytes per k-step inside the swizzle row
+            const uint64_t da = umma_desc_sw128(sa + off), db = umma_desc_sw128(sb + off);
+            umma_tf32(tmem_d, da, db, idesc, (kb | k) != 0);
+            if (p.split) {
+              umma_tf32(tmem_d, da, umma_desc_sw128(sbl + off), idesc, true);
+              umma_tf32(tmem_d, umma_desc_sw128(sal + off), db, idesc, true);
+            }
+          }
+          umma_commit(empty_bar + stage);                      // smem stage reusable once these MMAs retire
+          if (kb == n_kb - 1) umma_commit(tmem_full + buf);    // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------------ hi / lo split
+    const int t = threadIdx.x - 128;                           // 0..127
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t n_vec = (a_bytes + b_bytes) / 16;           // float4 units of A then B (contiguous: A, A_lo | B, B_lo)
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < n_kb; ++kb) {
+        mbar_wait(full_bar + stage, phase);
+        if (p.split) {
+          unsigned char* sa = smem + (size_t)stage * stage_bytes;
+          for (uint32_t i = t; i < n_vec; i += 128) {
+            const bool is_a = i < a_bytes / 16;
+            unsigned char* src = is_a ? sa + (size_t)i * 16 : sa + 2 * a_bytes + (size_t)(i - a_bytes / 16) * 16;
+            unsigned char* dst = src + (is_a ? a_bytes : b_bytes);
+            float4 x = *reinterpret_cast<float4*>(src);
+            float4 hi;   // round-to-nearest tf32: |lo| <= 2^-12 |x|, and hi is exact for the tensor core
+            hi.x = to_tf32(x.x); hi.y = to_tf32(x.y); hi.z = to_tf32(x.z); hi.w = to_tf32(x.w);
+            *reinterpret_cast<float4*>(src) = hi;
+            *reinterpret_cast<float4*>(dst) = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ready_bar + stage);
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 8) {
+    // ------------------------------------------------------------------ epilogue
+    const int ew = warp - 8;                                   // == warp % 4: TMEM lanes [32 ew, 32 ew + 32)
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(tmem_full + buf, (it >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row = tile * kBlockM + ew * 32 + lane;
+      const bool row_ok = row < p.M;
+      float* crow = p.C + (int64_t)row * p.ldc;
+      const float* rrow = p.R ? p.R + (int64_t)row * p.ldr : nullptr;
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * N + c0), v);
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                   __uint_as_float(v[j + 3]));
+            if (p.bias) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
+              o = add4(o, b);
+            }
+            if (rrow) {
+              const float4 r = __ldcs(reinterpret_cast<const float4*>(rrow + c0 + j));
+              if (p.rscale) {
+                const float4 s = __ldg(reinterpret_cast<const float4*>(p.rscale + c0 + j));
+                o.x = fmaf(s.x, r.x, o.x); o.y = fmaf(s.y, r.y, o.y); o.z = fmaf(s.z, r.z, o.z); o.w = fmaf(s.w, r.w, o.w);
+              } else {
+                o = add4(o, r);
+              }
+            }
+            st_stream_f4(crow + c0 + j, o);
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + buf);
+    }
+  }
+
+  // ------------------------------------------------------------------ teardown
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t cols = 2u * (uint32_t)N;
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(cols));
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// row-major fp32 matrix [rows x cols] with leading dimension ld -> tensor map with a [box_rows x 32] box, 128B swizzle
+static bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace gemm
+}  // namespace sn
+
+SN_API int sn_gemm_tf32_f32(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, const float* R,
+                            int64_t ldr, const float* rscale, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                            int flags, sn_stream_t stream) {
+  using namespace sn;
+  using namespace sn::gemm;
+  if (M < 0 || N <= 0 || K <= 0) return SN_ERR_ARG;
+  if (M == 0) return SN_OK;
+  if (!A || !B || !C || lda < K || ldb < K || ldc < N || (R && ldr < N)) return SN_ERR_ARG;
+  if ((N != 64 && N != 128 && N != 256) || K % kBlockK != 0 || M >= 0x7fffffffLL - kBlockM) return SN_ERR_UNSUPPORTED;
+  if (lda % 4 || ldb % 4 || ldc % 4 || (R && ldr % 4) || !aligned16(A) || !aligned16(B) || !aligned16(C) ||
+      (R && !aligned16(R)) || (bias && !aligned16(bias)) || (rscale && !aligned16(rscale)))
+    return SN_ERR_UNSUPPORTED;
+  CUtensorMap map_a, map_b;
+  if (!make_map(&map_a, A, M, K, lda, kBlockM) || !make_map(&map_b, B, N, K, ldb, (int)N)) return SN_ERR_UNSUPPORTED;
+  Params p;
+  p.bias = bias; p.R = R; p.rscale = rscale; p.C = C; p.ldr = ldr; p.ldc = ldc;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.split = (flags & SN_GEMM_SINGLE_PASS) ? 0 : 1;
+  int dev = 0, sms = 148, smem_optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const size_t stage_bytes = 2 * ((size_t)kBlockM * kBlockK * 4 + (size_t)N * kBlockK * 4);
+  int stages = (int)(((size_t)smem_optin - 2048) / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return SN_ERR_UNSUPPORTED;
+  p.stages = stages;
+  const size_t smem = stages * stage_bytes + 1024;
+  cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const int64_t tiles = ceil_div(M, kBlockM);
+  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  gemm_tf32_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+  return launch_status();
+}
