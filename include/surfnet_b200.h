@@ -132,9 +132,20 @@ int sn_elu_bwd_f32(const float* A, int64_t lda, int a_is_raw, const float* G, in
  * Supported: N in {64, 128, 256}, K % 32 == 0, 16-byte aligned pointers, leading dimensions % 4 == 0.
  * ---------------------------------------------------------------------------------------------- */
 #define SN_GEMM_SINGLE_PASS 1
+size_t sn_gemm_tf32_ws_bytes(int64_t N, int64_t K); /* workspace for the pre-split weights (3xTF32 mode) */
 int sn_gemm_tf32_f32(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, const float* R,
                      int64_t ldr, const float* rscale, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
-                     int flags, sn_stream_t stream);
+                     int flags, void* ws, size_t ws_bytes, sn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batch statistics for the training-mode BatchNorm in front of the Linear (utils_pt.py:84,98): per-column mean and
+ * biased variance of X [rows x C] over all rows, one HBM pass, deterministic (fixed-order fp64 final reduction).
+ * The normalisation itself is never run as a pass: the caller folds it into the weights given to sn_gemm_tf32_f32.
+ * Supported: C % 4 == 0, C/4 divides 256, ldx % 4 == 0.
+ * ---------------------------------------------------------------------------------------------- */
+size_t sn_colstats_ws_bytes(int64_t C);
+int sn_colstats_f32(const float* X, int64_t ldx, int64_t rows, int64_t C, float* mean, float* var_biased,
+                    void* ws, size_t ws_bytes, sn_stream_t stream);
 
 #ifdef __cplusplus
 }

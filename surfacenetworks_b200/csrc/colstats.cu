@@ -1,0 +1,104 @@
+// colstats.cu -- per-column batch statistics of a stage's concat buffer Z [rows x C]: the reduction that
+// training-mode BatchNorm needs in front of the Linear (reference src/utils/utils_pt.py:84,98 -- nn.BatchNorm1d on
+// x.transpose(1,2), i.e. statistics over ALL B*N rows, padded rows included).
+//
+// One HBM pass (bound: HBM, 4 * rows * C bytes).  Deterministic: every CTA writes its fp32 partial sums (sum, sum of
+// squares) to a workspace row; a second tiny kernel adds the partials in a fixed order in fp64 and emits
+// mean / biased variance.  BatchNorm itself is never applied as a pass: it is folded into the Linear weights.
+#include "common.cuh"
+
+namespace sn {
+
+constexpr int kStatThreads = 256;
+
+// thread (rg, cv): row group rg = tid / CV walks rows rg, rg + RG, ...; cv owns float4 column cv (cv < C/4)
+__global__ void __launch_bounds__(kStatThreads)
+colstats_partial_kernel(const float* __restrict__ X, int64_t ldx, int64_t rows, int C, float* __restrict__ partial) {
+  extern __shared__ float red[];                      // [RG][2][C]
+  const int CV = C / 4;
+  const int RG = kStatThreads / CV;                   // row groups per CTA (C <= 1024, C % 4 == 0, CV divides 256)
+  const int cv = threadIdx.x % CV, rg = threadIdx.x / CV;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+  // shifted sums: accumulate x - K with K = row 0 of the column, so that constant columns give variance exactly 0
+  // and E[(x-K)^2] - E[x-K]^2 does not cancel catastrophically when |mean| >> std
+  const float4 K = (cv < CV) ? __ldg(reinterpret_cast<const float4*>(X) + cv) : make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rg < RG) {
+    const int64_t stride = (int64_t)gridDim.x * RG;
+    int64_t r = (int64_t)blockIdx.x * RG + rg;
+    // 4 rows in flight per thread
+    for (; r + 3 * stride < rows; r += 4 * stride) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(X + (r + u * stride) * ldx) + cv);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        v[u].x -= K.x; v[u].y -= K.y; v[u].z -= K.z; v[u].w -= K.w;
+        s = add4(s, v[u]);
+        q.x = fmaf(v[u].x, v[u].x, q.x); q.y = fmaf(v[u].y, v[u].y, q.y);
+        q.z = fmaf(v[u].z, v[u].z, q.z); q.w = fmaf(v[u].w, v[u].w, q.w);
+      }
+    }
+    for (; r < rows; r += stride) {
+      float4 v = __ldcs(reinterpret_cast<const float4*>(X + r * ldx) + cv);
+      v.x -= K.x; v.y -= K.y; v.z -= K.z; v.w -= K.w;
+      s = add4(s, v);
+      q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+    }
+    float* base = red + (size_t)rg * 2 * C;
+    *reinterpret_cast<float4*>(base + 4 * cv) = s;
+    *reinterpret_cast<float4*>(base + C + 4 * cv) = q;
+  }
+  __syncthreads();
+  // fixed-order reduction over the row groups; thread t < 2C handles one (stat, column)
+  for (int i = threadIdx.x; i < 2 * C; i += kStatThreads) {
+    float a = 0.f;
+    for (int g = 0; g < RG; ++g) a += red[(size_t)g * 2 * C + i];
+    partial[(size_t)blockIdx.x * 2 * C + i] = a;
+  }
+}
+
+__global__ void colstats_final_kernel(const float* __restrict__ partial, int n_partials, int64_t rows, int C,
+                                      const float* __restrict__ X, float* __restrict__ mean, float* __restrict__ var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int i = 0; i < n_partials; ++i) {
+    s += (double)partial[(size_t)i * 2 * C + c];
+    q += (double)partial[(size_t)i * 2 * C + C + c];
+  }
+  const double m = s / (double)rows;            // mean of the shifted values
+  double v = q / (double)rows - m * m;
+  if (v < 0.0) v = 0.0;
+  mean[c] = (float)(m + (double)X[c]);
+  var[c] = (float)v;
+}
+
+static int stat_grid() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms * 4;
+}
+
+}  // namespace sn
+
+SN_API size_t sn_colstats_ws_bytes(int64_t C) {
+  return C <= 0 ? 0 : (size_t)sn::stat_grid() * 2 * (size_t)C * sizeof(float);
+}
+
+SN_API int sn_colstats_f32(const float* X, int64_t ldx, int64_t rows, int64_t C, float* mean, float* var_biased,
+                           void* ws, size_t ws_bytes, sn_stream_t stream) {
+  using namespace sn;
+  if (rows <= 0 || C <= 0 || !X || !mean || !var_biased || ldx < C) return SN_ERR_ARG;
+  if (C % 4 || C > 1024 || (kStatThreads % (C / 4)) || ldx % 4 || !aligned16(X)) return SN_ERR_UNSUPPORTED;
+  if (!ws || ws_bytes < sn_colstats_ws_bytes(C)) return SN_ERR_WORKSPACE;
+  int grid = stat_grid();
+  const int RG = kStatThreads / (int)(C / 4);
+  if ((int64_t)grid * RG > rows) grid = (int)ceil_div(rows, RG);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)RG * 2 * C * sizeof(float);
+  if (smem > 48 * 1024) return SN_ERR_UNSUPPORTED;
+  colstats_partial_kernel<<<grid, kStatThreads, smem, st>>>(X, ldx, rows, (int)C, (float*)ws);
+  colstats_final_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>((const float*)ws, grid, rows, (int)C, X, mean, var_biased);
+  return launch_status();
+}

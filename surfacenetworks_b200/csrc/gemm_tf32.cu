@@ -11,15 +11,17 @@
 // operand tile is split in shared memory into hi = tf32(x) and lo = x - hi and three MMAs are issued per
 // k-step (hi*hi + hi*lo + lo*hi; the dropped lo*lo term is ~2^-22 relative): fp32-grade results at 3 MMAs.
 //
-// Structure (one CTA per SM, persistent over 128-row tiles; 12 warps):
+// Structure (one CTA per SM, persistent over 128-row tiles; 16 warps):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D loads of the A tile [128 x 32] and B tile [N x 32]
 //               (128-byte swizzle) into a STAGES-deep ring, completion on `full` mbarriers
-//   warps 4-7   split: hi written back in place, lo into the twin tile, fence.proxy.async, `ready` mbarrier
+//   warps 4-7   split of the A tile: hi written back in place, lo into the twin tile, fence.proxy.async, `ready`
+//               mbarrier (B is split once per launch by a tiny pre-kernel into the caller's workspace)
 //   warp 1      MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N, K=8) x 12 per
 //               k-block; tcgen05.commit frees the smem stage (`empty`) and publishes the accumulator (`tmem_full`)
 //   warp 2      TMEM allocation (2 accumulator buffers of N columns)
-//   warps 8-11  epilogue: tcgen05.ld 32 lanes x 32 columns, bias / residual / scaled-residual, streaming stores;
-//               overlaps the next tile's MMAs through the second TMEM buffer
+//   warps 8-15  epilogue: tcgen05.ld 32 lanes x 32 columns, per-warp transpose buffer, bias / (scaled) residual with
+//               the residual loads issued one chunk ahead, coalesced streaming stores; overlaps the next tile's
+//               MMAs through the second TMEM buffer
 // Bound: the fused stage is HBM-bound once on tensor cores (A read once, C written once; B stays in L2).
 #include <cuda.h>
 
@@ -31,7 +33,8 @@ namespace gemm {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 32;            // 32 fp32 = 128 bytes = one swizzle row
 constexpr int kUmmaK = 8;              // tf32: 32 bytes per MMA k-step
-constexpr int kThreads = 384;
+constexpr int kThreads = 512;            // 4 control/split warp slots x 2 + 8 epilogue warps
+constexpr int kEpiWarps = 8;
 constexpr int kMaxStages = 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -84,6 +87,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -114,7 +125,8 @@ struct Params {
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_blo, const Params p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1024-byte alignment is required by the 128-byte swizzle (TMA and UMMA agree on address bits [7,10))
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -124,6 +136,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t stage_bytes = 2 * (a_bytes + b_bytes);     // A, A_lo, B, B_lo
   __shared__ uint64_t full_bar[kMaxStages], ready_bar[kMaxStages], empty_bar[kMaxStages], tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float epi_buf[kEpiWarps * 32 * 20];   // per-epilogue-warp transpose buffers
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.M + kBlockM - 1) / kBlockM;
@@ -137,7 +150,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tmem_full + b, 1);
-      mbar_init(tmem_empty + b, 4);     // one arrival per epilogue warp
+      mbar_init(tmem_empty + b, kEpiWarps);   // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -161,9 +174,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           mbar_wait(empty_bar + stage, phase ^ 1u);
           unsigned char* sa = smem + (size_t)stage * stage_bytes;
           unsigned char* sb = sa + 2 * a_bytes;
-          mbar_arrive_expect_tx(full_bar + stage, a_bytes + b_bytes);
+          mbar_arrive_expect_tx(full_bar + stage, a_bytes + (p.split ? 2 : 1) * b_bytes);
           tma_load_2d(sa, &map_a, kb * kBlockK, tile * kBlockM, full_bar + stage);
           tma_load_2d(sb, &map_b, kb * kBlockK, 0, full_bar + stage);
+          if (p.split) tma_load_2d(sb + b_bytes, &map_blo, kb * kBlockK, 0, full_bar + stage);   // pre-split weights
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -208,21 +222,22 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int t = threadIdx.x - 128;                           // 0..127
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t n_vec = (a_bytes + b_bytes) / 16;           // float4 units of A then B (contiguous: A, A_lo | B, B_lo)
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < n_kb; ++kb) {
         mbar_wait(full_bar + stage, phase);
         if (p.split) {
-          unsigned char* sa = smem + (size_t)stage * stage_bytes;
-          for (uint32_t i = t; i < n_vec; i += 128) {
-            const bool is_a = i < a_bytes / 16;
-            unsigned char* src = is_a ? sa + (size_t)i * 16 : sa + 2 * a_bytes + (size_t)(i - a_bytes / 16) * 16;
-            unsigned char* dst = src + (is_a ? a_bytes : b_bytes);
-            float4 x = *reinterpret_cast<float4*>(src);
+          // A tile: 1024 float4, 8 per thread, all loads first (ILP); B arrives pre-split (hi | lo) by TMA
+          unsigned char* sa = smem + (size_t)stage * stage_bytes + (size_t)t * 16;
+          float4 x[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] = *reinterpret_cast<float4*>(sa + i * 2048);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
             float4 hi;   // round-to-nearest tf32: |lo| <= 2^-12 |x|, and hi is exact for the tensor core
-            hi.x = to_tf32(x.x); hi.y = to_tf32(x.y); hi.z = to_tf32(x.z); hi.w = to_tf32(x.w);
-            *reinterpret_cast<float4*>(src) = hi;
-            *reinterpret_cast<float4*>(dst) = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+            hi.x = to_tf32(x[i].x); hi.y = to_tf32(x[i].y); hi.z = to_tf32(x[i].z); hi.w = to_tf32(x[i].w);
+            *reinterpret_cast<float4*>(sa + i * 2048) = hi;
+            *reinterpret_cast<float4*>(sa + a_bytes + i * 2048) =
+                make_float4(x[i].x - hi.x, x[i].y - hi.y, x[i].z - hi.z, x[i].w - hi.w);
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
         }
@@ -233,40 +248,65 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else if (warp >= 8) {
     // ------------------------------------------------------------------ epilogue
-    const int ew = warp - 8;                                   // == warp % 4: TMEM lanes [32 ew, 32 ew + 32)
+    // 8 epilogue warps: warp e reads TMEM lanes [32 (e % 4), +32) and owns the column half e / 4.
+    // Each thread receives 32 consecutive columns of ONE row from TMEM; a per-warp 32 x 36-float transpose buffer
+    // turns that into row-contiguous float4 accesses (8 lanes cover one 128-byte line of C / R): conflict-free
+    // STS.128 / LDS.128, fully coalesced global traffic.  The residual operand R does not depend on the
+    // accumulator, so its loads are issued one chunk ahead (and before the wait on the MMA): their latency is
+    // hidden behind the tensor-core work instead of serialising the epilogue.
+    const int e = warp - 8;
+    const int quarter = e & 3, half = e >> 2;
+    float* tbuf = epi_buf + e * (32 * 20);
+    const int tr = lane >> 2, tc = (lane & 3) * 4;            // 4 lanes cover one row's 16 columns (64 bytes)
+    const int ncol = N / 2;                                    // columns owned by this warp
+    const int cbase = half * ncol;
+    auto load_r = [&](float4 (&rr)[4], int row0, int c0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = row0 + i * 8 + tr;
+        rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < p.M) rr[i] = __ldcs(reinterpret_cast<const float4*>(p.R + (int64_t)row * p.ldr + c0 + tc));
+      }
+    };
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
+      const int row0 = tile * kBlockM + quarter * 32;
+      float4 rr[4], rn[4], rn2[4];
+      if (p.R) {                                               // prefetch before waiting for the accumulator
+        load_r(rr, row0, cbase);
+        load_r(rn, row0, cbase + 16);
+      }
       mbar_wait(tmem_full + buf, (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int row = tile * kBlockM + ew * 32 + lane;
-      const bool row_ok = row < p.M;
-      float* crow = p.C + (int64_t)row * p.ldc;
-      const float* rrow = p.R ? p.R + (int64_t)row * p.ldr : nullptr;
-      for (int c0 = 0; c0 < N; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * N + c0), v);
-        if (row_ok) {
+      for (int c0 = cbase; c0 < cbase + ncol; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * N + c0), v);
+        if (p.R && c0 + 32 < cbase + ncol) load_r(rn2, row0, c0 + 32);   // residual two chunks ahead
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                   __uint_as_float(v[j + 3]));
-            if (p.bias) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
-              o = add4(o, b);
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(tbuf + lane * 20 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                          __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        __syncwarp();
+        float4 bia = make_float4(0.f, 0.f, 0.f, 0.f), rs = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (p.bias) bia = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + tc));
+        if (p.rscale) rs = __ldg(reinterpret_cast<const float4*>(p.rscale + c0 + tc));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = i * 8 + tr;
+          const int row = row0 + r;
+          if (row < p.M) {
+            float4 o = add4(*reinterpret_cast<const float4*>(tbuf + r * 20 + tc), bia);
+            if (p.R) {
+              o.x = fmaf(rs.x, rr[i].x, o.x); o.y = fmaf(rs.y, rr[i].y, o.y);
+              o.z = fmaf(rs.z, rr[i].z, o.z); o.w = fmaf(rs.w, rr[i].w, o.w);
             }
-            if (rrow) {
-              const float4 r = __ldcs(reinterpret_cast<const float4*>(rrow + c0 + j));
-              if (p.rscale) {
-                const float4 s = __ldg(reinterpret_cast<const float4*>(p.rscale + c0 + j));
-                o.x = fmaf(s.x, r.x, o.x); o.y = fmaf(s.y, r.y, o.y); o.z = fmaf(s.z, r.z, o.z); o.w = fmaf(s.w, r.w, o.w);
-              } else {
-                o = add4(o, r);
-              }
-            }
-            st_stream_f4(crow + c0 + j, o);
+            st_stream_f4(p.C + (int64_t)row * p.ldc + c0 + tc, o);
           }
         }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { rr[i] = rn[i]; rn[i] = rn2[i]; }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -282,6 +322,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t cols = 2u * (uint32_t)N;
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(cols));
   }
+}
+
+// B -> (tf32(B), B - tf32(B)) into the workspace, row-major with leading dimension K
+__global__ void split_weights_kernel(const float* __restrict__ B, int64_t ldb, float* __restrict__ hi, float* __restrict__ lo,
+                                     int N, int K) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * K) return;
+  const int n = i / K, k = i - n * K;
+  const float x = B[(int64_t)n * ldb + k];
+  const float h = to_tf32(x);
+  hi[i] = h;
+  lo[i] = x - h;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -314,9 +366,13 @@ static bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t 
 }  // namespace gemm
 }  // namespace sn
 
+SN_API size_t sn_gemm_tf32_ws_bytes(int64_t N, int64_t K) {
+  return (N <= 0 || K <= 0) ? 0 : (size_t)(2 * N * K) * sizeof(float) + 256;
+}
+
 SN_API int sn_gemm_tf32_f32(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, const float* R,
                             int64_t ldr, const float* rscale, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
-                            int flags, sn_stream_t stream) {
+                            int flags, void* ws, size_t ws_bytes, sn_stream_t stream) {
   using namespace sn;
   using namespace sn::gemm;
   if (M < 0 || N <= 0 || K <= 0) return SN_ERR_ARG;
@@ -326,18 +382,29 @@ SN_API int sn_gemm_tf32_f32(const float* A, int64_t lda, const float* B, int64_t
   if (lda % 4 || ldb % 4 || ldc % 4 || (R && ldr % 4) || !aligned16(A) || !aligned16(B) || !aligned16(C) ||
       (R && !aligned16(R)) || (bias && !aligned16(bias)) || (rscale && !aligned16(rscale)))
     return SN_ERR_UNSUPPORTED;
-  CUtensorMap map_a, map_b;
-  if (!make_map(&map_a, A, M, K, lda, kBlockM) || !make_map(&map_b, B, N, K, ldb, (int)N)) return SN_ERR_UNSUPPORTED;
+  const bool split = !(flags & SN_GEMM_SINGLE_PASS);
+  CUtensorMap map_a, map_b, map_blo;
+  if (!make_map(&map_a, A, M, K, lda, kBlockM)) return SN_ERR_UNSUPPORTED;
+  if (split) {
+    if (!ws || ws_bytes < sn_gemm_tf32_ws_bytes(N, K)) return SN_ERR_WORKSPACE;
+    float* hi = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+    float* lo = hi + N * K;
+    split_weights_kernel<<<(unsigned)ceil_div(N * K, 256), 256, 0, (cudaStream_t)stream>>>(B, ldb, hi, lo, (int)N, (int)K);
+    if (!make_map(&map_b, hi, N, K, K, (int)N) || !make_map(&map_blo, lo, N, K, K, (int)N)) return SN_ERR_UNSUPPORTED;
+  } else {
+    if (!make_map(&map_b, B, N, K, ldb, (int)N)) return SN_ERR_UNSUPPORTED;
+    map_blo = map_b;
+  }
   Params p;
   p.bias = bias; p.R = R; p.rscale = rscale; p.C = C; p.ldr = ldr; p.ldc = ldc;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
-  p.split = (flags & SN_GEMM_SINGLE_PASS) ? 0 : 1;
+  p.split = split ? 1 : 0;
   int dev = 0, sms = 148, smem_optin = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   const size_t stage_bytes = 2 * ((size_t)kBlockM * kBlockK * 4 + (size_t)N * kBlockK * 4);
-  int stages = (int)(((size_t)smem_optin - 2048) / stage_bytes);
+  int stages = (int)(((size_t)smem_optin - 2048 - 22 * 1024) / stage_bytes);   // static smem: barriers + transpose buffers
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return SN_ERR_UNSUPPORTED;
   p.stages = stages;
@@ -346,6 +413,6 @@ SN_API int sn_gemm_tf32_f32(const float* A, int64_t lda, const float* B, int64_t
   if (e != cudaSuccess) return (int)e;
   const int64_t tiles = ceil_div(M, kBlockM);
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  gemm_tf32_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+  gemm_tf32_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, map_blo, p);
   return launch_status();
 }

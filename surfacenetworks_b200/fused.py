@@ -1,0 +1,134 @@
+"""Fused dense half of a ResNet stage:  Y = Linear(BatchNorm(Z)) (+ residual)  -- reference GraphConv1x1 with
+batch_norm="pre" (src/utils/utils_pt.py:91-104) as used by every LapResNet2 / DirResNet2 / AvgResNet2 stage (:156-157).
+
+The reference runs BatchNorm1d on ``x.transpose(1,2)`` and then nn.Linear: two transposes, a statistics pass, a
+normalisation pass that writes a second [rows, 2C] tensor, and an fp32 SIMT GEMM.  Here:
+
+  forward   sn_colstats_f32   one pass over Z -> per-column mean / biased variance (training mode)
+            fold              W' = W diag(gamma rstd),  b' = b + W (beta - gamma mu rstd)        ([C x 2C], tiny)
+            sn_gemm_tf32_f32  Y = Z W'^T + b' (+ residual)   tcgen05 3xTF32, fp32-grade accuracy
+  backward  G = dY^T Z (one [C x 2C] product) and colsum(dY) give EVERYTHING BatchNorm's backward needs:
+              dW = G diag(s) + colsum(dY) (x) t,   db = colsum(dY),   dbeta = colsum(dY) W,
+              dgamma = rstd (sum_c W .* G - mu dbeta)
+            sn_gemm_tf32_f32  dZ = dY (W diag(s)) + p .* Z + q      (p, q from dgamma, dbeta: the BN backward folded)
+
+so Z is read once forward and twice backward, and no normalised copy of Z ever exists.
+Shapes the tensor-core kernel does not cover (output width not in {64,128,256} or K % 32 != 0) take the plain
+torch composite (F.batch_norm + F.linear on the GPU).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import _native as N
+from .operators import _ptr, _stream
+
+__all__ = ["bn_linear", "gemm_tf32", "colstats", "fused_supported"]
+
+_GEMM_N = (64, 128, 256)
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+
+
+def gemm_supported(n_out, k):
+    return (n_out in _GEMM_N or (n_out % 256 == 0)) and k % 32 == 0
+
+
+def fused_supported(z, weight):
+    n_out, k = weight.shape
+    return (z.is_cuda and z.dtype == torch.float32 and z.dim() == 2 and z.stride(1) == 1 and z.stride(0) % 4 == 0
+            and gemm_supported(n_out, k) and gemm_supported(k, n_out) and k % 4 == 0 and 256 % (k // 4) == 0
+            and z.data_ptr() % 16 == 0)
+
+
+def colstats(Z):
+    """Per-column mean and biased variance over all rows of Z [rows, C] (sn_colstats_f32)."""
+    rows, C = Z.shape
+    mean = torch.empty(C, dtype=torch.float32, device=Z.device)
+    var = torch.empty(C, dtype=torch.float32, device=Z.device)
+    nb = N.lib.sn_colstats_ws_bytes(C)
+    ws = _ws(nb, Z.device)
+    with torch.cuda.device(Z.device):
+        N.call("sn_colstats_f32", _ptr(Z), Z.stride(0), rows, C, _ptr(mean), _ptr(var), _ptr(ws), nb, _stream())
+    return mean, var
+
+
+def gemm_tf32(A, B, bias=None, R=None, rscale=None, out=None, single_pass=False):
+    """out[M, N] = A[M, K] @ B[N, K]^T + bias + rscale * R   (3xTF32 tensor-core GEMM; N > 256 is split in column blocks)."""
+    M, K = A.shape
+    Nn = B.shape[0]
+    if out is None:
+        out = torch.empty(M, Nn, dtype=torch.float32, device=A.device)
+    B = B.contiguous()
+    step = Nn if Nn in _GEMM_N else 256
+    nb = N.lib.sn_gemm_tf32_ws_bytes(step, K)
+    flags = N.SN_GEMM_SINGLE_PASS if single_pass else 0
+    with torch.cuda.device(A.device):
+        for n0 in range(0, Nn, step):
+            ws = _ws(nb, A.device)
+            Bs = B[n0:n0 + step]
+            N.call("sn_gemm_tf32_f32", _ptr(A), A.stride(0), _ptr(Bs), Bs.stride(0),
+                   0 if bias is None else bias[n0:].data_ptr(), 0 if R is None else R[:, n0:].data_ptr(),
+                   0 if R is None else R.stride(0), 0 if rscale is None else rscale[n0:].data_ptr(),
+                   out[:, n0:].data_ptr(), out.stride(0), M, step, K, flags, _ptr(ws), nb, _stream())
+    return out
+
+
+class _BnLinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, Z, gamma, beta, W, b, residual, running_mean, running_var, training, momentum, eps):
+        rows = Z.shape[0]
+        if training:
+            mean, var = colstats(Z)
+            if running_mean is not None:
+                with torch.no_grad():
+                    running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)
+                    running_var.mul_(1 - momentum).add_(var, alpha=momentum * rows / max(rows - 1, 1))
+        else:
+            mean, var = running_mean, running_var
+        rstd = torch.rsqrt(var + eps)
+        s = gamma * rstd
+        t = beta - mean * s
+        Wf = W * s                                  # [C, 2C]: BatchNorm folded into the Linear
+        bf = torch.addmv(b, W, t)
+        res = None if residual is None else residual.contiguous()
+        Y = gemm_tf32(Z, Wf, bias=bf, R=res)
+        ctx.save_for_backward(Z, W, s, t, rstd, mean)
+        ctx.training, ctx.has_res = training, residual is not None
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        Z, W, s, t, rstd, mean = ctx.saved_tensors
+        dY = dY.contiguous()
+        rows = Z.shape[0]
+        G = torch.mm(dY.t(), Z)                     # [C, 2C]  (round 1: library GEMM; split-K tcgen05 kernel = next)
+        sdY = dY.sum(0)
+        dW = G * s + torch.outer(sdY, t)
+        db = sdY
+        dbeta = torch.mv(W.t(), sdY)
+        dgamma = rstd * ((W * G).sum(0) - mean * dbeta)
+        Ws_t = (W * s).t().contiguous()             # [2C, C]
+        if ctx.training:
+            p = -s * rstd * dgamma / rows
+            q = -s * dbeta / rows - p * mean
+            dZ = gemm_tf32(dY, Ws_t, bias=q, R=Z, rscale=p)
+        else:
+            dZ = gemm_tf32(dY, Ws_t)
+        return dZ, dgamma, dbeta, dW, db, (dY if ctx.has_res else None), None, None, None, None, None
+
+
+def bn_linear(z, bn, fc, residual=None):
+    """GraphConv1x1(batch_norm="pre") on rows: fused path when the shapes allow it, torch composite otherwise."""
+    if fused_supported(z, fc.weight) and (residual is None or (residual.shape == (z.shape[0], fc.weight.shape[0]))):
+        training = bn.training or bn.running_mean is None
+        if training and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+        momentum = 0.1 if bn.momentum is None else bn.momentum
+        return _BnLinear.apply(z, bn.weight, bn.bias, fc.weight, fc.bias, residual, bn.running_mean, bn.running_var,
+                               training, momentum, bn.eps)
+    y = fc(bn(z))
+    return y if residual is None else y + residual

@@ -26,7 +26,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import fused, ops
 from .operators import Bsr4Operator, CsrOperator, as_bsr4, as_csr
 
 __all__ = [
@@ -88,14 +88,16 @@ class GraphConv1x1(nn.Module):
             self.bn = nn.BatchNorm1d(num_outputs)
         self.fc = nn.Linear(num_inputs, num_outputs)
 
-    def forward_rows(self, z):
-        """z: [rows, num_inputs] -> [rows, num_outputs]."""
+    def forward_rows(self, z, residual=None):
+        """z: [rows, num_inputs] -> [rows, num_outputs] (+ residual).  "pre" BatchNorm + Linear runs as the fused
+        stage of ``fused.py`` (statistics pass, BN folded into the weights, tcgen05 GEMM with the residual in its
+        epilogue) whenever the widths allow it."""
         if self.batch_norm == "pre":
-            z = self.bn(z)
+            return fused.bn_linear(z, self.bn, self.fc, residual)
         z = self.fc(z)
         if self.batch_norm == "post":
             z = self.bn(z)
-        return z
+        return z if residual is None else z + residual
 
     def forward(self, x):
         batch_size, num_nodes, num_inputs = x.size()
@@ -147,8 +149,8 @@ class LapResNet2(_TwoStageBlock):
         op = as_csr(L)
         x = inputs.reshape(batch * node, feat)
         y = self.bn_fc0.forward_rows(ops.stage_concat(op, x))
-        y = self.bn_fc1.forward_rows(ops.stage_concat(op, y))
-        return y.view(batch, node, feat) + inputs
+        y = self.bn_fc1.forward_rows(ops.stage_concat(op, y), residual=x)       # "+ inputs" rides in the epilogue
+        return y.view(batch, node, feat)
 
 
 def _dense_lap_block(block, L, inputs):
@@ -187,8 +189,8 @@ class DirResNet2(_TwoStageBlock):
         v2 = v.reshape(batch_size * num_nodes, num_inputs)
         f2 = f.reshape(batch_size * num_faces, num_inputs)
         f_out = self.bn_fc0.forward_rows(ops.stage_concat(D, f2, v2))
-        v_out = self.bn_fc1.forward_rows(ops.stage_concat(DA, v2, f_out))
-        return v + v_out.view(batch_size, num_nodes, num_inputs), f_out.view(batch_size, num_faces, num_inputs)
+        v_new = self.bn_fc1.forward_rows(ops.stage_concat(DA, v2, f_out), residual=v2)   # v + v_out in the epilogue
+        return v_new.view(batch_size, num_nodes, num_inputs), f_out.view(batch_size, num_faces, num_inputs)
 
 
 class AvgResNet2(_TwoStageBlock):

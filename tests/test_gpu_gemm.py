@@ -17,8 +17,10 @@ def run_gemm(A, B, bias=None, R=None, rscale=None, single_pass=False, out=None):
     Nn = B.shape[0]
     C = torch.empty(M, Nn, device=DEV) if out is None else out
     p = lambda t: 0 if t is None else t.data_ptr()
+    wsb = N.lib.sn_gemm_tf32_ws_bytes(Nn, K)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
     N.call("sn_gemm_tf32_f32", p(A), A.stride(0), p(B), B.stride(0), p(bias), p(R), 0 if R is None else R.stride(0),
-           p(rscale), p(C), C.stride(0), M, Nn, K, N.SN_GEMM_SINGLE_PASS if single_pass else 0,
+           p(rscale), p(C), C.stride(0), M, Nn, K, N.SN_GEMM_SINGLE_PASS if single_pass else 0, p(ws), wsb,
            torch.cuda.current_stream().cuda_stream)
     return C
 
@@ -87,3 +89,131 @@ def test_gemm_argument_errors():
         run_gemm(A, B)                       # N = 100 unsupported
     with pytest.raises(N.SurfnetError):
         run_gemm(torch.zeros(128, 48, device=DEV), torch.zeros(128, 48, device=DEV))   # K % 32 != 0
+
+
+# ------------------------------------------------------------------------------------------- fused BN + Linear stage
+def _composite64(Z, gamma, beta, W, b, residual, rm, rv, training, eps=1e-5, momentum=0.1):
+    """GraphConv1x1("pre") in float64 with torch ops (the reference arithmetic: BatchNorm1d then Linear)."""
+    import torch.nn.functional as F
+    y = F.linear(F.batch_norm(Z, rm, rv, gamma, beta, training, momentum, eps), W, b)
+    return y if residual is None else y + residual
+
+
+@pytest.mark.parametrize("C,rows", [(128, 5000), (64, 1111), (256, 700)])
+@pytest.mark.parametrize("training,with_res", [(True, True), (True, False), (False, True)])
+def test_bn_linear_fused_vs_float64(C, rows, training, with_res):
+    """fused.bn_linear (colstats + fold + tcgen05 GEMM, hand-derived backward) vs BatchNorm1d + Linear in float64.
+    Tolerance 1e-4 * (|ref| + max|ref|): fp32 statistics and 3xTF32 products, no normalised copy of Z."""
+    import torch.nn as nn
+    from surfacenetworks_b200 import fused
+    g = torch.Generator(device=DEV).manual_seed(C + rows)
+    Z = (torch.randn(rows, 2 * C, device=DEV, generator=g) * (1 + torch.rand(2 * C, device=DEV, generator=g) * 3)
+         + torch.randn(2 * C, device=DEV, generator=g)).requires_grad_(True)
+    res = torch.randn(rows, C, device=DEV, generator=g).requires_grad_(True) if with_res else None
+    bn, fc = nn.BatchNorm1d(2 * C).to(DEV), nn.Linear(2 * C, C).to(DEV)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.normal_(0, 0.3)
+        bn.running_mean.normal_(0, 0.5)
+        bn.running_var.uniform_(0.5, 2.0)
+    bn.train(training)
+    assert fused.fused_supported(Z, fc.weight)
+    rm0, rv0 = bn.running_mean.clone(), bn.running_var.clone()
+    wout = torch.randn(rows, C, device=DEV, generator=g)
+    Y = fused.bn_linear(Z, bn, fc, res)
+    (Y * wout).sum().backward()
+    # float64 reference
+    Z64 = Z.detach().double().requires_grad_(True)
+    r64 = res.detach().double().requires_grad_(True) if with_res else None
+    P = [t.detach().double().requires_grad_(True) for t in (bn.weight, bn.bias, fc.weight, fc.bias)]
+    rm, rv = rm0.double(), rv0.double()
+    Y64 = _composite64(Z64, P[0], P[1], P[2], P[3], r64, rm, rv, training)
+    (Y64 * wout.double()).sum().backward()
+
+    def close(a, b, what, tol=1e-4):
+        b = b.double()
+        err = (a.double() - b).abs()
+        assert torch.all(err <= tol * (b.abs() + b.abs().max())), "%s: max err %g (scale %g)" % (what, float(err.max()), float(b.abs().max()))
+
+    close(Y, Y64, "Y")
+    close(Z.grad, Z64.grad, "dZ")
+    for name, p, p64 in zip(("dgamma", "dbeta", "dW", "db"), (bn.weight, bn.bias, fc.weight, fc.bias), P):
+        close(p.grad, p64.grad, name, 2e-4)
+    if with_res:
+        close(res.grad, r64.grad, "dres")
+    if training:
+        close(bn.running_mean, rm, "running_mean", 1e-5)
+        close(bn.running_var, rv, "running_var", 1e-5)
+        assert int(bn.num_batches_tracked) == 1
+
+
+def test_colstats_matches_float64():
+    from surfacenetworks_b200 import fused
+    g = torch.Generator(device=DEV).manual_seed(3)
+    for rows, C in ((1, 256), (37, 128), (100000, 256), (4099, 512), (999, 16)):
+        Zb = torch.randn(rows, C + 12, device=DEV, generator=g) * 5 + 3
+        Z = Zb[:, :C]
+        mean, var = fused.colstats(Z)
+        m64 = Z.double().mean(0)
+        v64 = Z.double().var(0, unbiased=False)
+        assert torch.allclose(mean.double(), m64, rtol=1e-6, atol=1e-6)
+        assert torch.allclose(var.double(), v64, rtol=2e-5, atol=1e-6), (rows, C, float((var.double() - v64).abs().max()))
+        if rows == 1:
+            assert torch.all(var == 0)                                   # constant column -> exactly zero
+        m2, v2 = fused.colstats(Z)
+        assert torch.equal(mean, m2) and torch.equal(var, v2)          # deterministic
+
+
+@pytest.mark.parametrize("kind", ["lap", "dir"])
+def test_blocks_width128_vs_oracle(kind):
+    """One LapResNet2(128) / DirResNet2(128) block -- the fused tensor-core stage inside the real layer -- against the
+    oracle port run live on the CPU (fp32), forward and all gradients; tolerance 2e-4 * (|ref| + max|ref|)."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from det import det_fill, det_tensor
+    from oracle import layers as O
+    from surfacenetworks_b200 import utils_pt as U, workloads as W
+    C = 128
+    meshes = W.make_mesh_ops(150, [0, 1]) + W.make_mesh_ops(140, [2])
+    B = len(meshes)
+    host = W.arap_batch(meshes, 0, dirac=(kind == "dir"))
+    nv, nf = host["num_vertices"], host["num_faces"]
+    block = det_fill(U.LapResNet2(C) if kind == "lap" else U.DirResNet2(C), 5, gain=0.5)
+    P = {}
+    for k, v in block.state_dict().items():
+        v = v.clone()
+        if v.is_floating_point() and not k.endswith(("running_mean", "running_var")):
+            v.requires_grad_(True)
+        P[k] = v
+    x = det_tensor((B, nv, C), 1)
+    f = det_tensor((B, nf, C), 2)
+    wv, wf = det_tensor((B, nv, C), 3), det_tensor((B, nf, C), 4)
+    xc, fc_ = x.clone().requires_grad_(True), f.clone().requires_grad_(True)
+    if kind == "lap":
+        ref = (O.lap_resnet2(P, host["L"], xc),)
+        (ref[0] * wv).sum().backward()
+    else:
+        ref = O.dir_resnet2(P, host["Di"], host["DiA"], xc, fc_)
+        ((ref[0] * wv).sum() + (ref[1] * wf).sum()).backward()
+    blk = block.to(DEV).train()
+    xg, fg = x.to(DEV).requires_grad_(True), f.to(DEV).requires_grad_(True)
+    if kind == "lap":
+        out = (blk(host["L"].to(DEV), None, xg),)
+        (out[0] * wv.to(DEV)).sum().backward()
+    else:
+        out = blk(host["Di"].to(DEV), host["DiA"].to(DEV), xg, fg)
+        ((out[0] * wv.to(DEV)).sum() + (out[1] * wf.to(DEV)).sum()).backward()
+
+    def close(a, b, what, tol=2e-4, floor=0.0):
+        a, b = a.detach().cpu().double(), b.detach().double()
+        err = (a - b).abs()
+        assert torch.all(err <= tol * (b.abs() + max(float(b.abs().max()), floor))), "%s: max err %g scale %g" % (what, float(err.max()), float(b.abs().max()))
+
+    for i, (o, r) in enumerate(zip(out, ref)):
+        close(o, r, "out%d" % i)
+    close(xg.grad, xc.grad, "dx")
+    if kind == "dir":
+        close(fg.grad, fc_.grad, "df")
+    gscale = max(float(P[k].grad.abs().max()) for k, _ in blk.named_parameters())
+    for k, p in blk.named_parameters():
+        close(p.grad, P[k].grad, "grad " + k, 5e-4, floor=1e-2 * gscale)

@@ -129,12 +129,14 @@ def test_eval_mode(golden, batch):
         close(f.cpu().numpy(), d["b_dir_eval/out1"], "dir eval f")
 
 
-def within_reference_noise(ours, ref32, ref64, what, k=4.0):
+def within_reference_noise(ours, ref32, ref64, what, k=10.0):
     """Model-level criterion.  Fifteen residual blocks with training-mode BatchNorm amplify fp32 rounding: on this
     fixture the reference's OWN fp32 result deviates from its fp64 result by 2.5% (outputs) and up to ~100% (gradients
     of the first layers).  So deep-stack parity is stated against the fp64 reference, in units of the reference's own
-    fp32 deviation: max|ours - ref64| <= k * max|ref32 - ref64| + 1e-5 * max|ref64|.  (Tight, per-block parity is
-    asserted in test_cube_blocks / test_batch_blocks.)"""
+    fp32 deviation: max|ours - ref64| <= k * max|ref32 - ref64| + 1e-5 * max|ref64|, k = 10: the tensor-core Linear
+    (3xTF32, ~1e-6 relative per product, tests/test_gpu_gemm.py) is ~4x noisier per GEMM than an fp32 SIMT GEMM and the
+    stack amplifies that like any other rounding.  (Tight, per-block parity is asserted in test_cube_blocks,
+    test_batch_blocks and test_gpu_gemm.py::test_blocks_width128_vs_oracle.)"""
     ours, ref32, ref64 = [np.asarray(a, dtype=np.float64) for a in (ours, ref32, ref64)]
     noise = np.abs(ref32 - ref64).max()
     err = np.abs(ours - ref64).max()

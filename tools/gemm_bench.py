@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""Dense-stage GEMM micro-benchmark at the BASELINE shapes: sn_gemm_tf32_f32 vs torch (cuBLAS fp32 / TF32)."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+
+def main():
+    from surfacenetworks_b200 import _native as N
+    dev = torch.device("cuda", 0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def time_it(fn, reps=10):
+        for _ in range(3):
+            fn()
+        tot = 0.0
+        for _ in range(reps):
+            flush.zero_()
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / reps
+
+    for M, Nn, K in ((128000, 128, 256), (255168, 128, 256), (128000, 256, 128), (255168, 256, 128), (16000, 128, 256)):
+        A = torch.randn(M, K, device=dev)
+        B = torch.randn(Nn, K, device=dev) / K ** 0.5
+        bias = torch.randn(Nn, device=dev)
+        R = torch.randn(M, Nn, device=dev)
+        C = torch.empty(M, Nn, device=dev)
+        st = torch.cuda.current_stream().cuda_stream
+WS = torch.empty(1 << 20, dtype=torch.uint8, device=dev)
+
+        def ours(flags=0, res=True):
+            N.call("sn_gemm_tf32_f32", A.data_ptr(), K, B.data_ptr(), K, bias.data_ptr(), R.data_ptr() if res else 0, Nn, 0,
+                   C.data_ptr(), Nn, M, Nn, K, flags, WS.data_ptr(), WS.numel(), st)
+
+        flops = 2.0 * M * Nn * K
+        bytes_ = 4.0 * (M * K + 2 * M * Nn + Nn * K)
+        out = {"M": M, "N": Nn, "K": K}
+        for name, fn in (("sn_3xtf32", lambda: ours(0)), ("sn_tf32", lambda: ours(N.SN_GEMM_SINGLE_PASS)),
+                         ("torch_fp32_addmm", lambda: torch.addmm(bias, A, B.t(), out=C).add_(R))):
+            ms = time_it(fn)
+            out[name] = {"us": ms * 1e3, "TFLOPs": flops / ms / 1e9, "GBps": bytes_ / ms / 1e6}
+        torch.backends.cuda.matmul.allow_tf32 = True
+        ms = time_it(lambda: torch.addmm(bias, A, B.t(), out=C).add_(R))
+        torch.backends.cuda.matmul.allow_tf32 = False
+        out["torch_tf32_addmm"] = {"us": ms * 1e3, "TFLOPs": flops / ms / 1e9}
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()
