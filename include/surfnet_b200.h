@@ -137,6 +137,17 @@ int sn_gemm_tf32_f32(const float* A, int64_t lda, const float* B, int64_t ldb, c
                      int64_t ldr, const float* rscale, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
                      int flags, void* ws, size_t ws_bytes, sn_stream_t stream);
 
+/* Weight-gradient product of a stage, reduction over the rows (split-K over the SMs, deterministic):
+ *
+ *   G[M x N] = A[R x M]^T * B[R x N]        M = 128, N % 32 == 0, 32 <= N <= 256
+ *
+ * With A = dY and B = Z (the stage's concat buffer) G gives dW of the Linear and, with colsum(dY), every reduction
+ * the BatchNorm backward needs (utils_pt.py:91-104 through autograd in the reference).  Same 3xTF32 precision and
+ * SN_GEMM_SINGLE_PASS flag as sn_gemm_tf32_f32; operands are read through MN-major tcgen05 descriptors. */
+size_t sn_gemm_tn_tf32_ws_bytes(int64_t R, int64_t N);
+int sn_gemm_tn_tf32_f32(const float* A, int64_t lda, const float* B, int64_t ldb, float* G, int64_t ldg, int64_t R,
+                        int64_t M, int64_t N, int flags, void* ws, size_t ws_bytes, sn_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Batch statistics for the training-mode BatchNorm in front of the Linear (utils_pt.py:84,98): per-column mean and
  * biased variance of X [rows x C] over all rows, one HBM pass, deterministic (fixed-order fp64 final reduction).

@@ -1,0 +1,313 @@
+// gemm_tn_tf32.cu -- the weight-gradient product of a stage on the tensor cores:
+//
+//   G[M x N] = A[R x M]^T * B[R x N]            (reduction over the R = B*V or B*F rows; M = 128, N <= 256)
+//
+// In the backward of Linear(BatchNorm(Z)) (reference GraphConv1x1, src/utils/utils_pt.py:91-104) this one product,
+// G = dY^T Z, yields dW and -- together with colsum(dY) -- everything BatchNorm's backward needs (see fused.py).
+// The reference gets it from autograd as an fp32 SIMT GEMM plus two BatchNorm reduction passes.
+//
+// Both operands are "MN-major" for the tensor core (the contraction index R is the slow axis of dY and Z), so the
+// tiles are loaded as 32-row x 32-float TMA boxes (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) and described to tcgen05 with
+// MN-major SWIZZLE_128B_BASE32B descriptors (LBO = 4 KB between 32-wide MN atoms, SBO = 512 B between 4-row K atoms).  Split-K: every CTA owns a
+// contiguous range of rows, accumulates its [128 x N] partial in TMEM (3xTF32: hi/lo split of both tiles in shared
+// memory) and writes it to a workspace; a second kernel adds the partials in a fixed order (deterministic).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace sn {
+namespace gemm_tn {
+
+constexpr int kM = 128;
+constexpr int kBlockK = 32;            // rows (contraction) per stage
+constexpr int kUmmaK = 8;
+constexpr int kThreads = 512;          // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-11 split, warps 12-15 epilogue
+constexpr int kBoxBytes = 32 * 32 * 4; // one TMA box: 32 rows x 128 bytes
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// MN-major tf32 operands have exactly one legal shared-memory layout on sm_100: SWIZZLE_128B_BASE32B
+// (CUTLASS: "for mn-major tf32 operands, SW128_32B is the only available smem layout").  Its atom is 4 K-rows of
+// 128 bytes (32 MN elements), 32-byte chunks XOR-ed with the row index mod 4 -- the pattern TMA produces with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  One MMA (K = 8) spans two atoms: SBO = 512 bytes; the next 32-wide MN atom
+// is the next TMA box: LBO = 4096 bytes.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffff) >> 4);
+  d |= (uint64_t)(kBoxBytes >> 4) << 16;         // leading byte offset
+  d |= (uint64_t)(512 >> 4) << 32;               // stride byte offset
+  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+  d |= (uint64_t)1 << 61;                        // layout type: SWIZZLE_128B_BASE32B
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+struct Params {
+  float* partial;        // [grid][kM][N]
+  int R, N;
+  int kb_per_cta;        // 32-row blocks per CTA
+  int n_kb;
+  int split;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int N = p.N;
+  const int a_boxes = kM / 32, b_boxes = N / 32;
+  const uint32_t a_bytes = a_boxes * kBoxBytes, b_bytes = b_boxes * kBoxBytes;
+  const uint32_t stage_bytes = 2 * (a_bytes + b_bytes);        // A, A_lo, B, B_lo
+  constexpr int kStages = 2;
+  __shared__ uint64_t full_bar[kStages], ready_bar[kStages], empty_bar[kStages], done_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb0 = blockIdx.x * p.kb_per_cta;
+  const int kb1 = min(kb0 + p.kb_per_cta, p.n_kb);
+  const int my_kb = max(kb1 - kb0, 0);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(ready_bar + s, 8);
+      mbar_init(empty_bar + s, 1);
+    }
+    mbar_init(&done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const uint32_t tmem_cols = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(empty_bar + stage, phase ^ 1u);
+        unsigned char* sa = smem + (size_t)stage * stage_bytes;
+        unsigned char* sb = sa + 2 * a_bytes;
+        mbar_arrive_expect_tx(full_bar + stage, a_bytes + b_bytes);
+        for (int i = 0; i < a_boxes; ++i) tma_load_2d(sa + i * kBoxBytes, &map_a, i * 32, kb * kBlockK, full_bar + stage);
+        for (int i = 0; i < b_boxes; ++i) tma_load_2d(sb + i * kBoxBytes, &map_b, i * 32, kb * kBlockK, full_bar + stage);
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // D = F32, A = B = TF32, both MN-major (bits 15, 16), N >> 3 at bit 17, M >> 4 at bit 24
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+                           ((uint32_t)(kM >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < my_kb; ++kb) {
+      mbar_wait(ready_bar + stage, phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint32_t sal = sa + a_bytes, sb = sa + 2 * a_bytes, sbl = sb + b_bytes;
+#pragma unroll
+        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+          const uint32_t off = k * 1024;                       // 8 K rows = one 1 KB group inside every box
+          const uint64_t da = umma_desc_mn_sw128(sa + off), db = umma_desc_mn_sw128(sb + off);
+          umma_tf32(tmem_base, da, db, idesc, (kb | k) != 0);
+          if (p.split) {
+            umma_tf32(tmem_base, da, umma_desc_mn_sw128(sbl + off), idesc, true);
+            umma_tf32(tmem_base, umma_desc_mn_sw128(sal + off), db, idesc, true);
+          }
+        }
+        umma_commit(empty_bar + stage);
+        if (kb == my_kb - 1) umma_commit(&done_bar);
+      }
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // hi / lo split of both tiles (elementwise, layout agnostic): 256 threads
+    const int t = threadIdx.x - 128;
+    int stage = 0;
+    uint32_t phase = 0;
+    const int n_a = a_bytes / 16, n_b = b_bytes / 16;
+    for (int kb = 0; kb < my_kb; ++kb) {
+      mbar_wait(full_bar + stage, phase);
+      unsigned char* sa = smem + (size_t)stage * stage_bytes;
+      unsigned char* sb = sa + 2 * a_bytes;
+      for (int i = t; i < n_a + n_b; i += 256) {
+        unsigned char* src = i < n_a ? sa + (size_t)i * 16 : sb + (size_t)(i - n_a) * 16;
+        const uint32_t lo_off = i < n_a ? a_bytes : b_bytes;
+        const float4 x = *reinterpret_cast<float4*>(src);
+        float4 hi;
+        hi.x = to_tf32(x.x); hi.y = to_tf32(x.y); hi.z = to_tf32(x.z); hi.w = to_tf32(x.w);
+        *reinterpret_cast<float4*>(src) = hi;
+        if (p.split) *reinterpret_cast<float4*>(src + lo_off) = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ready_bar + stage);
+      if (++stage == kStages) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp >= 12) {
+    // epilogue: this CTA's partial [128 x N] -> workspace
+    const int ew = warp - 12;
+    const int row = ew * 32 + lane;
+    float* out = p.partial + ((size_t)blockIdx.x * kM + row) * N;
+    if (my_kb > 0) {
+      mbar_wait(&done_bar, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(out + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                  __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      }
+    } else {
+      for (int c0 = 0; c0 < N; c0 += 4) *reinterpret_cast<float4*>(out + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+  }
+}
+
+// G[m][n] = sum over CTAs of partial[cta][m][n], fixed order
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int n_partials, int MN, float* __restrict__ G,
+                                       int64_t ldg, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= MN) return;
+  float acc = 0.f;
+  for (int c = 0; c < n_partials; ++c) acc += partial[(size_t)c * MN + i];
+  G[(int64_t)(i / N) * ldg + (i % N)] = acc;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+static bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int grid_for(int64_t n_kb, int* kb_per_cta) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t per = (n_kb + sms - 1) / sms;
+  if (per < 1) per = 1;
+  *kb_per_cta = (int)per;
+  return (int)((n_kb + per - 1) / per);
+}
+
+}  // namespace gemm_tn
+}  // namespace sn
+
+SN_API size_t sn_gemm_tn_tf32_ws_bytes(int64_t R, int64_t N) {
+  using namespace sn::gemm_tn;
+  if (R <= 0 || N <= 0) return 0;
+  int per;
+  const int grid = grid_for((R + kBlockK - 1) / kBlockK, &per);
+  return (size_t)grid * kM * (size_t)N * sizeof(float) + 256;
+}
+
+SN_API int sn_gemm_tn_tf32_f32(const float* A, int64_t lda, const float* B, int64_t ldb, float* G, int64_t ldg, int64_t R,
+                               int64_t M, int64_t N, int flags, void* ws, size_t ws_bytes, sn_stream_t stream) {
+  using namespace sn;
+  using namespace sn::gemm_tn;
+  if (R <= 0 || M <= 0 || N <= 0 || !A || !B || !G || lda < M || ldb < N || ldg < N) return SN_ERR_ARG;
+  if (M != kM || N % 32 != 0 || N > 256 || N < 32 || R >= 0x7fffffffLL - 64) return SN_ERR_UNSUPPORTED;
+  if (lda % 4 || ldb % 4 || !aligned16(A) || !aligned16(B)) return SN_ERR_UNSUPPORTED;
+  if (!ws || ws_bytes < sn_gemm_tn_tf32_ws_bytes(R, N)) return SN_ERR_WORKSPACE;
+  CUtensorMap map_a, map_b;
+  if (!make_map(&map_a, A, R, M, lda) || !make_map(&map_b, B, R, N, ldb)) return SN_ERR_UNSUPPORTED;
+  Params p;
+  p.partial = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  p.R = (int)R; p.N = (int)N;
+  p.n_kb = (int)((R + kBlockK - 1) / kBlockK);
+  const int grid = grid_for(p.n_kb, &p.kb_per_cta);
+  p.split = (flags & SN_GEMM_SINGLE_PASS) ? 0 : 1;
+  const size_t stage_bytes = 2 * ((size_t)(kM / 32) * kBoxBytes + (size_t)(N / 32) * kBoxBytes);
+  const size_t smem = 2 * stage_bytes + 1024;
+  cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  cudaStream_t st = (cudaStream_t)stream;
+  gemm_tn_kernel<<<grid, kThreads, smem, st>>>(map_a, map_b, p);
+  const int MN = (int)(kM * N);
+  reduce_partials_kernel<<<(MN + 255) / 256, 256, 0, st>>>(p.partial, grid, MN, G, ldg, (int)N);
+  return launch_status();
+}

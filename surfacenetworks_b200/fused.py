@@ -7,7 +7,8 @@ normalisation pass that writes a second [rows, 2C] tensor, and an fp32 SIMT GEMM
   forward   sn_colstats_f32   one pass over Z -> per-column mean / biased variance (training mode)
             fold              W' = W diag(gamma rstd),  b' = b + W (beta - gamma mu rstd)        ([C x 2C], tiny)
             sn_gemm_tf32_f32  Y = Z W'^T + b' (+ residual)   tcgen05 3xTF32, fp32-grade accuracy
-  backward  G = dY^T Z (one [C x 2C] product) and colsum(dY) give EVERYTHING BatchNorm's backward needs:
+  backward  sn_gemm_tn_tf32_f32  G = dY^T Z (one [C x 2C] split-K product) and colsum(dY) give EVERYTHING
+            BatchNorm's backward needs:
               dW = G diag(s) + colsum(dY) (x) t,   db = colsum(dY),   dbeta = colsum(dY) W,
               dgamma = rstd (sum_c W .* G - mu dbeta)
             sn_gemm_tf32_f32  dZ = dY (W diag(s)) + p .* Z + q      (p, q from dgamma, dbeta: the BN backward folded)
@@ -77,6 +78,27 @@ def gemm_tf32(A, B, bias=None, R=None, rscale=None, out=None, single_pass=False)
     return out
 
 
+def gemm_tn_supported(m, n):
+    return m % 128 == 0 and n % 32 == 0
+
+
+def gemm_tn_tf32(A, B, single_pass=False):
+    """G[M, N] = A[R, M]^T @ B[R, N] (split-K tcgen05 3xTF32, deterministic); M in 128-blocks, N in <=256-blocks."""
+    R, M = A.shape
+    Nn = B.shape[1]
+    G = torch.empty(M, Nn, dtype=torch.float32, device=A.device)
+    flags = N.SN_GEMM_SINGLE_PASS if single_pass else 0
+    with torch.cuda.device(A.device):
+        for m0 in range(0, M, 128):
+            for n0 in range(0, Nn, 256):
+                n = min(256, Nn - n0)
+                nb = N.lib.sn_gemm_tn_tf32_ws_bytes(R, n)
+                ws = _ws(nb, A.device)
+                N.call("sn_gemm_tn_tf32_f32", A[:, m0:].data_ptr(), A.stride(0), B[:, n0:].data_ptr(), B.stride(0),
+                       G[m0:, n0:].data_ptr(), G.stride(0), R, 128, n, flags, _ptr(ws), nb, _stream())
+    return G
+
+
 class _BnLinear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, Z, gamma, beta, W, b, residual, running_mean, running_var, training, momentum, eps):
@@ -105,8 +127,12 @@ class _BnLinear(torch.autograd.Function):
         Z, W, s, t, rstd, mean = ctx.saved_tensors
         dY = dY.contiguous()
         rows = Z.shape[0]
-        G = torch.mm(dY.t(), Z)                     # [C, 2C]  (round 1: library GEMM; split-K tcgen05 kernel = next)
-        sdY = dY.sum(0)
+        if gemm_tn_supported(dY.shape[1], Z.shape[1]):
+            G = gemm_tn_tf32(dY, Z)                 # [C, 2C] = dY^T Z: split-K tcgen05 (MN-major operands)
+            sdY = colstats(dY)[0] * rows            # colsum(dY) from the same deterministic statistics kernel
+        else:
+            G = torch.mm(dY.t(), Z)
+            sdY = dY.sum(0)
         dW = G * s + torch.outer(sdY, t)
         db = sdY
         dbeta = torch.mv(W.t(), sdY)

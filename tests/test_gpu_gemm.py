@@ -217,3 +217,33 @@ def test_blocks_width128_vs_oracle(kind):
     gscale = max(float(P[k].grad.abs().max()) for k, _ in blk.named_parameters())
     for k, p in blk.named_parameters():
         close(p.grad, P[k].grad, "grad " + k, 5e-4, floor=1e-2 * gscale)
+
+
+# ------------------------------------------------------------------------------------------- G = A^T B (split-K, MN-major)
+def run_gemm_tn(A, B, single_pass=False):
+    from surfacenetworks_b200 import _native as N
+    R, M = A.shape
+    Nn = B.shape[1]
+    G = torch.empty(M, Nn, device=DEV)
+    wsb = N.lib.sn_gemm_tn_tf32_ws_bytes(R, Nn)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+    N.call("sn_gemm_tn_tf32_f32", A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), G.data_ptr(), G.stride(0), R, M, Nn,
+           N.SN_GEMM_SINGLE_PASS if single_pass else 0, ws.data_ptr(), wsb, torch.cuda.current_stream().cuda_stream)
+    return G
+
+
+@pytest.mark.parametrize("R,N", [(32, 256), (8, 64), (1000, 256), (4133, 128), (128000, 256), (255168, 256)])
+def test_gemm_tn_matches_fp64(R, N):
+    g = torch.Generator(device=DEV).manual_seed(R + N)
+    A = torch.randn(R, 128, device=DEV, generator=g)
+    Bb = torch.randn(R, N + 32, device=DEV, generator=g) + 0.5
+    B = Bb[:, :N]                                   # strided operand (the concat buffer case)
+    G = run_gemm_tn(A, B)
+    torch.cuda.synchronize()
+    G64 = A.double().t() @ B.double()
+    mag = A.double().abs().t() @ B.double().abs()
+    err = (G.double() - G64).abs()
+    assert torch.all(err <= 2e-6 * mag), "3xTF32 G: max err/mag %g" % float((err / mag).max())
+    assert torch.equal(G, run_gemm_tn(A, B))          # deterministic split-K reduction
+    G1 = run_gemm_tn(A, B, single_pass=True)
+    assert torch.all((G1.double() - G64).abs() <= 2e-3 * mag)
