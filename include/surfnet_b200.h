@@ -158,6 +158,20 @@ size_t sn_colstats_ws_bytes(int64_t C);
 int sn_colstats_f32(const float* X, int64_t ldx, int64_t rows, int64_t C, float* mean, float* var_biased,
                     void* ws, size_t ws_bytes, sn_stream_t stream);
 
+/* O(C^2) glue of the fused dense stage, one launch each way.
+ * forward : s = gamma*rstd, t = beta - mean*s, Wf = W diag(s) [N x K], bf = b + W t, rstd = 1/sqrt(var+eps); when
+ *           running_mean/var are given they are updated with `momentum` (unbiased variance, rows/(rows-1)).
+ * backward: from G = dY^T Z [N x K] and sdY = colsum(dY) [N]:  dW, db, dgamma, dbeta, the coefficients p, q of
+ *           dZ = dY (W diag(s)) + p .* Z + q (training-mode BatchNorm backward folded), and WsT = (W diag(s))^T [K x N]. */
+int sn_bn_fold_fwd_f32(const float* mean, const float* var, const float* gamma, const float* beta, const float* W,
+                       const float* b, int64_t N, int64_t K, float eps, float* Wf, float* bf, float* s, float* t,
+                       float* rstd, float* running_mean, float* running_var, float momentum, int64_t rows,
+                       sn_stream_t stream);
+int sn_bn_fold_bwd_f32(const float* G, const float* sdY, const float* W, const float* s, const float* t,
+                       const float* rstd, const float* mean, int64_t N, int64_t K, int64_t rows, int training,
+                       float* dW, float* db, float* dgamma, float* dbeta, float* p, float* q, float* WsT,
+                       sn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

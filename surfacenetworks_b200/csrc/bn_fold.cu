@@ -1,0 +1,121 @@
+// bn_fold.cu -- the O(C^2) glue of the fused dense stage, one launch each way (replaces ~25 tiny elementwise launches).
+//
+// forward : BatchNorm (reference utils_pt.py:84,98) folded into the Linear (utils_pt.py:89,99):
+//             s = gamma * rstd, t = beta - mean * s, W' = W diag(s), b' = b + W t, running statistics update
+// backward: from G = dY^T Z and sdY = colsum(dY) (see fused.py):
+//             dW = G diag(s) + sdY (x) t, db = sdY, dbeta = W^T sdY, dgamma = rstd (sum_c W.*G - mean dbeta),
+//             p = -s rstd dgamma / n, q = -s dbeta / n - p mean, and the transposed, scaled weights (W diag(s))^T
+#include "common.cuh"
+
+namespace sn {
+
+constexpr int kFoldCols = 32;      // columns per CTA
+constexpr int kFoldRowGroups = 8;  // row groups per CTA (256 threads)
+
+// grid = ceil(K / 32) CTAs; thread (rg, c) handles rows rg, rg + 8, ... of column blockIdx.x * 32 + c
+__global__ void __launch_bounds__(kFoldCols * kFoldRowGroups)
+bn_fold_fwd_kernel(const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, const float* __restrict__ W, int N, int K, float eps,
+                   float* __restrict__ Wf, float* __restrict__ s_out, float* __restrict__ t_out, float* __restrict__ rstd_out,
+                   float* running_mean, float* running_var, float momentum, float unbias) {
+  const int c = threadIdx.x % kFoldCols, rg = threadIdx.x / kFoldCols;
+  const int k = blockIdx.x * kFoldCols + c;
+  if (k >= K) return;
+  const float m = mean[k], v = var[k];
+  const float rstd = rsqrtf(v + eps);
+  const float s = gamma[k] * rstd;
+  if (rg == 0) {
+    s_out[k] = s;
+    t_out[k] = beta[k] - m * s;
+    rstd_out[k] = rstd;
+    if (running_mean) {
+      running_mean[k] = (1.f - momentum) * running_mean[k] + momentum * m;
+      running_var[k] = (1.f - momentum) * running_var[k] + momentum * v * unbias;
+    }
+  }
+  for (int n = rg; n < N; n += kFoldRowGroups) Wf[(size_t)n * K + k] = W[(size_t)n * K + k] * s;
+}
+
+// b'[n] = b[n] + sum_k W[n,k] t[k]: one warp per output row, fixed-order lane partials + shuffle tree
+__global__ void __launch_bounds__(256)
+bn_fold_bias_kernel(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ t, int N, int K,
+                    float* __restrict__ bf) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float acc = 0.f;
+  for (int kk = lane; kk < K; kk += 32) acc = fmaf(W[(size_t)n * K + kk], t[kk], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) bf[n] = b[n] + acc;
+}
+
+__global__ void __launch_bounds__(kFoldCols * kFoldRowGroups)
+bn_fold_bwd_kernel(const float* __restrict__ G, const float* __restrict__ sdY, const float* __restrict__ W,
+                   const float* __restrict__ s, const float* __restrict__ t, const float* __restrict__ rstd,
+                   const float* __restrict__ mean, int N, int K, float inv_rows, int training, float* __restrict__ dW,
+                   float* __restrict__ db, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ p_out,
+                   float* __restrict__ q_out, float* __restrict__ WsT) {
+  __shared__ float red[2][kFoldRowGroups][kFoldCols];
+  const int c = threadIdx.x % kFoldCols, rg = threadIdx.x / kFoldCols;
+  const int k = blockIdx.x * kFoldCols + c;
+  float dbeta_p = 0.f, wg_p = 0.f;
+  if (k < K) {
+    const float sk = s[k], tk = t[k];
+    for (int n = rg; n < N; n += kFoldRowGroups) {
+      const float w = W[(size_t)n * K + k], g = G[(size_t)n * K + k], d = sdY[n];
+      dW[(size_t)n * K + k] = fmaf(g, sk, d * tk);
+      dbeta_p = fmaf(w, d, dbeta_p);
+      wg_p = fmaf(w, g, wg_p);
+      WsT[(size_t)k * N + n] = w * sk;
+    }
+  }
+  red[0][rg][c] = dbeta_p;
+  red[1][rg][c] = wg_p;
+  __syncthreads();
+  if (rg == 0 && k < K) {
+    float dbeta_k = 0.f, wg = 0.f;
+#pragma unroll
+    for (int g = 0; g < kFoldRowGroups; ++g) {   // fixed order
+      dbeta_k += red[0][g][c];
+      wg += red[1][g][c];
+    }
+    const float sk = s[k];
+    const float dgamma_k = rstd[k] * (wg - mean[k] * dbeta_k);
+    dgamma[k] = dgamma_k;
+    dbeta[k] = dbeta_k;
+    const float pk = training ? -sk * rstd[k] * dgamma_k * inv_rows : 0.f;
+    p_out[k] = pk;
+    q_out[k] = training ? -sk * dbeta_k * inv_rows - pk * mean[k] : 0.f;
+  }
+  if (blockIdx.x == 0)
+    for (int n = threadIdx.x; n < N; n += blockDim.x) db[n] = sdY[n];
+}
+
+}  // namespace sn
+
+SN_API int sn_bn_fold_fwd_f32(const float* mean, const float* var, const float* gamma, const float* beta, const float* W,
+                              const float* b, int64_t N, int64_t K, float eps, float* Wf, float* bf, float* s, float* t,
+                              float* rstd, float* running_mean, float* running_var, float momentum, int64_t rows,
+                              sn_stream_t stream) {
+  using namespace sn;
+  if (N <= 0 || K <= 0 || !mean || !var || !gamma || !beta || !W || !b || !Wf || !bf || !s || !t || !rstd) return SN_ERR_ARG;
+  const float unbias = rows > 1 ? (float)((double)rows / (double)(rows - 1)) : 1.f;
+  cudaStream_t st = (cudaStream_t)stream;
+  bn_fold_fwd_kernel<<<(unsigned)ceil_div(K, kFoldCols), kFoldCols * kFoldRowGroups, 0, st>>>(
+      mean, var, gamma, beta, W, (int)N, (int)K, eps, Wf, s, t, rstd, running_mean, running_var, momentum, unbias);
+  bn_fold_bias_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(W, b, t, (int)N, (int)K, bf);
+  return launch_status();
+}
+
+SN_API int sn_bn_fold_bwd_f32(const float* G, const float* sdY, const float* W, const float* s, const float* t,
+                              const float* rstd, const float* mean, int64_t N, int64_t K, int64_t rows, int training,
+                              float* dW, float* db, float* dgamma, float* dbeta, float* p, float* q, float* WsT,
+                              sn_stream_t stream) {
+  using namespace sn;
+  if (N <= 0 || K <= 0 || rows <= 0 || !G || !sdY || !W || !s || !t || !rstd || !mean || !dW || !db || !dgamma || !dbeta ||
+      !p || !q || !WsT)
+    return SN_ERR_ARG;
+  bn_fold_bwd_kernel<<<(unsigned)ceil_div(K, kFoldCols), kFoldCols * kFoldRowGroups, 0, (cudaStream_t)stream>>>(
+      G, sdY, W, s, t, rstd, mean, (int)N, (int)K, (float)(1.0 / (double)rows), training, dW, db, dgamma, dbeta, p, q, WsT);
+  return launch_status();
+}

@@ -46,6 +46,26 @@ elu_bwd_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict
   }
 }
 
+template <bool RAW>
+__global__ void __launch_bounds__(256)
+elu_bwd_vec4_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ G, int64_t ldg,
+                    const float* __restrict__ G2, int64_t ldg2, float* __restrict__ Y, int64_t ldy, int64_t rows, int C4) {
+  const int64_t total = rows * C4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / C4;
+    const int c = (int)(i - r * C4) * 4;
+    const float4 a = *reinterpret_cast<const float4*>(A + r * lda + c);
+    float4 g = __ldcs(reinterpret_cast<const float4*>(G + r * ldg + c));
+    if (G2) g = add4(g, __ldcs(reinterpret_cast<const float4*>(G2 + r * ldg2 + c)));
+    float4 y;
+    y.x = g.x * (a.x > 0.f ? 1.f : (RAW ? expf(a.x) : a.x + 1.f));
+    y.y = g.y * (a.y > 0.f ? 1.f : (RAW ? expf(a.y) : a.y + 1.f));
+    y.z = g.z * (a.z > 0.f ? 1.f : (RAW ? expf(a.z) : a.z + 1.f));
+    y.w = g.w * (a.w > 0.f ? 1.f : (RAW ? expf(a.w) : a.w + 1.f));
+    *reinterpret_cast<float4*>(Y + r * ldy + c) = y;
+  }
+}
+
 }  // namespace sn
 
 SN_API int sn_elu_f32(const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t rows, int64_t C,
@@ -71,6 +91,18 @@ SN_API int sn_elu_bwd_f32(const float* A, int64_t lda, int a_is_raw, const float
   if (rows < 0 || C < 0 || C > 0x7fffffffLL) return SN_ERR_ARG;
   if (rows == 0 || C == 0) return SN_OK;
   if (!A || !G || !Y || lda < C || ldg < C || ldy < C || (G2 && ldg2 < C)) return SN_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (C % 4 == 0) && (lda % 4 == 0) && (ldg % 4 == 0) && (ldy % 4 == 0) && (!G2 || ldg2 % 4 == 0) &&
+                   aligned16(A) && aligned16(G) && aligned16(Y) && (!G2 || aligned16(G2));
+  if (vec) {
+    const int64_t work = rows * (C / 4);
+    const unsigned vgrid = (unsigned)(ceil_div(work, 256) < 148 * 16 ? ceil_div(work, 256) : 148 * 16);
+    if (a_is_raw)
+      elu_bwd_vec4_kernel<true><<<vgrid, 256, 0, st>>>(A, lda, G, ldg, G2, ldg2, Y, ldy, rows, (int)(C / 4));
+    else
+      elu_bwd_vec4_kernel<false><<<vgrid, 256, 0, st>>>(A, lda, G, ldg, G2, ldg2, Y, ldy, rows, (int)(C / 4));
+    return launch_status();
+  }
   const unsigned grid = (unsigned)(ceil_div(rows * C, 256) < 148 * 16 ? ceil_div(rows * C, 256) : 148 * 16);
   if (a_is_raw)
     elu_bwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(A, lda, G, ldg, G2, ldg2, Y, ldy, rows, (int)C);

@@ -102,49 +102,54 @@ def gemm_tn_tf32(A, B, single_pass=False):
 class _BnLinear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, Z, gamma, beta, W, b, residual, running_mean, running_var, training, momentum, eps):
-        rows = Z.shape[0]
+        rows, K = Z.shape
+        Nn = W.shape[0]
+        dev = Z.device
         if training:
             mean, var = colstats(Z)
-            if running_mean is not None:
-                with torch.no_grad():
-                    running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)
-                    running_var.mul_(1 - momentum).add_(var, alpha=momentum * rows / max(rows - 1, 1))
         else:
             mean, var = running_mean, running_var
-        rstd = torch.rsqrt(var + eps)
-        s = gamma * rstd
-        t = beta - mean * s
-        Wf = W * s                                  # [C, 2C]: BatchNorm folded into the Linear
-        bf = torch.addmv(b, W, t)
+        W = W.contiguous()
+        Wf = torch.empty_like(W)                    # [C, 2C]: BatchNorm folded into the Linear
+        bf = torch.empty(Nn, dtype=torch.float32, device=dev)
+        stk = torch.empty(3, K, dtype=torch.float32, device=dev)          # s, t, rstd
+        update = training and running_mean is not None
+        with torch.cuda.device(dev):
+            N.call("sn_bn_fold_fwd_f32", _ptr(mean), _ptr(var), _ptr(gamma), _ptr(beta), _ptr(W), _ptr(b), Nn, K, float(eps),
+                   _ptr(Wf), _ptr(bf), _ptr(stk[0]), _ptr(stk[1]), _ptr(stk[2]), _ptr(running_mean) if update else 0,
+                   _ptr(running_var) if update else 0, float(momentum), rows, _stream())
         res = None if residual is None else residual.contiguous()
         Y = gemm_tf32(Z, Wf, bias=bf, R=res)
-        ctx.save_for_backward(Z, W, s, t, rstd, mean)
+        ctx.save_for_backward(Z, W, stk, mean)
         ctx.training, ctx.has_res = training, residual is not None
         return Y
 
     @staticmethod
     def backward(ctx, dY):
-        Z, W, s, t, rstd, mean = ctx.saved_tensors
+        Z, W, stk, mean = ctx.saved_tensors
         dY = dY.contiguous()
-        rows = Z.shape[0]
-        if gemm_tn_supported(dY.shape[1], Z.shape[1]):
+        rows, K = Z.shape
+        Nn = W.shape[0]
+        dev = Z.device
+        if gemm_tn_supported(Nn, K):
             G = gemm_tn_tf32(dY, Z)                 # [C, 2C] = dY^T Z: split-K tcgen05 (MN-major operands)
             sdY = colstats(dY)[0] * rows            # colsum(dY) from the same deterministic statistics kernel
         else:
             G = torch.mm(dY.t(), Z)
             sdY = dY.sum(0)
-        dW = G * s + torch.outer(sdY, t)
-        db = sdY
-        dbeta = torch.mv(W.t(), sdY)
-        dgamma = rstd * ((W * G).sum(0) - mean * dbeta)
-        Ws_t = (W * s).t().contiguous()             # [2C, C]
+        dW = torch.empty_like(W)
+        db = torch.empty(Nn, dtype=torch.float32, device=dev)
+        vec = torch.empty(4, K, dtype=torch.float32, device=dev)          # dgamma, dbeta, p, q
+        WsT = torch.empty(K, Nn, dtype=torch.float32, device=dev)         # (W diag(s))^T
+        with torch.cuda.device(dev):
+            N.call("sn_bn_fold_bwd_f32", _ptr(G), _ptr(sdY), _ptr(W), _ptr(stk[0]), _ptr(stk[1]), _ptr(stk[2]), _ptr(mean),
+                   Nn, K, rows, 1 if ctx.training else 0, _ptr(dW), _ptr(db), _ptr(vec[0]), _ptr(vec[1]), _ptr(vec[2]),
+                   _ptr(vec[3]), _ptr(WsT), _stream())
         if ctx.training:
-            p = -s * rstd * dgamma / rows
-            q = -s * dbeta / rows - p * mean
-            dZ = gemm_tf32(dY, Ws_t, bias=q, R=Z, rscale=p)
+            dZ = gemm_tf32(dY, WsT, bias=vec[3], R=Z, rscale=vec[2])
         else:
-            dZ = gemm_tf32(dY, Ws_t)
-        return dZ, dgamma, dbeta, dW, db, (dY if ctx.has_res else None), None, None, None, None, None
+            dZ = gemm_tf32(dY, WsT)
+        return dZ, vec[0], vec[1], dW, db, (dY if ctx.has_res else None), None, None, None, None, None
 
 
 def bn_linear(z, bn, fc, residual=None):
