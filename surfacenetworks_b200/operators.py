@@ -241,6 +241,20 @@ class Bsr4Operator:
     def release_source(self):
         self._source = None
 
+    def load_from(self, other):
+        """Overwrite this operator's device arrays with ``other``'s (same shape, block count within capacity), keeping
+        the buffers' addresses -- lets a captured CUDA graph be replayed on a new batch's operator."""
+        if (other.n_brows, other.n_bcols) != (self.n_brows, self.n_bcols):
+            raise ValueError("operator shapes differ")
+        if other.n_blocks > self.bcolind.numel():
+            raise ValueError("block count %d exceeds the slot capacity %d" % (other.n_blocks, self.bcolind.numel()))
+        nb = other.n_blocks
+        self.browptr.copy_(other.browptr, non_blocking=True)
+        self.bcolind[:nb].copy_(other.bcolind[:nb], non_blocking=True)
+        self.bval[:16 * nb].copy_(other.bval[:16 * nb], non_blocking=True)
+        self._n_blocks, self.max_row_blocks = nb, other.max_row_blocks
+        return self
+
     def algorithmic_bytes(self, C):
         return 4 * (self.n_brows + 1) + 68 * self.n_blocks + 4 * self.n_bcols * C + 4 * self.n_brows * C
 
