@@ -118,12 +118,23 @@ int sn_elu_f32(const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t rows,
 int sn_elu_bwd_f32(const float* A, int64_t lda, int a_is_raw, const float* G, int64_t ldg, const float* G2,
                    int64_t ldg2, float* Y, int64_t ldy, int64_t rows, int64_t C, sn_stream_t stream);
 
+/* Per-mesh (segment) column sums: out[s, c] = sum over the rows_per_seg rows of segment s of w[r] * X[r, c]
+ * (w NULL = 1).  With w = mask this is the numerator of global_average (utils_pt.py:120-122); unweighted it is the
+ * per-mesh gradient sum of its backward.  Deterministic (one CTA per segment, fixed-order reduction).
+ * sn_elu_bwd_group_f32: Y = (G + w[r] * GB[r / rows_per_seg]) * elu'(x) -- the backward of elu followed by
+ * global_average's broadcast term, A holding the activated values as in sn_elu_bwd_f32 (a_is_raw = 0). */
+int sn_segment_sum_f32(const float* X, int64_t ldx, const float* w, int64_t rows_per_seg, int64_t n_seg, int64_t C,
+                       float* out, sn_stream_t stream);
+int sn_elu_bwd_group_f32(const float* A, int64_t lda, const float* G, int64_t ldg, const float* GB, const float* w,
+                         int64_t rows_per_seg, float* Y, int64_t ldy, int64_t rows, int64_t C, sn_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Dense half of a stage on the tensor cores (tcgen05, kind::tf32, accumulators in TMEM):
  *
- *   C[M x N] = A[M x K] * B[N x K]^T + bias[N] + rscale[N] .* R[M x N]
+ *   C[M x N] = A[M x K] * B[N x K]^T + bias[N] + group_bias[row / rows_per_group][N] + rscale[N] .* R[M x N]
  *
- * bias, R, rscale may be NULL (rscale NULL with R given means R is added unscaled).  A is the stage's concat
+ * bias, group_bias, R, rscale may be NULL (rscale NULL with R given means R is added unscaled).  group_bias is the
+ * per-mesh term of AvgResNet2 (utils_pt.py:233,239: the broadcast global average times its half of the weights).  A is the stage's concat
  * buffer Z, B the Linear weight of GraphConv1x1 (utils_pt.py:89,99) with the training-mode BatchNorm of
  * utils_pt.py:84,98 folded in by the caller; R carries the block residual (utils_pt.py:180,220).  The same
  * entry point serves the backward product dZ = dY * W_s + p .* Z + q.
@@ -134,8 +145,9 @@ int sn_elu_bwd_f32(const float* A, int64_t lda, int a_is_raw, const float* G, in
 #define SN_GEMM_SINGLE_PASS 1
 size_t sn_gemm_tf32_ws_bytes(int64_t N, int64_t K); /* workspace for the pre-split weights (3xTF32 mode) */
 int sn_gemm_tf32_f32(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, const float* R,
-                     int64_t ldr, const float* rscale, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
-                     int flags, void* ws, size_t ws_bytes, sn_stream_t stream);
+                     int64_t ldr, const float* rscale, const float* group_bias, int64_t rows_per_group, float* C,
+                     int64_t ldc, int64_t M, int64_t N, int64_t K, int flags, void* ws, size_t ws_bytes,
+                     sn_stream_t stream);
 
 /* Weight-gradient product of a stage, reduction over the rows (split-K over the SMs, deterministic):
  *

@@ -153,3 +153,40 @@ def arap_lap_model(P, L, mask, inputs, layers=15, training=True):
 def arap_loss(outputs, targets, mask, batch_size):
     """src/as_rigid_as_possible/main.py:225-226."""
     return F.smooth_l1_loss(outputs * mask.expand_as(outputs), targets, reduction="sum") / batch_size
+
+
+def lap_resnet2_general(P, L, x, inner_layers=2, training=True):
+    """normal_predict _LapResNet2.forward, src/normal_predict/models.py:462-477 (bnmode='' -> "pre")."""
+    h = x
+    for i in range(inner_layers):
+        h = F.elu(h)
+        h = torch.cat([h, apply_laplacian(L, h)], 2)
+        h = graph_conv1x1(h, _sub(P, "bn_fc%d." % i), "pre", training)
+    n_out = h.shape[2]
+    if n_out <= x.shape[2]:
+        return h + x[:, :, :n_out]
+    return h + torch.cat([x] * 2, dim=2)
+
+
+def dir_deep_model(P, Di, DiA, mask, inputs, layers, training=True):
+    """normal_predict DirDeepModel.forward, src/normal_predict/models.py:255-274."""
+    b = inputs.shape[0]
+    v = graph_conv1x1(inputs, _sub(P, "conv1."))
+    f = v.new_zeros(b, DiA.shape[-1] // 4 // b, 128)
+    for i in range(layers):
+        Pi = _sub(P, "rn%d." % i)
+        if i % 2 == 0:
+            v, f = dir_resnet2(Pi, Di, DiA, v, f, training)
+        else:
+            v = avg_resnet2(Pi, mask, v, training)
+    return F.elu(graph_conv1x1(v, _sub(P, "conv2."), "pre", training))
+
+
+def lap_encoder(P, inputs, L, mask, training=True):
+    """mesh_mnist LapEncoder.forward, src/mesh_mnist/models_vae.py:38-51."""
+    x = graph_conv1x1(inputs, _sub(P, "conv1."))
+    for i in range(5):
+        x = lap_resnet2(_sub(P, "rn%d." % i), L, x, training)
+    x = F.elu(graph_conv1x1(F.elu(x), _sub(P, "bn_conv2."), "pre", training))
+    x = global_average(x, mask).squeeze()
+    return F.linear(x, P["fc_mu.weight"], P["fc_mu.bias"]), F.linear(x, P["fc_logvar.weight"], P["fc_logvar.bias"])

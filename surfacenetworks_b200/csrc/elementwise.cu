@@ -66,7 +66,81 @@ elu_bwd_vec4_kernel(const float* __restrict__ A, int64_t lda, const float* __res
   }
 }
 
+// one CTA per segment: thread (rg, cv) sums rows rg, rg + RG, ... of float4 column cv; fixed-order smem reduction
+__global__ void __launch_bounds__(256)
+segment_sum_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ w, int rows_per_seg, int C,
+                   float* __restrict__ out) {
+  extern __shared__ float red[];               // [RG][C]
+  const int CV = C / 4, RG = 256 / CV;
+  const int cv = threadIdx.x % CV, rg = threadIdx.x / CV;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_seg;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rg < RG) {
+    for (int r = rg; r < rows_per_seg; r += RG) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(X + (r0 + r) * ldx) + cv);
+      const float ww = w ? __ldg(w + r0 + r) : 1.f;
+      s.x = fmaf(ww, v.x, s.x); s.y = fmaf(ww, v.y, s.y); s.z = fmaf(ww, v.z, s.z); s.w = fmaf(ww, v.w, s.w);
+    }
+    *reinterpret_cast<float4*>(red + (size_t)rg * C + 4 * cv) = s;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float a = 0.f;
+    for (int g = 0; g < RG; ++g) a += red[(size_t)g * C + c];
+    out[(size_t)blockIdx.x * C + c] = a;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+elu_bwd_group_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ G, int64_t ldg,
+                     const float* __restrict__ GB, const float* __restrict__ w, int rows_per_seg, float* __restrict__ Y,
+                     int64_t ldy, int64_t rows, int C4) {
+  const int64_t total = rows * C4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / C4;
+    const int c = (int)(i - r * C4) * 4;
+    const float4 a = *reinterpret_cast<const float4*>(A + r * lda + c);
+    float4 g = __ldcs(reinterpret_cast<const float4*>(G + r * ldg + c));
+    const float4 gb = __ldg(reinterpret_cast<const float4*>(GB + (r / rows_per_seg) * (int64_t)(C4 * 4) + c));
+    const float ww = w ? __ldg(w + r) : 1.f;
+    g.x = fmaf(ww, gb.x, g.x); g.y = fmaf(ww, gb.y, g.y); g.z = fmaf(ww, gb.z, g.z); g.w = fmaf(ww, gb.w, g.w);
+    float4 y;
+    y.x = g.x * (a.x > 0.f ? 1.f : a.x + 1.f);
+    y.y = g.y * (a.y > 0.f ? 1.f : a.y + 1.f);
+    y.z = g.z * (a.z > 0.f ? 1.f : a.z + 1.f);
+    y.w = g.w * (a.w > 0.f ? 1.f : a.w + 1.f);
+    *reinterpret_cast<float4*>(Y + r * ldy + c) = y;
+  }
+}
+
 }  // namespace sn
+
+SN_API int sn_segment_sum_f32(const float* X, int64_t ldx, const float* w, int64_t rows_per_seg, int64_t n_seg, int64_t C,
+                              float* out, sn_stream_t stream) {
+  using namespace sn;
+  if (rows_per_seg <= 0 || n_seg < 0 || C <= 0 || !X || !out || ldx < C) return SN_ERR_ARG;
+  if (n_seg == 0) return SN_OK;
+  if (C % 4 || C > 1024 || (256 % (C / 4)) || ldx % 4 || !aligned16(X) || rows_per_seg > 0x7fffffffLL || n_seg > 0x7fffffffLL)
+    return SN_ERR_UNSUPPORTED;
+  const int RG = 256 / (int)(C / 4);
+  segment_sum_kernel<<<(unsigned)n_seg, 256, (size_t)RG * C * sizeof(float), (cudaStream_t)stream>>>(
+      X, ldx, w, (int)rows_per_seg, (int)C, out);
+  return launch_status();
+}
+
+SN_API int sn_elu_bwd_group_f32(const float* A, int64_t lda, const float* G, int64_t ldg, const float* GB, const float* w,
+                                int64_t rows_per_seg, float* Y, int64_t ldy, int64_t rows, int64_t C, sn_stream_t stream) {
+  using namespace sn;
+  if (rows < 0 || C <= 0 || rows_per_seg <= 0 || !A || !G || !GB || !Y || lda < C || ldg < C || ldy < C) return SN_ERR_ARG;
+  if (rows == 0) return SN_OK;
+  if (C % 4 || lda % 4 || ldg % 4 || ldy % 4 || !aligned16(A) || !aligned16(G) || !aligned16(GB) || !aligned16(Y) ||
+      rows_per_seg > 0x7fffffffLL)
+    return SN_ERR_UNSUPPORTED;
+  const int64_t work = rows * (C / 4);
+  const unsigned grid = (unsigned)(ceil_div(work, 256) < 148 * 16 ? ceil_div(work, 256) : 148 * 16);
+  elu_bwd_group_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, lda, G, ldg, GB, w, (int)rows_per_seg, Y, ldy, rows, (int)(C / 4));
+  return launch_status();
+}
 
 SN_API int sn_elu_f32(const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t rows, int64_t C,
                       sn_stream_t stream) {

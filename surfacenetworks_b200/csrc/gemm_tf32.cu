@@ -117,6 +117,8 @@ struct Params {
   const float* bias;     // [N] or null
   const float* R;        // [M x N] or null: out += rscale .* R
   const float* rscale;   // [N] or null (= 1)
+  const float* gbias;    // [ceil(M / rows_per_group) x N] or null: per-row-group bias (AvgResNet2's per-mesh term)
+  int rows_per_group;
   float* C;
   int64_t ldr, ldc;
   int M, N, K;
@@ -297,6 +299,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const int row = row0 + r;
           if (row < p.M) {
             float4 o = add4(*reinterpret_cast<const float4*>(tbuf + r * 20 + tc), bia);
+            if (p.gbias)
+              o = add4(o, __ldg(reinterpret_cast<const float4*>(p.gbias + (int64_t)(row / p.rows_per_group) * N + c0 + tc)));
             if (p.R) {
               o.x = fmaf(rs.x, rr[i].x, o.x); o.y = fmaf(rs.y, rr[i].y, o.y);
               o.z = fmaf(rs.z, rr[i].z, o.z); o.w = fmaf(rs.w, rr[i].w, o.w);
@@ -371,14 +375,16 @@ SN_API size_t sn_gemm_tf32_ws_bytes(int64_t N, int64_t K) {
 }
 
 SN_API int sn_gemm_tf32_f32(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, const float* R,
-                            int64_t ldr, const float* rscale, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
-                            int flags, void* ws, size_t ws_bytes, sn_stream_t stream) {
+                            int64_t ldr, const float* rscale, const float* group_bias, int64_t rows_per_group, float* C,
+                            int64_t ldc, int64_t M, int64_t N, int64_t K, int flags, void* ws, size_t ws_bytes,
+                            sn_stream_t stream) {
   using namespace sn;
   using namespace sn::gemm;
   if (M < 0 || N <= 0 || K <= 0) return SN_ERR_ARG;
   if (M == 0) return SN_OK;
   if (!A || !B || !C || lda < K || ldb < K || ldc < N || (R && ldr < N)) return SN_ERR_ARG;
   if ((N != 64 && N != 128 && N != 256) || K % kBlockK != 0 || M >= 0x7fffffffLL - kBlockM) return SN_ERR_UNSUPPORTED;
+  if (group_bias && (rows_per_group <= 0 || rows_per_group > 0x7fffffffLL || !aligned16(group_bias))) return SN_ERR_ARG;
   if (lda % 4 || ldb % 4 || ldc % 4 || (R && ldr % 4) || !aligned16(A) || !aligned16(B) || !aligned16(C) ||
       (R && !aligned16(R)) || (bias && !aligned16(bias)) || (rscale && !aligned16(rscale)))
     return SN_ERR_UNSUPPORTED;
@@ -397,6 +403,7 @@ SN_API int sn_gemm_tf32_f32(const float* A, int64_t lda, const float* B, int64_t
   }
   Params p;
   p.bias = bias; p.R = R; p.rscale = rscale; p.C = C; p.ldr = ldr; p.ldc = ldc;
+  p.gbias = group_bias; p.rows_per_group = group_bias ? (int)rows_per_group : 1;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
   p.split = split ? 1 : 0;
   int dev = 0, sms = 148, smem_optin = 0;

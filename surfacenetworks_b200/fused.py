@@ -57,13 +57,17 @@ def colstats(Z):
     return mean, var
 
 
-def gemm_tf32(A, B, bias=None, R=None, rscale=None, out=None, single_pass=False):
-    """out[M, N] = A[M, K] @ B[N, K]^T + bias + rscale * R   (3xTF32 tensor-core GEMM; N > 256 is split in column blocks)."""
+def gemm_tf32(A, B, bias=None, R=None, rscale=None, out=None, single_pass=False, group_bias=None, rows_per_group=0):
+    """out[M, N] = A[M, K] @ B[N, K]^T + bias + group_bias[row // rows_per_group] + rscale * R
+    (3xTF32 tensor-core GEMM; N > 256 is split in column blocks; B may be a row-strided view)."""
     M, K = A.shape
     Nn = B.shape[0]
     if out is None:
         out = torch.empty(M, Nn, dtype=torch.float32, device=A.device)
-    B = B.contiguous()
+    if B.stride(1) != 1 or B.stride(0) % 4 or B.data_ptr() % 16:
+        B = B.contiguous()
+    if group_bias is not None and Nn not in _GEMM_N:
+        raise ValueError("group_bias needs N in %s" % (_GEMM_N,))
     step = Nn if Nn in _GEMM_N else 256
     nb = N.lib.sn_gemm_tf32_ws_bytes(step, K)
     flags = N.SN_GEMM_SINGLE_PASS if single_pass else 0
@@ -74,7 +78,8 @@ def gemm_tf32(A, B, bias=None, R=None, rscale=None, out=None, single_pass=False)
             N.call("sn_gemm_tf32_f32", _ptr(A), A.stride(0), _ptr(Bs), Bs.stride(0),
                    0 if bias is None else bias[n0:].data_ptr(), 0 if R is None else R[:, n0:].data_ptr(),
                    0 if R is None else R.stride(0), 0 if rscale is None else rscale[n0:].data_ptr(),
-                   out[:, n0:].data_ptr(), out.stride(0), M, step, K, flags, _ptr(ws), nb, _stream())
+                   _ptr(group_bias), rows_per_group, out[:, n0:].data_ptr(), out.stride(0), M, step, K, flags, _ptr(ws), nb,
+                   _stream())
     return out
 
 
@@ -150,6 +155,122 @@ class _BnLinear(torch.autograd.Function):
         else:
             dZ = gemm_tf32(dY, WsT)
         return dZ, vec[0], vec[1], dW, db, (dY if ctx.has_res else None), None, None, None, None, None
+
+
+def segment_sum(X, rows_per_seg, n_seg, weight=None):
+    """out[s, :] = sum over segment s's rows of weight[r] * X[r, :]  (sn_segment_sum_f32; weight None = 1)."""
+    out = torch.empty(n_seg, X.shape[1], dtype=torch.float32, device=X.device)
+    with torch.cuda.device(X.device):
+        N.call("sn_segment_sum_f32", _ptr(X), X.stride(0), _ptr(weight), rows_per_seg, n_seg, X.shape[1], _ptr(out), _stream())
+    return out
+
+
+class _AvgStage(torch.autograd.Function):
+    """One AvgResNet2 stage (reference src/utils/utils_pt.py:230-243):
+
+        a = elu(x);  avg_b = sum_r mask a / sum_r mask   (global_average, :120-122);
+        Y = Linear(BatchNorm([a | avg_b broadcast over the mesh's rows])) (+ residual)
+
+    The broadcast half of the concat buffer is never built: its columns are per-mesh constants, so
+    Y[r] = W'_L a[r] + (W'_R avg_b + b') -- a K = C GEMM plus a per-mesh bias in the epilogue (group_bias) -- and its
+    BatchNorm statistics are the (equal-weight) statistics of the B per-mesh averages.  Backward: G_L = dY^T a
+    (split-K GEMM), G_R = (per-mesh sums of dY)^T avg; the usual folded BatchNorm backward on G = [G_L | G_R];
+    dZ_L through the GEMM epilogue; the gradient of the averages is a [B, C] computation that comes back to the rows
+    inside the ELU-backward kernel (sn_elu_bwd_group_f32).
+    """
+
+    @staticmethod
+    def forward(ctx, x, maskw, inv_cnt, gamma, beta, W, b, residual, running_mean, running_var, training, momentum, eps,
+                n_seg, rows_per_seg):
+        rows, C = x.shape
+        Nn = W.shape[0]
+        dev = x.device
+        a = torch.empty_like(x)
+        with torch.cuda.device(dev):
+            N.call("sn_elu_f32", _ptr(x), x.stride(0), _ptr(a), a.stride(0), rows, C, _stream())
+        avg = segment_sum(a, rows_per_seg, n_seg, maskw) * inv_cnt                # [B, C]
+        if training:
+            mean_l, var_l = colstats(a)
+            mean_r = avg.mean(0)
+            var_r = ((avg - mean_r) ** 2).mean(0)        # two-pass on [B, C]: the per-mesh averages are close together
+            mean, var = torch.cat([mean_l, mean_r]), torch.cat([var_l, var_r])
+        else:
+            mean, var = running_mean, running_var
+        W = W.contiguous()
+        K = 2 * C
+        Wf = torch.empty_like(W)
+        bf = torch.empty(Nn, dtype=torch.float32, device=dev)
+        stk = torch.empty(3, K, dtype=torch.float32, device=dev)
+        update = training and running_mean is not None
+        with torch.cuda.device(dev):
+            N.call("sn_bn_fold_fwd_f32", _ptr(mean), _ptr(var), _ptr(gamma), _ptr(beta), _ptr(W), _ptr(b), Nn, K, float(eps),
+                   _ptr(Wf), _ptr(bf), _ptr(stk[0]), _ptr(stk[1]), _ptr(stk[2]), _ptr(running_mean) if update else 0,
+                   _ptr(running_var) if update else 0, float(momentum), rows, _stream())
+        u = torch.addmm(bf, avg, Wf[:, C:].t())                                   # per-mesh bias [B, Nn]
+        res = None if residual is None else residual.contiguous()
+        Y = gemm_tf32(a, Wf[:, :C], R=res, group_bias=u, rows_per_group=rows_per_seg)
+        ctx.save_for_backward(a, avg, W, stk, mean, maskw, inv_cnt)
+        ctx.training, ctx.has_res, ctx.n_seg, ctx.rps = training, residual is not None, n_seg, rows_per_seg
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        a, avg, W, stk, mean, maskw, inv_cnt = ctx.saved_tensors
+        dY = dY.contiguous()
+        rows, C = a.shape
+        Nn = W.shape[0]
+        K = 2 * C
+        dev = a.device
+        SdY = segment_sum(dY, ctx.rps, ctx.n_seg)                                 # [B, Nn] per-mesh sums of dY
+        sdY = SdY.sum(0)
+        G = torch.empty(Nn, K, dtype=torch.float32, device=dev)
+        G[:, :C] = gemm_tn_tf32(dY, a)
+        G[:, C:] = torch.mm(SdY.t(), avg)
+        dW = torch.empty_like(W)
+        db = torch.empty(Nn, dtype=torch.float32, device=dev)
+        vec = torch.empty(4, K, dtype=torch.float32, device=dev)                  # dgamma, dbeta, p, q
+        WsT = torch.empty(K, Nn, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            N.call("sn_bn_fold_bwd_f32", _ptr(G), _ptr(sdY), _ptr(W), _ptr(stk[0]), _ptr(stk[1]), _ptr(stk[2]), _ptr(mean),
+                   Nn, K, rows, 1 if ctx.training else 0, _ptr(dW), _ptr(db), _ptr(vec[0]), _ptr(vec[1]), _ptr(vec[2]),
+                   _ptr(vec[3]), _ptr(WsT), _stream())
+        p, q = vec[2], vec[3]
+        dZl = gemm_tf32(dY, WsT[:C], bias=q[:C].contiguous(), R=a, rscale=p[:C].contiguous())
+        # gradient reaching the per-mesh averages: sum over the mesh's rows of dZ_R
+        gsum = torch.mm(SdY, WsT[C:].t()) + ctx.rps * (p[C:] * avg + q[C:])       # [B, C]
+        gb = (gsum * inv_cnt).contiguous()
+        dx = torch.empty_like(a)
+        with torch.cuda.device(dev):
+            N.call("sn_elu_bwd_group_f32", _ptr(a), a.stride(0), _ptr(dZl), dZl.stride(0), _ptr(gb), _ptr(maskw), ctx.rps,
+                   _ptr(dx), dx.stride(0), rows, C, _stream())
+        return (dx, None, None, vec[0], vec[1], dW, db, (dY if ctx.has_res else None), None, None, None, None, None,
+                None, None)
+
+
+def avg_stage_supported(x, weight):
+    n_out, k = weight.shape
+    C = x.shape[1]
+    return (x.is_cuda and x.dtype == torch.float32 and k == 2 * C and n_out in _GEMM_N and n_out % 128 == 0 and
+            C % 32 == 0 and C <= 256 and 256 % (C // 4) == 0 and x.stride(1) == 1 and x.stride(0) % 4 == 0 and
+            x.data_ptr() % 16 == 0)
+
+
+def avg_stage(x, mask, bn, fc, residual=None):
+    """elu -> [x | global_average] -> BatchNorm -> Linear (+ residual) for x [B, V, C] (AvgResNet2 stage); returns
+    [B*V, C_out] rows, or None when the shapes are outside the fused path."""
+    B, V, C = x.shape
+    x2 = x.reshape(B * V, C)
+    if not avg_stage_supported(x2, fc.weight) or mask.shape[0] != B or mask.shape[1] != V:
+        return None
+    maskw = mask.reshape(B * V).to(torch.float32).contiguous()
+    inv_cnt = (1.0 / mask.reshape(B, V).sum(1, keepdim=True).to(torch.float32)).contiguous()      # [B, 1]
+    training = bn.training or bn.running_mean is None
+    if training and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    res2 = None if residual is None else residual.reshape(B * V, -1)
+    return _AvgStage.apply(x2, maskw, inv_cnt, bn.weight, bn.bias, fc.weight, fc.bias, res2, bn.running_mean,
+                           bn.running_var, training, momentum, bn.eps, B, V)
 
 
 def bn_linear(z, bn, fc, residual=None):

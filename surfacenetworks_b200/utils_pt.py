@@ -194,9 +194,20 @@ class DirResNet2(_TwoStageBlock):
 
 
 class AvgResNet2(_TwoStageBlock):
-    """Global-average block, no sparse operator (utils_pt.py:222-243)."""
+    """Global-average block, no sparse operator (utils_pt.py:222-243):
+    x -> x + fc1(BN[e1 | avg(e1)]),  e1 = elu(fc0(BN[e0 | avg(e0)])),  e0 = elu(x), avg = masked mean over the mesh.
+
+    At the widths the tensor-core stage covers, each stage runs as ``fused.avg_stage``: the broadcast half of the
+    concat is never materialised (K = C GEMM + per-mesh bias).  Other widths take the torch composite below.
+    """
 
     def forward(self, L, mask, inputs):
+        B, V, C = inputs.size()
+        y = fused.avg_stage(inputs, mask, self.bn_fc0.bn, self.bn_fc0.fc) if inputs.is_cuda else None
+        if y is not None:
+            y = fused.avg_stage(y.view(B, V, -1), mask, self.bn_fc1.bn, self.bn_fc1.fc, residual=inputs)
+        if y is not None:
+            return y.view(B, V, -1)
         x = F.elu(inputs)
         x = self.bn_fc0(torch.cat([x, global_average(x, mask).expand_as(x)], 2))
         x = F.elu(x)

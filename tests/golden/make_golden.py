@@ -256,6 +256,42 @@ def main():
             arrays[k.replace("/g.", "/g64.")] = named64[k[len(tag) + 3:]].grad.numpy().copy()
     save("arap_models.npz", **arrays)
 
+    # ------------------------------------------------------------------ other callers
+    import importlib.util
+
+    def load(name, path):
+        spec = importlib.util.spec_from_file_location(name, path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+
+    np_models = load("ref_normal_models", os.path.join(REF_SRC, "normal_predict", "models.py"))
+    vae_models = load("ref_vae_models", os.path.join(REF_SRC, "mesh_mnist", "models_vae.py"))
+    arrays = {}
+    x3 = det_tensor((B, nv, 3), 61) * mask
+    arrays["x3"] = x3.numpy()
+    xin32 = det_tensor((B, nv, 32), 62)
+
+    def both_precisions(make, seed, args, tag, gain=0.25):
+        for dt, suffix in ((torch.float32, ""), (torch.float64, "64")):
+            m = det_fill(make(), seed, gain=gain).to(dt).train()
+            a = tuple((t.to(dt) if torch.is_tensor(t) and t.is_floating_point() else t) for t in args)
+            a = tuple(tuple(u.to(dt) for u in t) if isinstance(t, tuple) else t for t in a)
+            out = m(*a)
+            outs = out if isinstance(out, tuple) else (out,)
+            for i, o in enumerate(outs):
+                arrays["%s/out%d%s" % (tag, i, suffix)] = o.detach().numpy()
+
+    # normal_predict _LapResNet2 (models.py:447-477): generalised Laplacian block
+    both_precisions(lambda: np_models._LapResNet2(32, 64, inner_layers=3), 11, (Lb, mask, xin32), "lapgen_32_64_3", gain=0.5)
+    both_precisions(lambda: np_models._LapResNet2(32), 12, (Lb, mask, xin32), "lapgen_32", gain=0.5)
+    both_precisions(lambda: np_models._LapResNet2(32, 16, inner_layers=1), 15, (Lb, mask, xin32), "lapgen_32_16_1", gain=0.5)
+    # normal_predict DirDeepModel (models.py:234-274), 4 blocks
+    both_precisions(lambda: np_models.DirDeepModel(3, 1, layers=4), 13, ((Dib, DiAb), mask, x3), "dirdeep4")
+    # mesh_mnist VAE LapEncoder (models_vae.py:22-51), 5 x LapResNet2(128)
+    both_precisions(lambda: vae_models.LapEncoder(), 14, (x3, Lb, mask), "lapencoder")
+    save("callers.npz", **arrays)
+
 
 if __name__ == "__main__":
     main()

@@ -20,7 +20,7 @@ def run_gemm(A, B, bias=None, R=None, rscale=None, single_pass=False, out=None):
     wsb = N.lib.sn_gemm_tf32_ws_bytes(Nn, K)
     ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
     N.call("sn_gemm_tf32_f32", p(A), A.stride(0), p(B), B.stride(0), p(bias), p(R), 0 if R is None else R.stride(0),
-           p(rscale), p(C), C.stride(0), M, Nn, K, N.SN_GEMM_SINGLE_PASS if single_pass else 0, p(ws), wsb,
+           p(rscale), 0, 0, p(C), C.stride(0), M, Nn, K, N.SN_GEMM_SINGLE_PASS if single_pass else 0, p(ws), wsb,
            torch.cuda.current_stream().cuda_stream)
     return C
 
@@ -164,7 +164,7 @@ def test_colstats_matches_float64():
         assert torch.equal(mean, m2) and torch.equal(var, v2)          # deterministic
 
 
-@pytest.mark.parametrize("kind", ["lap", "dir"])
+@pytest.mark.parametrize("kind", ["lap", "dir", "avg"])
 def test_blocks_width128_vs_oracle(kind):
     """One LapResNet2(128) / DirResNet2(128) block -- the fused tensor-core stage inside the real layer -- against the
     oracle port run live on the CPU (fp32), forward and all gradients; tolerance 2e-4 * (|ref| + max|ref|)."""
@@ -176,9 +176,9 @@ def test_blocks_width128_vs_oracle(kind):
     C = 128
     meshes = W.make_mesh_ops(150, [0, 1]) + W.make_mesh_ops(140, [2])
     B = len(meshes)
-    host = W.arap_batch(meshes, 0, dirac=(kind == "dir"))
+    host = W.arap_batch(meshes, 0, dirac=(kind != "lap"))
     nv, nf = host["num_vertices"], host["num_faces"]
-    block = det_fill(U.LapResNet2(C) if kind == "lap" else U.DirResNet2(C), 5, gain=0.5)
+    block = det_fill({"lap": U.LapResNet2, "dir": U.DirResNet2, "avg": U.AvgResNet2}[kind](C), 5, gain=0.5)
     P = {}
     for k, v in block.state_dict().items():
         v = v.clone()
@@ -192,6 +192,9 @@ def test_blocks_width128_vs_oracle(kind):
     if kind == "lap":
         ref = (O.lap_resnet2(P, host["L"], xc),)
         (ref[0] * wv).sum().backward()
+    elif kind == "avg":
+        ref = (O.avg_resnet2(P, host["mask"], xc),)
+        (ref[0] * wv).sum().backward()
     else:
         ref = O.dir_resnet2(P, host["Di"], host["DiA"], xc, fc_)
         ((ref[0] * wv).sum() + (ref[1] * wf).sum()).backward()
@@ -199,6 +202,9 @@ def test_blocks_width128_vs_oracle(kind):
     xg, fg = x.to(DEV).requires_grad_(True), f.to(DEV).requires_grad_(True)
     if kind == "lap":
         out = (blk(host["L"].to(DEV), None, xg),)
+        (out[0] * wv.to(DEV)).sum().backward()
+    elif kind == "avg":
+        out = (blk(None, host["mask"].to(DEV), xg),)
         (out[0] * wv.to(DEV)).sum().backward()
     else:
         out = blk(host["Di"].to(DEV), host["DiA"].to(DEV), xg, fg)

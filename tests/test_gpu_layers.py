@@ -217,3 +217,24 @@ def test_state_dict_roundtrip_and_cpu_refusal(golden, batch):
     blk = U.LapResNet2(32)
     with pytest.raises(RuntimeError):
         blk(batch["L"].cpu(), None, torch.zeros(2, batch["nv"], 32))   # CPU tensors: loud failure, no fallback
+
+
+def test_other_callers(golden, batch):
+    """normal_predict _LapResNet2 / DirDeepModel and the mesh_mnist LapEncoder (5 x LapResNet2(128): the fused
+    tensor-core stage) against the reference's outputs; tolerance 5e-4 * (|ref| + max|ref|)."""
+    from surfacenetworks_b200 import models as M
+    B, d = batch, golden("callers")
+    x32 = det_tensor((2, B["nv"], 32), 62).to(DEV)
+    x3 = torch.from_numpy(d["x3"]).to(DEV)
+    with torch.no_grad():
+        for tag, mk, seed in (("lapgen_32_64_3", lambda: M.LapResNet2General(32, 64, inner_layers=3), 11),
+                              ("lapgen_32", lambda: M.LapResNet2General(32), 12),
+                              ("lapgen_32_16_1", lambda: M.LapResNet2General(32, 16, inner_layers=1), 15)):
+            m = det_fill(mk(), seed, gain=0.5).to(DEV).train()
+            close(m(B["L"], B["mask"], x32).cpu().numpy(), d[tag + "/out0"], tag, 5e-4)
+        m = det_fill(M.DirDeepModel(3, 1, layers=4), 13, gain=0.25).to(DEV).train()
+        close(m((B["Di"], B["DiA"]), B["mask"], x3).cpu().numpy(), d["dirdeep4/out0"], "dirdeep4", 5e-4)
+        m = det_fill(M.LapEncoder(), 14, gain=0.25).to(DEV).train()
+        mu, lv = m(x3, B["L"], B["mask"])
+        close(mu.cpu().numpy(), d["lapencoder/out0"], "lapencoder mu", 5e-4)
+        close(lv.cpu().numpy(), d["lapencoder/out1"], "lapencoder logvar", 5e-4)

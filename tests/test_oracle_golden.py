@@ -220,3 +220,22 @@ def test_arap_models(golden, batch, tag):
         if k.startswith(tag + "/g."):
             g = d[k]
             assert_close(P[k[len(tag) + 3:]].grad.numpy(), g, 1e-3, 1e-4 * np.abs(g).max(), k)
+
+
+def test_other_callers(golden, batch):
+    """normal_predict _LapResNet2 / DirDeepModel and the mesh_mnist LapEncoder."""
+    B, d = batch, golden("callers")
+    x32 = det_tensor((2, B["nv"], 32), 62)
+    x3 = torch.from_numpy(d["x3"])
+    with torch.no_grad():
+        for tag, mk, seed, inner in (("lapgen_32_64_3", lambda: M.LapResNet2General(32, 64, inner_layers=3), 11, 3),
+                                     ("lapgen_32", lambda: M.LapResNet2General(32), 12, 2),
+                                     ("lapgen_32_16_1", lambda: M.LapResNet2General(32, 16, inner_layers=1), 15, 1)):
+            P = params_of(mk(), seed, 0.5)
+            assert_close(O.lap_resnet2_general(P, B["L"], x32, inner).numpy(), d[tag + "/out0"], 2e-5, 2e-5, tag)
+        P = params_of(M.DirDeepModel(3, 1, layers=4), 13, 0.25)
+        assert_close(O.dir_deep_model(P, B["Di"], B["DiA"], B["mask"], x3, 4).numpy(), d["dirdeep4/out0"], 2e-5, 2e-5, "dirdeep4")
+        P = params_of(M.LapEncoder(), 14, 0.25)
+        mu, lv = O.lap_encoder(P, x3, B["L"], B["mask"])
+        assert_close(mu.numpy(), d["lapencoder/out0"], 2e-5, 2e-5, "lapencoder mu")
+        assert_close(lv.numpy(), d["lapencoder/out1"], 2e-5, 2e-5, "lapencoder logvar")

@@ -10,7 +10,7 @@ for M, Nn, K in ((20000,128,256),(40000,128,256),(128000, 128, 256),(255168,256,
     for flags in (0, 1):
         torch.cuda.synchronize(); t = time.time()
         for _ in range(5):
-            N.call("sn_gemm_tf32_f32", A.data_ptr(), K, B.data_ptr(), K, bias.data_ptr(), R.data_ptr(), Nn, 0, C.data_ptr(), Nn, M, Nn, K, flags, WS.data_ptr(), WS.numel(), st)
+            N.call("sn_gemm_tf32_f32", A.data_ptr(), K, B.data_ptr(), K, bias.data_ptr(), R.data_ptr(), Nn, 0, 0, 0, C.data_ptr(), Nn, M, Nn, K, flags, WS.data_ptr(), WS.numel(), st)
         torch.cuda.synchronize()
         print(M, Nn, K, flags, 'ms per launch', (time.time() - t) / 5 * 1e3, flush=True)
     ref = torch.addmm(bias, A, B.t()) + R

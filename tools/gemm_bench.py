@@ -38,7 +38,7 @@ def main():
 WS = torch.empty(1 << 20, dtype=torch.uint8, device=dev)
 
         def ours(flags=0, res=True):
-            N.call("sn_gemm_tf32_f32", A.data_ptr(), K, B.data_ptr(), K, bias.data_ptr(), R.data_ptr() if res else 0, Nn, 0,
+            N.call("sn_gemm_tf32_f32", A.data_ptr(), K, B.data_ptr(), K, bias.data_ptr(), R.data_ptr() if res else 0, Nn, 0, 0, 0,
                    C.data_ptr(), Nn, M, Nn, K, flags, WS.data_ptr(), WS.numel(), st)
 
         flops = 2.0 * M * Nn * K
