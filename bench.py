@@ -348,7 +348,7 @@ def run_b200(args):
     # ---- per-kernel timing pass (eager: a graph replay hides individual launches from CUDA events): the same K
     #      steps with events around every sn_* launch on the launching stream
     N.TIMER = N.KernelTimer(["sn_bsr4_spmm_f32", "sn_csr_spmm_f32", "sn_elu_f32", "sn_elu_bwd_f32", "sn_gemm_tf32_f32",
-                             "sn_gemm_tn_tf32_f32", "sn_colstats_f32", "sn_bn_fold_fwd_f32", "sn_bn_fold_bwd_f32"])
+                             "sn_gemm_tn_tf32_f32", "sn_colstats_f32", "sn_elu_colstats_f32", "sn_segment_sum_f32", "sn_elu_bwd_group_f32", "sn_bn_fold_fwd_f32", "sn_bn_fold_bwd_f32"])
     counts0 = dict(N.CALL_COUNTS)
     barrier()
     e0.record()

@@ -120,11 +120,12 @@ int sn_elu_bwd_f32(const float* A, int64_t lda, int a_is_raw, const float* G, in
 
 /* Per-mesh (segment) column sums: out[s, c] = sum over the rows_per_seg rows of segment s of w[r] * X[r, c]
  * (w NULL = 1).  With w = mask this is the numerator of global_average (utils_pt.py:120-122); unweighted it is the
- * per-mesh gradient sum of its backward.  Deterministic (one CTA per segment, fixed-order reduction).
+ * per-mesh gradient sum of its backward.  Deterministic (8 row slices per segment, fixed-order reductions).
  * sn_elu_bwd_group_f32: Y = (G + w[r] * GB[r / rows_per_seg]) * elu'(x) -- the backward of elu followed by
  * global_average's broadcast term, A holding the activated values as in sn_elu_bwd_f32 (a_is_raw = 0). */
+size_t sn_segment_sum_ws_bytes(int64_t n_seg, int64_t C);
 int sn_segment_sum_f32(const float* X, int64_t ldx, const float* w, int64_t rows_per_seg, int64_t n_seg, int64_t C,
-                       float* out, sn_stream_t stream);
+                       float* out, void* ws, size_t ws_bytes, sn_stream_t stream);
 int sn_elu_bwd_group_f32(const float* A, int64_t lda, const float* G, int64_t ldg, const float* GB, const float* w,
                          int64_t rows_per_seg, float* Y, int64_t ldy, int64_t rows, int64_t C, sn_stream_t stream);
 
@@ -169,6 +170,10 @@ int sn_gemm_tn_tf32_f32(const float* A, int64_t lda, const float* B, int64_t ldb
 size_t sn_colstats_ws_bytes(int64_t C);
 int sn_colstats_f32(const float* X, int64_t ldx, int64_t rows, int64_t C, float* mean, float* var_biased,
                     void* ws, size_t ws_bytes, sn_stream_t stream);
+/* sn_elu_f32 and sn_colstats_f32 of its OUTPUT in one pass: Y = elu(X), mean / var_biased = statistics of Y's columns
+ * (the left half of a stage's concat buffer needs no separate statistics pass).  Same workspace as sn_colstats_f32. */
+int sn_elu_colstats_f32(const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t rows, int64_t C, float* mean,
+                        float* var_biased, void* ws, size_t ws_bytes, sn_stream_t stream);
 
 /* O(C^2) glue of the fused dense stage, one launch each way.
  * forward : s = gamma*rstd, t = beta - mean*s, Wf = W diag(s) [N x K], bf = b + W t, rstd = 1/sqrt(var+eps); when

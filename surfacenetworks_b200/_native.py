@@ -43,10 +43,12 @@ SIGNATURES = {
                                   _ptr, _ptr, _ptr, _ptr]),
     "sn_colstats_ws_bytes": (_sz, [_i64]),
     "sn_colstats_f32": (_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _sz, _ptr]),
+    "sn_elu_colstats_f32": (_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _sz, _ptr]),
     "sn_gemm_tf32_ws_bytes": (_sz, [_i64, _i64]),
     "sn_gemm_tf32_f32": (_int, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _int,
                                 _ptr, _sz, _ptr]),
-    "sn_segment_sum_f32": (_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _ptr]),
+    "sn_segment_sum_ws_bytes": (_sz, [_i64, _i64]),
+    "sn_segment_sum_f32": (_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _ptr, _sz, _ptr]),
     "sn_elu_bwd_group_f32": (_int, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr]),
     "sn_elu_bwd_f32": (_int, [_ptr, _i64, _int, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr]),
 }

@@ -57,27 +57,90 @@ colstats_partial_kernel(const float* __restrict__ X, int64_t ldx, int64_t rows, 
   }
 }
 
-__global__ void colstats_final_kernel(const float* __restrict__ partial, int n_partials, int64_t rows, int C,
-                                      const float* __restrict__ X, float* __restrict__ mean, float* __restrict__ var) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// fixed-order fp64 reduction of the per-CTA partials: CTA = 32 columns x 8 partial groups; group g adds partials
+// g, g + 8, ... and the 8 group sums are added in order
+__global__ void __launch_bounds__(256)
+colstats_final_kernel(const float* __restrict__ partial, int n_partials, int64_t rows, int C, const float* __restrict__ X,
+                      float* __restrict__ mean, float* __restrict__ var) {
+  __shared__ double red[2][8][32];
+  const int lc = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lc;
   double s = 0.0, q = 0.0;
-  for (int i = 0; i < n_partials; ++i) {
-    s += (double)partial[(size_t)i * 2 * C + c];
-    q += (double)partial[(size_t)i * 2 * C + C + c];
+  if (c < C) {
+    for (int i = g; i < n_partials; i += 8) {
+      s += (double)partial[(size_t)i * 2 * C + c];
+      q += (double)partial[(size_t)i * 2 * C + C + c];
+    }
   }
-  const double m = s / (double)rows;            // mean of the shifted values
-  double v = q / (double)rows - m * m;
-  if (v < 0.0) v = 0.0;
-  mean[c] = (float)(m + (double)X[c]);
-  var[c] = (float)v;
+  red[0][g][lc] = s;
+  red[1][g][lc] = q;
+  __syncthreads();
+  if (g == 0 && c < C) {
+    s = 0.0;
+    q = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s += red[0][k][lc];
+      q += red[1][k][lc];
+    }
+    const double m = s / (double)rows;            // mean of the shifted values
+    double v = q / (double)rows - m * m;
+    if (v < 0.0) v = 0.0;
+    mean[c] = (float)(m + (double)X[c]);
+    var[c] = (float)v;
+  }
+}
+
+// Activation pass with the statistics fused in: Y = elu(X) AND the per-CTA partial sums of Y's columns (same partial
+// layout and final kernel as above), so the left half of a stage's concat buffer never needs a separate statistics
+// pass.  gridDim.x * RG row slots are walked with a fixed stride, every thread keeps one float4 column.
+__global__ void __launch_bounds__(kStatThreads)
+elu_colstats_kernel(const float* __restrict__ X, int64_t ldx, float* __restrict__ Y, int64_t ldy, int64_t rows, int C,
+                    float* __restrict__ partial) {
+  extern __shared__ float red[];                      // [RG][2][C]
+  const int CV = C / 4;
+  const int RG = kStatThreads / CV;
+  const int cv = threadIdx.x % CV, rg = threadIdx.x / CV;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+  const float4 K = elu4(__ldg(reinterpret_cast<const float4*>(X) + cv));     // shift = activated row 0
+  const int64_t stride = (int64_t)gridDim.x * RG;
+  int64_t r = (int64_t)blockIdx.x * RG + rg;
+  for (; r + stride < rows; r += 2 * stride) {          // two rows in flight per thread
+    float4 v0 = __ldcs(reinterpret_cast<const float4*>(X + r * ldx) + cv);
+    float4 v1 = __ldcs(reinterpret_cast<const float4*>(X + (r + stride) * ldx) + cv);
+    v0 = elu4(v0);
+    v1 = elu4(v1);
+    *(reinterpret_cast<float4*>(Y + r * ldy) + cv) = v0;
+    *(reinterpret_cast<float4*>(Y + (r + stride) * ldy) + cv) = v1;
+    v0.x -= K.x; v0.y -= K.y; v0.z -= K.z; v0.w -= K.w;
+    v1.x -= K.x; v1.y -= K.y; v1.z -= K.z; v1.w -= K.w;
+    s = add4(s, add4(v0, v1));
+    q.x = fmaf(v0.x, v0.x, fmaf(v1.x, v1.x, q.x)); q.y = fmaf(v0.y, v0.y, fmaf(v1.y, v1.y, q.y));
+    q.z = fmaf(v0.z, v0.z, fmaf(v1.z, v1.z, q.z)); q.w = fmaf(v0.w, v0.w, fmaf(v1.w, v1.w, q.w));
+  }
+  for (; r < rows; r += stride) {
+    float4 v = elu4(__ldcs(reinterpret_cast<const float4*>(X + r * ldx) + cv));
+    *(reinterpret_cast<float4*>(Y + r * ldy) + cv) = v;
+    v.x -= K.x; v.y -= K.y; v.z -= K.z; v.w -= K.w;
+    s = add4(s, v);
+    q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+  }
+  float* base = red + (size_t)rg * 2 * C;
+  *reinterpret_cast<float4*>(base + 4 * cv) = s;
+  *reinterpret_cast<float4*>(base + C + 4 * cv) = q;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += kStatThreads) {
+    float a = 0.f;
+    for (int g = 0; g < RG; ++g) a += red[(size_t)g * 2 * C + i];
+    partial[(size_t)blockIdx.x * 2 * C + i] = a;
+  }
 }
 
 static int stat_grid() {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return sms * 4;
+  return sms * 8;   // 8 CTAs x 256 threads per SM: full occupancy, one partial row per CTA
 }
 
 }  // namespace sn
@@ -99,6 +162,25 @@ SN_API int sn_colstats_f32(const float* X, int64_t ldx, int64_t rows, int64_t C,
   const size_t smem = (size_t)RG * 2 * C * sizeof(float);
   if (smem > 48 * 1024) return SN_ERR_UNSUPPORTED;
   colstats_partial_kernel<<<grid, kStatThreads, smem, st>>>(X, ldx, rows, (int)C, (float*)ws);
-  colstats_final_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>((const float*)ws, grid, rows, (int)C, X, mean, var_biased);
+  colstats_final_kernel<<<(unsigned)ceil_div(C, 32), 256, 0, st>>>((const float*)ws, grid, rows, (int)C, X, mean, var_biased);
+  return launch_status();
+}
+
+SN_API int sn_elu_colstats_f32(const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t rows, int64_t C, float* mean,
+                               float* var_biased, void* ws, size_t ws_bytes, sn_stream_t stream) {
+  using namespace sn;
+  if (rows <= 0 || C <= 0 || !X || !Y || !mean || !var_biased || ldx < C || ldy < C) return SN_ERR_ARG;
+  if (C % 4 || C > 1024 || (kStatThreads % (C / 4)) || ldx % 4 || ldy % 4 || !aligned16(X) || !aligned16(Y))
+    return SN_ERR_UNSUPPORTED;
+  if (!ws || ws_bytes < sn_colstats_ws_bytes(C)) return SN_ERR_WORKSPACE;
+  int grid = stat_grid();
+  const int RG = kStatThreads / (int)(C / 4);
+  if ((int64_t)grid * RG > rows) grid = (int)ceil_div(rows, RG);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)RG * 2 * C * sizeof(float);
+  if (smem > 48 * 1024) return SN_ERR_UNSUPPORTED;
+  elu_colstats_kernel<<<grid, kStatThreads, smem, st>>>(X, ldx, Y, ldy, rows, (int)C, (float*)ws);
+  // the shift used by the partial sums is the activated row 0, which the kernel above has just written to Y
+  colstats_final_kernel<<<(unsigned)ceil_div(C, 32), 256, 0, st>>>((const float*)ws, grid, rows, (int)C, Y, mean, var_biased);
   return launch_status();
 }

@@ -66,17 +66,21 @@ elu_bwd_vec4_kernel(const float* __restrict__ A, int64_t lda, const float* __res
   }
 }
 
-// one CTA per segment: thread (rg, cv) sums rows rg, rg + RG, ... of float4 column cv; fixed-order smem reduction
+// grid = (n_seg, kSegSplit): CTA (s, j) sums the j-th slice of segment s's rows; thread (rg, cv) walks rows of float4
+// column cv; fixed-order smem reduction; partial[s][j][C].  A second tiny kernel adds the kSegSplit slices in order.
+constexpr int kSegSplit = 8;
 __global__ void __launch_bounds__(256)
 segment_sum_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ w, int rows_per_seg, int C,
-                   float* __restrict__ out) {
+                   float* __restrict__ partial) {
   extern __shared__ float red[];               // [RG][C]
   const int CV = C / 4, RG = 256 / CV;
   const int cv = threadIdx.x % CV, rg = threadIdx.x / CV;
+  const int slice = (rows_per_seg + kSegSplit - 1) / kSegSplit;
+  const int rb = blockIdx.y * slice, re = min(rb + slice, rows_per_seg);
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_seg;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (rg < RG) {
-    for (int r = rg; r < rows_per_seg; r += RG) {
+    for (int r = rb + rg; r < re; r += RG) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(X + (r0 + r) * ldx) + cv);
       const float ww = w ? __ldg(w + r0 + r) : 1.f;
       s.x = fmaf(ww, v.x, s.x); s.y = fmaf(ww, v.y, s.y); s.z = fmaf(ww, v.z, s.z); s.w = fmaf(ww, v.w, s.w);
@@ -87,8 +91,18 @@ segment_sum_kernel(const float* __restrict__ X, int64_t ldx, const float* __rest
   for (int c = threadIdx.x; c < C; c += 256) {
     float a = 0.f;
     for (int g = 0; g < RG; ++g) a += red[(size_t)g * C + c];
-    out[(size_t)blockIdx.x * C + c] = a;
+    partial[((size_t)blockIdx.x * kSegSplit + blockIdx.y) * C + c] = a;
   }
+}
+__global__ void segment_sum_final_kernel(const float* __restrict__ partial, int64_t n, int C, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // i = seg * C + c
+  if (i >= n) return;
+  const int64_t sgm = i / C;
+  const int c = (int)(i - sgm * C);
+  float a = 0.f;
+#pragma unroll
+  for (int j = 0; j < kSegSplit; ++j) a += partial[(sgm * kSegSplit + j) * C + c];
+  out[i] = a;
 }
 
 __global__ void __launch_bounds__(256)
@@ -115,16 +129,24 @@ elu_bwd_group_kernel(const float* __restrict__ A, int64_t lda, const float* __re
 
 }  // namespace sn
 
+SN_API size_t sn_segment_sum_ws_bytes(int64_t n_seg, int64_t C) {
+  return (n_seg <= 0 || C <= 0) ? 0 : (size_t)n_seg * sn::kSegSplit * (size_t)C * sizeof(float);
+}
+
 SN_API int sn_segment_sum_f32(const float* X, int64_t ldx, const float* w, int64_t rows_per_seg, int64_t n_seg, int64_t C,
-                              float* out, sn_stream_t stream) {
+                              float* out, void* ws, size_t ws_bytes, sn_stream_t stream) {
   using namespace sn;
   if (rows_per_seg <= 0 || n_seg < 0 || C <= 0 || !X || !out || ldx < C) return SN_ERR_ARG;
   if (n_seg == 0) return SN_OK;
   if (C % 4 || C > 1024 || (256 % (C / 4)) || ldx % 4 || !aligned16(X) || rows_per_seg > 0x7fffffffLL || n_seg > 0x7fffffffLL)
     return SN_ERR_UNSUPPORTED;
+  if (!ws || ws_bytes < sn_segment_sum_ws_bytes(n_seg, C)) return SN_ERR_WORKSPACE;
+  if (n_seg > 65535LL * 1024) return SN_ERR_UNSUPPORTED;
   const int RG = 256 / (int)(C / 4);
-  segment_sum_kernel<<<(unsigned)n_seg, 256, (size_t)RG * C * sizeof(float), (cudaStream_t)stream>>>(
-      X, ldx, w, (int)rows_per_seg, (int)C, out);
+  cudaStream_t st = (cudaStream_t)stream;
+  segment_sum_kernel<<<dim3((unsigned)n_seg, kSegSplit), 256, (size_t)RG * C * sizeof(float), st>>>(
+      X, ldx, w, (int)rows_per_seg, (int)C, (float*)ws);
+  segment_sum_final_kernel<<<(unsigned)ceil_div(n_seg * C, 256), 256, 0, st>>>((const float*)ws, n_seg * C, (int)C, out);
   return launch_status();
 }
 

@@ -57,6 +57,25 @@ def colstats(Z):
     return mean, var
 
 
+def elu_colstats(X, out):
+    """out = elu(X) and the column statistics (mean, biased variance) of out in ONE pass (sn_elu_colstats_f32)."""
+    rows, C = X.shape
+    mean = torch.empty(C, dtype=torch.float32, device=X.device)
+    var = torch.empty(C, dtype=torch.float32, device=X.device)
+    nb = N.lib.sn_colstats_ws_bytes(C)
+    ws = _ws(nb, X.device)
+    with torch.cuda.device(X.device):
+        N.call("sn_elu_colstats_f32", _ptr(X), X.stride(0), _ptr(out), out.stride(0), rows, C, _ptr(mean), _ptr(var),
+               _ptr(ws), nb, _stream())
+    return mean, var
+
+
+def elu_colstats_supported(X, out):
+    C = X.shape[1]
+    return (C % 4 == 0 and C <= 1024 and 256 % (C // 4) == 0 and X.stride(0) % 4 == 0 and out.stride(0) % 4 == 0 and
+            X.data_ptr() % 16 == 0 and out.data_ptr() % 16 == 0 and X.shape[0] > 0)
+
+
 def gemm_tf32(A, B, bias=None, R=None, rscale=None, out=None, single_pass=False, group_bias=None, rows_per_group=0):
     """out[M, N] = A[M, K] @ B[N, K]^T + bias + group_bias[row // rows_per_group] + rscale * R
     (3xTF32 tensor-core GEMM; N > 256 is split in column blocks; B may be a row-strided view)."""
@@ -106,12 +125,17 @@ def gemm_tn_tf32(A, B, single_pass=False):
 
 class _BnLinear(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, Z, gamma, beta, W, b, residual, running_mean, running_var, training, momentum, eps):
+    def forward(ctx, Z, gamma, beta, W, b, residual, running_mean, running_var, training, momentum, eps, left_stats):
         rows, K = Z.shape
         Nn = W.shape[0]
         dev = Z.device
         if training:
-            mean, var = colstats(Z)
+            if left_stats is not None:                # left half already reduced by the fused ELU pass (ops.stage_concat)
+                Cl = left_stats[0].numel()
+                mr, vr = colstats(Z[:, Cl:])
+                mean, var = torch.cat([left_stats[0], mr]), torch.cat([left_stats[1], vr])
+            else:
+                mean, var = colstats(Z)
         else:
             mean, var = running_mean, running_var
         W = W.contiguous()
@@ -154,14 +178,17 @@ class _BnLinear(torch.autograd.Function):
             dZ = gemm_tf32(dY, WsT, bias=vec[3], R=Z, rscale=vec[2])
         else:
             dZ = gemm_tf32(dY, WsT)
-        return dZ, vec[0], vec[1], dW, db, (dY if ctx.has_res else None), None, None, None, None, None
+        return dZ, vec[0], vec[1], dW, db, (dY if ctx.has_res else None), None, None, None, None, None, None
 
 
 def segment_sum(X, rows_per_seg, n_seg, weight=None):
     """out[s, :] = sum over segment s's rows of weight[r] * X[r, :]  (sn_segment_sum_f32; weight None = 1)."""
     out = torch.empty(n_seg, X.shape[1], dtype=torch.float32, device=X.device)
+    nb = N.lib.sn_segment_sum_ws_bytes(n_seg, X.shape[1])
+    ws = _ws(nb, X.device)
     with torch.cuda.device(X.device):
-        N.call("sn_segment_sum_f32", _ptr(X), X.stride(0), _ptr(weight), rows_per_seg, n_seg, X.shape[1], _ptr(out), _stream())
+        N.call("sn_segment_sum_f32", _ptr(X), X.stride(0), _ptr(weight), rows_per_seg, n_seg, X.shape[1], _ptr(out),
+               _ptr(ws), nb, _stream())
     return out
 
 
@@ -186,11 +213,13 @@ class _AvgStage(torch.autograd.Function):
         Nn = W.shape[0]
         dev = x.device
         a = torch.empty_like(x)
-        with torch.cuda.device(dev):
-            N.call("sn_elu_f32", _ptr(x), x.stride(0), _ptr(a), a.stride(0), rows, C, _stream())
+        if training:
+            mean_l, var_l = elu_colstats(x, a)                                    # activation + statistics in one pass
+        else:
+            with torch.cuda.device(dev):
+                N.call("sn_elu_f32", _ptr(x), x.stride(0), _ptr(a), a.stride(0), rows, C, _stream())
         avg = segment_sum(a, rows_per_seg, n_seg, maskw) * inv_cnt                # [B, C]
         if training:
-            mean_l, var_l = colstats(a)
             mean_r = avg.mean(0)
             var_r = ((avg - mean_r) ** 2).mean(0)        # two-pass on [B, C]: the per-mesh averages are close together
             mean, var = torch.cat([mean_l, mean_r]), torch.cat([var_l, var_r])
@@ -280,7 +309,10 @@ def bn_linear(z, bn, fc, residual=None):
         if training and bn.num_batches_tracked is not None:
             bn.num_batches_tracked += 1
         momentum = 0.1 if bn.momentum is None else bn.momentum
+        left = getattr(z, "_sn_left_stats", None) if training else None
+        if left is not None and not (z.shape[1] - left[0].numel()) % 4 == 0:
+            left = None
         return _BnLinear.apply(z, bn.weight, bn.bias, fc.weight, fc.bias, residual, bn.running_mean, bn.running_var,
-                               training, momentum, bn.eps)
+                               training, momentum, bn.eps, left)
     y = fc(bn(z))
     return y if residual is None else y + residual

@@ -12,6 +12,7 @@ from __future__ import annotations
 import torch
 
 from . import _native as N
+from . import fused
 from .operators import Bsr4Operator, CsrOperator, _check_dense, _ptr, _stream
 
 __all__ = ["spmm", "stage_concat", "elu_into"]
@@ -71,12 +72,16 @@ class _StageConcat(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x_self, x_gather, op, same):
+    def forward(ctx, x_self, x_gather, op, same, want_stats):
         xs = x_self.contiguous()
         rows_out, C = xs.shape
         Z = torch.empty(rows_out, 2 * C, dtype=torch.float32, device=xs.device)
         left, right = Z[:, :C], Z[:, C:]
-        elu_into(xs, left)
+        stats = None
+        if want_stats and fused.elu_colstats_supported(xs, left):
+            stats = fused.elu_colstats(xs, left)          # activation + BatchNorm statistics of the left half, one pass
+        else:
+            elu_into(xs, left)
         if same:
             op.apply(left, out=right)                     # gather from the activated left half (row stride 2C)
             ctx.save_for_backward(Z)
@@ -87,10 +92,14 @@ class _StageConcat(torch.autograd.Function):
             op.apply(act, out=right)
             ctx.save_for_backward(Z, act)
         ctx.op, ctx.same, ctx.C = op, same, C
-        return Z
+        if stats is None:
+            empty = Z.new_empty(0)
+            stats = (empty, empty.clone())
+        ctx.mark_non_differentiable(stats[0], stats[1])
+        return Z, stats[0], stats[1]
 
     @staticmethod
-    def backward(ctx, gZ):
+    def backward(ctx, gZ, _gm=None, _gv=None):
         op, C = ctx.op, ctx.C
         gZ = gZ.contiguous()
         g_left, g_right = gZ[:, :C], gZ[:, C:]
@@ -98,16 +107,22 @@ class _StageConcat(torch.autograd.Function):
             (Z,) = ctx.saved_tensors
             t = op.T.apply(g_right)                       # S^T g
             _elu_bwd(Z[:, :C], False, g_left, t, t)       # (g_left + S^T g) * elu'(x), in place
-            return t, None, None, None
+            return t, None, None, None, None
         Z, act = ctx.saved_tensors
         g_self = torch.empty(gZ.shape[0], C, dtype=torch.float32, device=gZ.device)
         _elu_bwd(Z[:, :C], False, g_left, None, g_self)
         t = op.T.apply(g_right)
         _elu_bwd(act, False, t, None, t)
-        return g_self, t, None, None
+        return g_self, t, None, None, None
 
 
-def stage_concat(op, x_self, x_gather=None):
-    """``[elu(x_self) | op @ elu(x_gather)]`` as one [rows, 2C] buffer; ``x_gather=None`` means x_self."""
+def stage_concat(op, x_self, x_gather=None, want_stats=True):
+    """``[elu(x_self) | op @ elu(x_gather)]`` as one [rows, 2C] buffer; ``x_gather=None`` means x_self.
+
+    With ``want_stats`` the activation pass also reduces the left half's BatchNorm statistics; they ride on the
+    returned tensor (``Z._sn_left_stats``) and ``fused.bn_linear`` then only reduces the right half."""
     same = x_gather is None
-    return _StageConcat.apply(x_self, x_self if same else x_gather, op, same)
+    Z, mean_l, var_l = _StageConcat.apply(x_self, x_self if same else x_gather, op, same, want_stats)
+    if mean_l.numel():
+        Z._sn_left_stats = (mean_l, var_l)
+    return Z

@@ -222,7 +222,7 @@ def test_blocks_width128_vs_oracle(kind):
         close(fg.grad, fc_.grad, "df")
     gscale = max(float(P[k].grad.abs().max()) for k, _ in blk.named_parameters())
     for k, p in blk.named_parameters():
-        close(p.grad, P[k].grad, "grad " + k, 5e-4, floor=1e-2 * gscale)
+        close(p.grad, P[k].grad, "grad " + k, 1e-3, floor=1e-2 * gscale)
 
 
 # ------------------------------------------------------------------------------------------- G = A^T B (split-K, MN-major)
