@@ -191,6 +191,22 @@ def measured_peaks():
     return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the Dirac kernel from the committed ncu --set full capture (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "r1_bsr4_ncu_summary.json")
+    try:
+        with open(path) as fh:
+            d = json.load(fh)
+        row = d["r1f_stream (current hot kernel)"][0]
+        rd = float(row["dram__bytes_read.sum"].split()[0]) * 1e6
+        wr = float(row["dram__bytes_write.sum"].split()[0]) * 1e6
+        return rd + wr, ("ncu --set full, bsr4_spmm_stream_kernel D at cfg3 size: dram__bytes_read.sum %.1f MB + "
+                         "dram__bytes_write.sum %.1f MB (profiles/r1_bsr4_ncu_summary.json; part of Y is still "
+                         "dirty in L2 when the kernel ends)" % (rd / 1e6, wr / 1e6))
+    except Exception:
+        return None, None
+
+
 def spmm_sweep(dev):
     """Operator-only numbers named by BASELINE.json's metric: GB/s (canonical bytes) and GFLOP/s per SpMM family."""
     from surfacenetworks_b200 import operators as OP, workloads as W
@@ -368,8 +384,10 @@ def run_b200(args):
     bsr_bytes = sum(v["bytes"] for v in bsr)
     bsr_launches = sum(v["launches"] for v in bsr)
     achieved = bsr_bytes / (bsr_ms / 1e3) / 1e9 if bsr_ms > 0 else 0.0
-    roofline = {"kernel": "bsr4_spmm_vec4_kernel (sn_bsr4_spmm_f32: D, D*, D^T, D*^T at C=128)", "bound": "hbm",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic, traffic_src = ncu_traffic()
+    roofline = {"kernel": "bsr4_spmm_stream_kernel (sn_bsr4_spmm_f32: D, D*, D^T, D*^T at C=128)", "bound": "hbm",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": peak_src, "launches_timed": bsr_launches,
                 "avg_launch_us": bsr_ms / max(bsr_launches, 1) * 1e3,
                 "alg_bytes_per_launch": bsr_bytes / max(bsr_launches, 1),

@@ -57,19 +57,19 @@ colstats_partial_kernel(const float* __restrict__ X, int64_t ldx, int64_t rows, 
   }
 }
 
-// fixed-order fp64 reduction of the per-CTA partials: CTA = 32 columns x 8 partial groups; group g adds partials
-// g, g + 8, ... and the 8 group sums are added in order
-__global__ void __launch_bounds__(256)
+// fixed-order fp64 reduction of the per-CTA partials: CTA = 32 columns x 32 partial groups (1024 threads); group g
+// adds partials g, g + 32, ... (independent loads, short dependent chains) and the 32 group sums are added in order
+__global__ void __launch_bounds__(1024)
 colstats_final_kernel(const float* __restrict__ partial, int n_partials, int64_t rows, int C, const float* __restrict__ X,
                       float* __restrict__ mean, float* __restrict__ var) {
-  __shared__ double red[2][8][32];
+  __shared__ double red[2][32][33];
   const int lc = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lc;
   double s = 0.0, q = 0.0;
   if (c < C) {
-    for (int i = g; i < n_partials; i += 8) {
-      s += (double)partial[(size_t)i * 2 * C + c];
-      q += (double)partial[(size_t)i * 2 * C + C + c];
+    for (int i = g; i < n_partials; i += 32) {
+      s += (double)__ldg(partial + (size_t)i * 2 * C + c);
+      q += (double)__ldg(partial + (size_t)i * 2 * C + C + c);
     }
   }
   red[0][g][lc] = s;
@@ -78,8 +78,7 @@ colstats_final_kernel(const float* __restrict__ partial, int n_partials, int64_t
   if (g == 0 && c < C) {
     s = 0.0;
     q = 0.0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < 32; ++k) {
       s += red[0][k][lc];
       q += red[1][k][lc];
     }
@@ -140,7 +139,7 @@ static int stat_grid() {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return sms * 8;   // 8 CTAs x 256 threads per SM: full occupancy, one partial row per CTA
+  return sms * 6;   // 6 CTAs x 256 threads per SM, one partial row per CTA
 }
 
 }  // namespace sn
@@ -162,7 +161,7 @@ SN_API int sn_colstats_f32(const float* X, int64_t ldx, int64_t rows, int64_t C,
   const size_t smem = (size_t)RG * 2 * C * sizeof(float);
   if (smem > 48 * 1024) return SN_ERR_UNSUPPORTED;
   colstats_partial_kernel<<<grid, kStatThreads, smem, st>>>(X, ldx, rows, (int)C, (float*)ws);
-  colstats_final_kernel<<<(unsigned)ceil_div(C, 32), 256, 0, st>>>((const float*)ws, grid, rows, (int)C, X, mean, var_biased);
+  colstats_final_kernel<<<(unsigned)ceil_div(C, 32), 1024, 0, st>>>((const float*)ws, grid, rows, (int)C, X, mean, var_biased);
   return launch_status();
 }
 
@@ -181,6 +180,6 @@ SN_API int sn_elu_colstats_f32(const float* X, int64_t ldx, float* Y, int64_t ld
   if (smem > 48 * 1024) return SN_ERR_UNSUPPORTED;
   elu_colstats_kernel<<<grid, kStatThreads, smem, st>>>(X, ldx, Y, ldy, rows, (int)C, (float*)ws);
   // the shift used by the partial sums is the activated row 0, which the kernel above has just written to Y
-  colstats_final_kernel<<<(unsigned)ceil_div(C, 32), 256, 0, st>>>((const float*)ws, grid, rows, (int)C, Y, mean, var_biased);
+  colstats_final_kernel<<<(unsigned)ceil_div(C, 32), 1024, 0, st>>>((const float*)ws, grid, rows, (int)C, Y, mean, var_biased);
   return launch_status();
 }
