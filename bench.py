@@ -459,11 +459,66 @@ def run_b200(args):
         e2e = {"value": B * world / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "path": e2e_path}
 
+    # ---- end-to-end with GPU-resident operators: every mesh's D / D* were converted once into a
+    #      MeshOperatorCache; each step draws a new permutation of the rank's meshes, gathers + copies that batch's
+    #      inputs / targets / mask from pinned host memory, assembles the batch operators (and transposes) on the GPU
+    #      straight into the captured step's operator slots, replays the graph and reads the loss back.
+    e2e_cached = None
+    if not args.no_e2e and graph is not None:
+        cache = OP.MeshOperatorCache(dev)
+        for i, m in enumerate(meshes):
+            cache.add(("Di", i), m.Di, "bsr4")
+            cache.add(("DiA", i), m.DiA, "bsr4")
+        rng = np.random.default_rng(1234 + rank)
+        stage_pinned = [{k: torch.empty_like(pinned[k]).pin_memory() for k in ("inputs", "targets", "mask")} for _ in range(2)]
+        copy_stream = torch.cuda.Stream()
+        io_bytes = sum(pinned[k].numel() * pinned[k].element_size() for k in ("inputs", "targets", "mask"))
+
+        def stage_io(slot):
+            perm = rng.permutation(B)
+            pt = torch.from_numpy(perm)
+            hs = stage_pinned[slot]
+            for k in ("inputs", "targets", "mask"):
+                torch.index_select(pinned[k], 0, pt, out=hs[k])
+            with torch.cuda.stream(copy_stream):
+                d = {k: hs[k].to(dev, non_blocking=True) for k in ("inputs", "targets", "mask")}
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return perm, d, ev
+
+        def cached_loop(n):
+            staged = stage_io(0)
+            for it in range(n):
+                perm, d, ev = staged
+                cur = torch.cuda.current_stream()
+                cur.wait_event(ev)
+                for k in ("inputs", "targets", "mask"):
+                    res[k].copy_(d[k], non_blocking=True)
+                    d[k].record_stream(cur)
+                cache.assemble([("Di", int(i)) for i in perm], "bsr4", nf, nv, out=Dop)
+                cache.assemble([("DiA", int(i)) for i in perm], "bsr4", nv, nf, out=DAop)
+                graph.replay()
+                staged = stage_io((it + 1) & 1)            # next batch's gather + H2D overlap the running step
+                float(static_loss.detach())
+
+        cached_loop(Wu)
+        barrier()
+        e0.record()
+        cached_loop(K)
+        e1.record()
+        barrier()
+        ms_c = max_over_ranks(e0.elapsed_time(e1)) / K
+        e2e_cached = {"value": B * world / (ms_c / 1e3), "unit": UNIT, "h2d_bytes_per_step": io_bytes + 4 * 6 * 8 * B,
+                      "d2h_bytes_per_step": 4, "ms_per_step": ms_c,
+                      "path": "MeshOperatorCache (per-mesh BSR4 resident on the GPU) -> per step: random batch permutation, "
+                              "pinned inputs/targets/mask H2D on a copy stream, sn_assemble_block_diag of D, D*, D^T, D*^T "
+                              "into the captured step's operator slots, CUDA-graph replay, loss.item()"}
+
     if rank != 0:
         return
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wu,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(args, world), "clocks": clock_info, "e2e": e2e,
+            "data": "synthetic", "config": workload_config(args, world), "clocks": clock_info, "e2e": e2e, "e2e_cached_operators": e2e_cached,
             "gpu_launches": launches, "step_mode": graph_note, "ms_per_step_eager": ms_eager_total / K, "roofline": roofline, "kernels": kernels, "final_loss": final_loss,
             "padded": {"num_vertices": nv, "num_faces": nf, "dirac_blocks": Dop.n_blocks},
             "grad_allreduce_bytes": grads.nbytes}

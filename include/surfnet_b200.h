@@ -88,6 +88,16 @@ int sn_csr32_to_bsr4_count(const int32_t* rowptr, const int32_t* colind, int64_t
 int sn_csr32_to_bsr4_fill(const int32_t* rowptr, const int32_t* colind, const float* val, int64_t n_rows,
                           const int32_t* browptr, int32_t* bcolind, float* bval, sn_stream_t stream);
 
+/* GPU-resident batch assembly: block-diagonal concatenation of per-mesh CSR32 (vals_per_entry = 1) or BSR4
+ * (vals_per_entry = 16) operators that already live on the device, every mesh padded to rows_pad x cols_pad (block)
+ * rows / columns -- what sparse_diag_cat(...).coalesce() + upload does per step in the reference (utils_pt.py:41-53,
+ * as_rigid_as_possible/main.py:172-183).  `parts` is a device table of 6 int64 per mesh: rowptr pointer, colind
+ * pointer, value pointer, rows, entries (nnz / blocks), exclusive prefix sum of entries.  Outputs: rowptr_out
+ * [n_parts*rows_pad + 1], colind_out / val_out [total_entries (* 16)]. */
+int sn_assemble_block_diag(const int64_t* parts, int64_t n_parts, int64_t rows_pad, int64_t cols_pad,
+                           int64_t total_entries, int vals_per_entry, int32_t* rowptr_out, int32_t* colind_out,
+                           float* val_out, sn_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Operator application.
  *

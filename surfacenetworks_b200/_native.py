@@ -32,6 +32,7 @@ SIGNATURES = {
     "sn_csr32_to_bsr4_ws_bytes": (_sz, [_i64]),
     "sn_csr32_to_bsr4_count": (_int, [_ptr, _ptr, _i64, _ptr, _ptr, _sz, _ptr]),
     "sn_csr32_to_bsr4_fill": (_int, [_ptr, _ptr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr]),
+    "sn_assemble_block_diag": (_int, [_ptr, _i64, _i64, _i64, _i64, _int, _ptr, _ptr, _ptr, _ptr]),
     "sn_csr_spmm_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _int, _ptr]),
     "sn_bsr4_spmm_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _int, _ptr]),
     "sn_elu_f32": (_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _ptr]),

@@ -17,7 +17,7 @@ import torch
 
 from . import _native as N
 
-__all__ = ["CsrOperator", "Bsr4Operator", "as_csr", "as_bsr4", "clear_cache"]
+__all__ = ["CsrOperator", "Bsr4Operator", "as_csr", "as_bsr4", "clear_cache", "MeshOperatorCache"]
 
 
 def _ptr(t):
@@ -325,3 +325,93 @@ def as_bsr4(S):
     if isinstance(S, CsrOperator):
         raise TypeError("expected a Dirac (4x4-block) operator, got a CsrOperator")
     return _cached(S, "bsr4", Bsr4Operator.from_torch_coo)
+
+
+# ---------------------------------------------------------------------------------------------------
+class MeshOperatorCache:
+    """Per-mesh operators resident on the GPU + batch assembly on the GPU.
+
+    The reference converts every sampled mesh's scipy operators to torch COO, concatenates, sorts and uploads them on
+    every training step (src/as_rigid_as_possible/main.py:142-185 -> utils_pt.sparse_diag_cat).  With this cache each
+    mesh is converted once (``add``); ``assemble`` builds the block-diagonal batch operator -- and its transpose, for
+    backward -- from the cached parts with sn_assemble_block_diag, optionally straight into existing operator
+    buffers (``out=``) so a captured CUDA graph can be replayed on the new batch.
+    """
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self._ops = {}
+
+    def __contains__(self, key):
+        return key in self._ops
+
+    def add(self, key, S, kind):
+        """Register mesh ``key``'s operator: ``S`` is a torch sparse COO tensor (any device) or a scipy matrix;
+        ``kind`` is "csr" (Laplacian) or "bsr4" (Dirac / adjoint).  Converts it and its transpose on the GPU."""
+        if not isinstance(S, torch.Tensor):
+            import numpy as np
+            S = S.tocoo()
+            S = torch.sparse_coo_tensor(torch.from_numpy(np.stack([S.row, S.col]).astype(np.int64)),
+                                        torch.from_numpy(S.data.astype(np.float32)), S.shape)
+        S = S.to(self.device)
+        op = (CsrOperator if kind == "csr" else Bsr4Operator).from_torch_coo(S if S.is_coalesced() else S.coalesce())
+        op.T                      # build the transpose once
+        op.release_source()
+        op.T.release_source()
+        self._ops[(key, kind)] = op
+        return op
+
+    def get(self, key, kind):
+        return self._ops[(key, kind)]
+
+    @staticmethod
+    def _arrays(op):
+        if op.kind == "csr":
+            return op.rowptr, op.colind, op.val, op.n_rows, op.nnz
+        return op.browptr, op.bcolind, op.bval, op.n_brows, op.n_blocks
+
+    def _assemble_one(self, parts, kind, rows_pad, cols_pad, out):
+        dev = self.device
+        table, off = [], 0
+        for op in parts:
+            rp, ci, va, n_rows, n_ent = self._arrays(op)
+            if n_rows > rows_pad:
+                raise ValueError("mesh operator has %d rows, more than the padded size %d" % (n_rows, rows_pad))
+            table += [rp.data_ptr(), ci.data_ptr(), va.data_ptr(), n_rows, n_ent, off]
+            off += n_ent
+        table = torch.tensor(table, dtype=torch.int64).to(dev, non_blocking=True)
+        n = len(parts)
+        vpe = 1 if kind == "csr" else 16
+        if out is None:
+            rowptr = torch.empty(n * rows_pad + 1, dtype=torch.int32, device=dev)
+            colind = torch.empty(max(off, 1), dtype=torch.int32, device=dev)
+            val = torch.empty(max(off, 1) * vpe, dtype=torch.float32, device=dev)
+        else:
+            rowptr, colind, val = self._arrays(out)[:3]
+            if rowptr.numel() != n * rows_pad + 1 or colind.numel() < off:
+                raise ValueError("output operator buffers do not fit this batch")
+        with torch.cuda.device(dev):
+            N.call("sn_assemble_block_diag", _ptr(table), n, rows_pad, cols_pad, off, vpe, _ptr(rowptr), _ptr(colind),
+                   _ptr(val), _stream())
+        if out is not None:
+            if kind == "csr":
+                out._nnz = off
+            else:
+                out._n_blocks = off
+                out.max_row_blocks = max(op.max_row_blocks for op in parts)
+            return out
+        if kind == "csr":
+            return CsrOperator(rowptr, colind[:off] if off else colind, val[:off] if off else val, n * rows_pad,
+                               n * cols_pad, None, off)
+        return Bsr4Operator(rowptr, colind[:off] if off else colind, val[:16 * off] if off else val, n * rows_pad,
+                            n * cols_pad, None, off, max(op.max_row_blocks for op in parts))
+
+    def assemble(self, keys, kind, rows_pad, cols_pad, out=None):
+        """Block-diagonal batch operator of the meshes ``keys`` (in order), each padded to ``rows_pad x cols_pad``
+        (block rows / columns for "bsr4", scalar for "csr"), with its transpose attached.  ``out``: an operator of
+        the same batch shape whose buffers (and whose transpose's) are overwritten in place."""
+        parts = [self._ops[(k, kind)] for k in keys]
+        fwd = self._assemble_one(parts, kind, rows_pad, cols_pad, out)
+        bwd = self._assemble_one([p.T for p in parts], kind, cols_pad, rows_pad, None if out is None else out.T)
+        fwd._T, bwd._T = bwd, fwd
+        return fwd

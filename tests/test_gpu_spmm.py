@@ -343,3 +343,42 @@ def test_error_paths():
     assert N.lib.sn_bsr4_spmm_f32(1, 1, 1, 1, 6, 1, 6, 2, 6, 0, 0) == N.SN_ERR_UNSUPPORTED   # C % 4 != 0
     with pytest.raises(N.SurfnetError):
         N.call("sn_csr_spmm_f32", 0, 0, 0, 0, 4, 0, 4, 2, 4, 0, 0)
+
+
+def test_gpu_batch_assembly_matches_host_assembly():
+    """MeshOperatorCache.assemble (sn_assemble_block_diag) == converting the host-assembled block-diagonal COO:
+    identical row pointers / column indices / values for D, D*, L and their transposes, ragged meshes padded."""
+    from surfacenetworks_b200 import utils_pt as U, workloads as W
+    O = ops_mod()
+    meshes = W.make_mesh_ops(120, [0, 1]) + W.make_mesh_ops(97, [2]) + W.make_mesh_ops(120, [3])
+    nv = max(m.num_vertices for m in meshes)
+    nf = max(m.num_faces for m in meshes)
+    cache = O.MeshOperatorCache(DEV)
+    for i, m in enumerate(meshes):
+        cache.add(("Di", i), m.Di, "bsr4")
+        cache.add(("DiA", i), U.sp_sparse_to_pt_sparse(m.DiA), "bsr4")     # scipy and torch COO inputs both work
+        cache.add(("L", i), m.L, "csr")
+    order = [2, 0, 3, 1]
+    sel = [meshes[i] for i in order]
+    host = W.arap_batch(sel, 0)
+    for name, rows_pad, cols_pad in (("Di", nf, nv), ("DiA", nv, nf)):
+        ref = O.Bsr4Operator.from_torch_coo(host[name].to(DEV))
+        got = cache.assemble([(name, i) for i in order], "bsr4", rows_pad, cols_pad)
+        for a, b in ((got, ref), (got.T, ref.T)):
+            assert (a.n_brows, a.n_bcols, a.n_blocks) == (b.n_brows, b.n_bcols, b.n_blocks)
+            assert torch.equal(a.browptr, b.browptr) and torch.equal(a.bcolind, b.bcolind) and torch.equal(a.bval, b.bval)
+        # in-place re-assembly of another batch into the same buffers (CUDA-graph replay case)
+        slot = cache.assemble([(name, i) for i in order], "bsr4", rows_pad, cols_pad)
+        ptrs = (slot.browptr.data_ptr(), slot.bval.data_ptr(), slot.T.bval.data_ptr())
+        order2 = [1, 3, 0, 2]
+        cache.assemble([(name, i) for i in order2], "bsr4", rows_pad, cols_pad, out=slot)
+        ref2 = O.Bsr4Operator.from_torch_coo(W.arap_batch([meshes[i] for i in order2], 0)[name].to(DEV))
+        assert ptrs == (slot.browptr.data_ptr(), slot.bval.data_ptr(), slot.T.bval.data_ptr())
+        assert torch.equal(slot.browptr, ref2.browptr) and torch.equal(slot.bcolind, ref2.bcolind)
+        assert torch.equal(slot.bval, ref2.bval) and torch.equal(slot.T.bval, ref2.T.bval)
+        x = torch.randn(slot.n_bcols, 128, device=DEV)
+        assert torch.equal(slot.apply(x), ref2.apply(x))
+    refL = O.CsrOperator.from_torch_coo(W.lap_batch(sel)["L"].to(DEV))
+    gotL = cache.assemble([("L", i) for i in order], "csr", nv, nv)
+    for a, b in ((gotL, refL), (gotL.T, refL.T)):
+        assert torch.equal(a.rowptr, b.rowptr) and torch.equal(a.colind, b.colind) and torch.equal(a.val, b.val)
