@@ -48,7 +48,9 @@ typedef void* sn_stream_t; /* cudaStream_t */
 
 /* flags for the SpMM entry points */
 #define SN_SPMM_ELU_INPUT 1     /* apply ELU(alpha=1) to the gathered dense operand: Y = S * elu(X)  */
-#define SN_SPMM_DIRECT_GATHER 2 /* sn_bsr4_spmm_f32: force the direct-gather kernel (no smem streaming) */
+#define SN_SPMM_DIRECT_GATHER 2 /* force the first-generation direct-gather kernel (one row per lane group)       */
+#define SN_SPMM_SMEM_STREAM 4   /* sn_bsr4_spmm_f32: force the cp.async shared-memory streaming kernel (C=128/256/512) */
+#define SN_SPMM_VARIANT(v) (((v) & 15) << 8) /* tuning variant of the row-group kernel (benchmarks only; 0 = default) */
 
 int sn_version(void);
 const char* sn_status_string(int status);
@@ -106,8 +108,10 @@ int sn_assemble_block_diag(const int64_t* parts, int64_t n_parts, int64_t rows_p
  *                    Y[r, p*C/4 + c] = sum_{blocks (r,j)} sum_q block[p][q] * X[j, q*C/4 + c],  C % 4 == 0
  * X rows are addressed through colind, so X must have at least n_cols rows.  Accumulation is fp32 FMA
  * in ascending storage order (bit-reproducible run to run).  X and Y must not alias.
- * sn_bsr4_spmm_f32 runs the streaming kernel (persistent CTAs, cp.async gathers through a shared-memory double
- * buffer, prefetched indices) for C = 128 / 256 / 512 and the direct-gather kernel for other widths.
+ * Both entry points run the row-group kernel (spmm_rowgroup.cu: C/16 lanes own a sparse row and keep the whole 4x4
+ * block product in registers, software-pipelined LDG.128 gathers, per-warp index rings in shared memory) for
+ * C in {16, 32, 64, 128, 256, 512} with 16-byte aligned operands, and the direct-gather kernels for other widths /
+ * alignments.  SN_SPMM_SMEM_STREAM / SN_SPMM_DIRECT_GATHER select the earlier kernels (kept for A/B measurements).
  * ---------------------------------------------------------------------------------------------- */
 int sn_csr_spmm_f32(const int32_t* rowptr, const int32_t* colind, const float* val,
                     const float* X, int64_t ldx, float* Y, int64_t ldy,

@@ -64,6 +64,15 @@ SN_ERR_ARG, SN_ERR_UNSUPPORTED, SN_ERR_WORKSPACE, SN_ERR_OVERFLOW = -1, -2, -3, 
 SN_COO_SORTED = 1
 SN_SPMM_ELU_INPUT = 1
 SN_SPMM_DIRECT_GATHER = 2
+SN_SPMM_SMEM_STREAM = 4
+
+
+def spmm_flags(elu_input=False, direct_gather=False, smem_stream=False, variant=0):
+    """flags word of sn_csr_spmm_f32 / sn_bsr4_spmm_f32 (include/surfnet_b200.h)."""
+    return ((SN_SPMM_ELU_INPUT if elu_input else 0) | (SN_SPMM_DIRECT_GATHER if direct_gather else 0)
+            | (SN_SPMM_SMEM_STREAM if smem_stream else 0) | ((int(variant) & 15) << 8))
+
+
 SN_GEMM_SINGLE_PASS = 1
 
 

@@ -128,6 +128,9 @@ static int launch_vec4(const int32_t* browptr, const int32_t* bcolind, const flo
 
 int launch_bsr4_stream(const int32_t* browptr, const int32_t* bcolind, const float* bval, const float* X, int64_t ldx,
                        float* Y, int64_t ldy, int64_t n_brows, int64_t C, bool elu, cudaStream_t st);
+int launch_bsr4_rowgroup(const int32_t* browptr, const int32_t* bcolind, const float* bval, const float* X,
+                         int64_t ldx, float* Y, int64_t ldy, int64_t n_brows, int64_t C, bool elu, int variant,
+                         cudaStream_t st);
 
 }  // namespace sn
 
@@ -153,8 +156,11 @@ SN_API int sn_bsr4_spmm_f32(const int32_t* browptr, const int32_t* bcolind, cons
       bsr4_spmm_scalar_kernel<false><<<(unsigned)grid, 256, 0, st>>>(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C4);
     return launch_status();
   }
-  if (!(flags & SN_SPMM_DIRECT_GATHER)) {  // streaming kernel: C = 128 / 256 / 512
+  if (flags & SN_SPMM_SMEM_STREAM) {       // cp.async streaming kernel: C = 128 / 256 / 512
     const int rc = launch_bsr4_stream(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C, elu, st);
+    if (rc != SN_ERR_UNSUPPORTED) return rc;
+  } else if (!(flags & SN_SPMM_DIRECT_GATHER)) {  // row-group kernel: C = 16 ... 512 (powers of two)
+    const int rc = launch_bsr4_rowgroup(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C, elu, (flags >> 8) & 15, st);
     if (rc != SN_ERR_UNSUPPORTED) return rc;
   }
   const int v = C4 / 4;  // float4 columns per quaternion component

@@ -119,6 +119,9 @@ static int launch_vec4(const int32_t* rowptr, const int32_t* colind, const float
   return launch_status();
 }
 
+int launch_csr_rowgroup(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X, int64_t ldx,
+                        float* Y, int64_t ldy, int64_t n_rows, int64_t C, bool elu, int variant, cudaStream_t st);
+
 }  // namespace sn
 
 SN_API int sn_csr_spmm_f32(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X,
@@ -140,6 +143,10 @@ SN_API int sn_csr_spmm_f32(const int32_t* rowptr, const int32_t* colind, const f
     else
       csr_spmm_scalar_kernel<false><<<(unsigned)grid, 256, 0, st>>>(rowptr, colind, val, X, ldx, Y, ldy, n_rows, (int)C);
     return launch_status();
+  }
+  if (!(flags & SN_SPMM_DIRECT_GATHER)) {  // row-group kernel: C = 16 ... 512
+    const int rc = launch_csr_rowgroup(rowptr, colind, val, X, ldx, Y, ldy, n_rows, C, elu, (flags >> 8) & 15, st);
+    if (rc != SN_ERR_UNSUPPORTED) return rc;
   }
   const int64_t v = C / 4;  // float4 columns
   if (v <= 1) return launch_vec4<1>(rowptr, colind, val, X, ldx, Y, ldy, n_rows, (int)C, elu, st);

@@ -151,7 +151,7 @@ class CsrOperator:
     def flops(self, C):
         return 2 * self.nnz * C
 
-    def apply(self, X, out=None, elu_input=False):
+    def apply(self, X, out=None, elu_input=False, direct_gather=False, variant=0):
         """``out[n_rows, C] = S @ (elu(X) if elu_input else X)``; X: [>= n_cols, C] (row stride free)."""
         _check_dense(X, "X")
         if X.shape[0] < self.n_cols:
@@ -166,7 +166,8 @@ class CsrOperator:
             N.TIMER.annotate("csr %dx%d C=%d" % (self.n_rows, self.n_cols, C), self.algorithmic_bytes(C), self.flops(C))
         with torch.cuda.device(X.device):
             N.call("sn_csr_spmm_f32", _ptr(self.rowptr), _ptr(self.colind), _ptr(self.val), _ptr(X), X.stride(0),
-                   _ptr(out), out.stride(0), self.n_rows, C, N.SN_SPMM_ELU_INPUT if elu_input else 0, _stream())
+                   _ptr(out), out.stride(0), self.n_rows, C, N.spmm_flags(elu_input, direct_gather, False, variant),
+                   _stream())
         return out
 
 
@@ -262,7 +263,7 @@ class Bsr4Operator:
         """Reference-stored nnz count (12 per Dirac block) by default; pass 16 for dense-block FLOPs."""
         return 2 * stored_nnz_per_block * self.n_blocks * (C // 4)
 
-    def apply(self, X, out=None, elu_input=False, direct_gather=False):
+    def apply(self, X, out=None, elu_input=False, direct_gather=False, smem_stream=False, variant=0):
         _check_dense(X, "X")
         if X.shape[0] < self.n_bcols:
             raise ValueError("X has %d rows, operator has %d block columns" % (X.shape[0], self.n_bcols))
@@ -277,7 +278,7 @@ class Bsr4Operator:
         if N.TIMER is not None:
             N.TIMER.annotate("bsr4 %dx%d C=%d" % (self.n_brows, self.n_bcols, C), self.algorithmic_bytes(C), self.flops(C))
         with torch.cuda.device(X.device):
-            flags = (N.SN_SPMM_ELU_INPUT if elu_input else 0) | (N.SN_SPMM_DIRECT_GATHER if direct_gather else 0)
+            flags = N.spmm_flags(elu_input, direct_gather, smem_stream, variant)
             N.call("sn_bsr4_spmm_f32", _ptr(self.browptr), _ptr(self.bcolind), _ptr(self.bval),
                    _ptr(X), X.stride(0), _ptr(out), out.stride(0), self.n_brows, C, flags, _stream())
         return out

@@ -188,7 +188,11 @@ def test_csr_feature_widths_and_strides(C):
     x = det_array((n, C), 100 + C)
     xg = torch.from_numpy(x).to(DEV)
     y64, bound = c_oracle.coo_mm_f64(row, col, val, n, x)
-    within_bound(op.apply(xg).cpu().numpy(), y64, bound, "contiguous")
+    y = op.apply(xg)
+    within_bound(y.cpu().numpy(), y64, bound, "contiguous")
+    within_bound(op.apply(xg, direct_gather=True).cpu().numpy(), y64, bound, "direct-gather kernel")
+    for variant in (1, 2, 4, 5):        # tuning variants of the row-group kernel share its summation order
+        assert torch.equal(y, op.apply(xg, variant=variant)), "row-group variant %d" % variant
     Z = torch.zeros(n, 2 * C + 4, device=DEV)
     Z[:, :C] = xg
     op.apply(Z[:, :C], out=Z[:, C:2 * C])
@@ -210,8 +214,12 @@ def test_bsr4_feature_widths_and_strides(golden, C):
     y64, bound = c_oracle.dirac_view_mm_f64(idx[0], idx[1], val, 2 * nf, x)
     y = Di.apply(xg)
     within_bound(y.cpu().numpy(), y64, bound, "contiguous")
-    # streaming kernel (C = 128/256/512) and direct-gather kernel use the same summation order: bit-identical
-    assert torch.equal(y, Di.apply(xg, direct_gather=True))
+    for variant in (1, 2, 4, 5):        # tuning variants of the row-group kernel share its summation order
+        assert torch.equal(y, Di.apply(xg, variant=variant)), "row-group variant %d" % variant
+    # cp.async streaming kernel (C = 128/256/512) and direct-gather kernel use the same summation order: bit-identical
+    yd = Di.apply(xg, direct_gather=True)
+    within_bound(yd.cpu().numpy(), y64, bound, "direct-gather kernel")
+    assert torch.equal(yd, Di.apply(xg, smem_stream=True))
     Xs = torch.zeros(2 * nv, 2 * C, device=DEV)
     Xs[:, :C] = xg
     Z = torch.zeros(2 * nf, 2 * C, device=DEV)
@@ -220,6 +228,72 @@ def test_bsr4_feature_widths_and_strides(golden, C):
     assert torch.all(Z[:, :C] == 0)
     y64, bound = c_oracle.dirac_view_mm_f64(idx[0], idx[1], val, 2 * nf, c_oracle.elu_f32(x))
     within_bound(Di.apply(xg, elu_input=True).cpu().numpy(), y64, bound, "elu on load", k=64)
+
+
+# ------------------------------------------------------------------------------------------- row-group kernel paths
+@pytest.mark.parametrize("C", [16, 32, 64, 128, 256, 512])
+def test_rowgroup_long_rows_and_empty_runs(C):
+    """Row-group kernel (spmm_rowgroup.cu) corner paths: rows far longer than the staged index ring (global-load
+    fallback), runs of empty rows at the start / middle / end of a warp-tile, one dense row among empty ones,
+    row counts that are not a multiple of the warp-tile, both tile lengths (variants 4 / 5)."""
+    O = ops_mod()
+    rng = np.random.default_rng(1000 + C)
+    n_rows, n_cols = 333, 190
+    lens = rng.integers(0, 4, n_rows)
+    lens[5] = 150                       # longer than any staged ring
+    lens[40:90] = 0                     # empty warp-tiles
+    lens[90] = 97
+    lens[300:] = rng.integers(20, 60, n_rows - 300)
+    lens[-1] = 0
+    row = np.repeat(np.arange(n_rows), lens).astype(np.int64)
+    col = np.concatenate([np.sort(rng.choice(n_cols, n, replace=False)) for n in lens]).astype(np.int64) \
+        if row.size else np.zeros(0, np.int64)
+    val = rng.standard_normal(row.size).astype(np.float32)
+    op = O.CsrOperator.from_torch_coo(coo_cuda(np.stack([row, col]), val, (n_rows, n_cols), True))
+    x = det_array((n_cols, C), 300 + C)
+    xg = torch.from_numpy(x).to(DEV)
+    y64, bound = c_oracle.coo_mm_f64(row, col, val, n_rows, x)
+    y = op.apply(xg)
+    within_bound(y.cpu().numpy(), y64, bound, "csr rowgroup")
+    for variant in (1, 2, 4, 5):
+        assert torch.equal(y, op.apply(xg, variant=variant)), "csr variant %d" % variant
+    # the same pattern as 4x4 blocks (dense random blocks): block row r has lens[r] blocks
+    blk = rng.standard_normal((row.size, 4, 4)).astype(np.float32)
+    p, q = np.meshgrid(np.arange(4), np.arange(4), indexing="ij")
+    brow = (4 * row[:, None, None] + p).ravel()
+    bcol = (4 * col[:, None, None] + q).ravel()
+    opb = O.Bsr4Operator.from_torch_coo(coo_cuda(np.stack([brow, bcol]), blk.ravel(), (4 * n_rows, 4 * n_cols), False))
+    assert opb.n_blocks == row.size
+    y64, bound = c_oracle.dirac_view_mm_f64(brow, bcol, blk.ravel(), n_rows, x)
+    y = opb.apply(xg)
+    within_bound(y.cpu().numpy(), y64, bound, "bsr4 rowgroup")
+    within_bound(opb.apply(xg, direct_gather=True).cpu().numpy(), y64, bound, "bsr4 direct")
+    for variant in (1, 2, 4, 5):
+        assert torch.equal(y, opb.apply(xg, variant=variant)), "bsr4 variant %d" % variant
+
+
+@pytest.mark.parametrize("C,n_rows", [(16, 480_000), (64, 200_000), (128, 150_001), (512, 40_000)])
+def test_rowgroup_persistent_warps(C, n_rows):
+    """Enough warp-tiles that every persistent warp walks several of them (index ring rotation, both tile lengths)."""
+    O = ops_mod()
+    rng = np.random.default_rng(C)
+    n_cols = 50_000
+    nnz = 6 * n_rows
+    row = np.sort(rng.integers(0, n_rows, nnz)).astype(np.int64)
+    col = rng.integers(0, n_cols, nnz).astype(np.int64)
+    val = rng.standard_normal(nnz).astype(np.float32)
+    op = O.CsrOperator.from_torch_coo(coo_cuda(np.stack([row, col]), val, (n_rows, n_cols), False))
+    x = det_array((n_cols, C), 7)
+    xg = torch.from_numpy(x).to(DEV)
+    y = op.apply(xg)
+    yd = op.apply(xg, direct_gather=True)
+    mag = O.CsrOperator(op.rowptr, op.colind, op.val.abs(), op.n_rows, op.n_cols).apply(xg.abs(), direct_gather=True)
+    assert torch.all((y - yd).abs() <= 64 * EPS32 * mag + 1e-30)
+    for variant in (4, 5):
+        assert torch.equal(y, op.apply(xg, variant=variant)), "variant %d" % variant
+    # oracle check on a row sample (full fp64 product of 480k x 16 ... 150k x 128 stays cheap on the CPU)
+    y64, bound = c_oracle.coo_mm_f64(row, col, val, n_rows, x)
+    within_bound(y.cpu().numpy(), y64, bound, "csr persistent")
 
 
 def test_elu_kernels():
@@ -274,11 +348,21 @@ def test_mesh_operators_vs_oracle(V, B, C):
         assert torch.equal(y, op.apply(ing)), "run-to-run bit reproducibility"
         if kind == "bsr4":
             assert op.max_row_blocks >= 3
-            assert torch.equal(y, op.apply(ing, direct_gather=True)), "streaming vs direct-gather kernel"
+            yd = op.apply(ing, direct_gather=True)
+            within_bound(yd.cpu().numpy(), y64, bound, "direct-gather kernel")
+            assert torch.equal(yd, op.apply(ing, smem_stream=True)), "streaming vs direct-gather kernel"
+            for variant in (1, 2, 4, 5):
+                assert torch.equal(y, op.apply(ing, variant=variant)), "row-group variant %d" % variant
             within_bound(op.T.apply(y).cpu().numpy(), *c_oracle.dirac_view_mm_f64(idx[1], idx[0], val, S.shape[1] // 4, y.cpu().numpy()), "bsr4^T")
         # the reference's own path on the same inputs (CPU torch.mm) obeys the same bound
         ref = torch.mm(S, torch.from_numpy(inp).view(S.shape[1], -1)).view(rows, C).numpy()
         within_bound(ref, y64, bound, "reference torch.mm")
+
+
+def op_abs_of(O, op, kind):
+    if kind == "csr":
+        return O.CsrOperator(op.rowptr, op.colind, op.val.abs(), op.n_rows, op.n_cols)
+    return O.Bsr4Operator(op.browptr, op.bcolind, op.bval.abs(), op.n_brows, op.n_bcols)
 
 
 def test_full_size_properties():
@@ -305,6 +389,10 @@ def test_full_size_properties():
         z = torch.randn(n_in, C, device=DEV, generator=g)
         y = torch.randn(n_out, C, device=DEV, generator=g)
         Sx = op.apply(x)
+        # row-group kernel vs the direct-gather kernel (validated against the oracle at the smaller sizes above)
+        assert torch.all((Sx - op.apply(x, direct_gather=True)).abs() <= 64 * EPS32 * op_abs_of(O, op, kind).apply(x.abs()) + 1e-30)
+        for variant in (1, 2, 4, 5):
+            assert torch.equal(Sx, op.apply(x, variant=variant)), (kind, variant)
         lhs = (Sx.double() * y.double()).sum().item()
         rhs = (x.double() * op.T.apply(y).double()).sum().item()
         scale = (Sx.double().abs() * y.double().abs()).sum().item()
@@ -312,10 +400,7 @@ def test_full_size_properties():
         lin = op.apply(0.5 * x - 2.0 * z)
         ref = 0.5 * Sx - 2.0 * op.apply(z)
         absS = op.apply(x.abs() + z.abs()).abs() + 1.0   # loose magnitude proxy
-        if kind == "csr":
-            op_abs = O.CsrOperator(op.rowptr, op.colind, op.val.abs(), op.n_rows, op.n_cols)
-        else:
-            op_abs = O.Bsr4Operator(op.browptr, op.bcolind, op.bval.abs(), op.n_brows, op.n_bcols)
+        op_abs = op_abs_of(O, op, kind)
         mag = op_abs.apply(0.5 * x.abs() + 2.0 * z.abs())
         assert torch.all((lin - ref).abs() <= 64 * EPS32 * mag + 1e-30), kind
         del absS

@@ -25,7 +25,9 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--distinct", type=int, default=8, help="distinct meshes (repeated to fill the batch)")
     ap.add_argument("--ops", default="D,Dstar,L")
-    ap.add_argument("--variants", default="stream,direct,stream+elu,direct+elu")
+    ap.add_argument("--variants", default="rg,rg1,rg2,rg4,rg5,smem,direct,rg+elu",
+                    help="rg[N] = row-group kernel (tuning variant N), smem = cp.async streaming kernel (BSR4 only), "
+                         "direct = first-generation direct-gather kernel; +elu = ELU on load")
     args = ap.parse_args()
     from surfacenetworks_b200 import operators as OP, workloads as W
     dev = torch.device("cuda", 0)
@@ -72,11 +74,13 @@ def main():
         ncols = op.n_bcols if op.kind == "bsr4" else op.n_cols
         X = torch.randn(ncols, C, device=dev)
         Y = op.apply(X)
-        variants = args.variants.split(",") if op.kind == "bsr4" else ["direct", "direct+elu"]
+        variants = [v for v in args.variants.split(",") if op.kind == "bsr4" or not v.startswith("smem")]
         for v in variants:
-            kw = {"elu_input": "elu" in v}
+            kw = {"elu_input": "elu" in v, "direct_gather": v.startswith("direct")}
             if op.kind == "bsr4":
-                kw["direct_gather"] = v.startswith("direct")
+                kw["smem_stream"] = v.startswith("smem")
+            if v.startswith("rg") and v[2:3].isdigit():
+                kw["variant"] = int(v[2])
             ms, best = time_it(lambda: op.apply(X, out=Y, **kw))
             gb = op.algorithmic_bytes(C) / 1e9
             print(json.dumps({"op": name, "variant": v, "rows": op.n_brows if op.kind == "bsr4" else op.n_rows,
