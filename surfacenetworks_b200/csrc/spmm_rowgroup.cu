@@ -38,7 +38,10 @@ __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 // base + a * b with 32-bit a, b and a 64-bit base: one IMAD.WIDE.U32
 __device__ __forceinline__ const char* ptr_mad(const char* base, uint32_t a, uint32_t b) {
   uint64_t r;
@@ -46,40 +49,44 @@ __device__ __forceinline__ const char* ptr_mad(const char* base, uint32_t a, uin
   return reinterpret_cast<const char*>(r);
 }
 
-template <int LPR, int RPG>
+template <int LPR, int RPG, int BLK, int PD>
 struct Geo {
   static constexpr int G = 32 / LPR;        // row groups per warp
   static constexpr int WR = G * RPG;        // rows per warp-tile
-  static constexpr int CAP = WR * 10;       // staged column indices per warp-tile (excess: global loads)
+  static constexpr int CAP = WR * 10;       // staged column indices (and CSR values) per warp-tile (excess: global loads)
   static constexpr int BPS = WR + 4;        // ints per row-pointer buffer (WR + 1 used, +1 read past the end)
-  static constexpr int WARP_INTS = 3 * BPS + 2 * CAP;
-  static constexpr size_t kSmem = (size_t)kWarps * WARP_INTS * sizeof(int);
+  static constexpr int WRING = BLK == 4 ? PD * G * 32 : 0;      // floats: PD stages x G groups x one pair of blocks
+  static constexpr int WARP_WORDS = ((WRING + 3 * BPS + 2 * CAP + (BLK == 1 ? 2 * CAP : 0)) + 3) / 4 * 4;
+  static constexpr size_t kSmem = (size_t)kWarps * WARP_WORDS * 4;
 };
 
 }  // namespace
 
 // LPR lanes per row (C = 16 LPR); RPG rows per row group per warp-tile; BLK = 4: BSR4 (16 values per entry, rotated
-// column-major, see sn_csr32_to_bsr4_fill), BLK = 1: CSR (one value per entry); PD = prefetch depth (entries in flight
-// per row group); MINB = CTAs per SM the register allocation is tuned for.
+// column-major, see sn_csr32_to_bsr4_fill), BLK = 1: CSR (one value per entry); PD = pipeline depth in stages of TWO
+// entries per row group; MINB = CTAs per SM the register allocation is tuned for.
 template <int LPR, int RPG, int BLK, bool ELU, int PD, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB)
 rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
                      const float* __restrict__ val, const float* __restrict__ X, uint32_t ldxb,
                      float* __restrict__ Y, uint32_t ldyb, int n_rows, int n_wtiles) {
-  using Gm = Geo<LPR, RPG>;
+  using Gm = Geo<LPR, RPG, BLK, PD>;
   constexpr int C = 16 * LPR;
   constexpr int kQuarterBytes = C;             // (C/4 floats) * 4 bytes
-  constexpr int WR = Gm::WR, CAP = Gm::CAP, BPS = Gm::BPS;
-  constexpr int NW = BLK == 4 ? 4 : 1;         // float4 weight registers per entry
-  extern __shared__ int smem_i[];
+  constexpr int G = Gm::G, WR = Gm::WR, CAP = Gm::CAP, BPS = Gm::BPS;
+  extern __shared__ __align__(16) int smem_i[];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int* bp_buf = smem_i + warp * Gm::WARP_INTS;   // [3][BPS]
-  int* bc_buf = bp_buf + 3 * BPS;                // [2][CAP]
+  int* wbase = smem_i + warp * Gm::WARP_WORDS;
+  float* wring = reinterpret_cast<float*>(wbase);        // [PD][G][32]   (BSR4 only; 16-byte aligned)
+  int* bp_buf = wbase + Gm::WRING;                       // [3][BPS]
+  int* bc_buf = bp_buf + 3 * BPS;                        // [2][CAP]
+  float* bv_buf = reinterpret_cast<float*>(bc_buf + 2 * CAP);   // [2][CAP]  (CSR only)
   const int g = lane / LPR, t = lane % LPR;
   const char* Xl = reinterpret_cast<const char*>(X) + t * 16;   // this lane's float4 of quarter 0 of every row
   char* Yl = reinterpret_cast<char*>(Y) + t * 16;
   const char* vbase = reinterpret_cast<const char*>(val);
+  const float* wslot0 = wring + g * 32;                  // this group's pair in stage 0
   const int wstride = gridDim.x * kWarps;
   int wt = blockIdx.x * kWarps + warp;
   if (wt >= n_wtiles) return;                    // warps never synchronise with each other
@@ -95,33 +102,37 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
     if (tile < n_wtiles) {
       const int k0 = bp_buf[bpb * BPS], k1 = bp_buf[bpb * BPS + WR];
       const int n = min(k1 - k0, CAP);
-      for (int i = lane; i < n; i += 32) cp_async4(bc_buf + buf * CAP + i, colind + k0 + i);
+      for (int i = lane; i < n; i += 32) {
+        cp_async4(bc_buf + buf * CAP + i, colind + k0 + i);
+        if (BLK == 1) cp_async4(bv_buf + buf * CAP + i, val + k0 + i);
+      }
     }
   };
 
   prefetch_bp(wt, 0);
   cp_async_commit();
-  cp_async_wait_all();
+  cp_async_wait<0>();
   __syncwarp();
   prefetch_bc(wt, 0, 0);
   prefetch_bp(wt + wstride, 1);
   cp_async_commit();
-  cp_async_wait_all();
+  cp_async_wait<0>();
   __syncwarp();
 
-  float4 xs[PD][4], ws[PD][NW];
+  float4 xs[PD][8];        // gathered rows of the two entries of each stage in flight
+  float2 wv[PD];           // CSR: their two values
 #pragma unroll
   for (int s = 0; s < PD; ++s) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) xs[s][q] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int q = 0; q < NW; ++q) ws[s][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < 8; ++q) xs[s][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    wv[s] = make_float2(0.f, 0.f);
   }
 
   int b3 = 0, b2 = 0;    // ring positions: row-pointer buffer (mod 3) and column-index buffer (mod 2) of this tile
   for (; wt < n_wtiles; wt += wstride) {
     const int* bp = bp_buf + b3 * BPS;
     const int* bc = bc_buf + b2 * CAP;
+    const float* bv = bv_buf + b2 * CAP;
     const int b3n = b3 == 2 ? 0 : b3 + 1, b3nn = b3n == 2 ? 0 : b3n + 1;
     // indices of the next two warp-tiles travel while this one is computed
     prefetch_bc(wt + wstride, b3n, b2 ^ 1);
@@ -132,7 +143,7 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
     const int rl0 = g * RPG;                                // the group's first row inside the warp-tile
     const int kend = bp[rl0 + RPG];
     int k = bp[rl0];                                        // next entry to accumulate
-    const int n_iter = __reduce_max_sync(0xffffffffu, kend - k);
+    const int n_iter = __reduce_max_sync(0xffffffffu, (kend - k + 1) >> 1);   // stages of two entries
     int r = 0;                                              // row inside the group
     int next_end = bp[rl0 + 1];
     const uint32_t grow0 = (uint32_t)wt * WR + rl0;
@@ -156,54 +167,84 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
         next_end = bp[rl0 + r + 1];
       }
     };
-    auto load = [&](float4 (&x)[4], float4 (&w)[NW], int kk) {
+    // stage s <- entries kk, kk + 1 of this group's run: X rows to registers; BSR4 values (one 128-byte pair per
+    // group) to the shared-memory ring with 16-byte cp.async, CSR values from the staged tile ring
+    auto load = [&](const int s, float4 (&x)[8], float2& w2, int kk) {
       if (kk < kend) {
         const int rel = kk - k0;
-        const int j = rel < CAP ? bc[rel] : __ldg(colind + kk);
-        const char* xp = ptr_mad(Xl, (uint32_t)j, ldxb);
+        const int j0 = rel < CAP ? bc[rel] : __ldg(colind + kk);
+        const char* xp0 = ptr_mad(Xl, (uint32_t)j0, ldxb);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) x[q] = __ldg(reinterpret_cast<const float4*>(xp + q * kQuarterBytes));
+        for (int q = 0; q < 4; ++q) x[q] = __ldg(reinterpret_cast<const float4*>(xp0 + q * kQuarterBytes));
         if (BLK == 4) {
-          const char* wp = ptr_mad(vbase, (uint32_t)kk, 64u);
+          const uint32_t dst = smem_u32(wslot0 + s * G * 32);
+          const char* src = ptr_mad(vbase, (uint32_t)kk, 64u);
 #pragma unroll
-          for (int q = 0; q < NW; ++q) w[q] = __ldg(reinterpret_cast<const float4*>(wp + q * 16));
+          for (int u0 = 0; u0 < 8; u0 += LPR) {
+            const int u = u0 + t;                           // 16-byte unit of the pair this lane copies
+            if (u < 8 && kk + (u >> 2) < kend)
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + u * 16), "l"(src + u * 16)
+                           : "memory");
+          }
         } else {
-          w[0].x = __ldg(reinterpret_cast<const float*>(ptr_mad(vbase, (uint32_t)kk, 4u)));
+          w2.x = rel < CAP ? bv[rel] : __ldg(val + kk);
+        }
+        if (kk + 1 < kend) {
+          const int j1 = rel + 1 < CAP ? bc[rel + 1] : __ldg(colind + kk + 1);
+          const char* xp1 = ptr_mad(Xl, (uint32_t)j1, ldxb);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) x[4 + q] = __ldg(reinterpret_cast<const float4*>(xp1 + q * kQuarterBytes));
+          if (BLK == 1) w2.y = rel + 1 < CAP ? bv[rel + 1] : __ldg(val + kk + 1);
         }
       }
+      if (BLK == 4) cp_async_commit();                      // every lane, every call: uniform group counting
     };
-    auto compute = [&](float4 (&x)[4], float4 (&w)[NW]) {
-      // finished lanes (k == kend) run the FMAs on stale registers; their accumulators are never stored
+    auto fma_entry = [&](const float4* x, const float* wsm, float wscalar) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float4 xv = ELU ? elu4(x[q]) : x[q];
-        if (BLK == 4) {       // w[q] = (B[q][q], B[q+1][q], B[q+2][q], B[q+3][q]), rows mod 4
-          acc[q] = fma4(w[q].x, xv, acc[q]);
-          acc[(q + 1) & 3] = fma4(w[q].y, xv, acc[(q + 1) & 3]);
-          acc[(q + 2) & 3] = fma4(w[q].z, xv, acc[(q + 2) & 3]);
-          acc[(q + 3) & 3] = fma4(w[q].w, xv, acc[(q + 3) & 3]);
+        if (BLK == 4) {       // w = (B[q][q], B[q+1][q], B[q+2][q], B[q+3][q]), rows mod 4
+          const float4 w = *reinterpret_cast<const float4*>(wsm + 4 * q);
+          acc[q] = fma4(w.x, xv, acc[q]);
+          acc[(q + 1) & 3] = fma4(w.y, xv, acc[(q + 1) & 3]);
+          acc[(q + 2) & 3] = fma4(w.z, xv, acc[(q + 2) & 3]);
+          acc[(q + 3) & 3] = fma4(w.w, xv, acc[(q + 3) & 3]);
         } else {
-          acc[q] = fma4(w[0].x, xv, acc[q]);
+          acc[q] = fma4(wscalar, xv, acc[q]);
         }
       }
+    };
+    auto compute = [&](const int s, float4 (&x)[8], const float2& w2) {
+      const float* wsm = wslot0 + s * G * 32;
+      if (BLK == 4) {
+        cp_async_wait<PD - 1>();      // this lane's share of stage s has landed ...
+        __syncwarp();                 // ... and the other lanes' shares
+      }
       if (k < kend) {
+        fma_entry(x, wsm, w2.x);
         ++k;
         flush();
+        if (k < kend) {
+          fma_entry(x + 4, wsm + 16, w2.y);
+          ++k;
+          flush();
+        }
       }
+      if (BLK == 4) __syncwarp();     // everyone has read stage s before its slot is refilled
     };
 
     flush();                                               // leading empty rows
 #pragma unroll
-    for (int s = 0; s < PD; ++s) load(xs[s], ws[s], k + s);
+    for (int s = 0; s < PD; ++s) load(s, xs[s], wv[s], k + 2 * s);
     for (int i = 0; i < n_iter; i += PD) {
 #pragma unroll
       for (int s = 0; s < PD; ++s) {
-        compute(xs[s], ws[s]);
-        load(xs[s], ws[s], k + PD - 1);
+        compute(s, xs[s], wv[s]);
+        load(s, xs[s], wv[s], k + 2 * (PD - 1));
       }
     }
 
-    cp_async_wait_all();          // this lane's share of the index prefetch has landed ...
+    cp_async_wait<0>();           // this lane's share of the index prefetch has landed ...
     __syncwarp();                 // ... and the other lanes'; everyone is done with this tile's bp / bc
     b3 = b3n;
     b2 ^= 1;
@@ -212,43 +253,94 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
 
 namespace {
 
-template <int LPR, int RPG, int BLK, int PD, int MINB>
-int launch_rg(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X, int64_t ldx, float* Y,
-              int64_t ldy, int64_t n_rows, bool elu, cudaStream_t st) {
-  using Gm = Geo<LPR, RPG>;
-  auto kern = elu ? rowgroup_spmm_kernel<LPR, RPG, BLK, true, PD, MINB>
-                  : rowgroup_spmm_kernel<LPR, RPG, BLK, false, PD, MINB>;
-  cudaError_t e;
-  if (Gm::kSmem > 48 * 1024) {
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::kSmem);
-    if (e != cudaSuccess) return (int)e;
-  }
-  int dev = 0, sms = 148, per_sm = 1;
+struct DeviceInfo { int sms; };
+inline DeviceInfo device_info() {
+  int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, Gm::kSmem);
-  if (e != cudaSuccess) return (int)e;
-  if (per_sm < 1) return SN_ERR_UNSUPPORTED;
-  const int64_t n_wtiles = ceil_div(n_rows, Gm::WR);
-  const int64_t ctas = ceil_div(n_wtiles, kWarps);
-  const int64_t grid = ctas < (int64_t)sms * per_sm ? ctas : (int64_t)sms * per_sm;
-  kern<<<(unsigned)grid, kThreads, Gm::kSmem, st>>>(rowptr, colind, val, X, (uint32_t)(ldx * 4), Y,
-                                                    (uint32_t)(ldy * 4), (int)n_rows, (int)n_wtiles);
-  return launch_status();
+  return {sms};
 }
 
-// Small operators get short warp-tiles (more warps busy), large ones long tiles (index staging amortised).
+template <int LPR, int RPG, int BLK, int PD, int MINB>
+struct Launcher {
+  using Gm = Geo<LPR, RPG, BLK, PD>;
+  // persistent warps resident on the device for this instantiation (0: kernel cannot run)
+  static int64_t resident_warps(bool elu, int sms) {
+    // occupancy is a property of (kernel, device model): queried once per process and device ordinal (a benign race:
+    // concurrent first calls compute the same value)
+    static int64_t cached[2][32] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const bool cacheable = dev >= 0 && dev < 32;
+    if (cacheable && cached[elu][dev] != 0) return cached[elu][dev] < 0 ? 0 : cached[elu][dev];
+    const int64_t w = query_resident_warps(elu, sms);
+    if (cacheable) cached[elu][dev] = w > 0 ? w : -1;
+    return w;
+  }
+  static int64_t query_resident_warps(bool elu, int sms) {
+    auto kern = elu ? rowgroup_spmm_kernel<LPR, RPG, BLK, true, PD, MINB>
+                    : rowgroup_spmm_kernel<LPR, RPG, BLK, false, PD, MINB>;
+    if (Gm::kSmem > 48 * 1024 &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::kSmem) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, Gm::kSmem) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    return (int64_t)sms * per_sm * kWarps;
+  }
+  // fraction of the resident warps' time spent on tiles when every warp walks ceil(tiles / warps) of them
+  static double efficiency(int64_t n_rows, int64_t warps) {
+    if (warps <= 0) return 0.0;
+    const int64_t tiles = ceil_div(n_rows, Gm::WR);
+    const int64_t w = tiles < warps ? tiles : warps;
+    return (double)tiles / (double)(ceil_div(tiles, w) * warps);
+  }
+  static int launch(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X, int64_t ldx,
+                    float* Y, int64_t ldy, int64_t n_rows, bool elu, int64_t warps, cudaStream_t st) {
+    if (warps <= 0) return SN_ERR_UNSUPPORTED;
+    auto kern = elu ? rowgroup_spmm_kernel<LPR, RPG, BLK, true, PD, MINB>
+                    : rowgroup_spmm_kernel<LPR, RPG, BLK, false, PD, MINB>;
+    const int64_t n_wtiles = ceil_div(n_rows, Gm::WR);
+    const int64_t ctas = ceil_div(n_wtiles, kWarps);
+    const int64_t grid = ctas < warps / kWarps ? ctas : warps / kWarps;
+    kern<<<(unsigned)grid, kThreads, Gm::kSmem, st>>>(rowptr, colind, val, X, (uint32_t)(ldx * 4), Y,
+                                                      (uint32_t)(ldy * 4), (int)n_rows, (int)n_wtiles);
+    return launch_status();
+  }
+};
+
+// Warp-tile length: long tiles amortise the index staging and the pipeline fill per tile, short tiles keep every
+// persistent warp busy on small operators and shrink the last-wave quantisation (each warp walks an integer number of
+// tiles).  Pick the longest of {4 RS, 2 RS, RS} rows per group whose quantisation efficiency is >= 0.93, else the
+// most efficient one.  tile_mode 1 / 2 / 3 force short / medium / long (benchmarks).
 template <int LPR, int BLK, int PD, int MINB>
 int launch_lpr(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X, int64_t ldx, float* Y,
                int64_t ldy, int64_t n_rows, bool elu, int tile_mode, cudaStream_t st) {
   constexpr int G = 32 / LPR;
   constexpr int RS = G >= 4 ? 1 : 4 / G;      // short tile: >= 4 rows per warp
-  constexpr int RL = 4 * RS;                  // long tile: >= 16 rows per warp
-  const int64_t long_tiles = n_rows / (G * RL);
-  const bool use_long = tile_mode == 2 || (tile_mode == 0 && long_tiles >= 2 * 148 * kWarps * 2);
-  if (use_long)
-    return launch_rg<LPR, RL, BLK, PD, MINB>(rowptr, colind, val, X, ldx, Y, ldy, n_rows, elu, st);
-  return launch_rg<LPR, RS, BLK, PD, MINB>(rowptr, colind, val, X, ldx, Y, ldy, n_rows, elu, st);
+  using LS = Launcher<LPR, RS, BLK, PD, MINB>;
+  using LM = Launcher<LPR, 2 * RS, BLK, PD, MINB>;
+  using LL = Launcher<LPR, 4 * RS, BLK, PD, MINB>;
+  const int sms = device_info().sms;
+  const int64_t ws = LS::resident_warps(elu, sms), wm = LM::resident_warps(elu, sms), wl = LL::resident_warps(elu, sms);
+  int pick = tile_mode;
+  if (pick < 1 || pick > 3) {
+    const double es = LS::efficiency(n_rows, ws), em = LM::efficiency(n_rows, wm), el = LL::efficiency(n_rows, wl);
+    // a tile length only qualifies when it gives every resident warp at least one tile
+    const bool ql = wl > 0 && ceil_div(n_rows, G * 4 * RS) >= wl, qm = wm > 0 && ceil_div(n_rows, G * 2 * RS) >= wm;
+    if (ql && el >= 0.93) pick = 3;
+    else if (qm && em >= 0.93) pick = 2;
+    else if (ql && el >= em && el >= es) pick = 3;
+    else if (qm && em >= es) pick = 2;
+    else pick = 1;
+  }
+  if (pick == 3) return LL::launch(rowptr, colind, val, X, ldx, Y, ldy, n_rows, elu, wl, st);
+  if (pick == 2) return LM::launch(rowptr, colind, val, X, ldx, Y, ldy, n_rows, elu, wm, st);
+  return LS::launch(rowptr, colind, val, X, ldx, Y, ldy, n_rows, elu, ws, st);
 }
 
 template <int BLK>
@@ -256,24 +348,16 @@ int launch_family(const int32_t* rowptr, const int32_t* colind, const float* val
                   float* Y, int64_t ldy, int64_t n_rows, int64_t C, bool elu, int variant, cudaStream_t st) {
   // ldx / ldy in bytes and entry offsets (64 B per block) must fit 32 bits
   if (n_rows >= 0x7fffff00LL || ldx >= (1LL << 30) || ldy >= (1LL << 30)) return SN_ERR_UNSUPPORTED;
-  const int tile_mode = variant == 4 ? 1 : variant == 5 ? 2 : 0;   // 1: force short warp-tiles, 2: force long
+  // tuning variants (tools/spmm_bench.py --variants rgN): 1 / 2 / 3 force short / medium / long warp-tiles,
+  // 4 = one stage in flight and 3 CTAs per SM (C = 128 / 256 only)
+  const int tile_mode = variant >= 1 && variant <= 3 ? variant : 0;
 #define SN_RG(LPR, PD, MINB) launch_lpr<LPR, BLK, PD, MINB>(rowptr, colind, val, X, ldx, Y, ldy, n_rows, elu, tile_mode, st)
   switch (C) {
     case 16: return SN_RG(1, 2, 2);
     case 32: return SN_RG(2, 2, 2);
     case 64: return SN_RG(4, 2, 2);
-    case 128:
-      switch (variant) {           // tuning variants (tools/spmm_bench.py --variants rg1,rg2; rg4 / rg5 force short / long tiles)
-        case 1: return SN_RG(8, 1, 3);
-        case 2: return SN_RG(8, 3, 2);
-        default: return SN_RG(8, 2, 2);
-      }
-    case 256:
-      switch (variant) {
-        case 1: return SN_RG(16, 1, 3);
-        case 2: return SN_RG(16, 3, 2);
-        default: return SN_RG(16, 2, 2);
-      }
+    case 128: return variant == 4 ? SN_RG(8, 1, 3) : SN_RG(8, 2, 2);
+    case 256: return variant == 4 ? SN_RG(16, 1, 3) : SN_RG(16, 2, 2);
     case 512: return SN_RG(32, 2, 2);
     default: return SN_ERR_UNSUPPORTED;
   }
