@@ -110,7 +110,7 @@ int sn_assemble_block_diag(const int64_t* parts, int64_t n_parts, int64_t rows_p
  * in ascending storage order (bit-reproducible run to run).  X and Y must not alias.
  * Both entry points run the row-group kernel (spmm_rowgroup.cu: C/16 lanes own a sparse row and keep the whole 4x4
  * block product in registers, software-pipelined LDG.128 gathers, per-warp index rings in shared memory) for
- * C in {16, 32, 64, 128, 256, 512} with 16-byte aligned operands, and the direct-gather kernels for other widths /
+ * C in {32, 64, 128, 256, 512} with 16-byte aligned operands, and the direct-gather kernels for other widths /
  * alignments.  SN_SPMM_SMEM_STREAM / SN_SPMM_DIRECT_GATHER select the earlier kernels (kept for A/B measurements).
  * ---------------------------------------------------------------------------------------------- */
 int sn_csr_spmm_f32(const int32_t* rowptr, const int32_t* colind, const float* val,

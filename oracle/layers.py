@@ -190,3 +190,31 @@ def lap_encoder(P, inputs, L, mask, training=True):
     x = F.elu(graph_conv1x1(F.elu(x), _sub(P, "bn_conv2."), "pre", training))
     x = global_average(x, mask).squeeze()
     return F.linear(x, P["fc_mu.weight"], P["fc_mu.bias"]), F.linear(x, P["fc_logvar.weight"], P["fc_logvar.bias"])
+
+
+def dc_dir_model(P, Di, DiA, mask, inputs, layers, training=True):
+    """dense_correspondence DirModel.forward, src/dense_correspondence/models.py:161-182 (2-D block-diagonal operators)."""
+    b = inputs.shape[0]
+    v = graph_conv1x1(inputs, _sub(P, "conv1."))
+    f = v.new_zeros(b, DiA.shape[-1] // 4 // b, 128)
+    for i in range(layers):
+        Pi = _sub(P, "rn%d." % i)
+        if i % 2 == 0:
+            v, f = dir_resnet2(Pi, Di, DiA, v, f, training)
+        else:
+            v = avg_resnet2(Pi, mask, v, training)
+    x = graph_conv1x1(F.elu(v), _sub(P, "conv2."), "pre", training)
+    return x + inputs[:, :, -3:].repeat(1, 1, 40)
+
+
+def siamese(P, op_a, op_b, input_a, input_b, layers, tower="dirac", training=True):
+    """dense_correspondence SiameseModel.forward, src/dense_correspondence/models.py:199-203: shared tower on both
+    shapes, then torch.bmm(FA, FB^T).  BatchNorm running statistics are not tracked by this functional restatement."""
+    Pm = _sub(P, "model.")
+    if tower == "dirac":
+        FA = dc_dir_model(Pm, *op_a, input_a, layers, training)
+        FB = dc_dir_model(Pm, *op_b, input_b, layers, training)
+    else:
+        FA = arap_lap_model(Pm, *op_a, input_a, layers, training)
+        FB = arap_lap_model(Pm, *op_b, input_b, layers, training)
+    return torch.bmm(FA, FB.transpose(1, 2))

@@ -49,13 +49,13 @@ __device__ __forceinline__ const char* ptr_mad(const char* base, uint32_t a, uin
   return reinterpret_cast<const char*>(r);
 }
 
-template <int LPR, int RPG, int BLK, int PD>
+template <int LPR, int RPG, int BLK, int PD, int EPS>
 struct Geo {
   static constexpr int G = 32 / LPR;        // row groups per warp
   static constexpr int WR = G * RPG;        // rows per warp-tile
   static constexpr int CAP = WR * 10;       // staged column indices (and CSR values) per warp-tile (excess: global loads)
   static constexpr int BPS = WR + 4;        // ints per row-pointer buffer (WR + 1 used, +1 read past the end)
-  static constexpr int WRING = BLK == 4 ? PD * G * 32 : 0;      // floats: PD stages x G groups x one pair of blocks
+  static constexpr int WRING = BLK == 4 ? PD * G * 16 * EPS : 0;   // floats: PD stages x G groups x EPS blocks
   static constexpr int WARP_WORDS = ((WRING + 3 * BPS + 2 * CAP + (BLK == 1 ? 2 * CAP : 0)) + 3) / 4 * 4;
   static constexpr size_t kSmem = (size_t)kWarps * WARP_WORDS * 4;
 };
@@ -63,14 +63,14 @@ struct Geo {
 }  // namespace
 
 // LPR lanes per row (C = 16 LPR); RPG rows per row group per warp-tile; BLK = 4: BSR4 (16 values per entry, rotated
-// column-major, see sn_csr32_to_bsr4_fill), BLK = 1: CSR (one value per entry); PD = pipeline depth in stages of TWO
-// entries per row group; MINB = CTAs per SM the register allocation is tuned for.
-template <int LPR, int RPG, int BLK, bool ELU, int PD, int MINB>
+// column-major, see sn_csr32_to_bsr4_fill), BLK = 1: CSR (one value per entry); PD = pipeline depth in stages of EPS
+// consecutive entries per row group; MINB = CTAs per SM the register allocation is tuned for.
+template <int LPR, int RPG, int BLK, bool ELU, int PD, int EPS, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB)
 rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
                      const float* __restrict__ val, const float* __restrict__ X, uint32_t ldxb,
                      float* __restrict__ Y, uint32_t ldyb, int n_rows, int n_wtiles) {
-  using Gm = Geo<LPR, RPG, BLK, PD>;
+  using Gm = Geo<LPR, RPG, BLK, PD, EPS>;
   constexpr int C = 16 * LPR;
   constexpr int kQuarterBytes = C;             // (C/4 floats) * 4 bytes
   constexpr int G = Gm::G, WR = Gm::WR, CAP = Gm::CAP, BPS = Gm::BPS;
@@ -78,7 +78,7 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* wbase = smem_i + warp * Gm::WARP_WORDS;
-  float* wring = reinterpret_cast<float*>(wbase);        // [PD][G][32]   (BSR4 only; 16-byte aligned)
+  float* wring = reinterpret_cast<float*>(wbase);        // [PD][G][16 EPS]   (BSR4 only; 16-byte aligned)
   int* bp_buf = wbase + Gm::WRING;                       // [3][BPS]
   int* bc_buf = bp_buf + 3 * BPS;                        // [2][CAP]
   float* bv_buf = reinterpret_cast<float*>(bc_buf + 2 * CAP);   // [2][CAP]  (CSR only)
@@ -86,7 +86,8 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
   const char* Xl = reinterpret_cast<const char*>(X) + t * 16;   // this lane's float4 of quarter 0 of every row
   char* Yl = reinterpret_cast<char*>(Y) + t * 16;
   const char* vbase = reinterpret_cast<const char*>(val);
-  const float* wslot0 = wring + g * 32;                  // this group's pair in stage 0
+  constexpr int kSlot = G * 16 * EPS;                    // floats per stage of the value ring
+  const float* wslot0 = wring + g * 16 * EPS;            // this group's blocks in stage 0
   const int wstride = gridDim.x * kWarps;
   int wt = blockIdx.x * kWarps + warp;
   if (wt >= n_wtiles) return;                    // warps never synchronise with each other
@@ -119,13 +120,14 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
   cp_async_wait<0>();
   __syncwarp();
 
-  float4 xs[PD][8];        // gathered rows of the two entries of each stage in flight
-  float2 wv[PD];           // CSR: their two values
+  float4 xs[PD][4 * EPS];  // gathered rows of the EPS entries of each stage in flight
+  float wv[PD][EPS];       // CSR: their values
 #pragma unroll
   for (int s = 0; s < PD; ++s) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) xs[s][q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    wv[s] = make_float2(0.f, 0.f);
+    for (int q = 0; q < 4 * EPS; ++q) xs[s][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int e = 0; e < EPS; ++e) wv[s][e] = 0.f;
   }
 
   int b3 = 0, b2 = 0;    // ring positions: row-pointer buffer (mod 3) and column-index buffer (mod 2) of this tile
@@ -143,7 +145,7 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
     const int rl0 = g * RPG;                                // the group's first row inside the warp-tile
     const int kend = bp[rl0 + RPG];
     int k = bp[rl0];                                        // next entry to accumulate
-    const int n_iter = __reduce_max_sync(0xffffffffu, (kend - k + 1) >> 1);   // stages of two entries
+    const int n_iter = __reduce_max_sync(0xffffffffu, (kend - k + EPS - 1) / EPS);   // stages of EPS entries
     int r = 0;                                              // row inside the group
     int next_end = bp[rl0 + 1];
     const uint32_t grow0 = (uint32_t)wt * WR + rl0;
@@ -167,37 +169,32 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
         next_end = bp[rl0 + r + 1];
       }
     };
-    // stage s <- entries kk, kk + 1 of this group's run: X rows to registers; BSR4 values (one 128-byte pair per
-    // group) to the shared-memory ring with 16-byte cp.async, CSR values from the staged tile ring
-    auto load = [&](const int s, float4 (&x)[8], float2& w2, int kk) {
-      if (kk < kend) {
-        const int rel = kk - k0;
-        const int j0 = rel < CAP ? bc[rel] : __ldg(colind + kk);
-        const char* xp0 = ptr_mad(Xl, (uint32_t)j0, ldxb);
+    // stage s <- entries kk .. kk + EPS - 1 of this group's run: X rows to registers; BSR4 values (64 bytes per
+    // entry) to the shared-memory ring with 16-byte cp.async, CSR values from the staged tile ring
+    auto load = [&](const int s, float4 (&x)[4 * EPS], float (&w)[EPS], int kk) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) x[q] = __ldg(reinterpret_cast<const float4*>(xp0 + q * kQuarterBytes));
-        if (BLK == 4) {
-          const uint32_t dst = smem_u32(wslot0 + s * G * 32);
-          const char* src = ptr_mad(vbase, (uint32_t)kk, 64u);
+      for (int e = 0; e < EPS; ++e) {
+        if (kk + e < kend) {
+          const int rel = kk + e - k0;
+          const int j = rel < CAP ? bc[rel] : __ldg(colind + kk + e);
+          const char* xp = ptr_mad(Xl, (uint32_t)j, ldxb);
 #pragma unroll
-          for (int u0 = 0; u0 < 8; u0 += LPR) {
-            const int u = u0 + t;                           // 16-byte unit of the pair this lane copies
-            if (u < 8 && kk + (u >> 2) < kend)
-              asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + u * 16), "l"(src + u * 16)
-                           : "memory");
-          }
-        } else {
-          w2.x = rel < CAP ? bv[rel] : __ldg(val + kk);
-        }
-        if (kk + 1 < kend) {
-          const int j1 = rel + 1 < CAP ? bc[rel + 1] : __ldg(colind + kk + 1);
-          const char* xp1 = ptr_mad(Xl, (uint32_t)j1, ldxb);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) x[4 + q] = __ldg(reinterpret_cast<const float4*>(xp1 + q * kQuarterBytes));
-          if (BLK == 1) w2.y = rel + 1 < CAP ? bv[rel + 1] : __ldg(val + kk + 1);
+          for (int q = 0; q < 4; ++q) x[4 * e + q] = __ldg(reinterpret_cast<const float4*>(xp + q * kQuarterBytes));
+          if (BLK == 1) w[e] = rel < CAP ? bv[rel] : __ldg(val + kk + e);
         }
       }
-      if (BLK == 4) cp_async_commit();                      // every lane, every call: uniform group counting
+      if (BLK == 4) {
+        const uint32_t dst = smem_u32(wslot0 + s * kSlot);
+        const char* src = ptr_mad(vbase, (uint32_t)kk, 64u);
+#pragma unroll
+        for (int u0 = 0; u0 < 4 * EPS; u0 += LPR) {
+          const int u = u0 + t;                             // 16-byte unit of the stage this lane copies
+          if (u < 4 * EPS && kk + (u >> 2) < kend)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + u * 16), "l"(src + u * 16)
+                         : "memory");
+        }
+        cp_async_commit();                                  // every lane, every call: uniform group counting
+      }
     };
     auto fma_entry = [&](const float4* x, const float* wsm, float wscalar) {
 #pragma unroll
@@ -214,18 +211,16 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
         }
       }
     };
-    auto compute = [&](const int s, float4 (&x)[8], const float2& w2) {
-      const float* wsm = wslot0 + s * G * 32;
+    auto compute = [&](const int s, float4 (&x)[4 * EPS], const float (&w)[EPS]) {
+      const float* wsm = wslot0 + s * kSlot;
       if (BLK == 4) {
         cp_async_wait<PD - 1>();      // this lane's share of stage s has landed ...
         __syncwarp();                 // ... and the other lanes' shares
       }
-      if (k < kend) {
-        fma_entry(x, wsm, w2.x);
-        ++k;
-        flush();
-        if (k < kend) {
-          fma_entry(x + 4, wsm + 16, w2.y);
+#pragma unroll
+      for (int e = 0; e < EPS; ++e) {
+        if (k < kend) {               // a run that ends inside the stage skips the remaining entries
+          fma_entry(x + 4 * e, wsm + 16 * e, w[e]);
           ++k;
           flush();
         }
@@ -235,12 +230,12 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
 
     flush();                                               // leading empty rows
 #pragma unroll
-    for (int s = 0; s < PD; ++s) load(s, xs[s], wv[s], k + 2 * s);
+    for (int s = 0; s < PD; ++s) load(s, xs[s], wv[s], k + EPS * s);
     for (int i = 0; i < n_iter; i += PD) {
 #pragma unroll
       for (int s = 0; s < PD; ++s) {
         compute(s, xs[s], wv[s]);
-        load(s, xs[s], wv[s], k + 2 * (PD - 1));
+        load(s, xs[s], wv[s], k + EPS * (PD - 1));
       }
     }
 
@@ -261,9 +256,9 @@ inline DeviceInfo device_info() {
   return {sms};
 }
 
-template <int LPR, int RPG, int BLK, int PD, int MINB>
+template <int LPR, int RPG, int BLK, int PD, int EPS, int MINB>
 struct Launcher {
-  using Gm = Geo<LPR, RPG, BLK, PD>;
+  using Gm = Geo<LPR, RPG, BLK, PD, EPS>;
   // persistent warps resident on the device for this instantiation (0: kernel cannot run)
   static int64_t resident_warps(bool elu, int sms) {
     // occupancy is a property of (kernel, device model): queried once per process and device ordinal (a benign race:
@@ -278,8 +273,8 @@ struct Launcher {
     return w;
   }
   static int64_t query_resident_warps(bool elu, int sms) {
-    auto kern = elu ? rowgroup_spmm_kernel<LPR, RPG, BLK, true, PD, MINB>
-                    : rowgroup_spmm_kernel<LPR, RPG, BLK, false, PD, MINB>;
+    auto kern = elu ? rowgroup_spmm_kernel<LPR, RPG, BLK, true, PD, EPS, MINB>
+                    : rowgroup_spmm_kernel<LPR, RPG, BLK, false, PD, EPS, MINB>;
     if (Gm::kSmem > 48 * 1024 &&
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::kSmem) != cudaSuccess) {
       cudaGetLastError();
@@ -302,8 +297,8 @@ struct Launcher {
   static int launch(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X, int64_t ldx,
                     float* Y, int64_t ldy, int64_t n_rows, bool elu, int64_t warps, cudaStream_t st) {
     if (warps <= 0) return SN_ERR_UNSUPPORTED;
-    auto kern = elu ? rowgroup_spmm_kernel<LPR, RPG, BLK, true, PD, MINB>
-                    : rowgroup_spmm_kernel<LPR, RPG, BLK, false, PD, MINB>;
+    auto kern = elu ? rowgroup_spmm_kernel<LPR, RPG, BLK, true, PD, EPS, MINB>
+                    : rowgroup_spmm_kernel<LPR, RPG, BLK, false, PD, EPS, MINB>;
     const int64_t n_wtiles = ceil_div(n_rows, Gm::WR);
     const int64_t ctas = ceil_div(n_wtiles, kWarps);
     const int64_t grid = ctas < warps / kWarps ? ctas : warps / kWarps;
@@ -317,14 +312,14 @@ struct Launcher {
 // persistent warp busy on small operators and shrink the last-wave quantisation (each warp walks an integer number of
 // tiles).  Pick the longest of {4 RS, 2 RS, RS} rows per group whose quantisation efficiency is >= 0.93, else the
 // most efficient one.  tile_mode 1 / 2 / 3 force short / medium / long (benchmarks).
-template <int LPR, int BLK, int PD, int MINB>
+template <int LPR, int BLK, int PD, int EPS, int MINB>
 int launch_lpr(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X, int64_t ldx, float* Y,
                int64_t ldy, int64_t n_rows, bool elu, int tile_mode, cudaStream_t st) {
   constexpr int G = 32 / LPR;
   constexpr int RS = G >= 4 ? 1 : 4 / G;      // short tile: >= 4 rows per warp
-  using LS = Launcher<LPR, RS, BLK, PD, MINB>;
-  using LM = Launcher<LPR, 2 * RS, BLK, PD, MINB>;
-  using LL = Launcher<LPR, 4 * RS, BLK, PD, MINB>;
+  using LS = Launcher<LPR, RS, BLK, PD, EPS, MINB>;
+  using LM = Launcher<LPR, 2 * RS, BLK, PD, EPS, MINB>;
+  using LL = Launcher<LPR, 4 * RS, BLK, PD, EPS, MINB>;
   const int sms = device_info().sms;
   const int64_t ws = LS::resident_warps(elu, sms), wm = LM::resident_warps(elu, sms), wl = LL::resident_warps(elu, sms);
   int pick = tile_mode;
@@ -348,25 +343,37 @@ int launch_family(const int32_t* rowptr, const int32_t* colind, const float* val
                   float* Y, int64_t ldy, int64_t n_rows, int64_t C, bool elu, int variant, cudaStream_t st) {
   // ldx / ldy in bytes and entry offsets (64 B per block) must fit 32 bits
   if (n_rows >= 0x7fffff00LL || ldx >= (1LL << 30) || ldy >= (1LL << 30)) return SN_ERR_UNSUPPORTED;
-  // tuning variants (tools/spmm_bench.py --variants rgN): 1 / 2 / 3 force short / medium / long warp-tiles,
-  // 4 = one stage in flight and 3 CTAs per SM (C = 128 / 256 only)
+  // tuning variants (tools/spmm_bench.py --variants rgN): 1 / 2 / 3 force short / medium / long warp-tiles;
+  // 4 ... 9 (C = 128 / 256 only) change the pipeline shape: (stages in flight, entries per stage, CTAs per SM)
   const int tile_mode = variant >= 1 && variant <= 3 ? variant : 0;
-#define SN_RG(LPR, PD, MINB) launch_lpr<LPR, BLK, PD, MINB>(rowptr, colind, val, X, ldx, Y, ldy, n_rows, elu, tile_mode, st)
+#define SN_RG(LPR, PD, EPS, MINB) \
+  launch_lpr<LPR, BLK, PD, EPS, MINB>(rowptr, colind, val, X, ldx, Y, ldy, n_rows, elu, tile_mode, st)
+#define SN_RG_TUNE(LPR)                          \
+  switch (variant) {                             \
+    case 4: return SN_RG(LPR, 2, 2, 2);          \
+    case 5: return SN_RG(LPR, 1, 1, 4);          \
+    case 6: return SN_RG(LPR, 2, 1, 3);          \
+    case 7: return SN_RG(LPR, 3, 1, 2);          \
+    case 8: return SN_RG(LPR, 2, 1, 4);          \
+    case 9: return SN_RG(LPR, 3, 1, 3);          \
+    default: return SN_RG(LPR, 1, 2, 3);         \
+  }
   switch (C) {
-    case 16: return SN_RG(1, 2, 2);
-    case 32: return SN_RG(2, 2, 2);
-    case 64: return SN_RG(4, 2, 2);
-    case 128: return variant == 4 ? SN_RG(8, 1, 3) : SN_RG(8, 2, 2);
-    case 256: return variant == 4 ? SN_RG(16, 1, 3) : SN_RG(16, 2, 2);
-    case 512: return SN_RG(32, 2, 2);
+    case 32: return SN_RG(2, 1, 2, 3);
+    case 64: return SN_RG(4, 1, 2, 3);
+    case 128: SN_RG_TUNE(8)
+    case 256: SN_RG_TUNE(16)
+    case 512: return SN_RG(32, 1, 2, 3);
     default: return SN_ERR_UNSUPPORTED;
   }
+#undef SN_RG_TUNE
 #undef SN_RG
 }
 
 }  // namespace
 
-// Both return SN_ERR_UNSUPPORTED when the kernel does not apply (C not in {16,...,512}); callers fall back.
+// Both return SN_ERR_UNSUPPORTED when the kernel does not apply (C not in {32,...,512}); callers fall back to the
+// direct-gather kernels (at C = 16 a row is one 64-byte segment and a lane per row has nothing left to share).
 int launch_bsr4_rowgroup(const int32_t* browptr, const int32_t* bcolind, const float* bval, const float* X,
                          int64_t ldx, float* Y, int64_t ldy, int64_t n_brows, int64_t C, bool elu, int variant,
                          cudaStream_t st) {

@@ -6,6 +6,9 @@ kernels see.  Same constructor arguments, ``forward`` signatures and ``state_dic
         src/as_rigid_as_possible/models.py:21-52 (Model), :108-152 (DirModel), :54-78, :80-105
     LapEncoder                      src/mesh_mnist/models_vae.py:22-51   (5 x LapResNet2(128), cfg2)
     DirDeepModel                    src/normal_predict/models.py:234-280 (30-block Dirac stack)
+    DcLapModel / DcDirModel / SiameseModel
+        src/dense_correspondence/models.py:21-48 (Model), :140-182 (DirModel), :184-203 (SiameseModel: the
+        FA . FB^T correlation of BASELINE cfg5)
     LapResNet2General               src/normal_predict/models.py:447-477 (_LapResNet2: inner_layers, in != out)
 
 Everything here is a thin loop over ``utils_pt`` blocks; the arithmetic lives in libsurfnet_b200.
@@ -20,7 +23,8 @@ from . import ops
 from . import utils_pt as utils
 from .operators import as_bsr4, as_csr
 
-__all__ = ["ArapLapModel", "ArapDirModel", "ArapAvgModel", "ArapMlpModel", "LapEncoder", "DirDeepModel", "LapResNet2General", "arap_loss"]
+__all__ = ["ArapLapModel", "ArapDirModel", "ArapAvgModel", "ArapMlpModel", "LapEncoder", "DirDeepModel", "LapResNet2General", "DcLapModel",
+           "DcDirModel", "SiameseModel", "arap_loss"]
 
 
 def _add_blocks(model, kinds, width):
@@ -195,3 +199,70 @@ class DirDeepModel(nn.Module):
         own = self.state_dict()
         own.update({k: v for k, v in pre_dict.items() if k in own})
         self.load_state_dict(own)
+
+
+class DcLapModel(nn.Module):
+    """dense_correspondence ``Model(layer)`` (models.py:21-48): conv1(3->128), Lap / Avg blocks, conv2(128->120)."""
+
+    def __init__(self, layer):
+        super().__init__()
+        self.conv1 = utils.GraphConv1x1(3, 128, batch_norm=None)
+        self.layer = layer
+        _add_blocks(self, [utils.LapResNet2 if i % 2 == 0 else utils.AvgResNet2 for i in range(layer)], 128)
+        self.conv2 = utils.GraphConv1x1(128, 120, batch_norm="pre")
+
+    def forward(self, L, mask, inputs):
+        Lop = L if isinstance(L, torch.Tensor) and L.layout == torch.strided else as_csr(L)
+        x = self.conv1(inputs)
+        for i in range(self.layer):
+            x = self._modules["rn{}".format(i)](Lop, mask, x)
+        return self.conv2(F.elu(x)) + _last3_tiled(inputs, 40)
+
+
+class DcDirModel(nn.Module):
+    """dense_correspondence ``DirModel(layer)`` (models.py:140-182).  The reference reads the face count from
+    ``DiA.size(2)`` (:166), which only exists for 3-D operators whose DirResNet2 branch is dead (SURVEY appendix A);
+    here 2-D block-diagonal and 3-D operators both work."""
+
+    def __init__(self, layer):
+        super().__init__()
+        self.conv1 = utils.GraphConv1x1(3, 128, batch_norm=None)
+        self.layer = layer
+        _add_blocks(self, [utils.DirResNet2 if i % 2 == 0 else utils.AvgResNet2 for i in range(layer)], 128)
+        self.do = nn.Dropout2d()  # declared and unused by the reference
+        self.conv2 = utils.GraphConv1x1(128, 120, batch_norm="pre")
+
+    def forward(self, Di, DiA, mask, inputs):
+        batch_size = inputs.size(0)
+        D, DA = as_bsr4(Di), as_bsr4(DiA)
+        v = self.conv1(inputs)
+        f = v.new_zeros(batch_size, DA.n_bcols // batch_size, 128)
+        for i in range(self.layer):
+            if i % 2 == 0:
+                v, f = self._modules["rn{}".format(i)](D, DA, v, f)
+            else:
+                v = self._modules["rn{}".format(i)](None, mask, v)
+        return self.conv2(F.elu(v)) + _last3_tiled(inputs, 40)
+
+
+class SiameseModel(nn.Module):
+    """dense_correspondence ``SiameseModel(model, layer)`` (models.py:184-203): one shared tower applied to both shapes,
+    then the all-pairs feature correlation ``FA @ FB^T`` ([B, Na, 120] x [B, 120, Nb] -> [B, Na, Nb]).
+
+    The towers run on the libsurfnet_b200 kernels.  The correlation is a plain dense GEMM whose cost is writing the
+    Na x Nb result (196 MB per 7000-vertex pair, ~30 us of HBM time against 11.8 GFLOP): it stays on cuBLAS
+    (``torch.bmm``), like the reference (:203)."""
+
+    def __init__(self, model="dirac", layer=15):
+        super().__init__()
+        if "dir" in model:
+            self.model = DcDirModel(layer)
+        elif "lap" in model:
+            self.model = DcLapModel(layer)
+        else:
+            raise ValueError("SiameseModel: supported towers are 'dirac' and 'lap', got %r" % (model,))
+
+    def forward(self, OperationA, OperationB, inputA, inputB):
+        FA = self.model(*OperationA, inputA)
+        FB = self.model(*OperationB, inputB)
+        return torch.bmm(FA, FB.transpose(1, 2))

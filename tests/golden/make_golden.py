@@ -94,6 +94,9 @@ def run_block(module, args, tensor_inputs, out_weights):
 
 
 def save(name, **arrays):
+    only = os.environ.get("SN_GOLDEN_ONLY")          # e.g. SN_GOLDEN_ONLY=siamese.npz: leave the other files untouched
+    if only and name not in only.split(","):
+        return
     path = os.path.join(HERE, name)
     np.savez_compressed(path, **arrays)
     print("wrote %-22s %7.1f kB  (%d arrays)" % (name, os.path.getsize(path) / 1e3, len(arrays)))
@@ -291,6 +294,17 @@ def main():
     # mesh_mnist VAE LapEncoder (models_vae.py:22-51), 5 x LapResNet2(128)
     both_precisions(lambda: vae_models.LapEncoder(), 14, (x3, Lb, mask), "lapencoder")
     save("callers.npz", **arrays)
+
+    # ------------------------------------------------------------------ dense_correspondence SiameseModel (8(f) f4)
+    # models.py:184-203: shared tower on both shapes + torch.bmm(FA, FB^T).  Only the 'lap' tower runs in the
+    # reference (the Dirac tower reads DiA.size(2) on a 2-D operator).
+    dc_models = load("ref_dc_models", os.path.join(REF_SRC, "dense_correspondence", "models.py"))
+    arrays = {}
+    xb3 = det_tensor((B, nv, 3), 63) * mask
+    arrays["xa"], arrays["xb"] = x3.numpy(), xb3.numpy()
+    both_precisions(lambda: dc_models.SiameseModel("lap", 3), 16, ((Lb, mask), (Lb, mask), x3, xb3), "siamese_lap3")
+    both_precisions(lambda: dc_models.Model(5), 17, (Lb, mask, x3), "dclap5")
+    save("siamese.npz", **arrays)
 
 
 if __name__ == "__main__":
