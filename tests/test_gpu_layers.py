@@ -238,3 +238,30 @@ def test_other_callers(golden, batch):
         mu, lv = m(x3, B["L"], B["mask"])
         close(mu.cpu().numpy(), d["lapencoder/out0"], "lapencoder mu", 5e-4)
         close(lv.cpu().numpy(), d["lapencoder/out1"], "lapencoder logvar", 5e-4)
+
+
+def test_dense_correspondence_siamese(golden, batch):
+    """dense_correspondence Model(5) and SiameseModel('lap', 3) (shared tower + FA . FB^T) against the
+    reference's outputs (tests/golden/siamese.npz); the Dirac tower -- which the reference cannot run on 2-D operators
+    (appendix A) -- against the oracle restatement.  Tolerance 5e-4 * (|ref| + max|ref|)."""
+    from oracle import layers as O
+    from surfacenetworks_b200 import models as M
+    B, d = batch, golden("siamese")
+    xa, xb = torch.from_numpy(d["xa"]).to(DEV), torch.from_numpy(d["xb"]).to(DEV)
+    with torch.no_grad():
+        m = det_fill(M.DcLapModel(5), 17, gain=0.25).to(DEV).train()
+        close(m(B["L"], B["mask"], xa).cpu().numpy(), d["dclap5/out0"], "dc Model(5)", 5e-4)
+        m = det_fill(M.SiameseModel("lap", 3), 16, gain=0.25).to(DEV).train()
+        out = m((B["L"], B["mask"]), (B["L"], B["mask"]), xa, xb)
+        assert tuple(out.shape) == (xa.shape[0], xa.shape[1], xb.shape[1])
+        close(out.cpu().numpy(), d["siamese_lap3/out0"], "siamese lap3", 5e-4)
+        # Dirac tower: oracle restatement on the CPU with the same parameters
+        m = det_fill(M.SiameseModel("dirac", 3), 18, gain=0.25)
+        P = {k: v.clone() for k, v in m.state_dict().items()}
+        ops_cpu = (B["Di"].cpu(), B["DiA"].cpu(), B["mask"].cpu())
+        ref = O.siamese(P, ops_cpu, ops_cpu, xa.cpu(), xb.cpu(), 3, "dirac")
+        m = m.to(DEV).train()
+        ops_gpu = (B["Di"], B["DiA"], B["mask"])
+        close(m(ops_gpu, ops_gpu, xa, xb).cpu().numpy(), ref.numpy(), "siamese dirac3 vs oracle", 5e-4)
+    with pytest.raises(ValueError):
+        M.SiameseModel("gat")

@@ -239,3 +239,16 @@ def test_other_callers(golden, batch):
         mu, lv = O.lap_encoder(P, x3, B["L"], B["mask"])
         assert_close(mu.numpy(), d["lapencoder/out0"], 2e-5, 2e-5, "lapencoder mu")
         assert_close(lv.numpy(), d["lapencoder/out1"], 2e-5, 2e-5, "lapencoder logvar")
+
+
+def test_dense_correspondence_siamese(golden, batch):
+    """dense_correspondence Model(5) and SiameseModel('lap', 3) (models.py:21-48,184-203): oracle vs the reference."""
+    B, d = batch, golden("siamese")
+    xa, xb = torch.from_numpy(d["xa"]), torch.from_numpy(d["xb"])
+    with torch.no_grad():
+        P = params_of(M.DcLapModel(5), 17, 0.25)
+        assert_close(O.arap_lap_model(P, B["L"], B["mask"], xa, 5).numpy(), d["dclap5/out0"], 2e-5, 2e-5, "dc Model(5)")
+        P = params_of(M.SiameseModel("lap", 3), 16, 0.25)
+        out = O.siamese(P, (B["L"], B["mask"]), (B["L"], B["mask"]), xa, xb, 3, "lap")
+        scale = float(np.abs(d["siamese_lap3/out0"]).max())
+        assert_close(out.numpy(), d["siamese_lap3/out0"], 1e-4, 1e-5 * scale, "siamese lap3")
