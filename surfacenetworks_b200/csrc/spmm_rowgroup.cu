@@ -344,26 +344,24 @@ int launch_family(const int32_t* rowptr, const int32_t* colind, const float* val
   // ldx / ldy in bytes and entry offsets (64 B per block) must fit 32 bits
   if (n_rows >= 0x7fffff00LL || ldx >= (1LL << 30) || ldy >= (1LL << 30)) return SN_ERR_UNSUPPORTED;
   // tuning variants (tools/spmm_bench.py --variants rgN): 1 / 2 / 3 force short / medium / long warp-tiles;
-  // 4 ... 9 (C = 128 / 256 only) change the pipeline shape: (stages in flight, entries per stage, CTAs per SM)
+  // 4 / 5 (C = 128 / 256 only) change the pipeline shape (stages in flight, entries per stage, CTAs per SM).
+  // Measured on B200 at 64 x 2000 V (profiles/r1_spmm_rowgroup_notes.md): occupancy beats per-warp prefetch depth --
+  // (1, 1, 4) = 32 warps per SM with one entry in flight per row group is the fastest shape at every width.
   const int tile_mode = variant >= 1 && variant <= 3 ? variant : 0;
 #define SN_RG(LPR, PD, EPS, MINB) \
   launch_lpr<LPR, BLK, PD, EPS, MINB>(rowptr, colind, val, X, ldx, Y, ldy, n_rows, elu, tile_mode, st)
 #define SN_RG_TUNE(LPR)                          \
   switch (variant) {                             \
-    case 4: return SN_RG(LPR, 2, 2, 2);          \
-    case 5: return SN_RG(LPR, 1, 1, 4);          \
-    case 6: return SN_RG(LPR, 2, 1, 3);          \
-    case 7: return SN_RG(LPR, 3, 1, 2);          \
-    case 8: return SN_RG(LPR, 2, 1, 4);          \
-    case 9: return SN_RG(LPR, 3, 1, 3);          \
-    default: return SN_RG(LPR, 1, 2, 3);         \
+    case 4: return SN_RG(LPR, 1, 2, 3);          \
+    case 5: return SN_RG(LPR, 2, 1, 3);          \
+    default: return SN_RG(LPR, 1, 1, 4);         \
   }
   switch (C) {
-    case 32: return SN_RG(2, 1, 2, 3);
-    case 64: return SN_RG(4, 1, 2, 3);
+    case 32: return SN_RG(2, 1, 1, 4);
+    case 64: return SN_RG(4, 1, 1, 4);
     case 128: SN_RG_TUNE(8)
     case 256: SN_RG_TUNE(16)
-    case 512: return SN_RG(32, 1, 2, 3);
+    case 512: return SN_RG(32, 1, 1, 4);
     default: return SN_ERR_UNSUPPORTED;
   }
 #undef SN_RG_TUNE

@@ -191,7 +191,7 @@ def test_csr_feature_widths_and_strides(C):
     y = op.apply(xg)
     within_bound(y.cpu().numpy(), y64, bound, "contiguous")
     within_bound(op.apply(xg, direct_gather=True).cpu().numpy(), y64, bound, "direct-gather kernel")
-    for variant in (1, 2, 3, 4, 5, 6, 7, 8, 9):        # tuning variants of the row-group kernel share its summation order
+    for variant in (1, 2, 3, 4, 5):        # tuning variants of the row-group kernel share its summation order
         assert torch.equal(y, op.apply(xg, variant=variant)), "row-group variant %d" % variant
     Z = torch.zeros(n, 2 * C + 4, device=DEV)
     Z[:, :C] = xg
@@ -214,7 +214,7 @@ def test_bsr4_feature_widths_and_strides(golden, C):
     y64, bound = c_oracle.dirac_view_mm_f64(idx[0], idx[1], val, 2 * nf, x)
     y = Di.apply(xg)
     within_bound(y.cpu().numpy(), y64, bound, "contiguous")
-    for variant in (1, 2, 3, 4, 5, 6, 7, 8, 9):        # tuning variants of the row-group kernel share its summation order
+    for variant in (1, 2, 3, 4, 5):        # tuning variants of the row-group kernel share its summation order
         assert torch.equal(y, Di.apply(xg, variant=variant)), "row-group variant %d" % variant
     # cp.async streaming kernel (C = 128/256/512) and direct-gather kernel use the same summation order: bit-identical
     yd = Di.apply(xg, direct_gather=True)
@@ -255,7 +255,7 @@ def test_rowgroup_long_rows_and_empty_runs(C):
     y64, bound = c_oracle.coo_mm_f64(row, col, val, n_rows, x)
     y = op.apply(xg)
     within_bound(y.cpu().numpy(), y64, bound, "csr rowgroup")
-    for variant in (1, 2, 3, 4, 5, 6, 7, 8, 9):
+    for variant in (1, 2, 3, 4, 5):
         assert torch.equal(y, op.apply(xg, variant=variant)), "csr variant %d" % variant
     # the same pattern as 4x4 blocks (dense random blocks): block row r has lens[r] blocks
     blk = rng.standard_normal((row.size, 4, 4)).astype(np.float32)
@@ -268,7 +268,7 @@ def test_rowgroup_long_rows_and_empty_runs(C):
     y = opb.apply(xg)
     within_bound(y.cpu().numpy(), y64, bound, "bsr4 rowgroup")
     within_bound(opb.apply(xg, direct_gather=True).cpu().numpy(), y64, bound, "bsr4 direct")
-    for variant in (1, 2, 3, 4, 5, 6, 7, 8, 9):
+    for variant in (1, 2, 3, 4, 5):
         assert torch.equal(y, opb.apply(xg, variant=variant)), "bsr4 variant %d" % variant
 
 
@@ -351,7 +351,7 @@ def test_mesh_operators_vs_oracle(V, B, C):
             yd = op.apply(ing, direct_gather=True)
             within_bound(yd.cpu().numpy(), y64, bound, "direct-gather kernel")
             assert torch.equal(yd, op.apply(ing, smem_stream=True)), "streaming vs direct-gather kernel"
-            for variant in (1, 2, 3, 4, 5, 6, 7, 8, 9):
+            for variant in (1, 2, 3, 4, 5):
                 assert torch.equal(y, op.apply(ing, variant=variant)), "row-group variant %d" % variant
             within_bound(op.T.apply(y).cpu().numpy(), *c_oracle.dirac_view_mm_f64(idx[1], idx[0], val, S.shape[1] // 4, y.cpu().numpy()), "bsr4^T")
         # the reference's own path on the same inputs (CPU torch.mm) obeys the same bound
@@ -391,7 +391,7 @@ def test_full_size_properties():
         Sx = op.apply(x)
         # row-group kernel vs the direct-gather kernel (validated against the oracle at the smaller sizes above)
         assert torch.all((Sx - op.apply(x, direct_gather=True)).abs() <= 64 * EPS32 * op_abs_of(O, op, kind).apply(x.abs()) + 1e-30)
-        for variant in (1, 2, 3, 4, 5, 6, 7, 8, 9):
+        for variant in (1, 2, 3, 4, 5):
             assert torch.equal(Sx, op.apply(x, variant=variant)), (kind, variant)
         lhs = (Sx.double() * y.double()).sum().item()
         rhs = (x.double() * op.T.apply(y).double()).sum().item()

@@ -28,14 +28,14 @@ def main():
             tot += e0.elapsed_time(e1)
         return tot / reps
 
-    for M, Nn, K in ((128000, 128, 256), (255168, 128, 256), (128000, 256, 128), (255168, 256, 128), (16000, 128, 256)):
+    for M, Nn, K in ((128000, 128, 256), (255168, 128, 256), (128000, 256, 128), (255168, 256, 128), (16000, 128, 256), (128000, 128, 128)):
         A = torch.randn(M, K, device=dev)
         B = torch.randn(Nn, K, device=dev) / K ** 0.5
         bias = torch.randn(Nn, device=dev)
         R = torch.randn(M, Nn, device=dev)
         C = torch.empty(M, Nn, device=dev)
         st = torch.cuda.current_stream().cuda_stream
-WS = torch.empty(1 << 20, dtype=torch.uint8, device=dev)
+        WS = torch.empty(1 << 20, dtype=torch.uint8, device=dev)
 
         def ours(flags=0, res=True):
             N.call("sn_gemm_tf32_f32", A.data_ptr(), K, B.data_ptr(), K, bias.data_ptr(), R.data_ptr() if res else 0, Nn, 0, 0, 0,
@@ -45,6 +45,7 @@ WS = torch.empty(1 << 20, dtype=torch.uint8, device=dev)
         bytes_ = 4.0 * (M * K + 2 * M * Nn + Nn * K)
         out = {"M": M, "N": Nn, "K": K}
         for name, fn in (("sn_3xtf32", lambda: ours(0)), ("sn_tf32", lambda: ours(N.SN_GEMM_SINGLE_PASS)),
+                         ("sn_3xtf32_nores", lambda: ours(0, False)),
                          ("torch_fp32_addmm", lambda: torch.addmm(bias, A, B.t(), out=C).add_(R))):
             ms = time_it(fn)
             out[name] = {"us": ms * 1e3, "TFLOPs": flops / ms / 1e9, "GBps": bytes_ / ms / 1e6}
