@@ -101,6 +101,30 @@ int sn_assemble_block_diag(const int64_t* parts, int64_t n_parts, int64_t rows_p
                            float* val_out, sn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Operator construction on the GPU (the step in front of the path; reference src/utils/mesh.py:17-125,
+ * src/utils/graph.py:40-49, recipe src/as_rigid_as_possible/add_laplacian.py:39-70 -- O(V^2) dense numpy, offline).
+ *
+ * A batch of n_meshes triangle meshes, every mesh padded to v_pad vertices and f_pad faces:
+ *   V [n_meshes, v_pad, 3] fp64 positions;  F [n_meshes, f_pad, 3] int32 LOCAL vertex indices, a face with a negative
+ *   (or >= v_pad) index is padding.  A vertex may belong to at most 64 faces (status reports the violation).
+ * Outputs are the block-diagonal batch operators in the formats of the SpMM entry points, values computed in fp64 with
+ * the reference's operation order and rounded to fp32 once (the reference's .astype('float32')):
+ *   sn_mesh_dirac_bsr4   : D  [n*f_pad x n*v_pad] block rows/cols: d_browptr [n*f_pad + 1], d_bcolind [<= 3 n f_pad],
+ *                          d_bval [<= 48 n f_pad];  D* [n*v_pad x n*f_pad]: da_browptr [n*v_pad + 1], da_bcolind /
+ *                          da_bval with the same capacities.  Block counts = the last row pointers.
+ *   sn_mesh_laplacian_csr: L  [n*v_pad x n*v_pad]: rowptr [n*v_pad + 1], colind / val [<= n (v_pad + 6 f_pad)].
+ * status: one device int32, 0 on success, otherwise the largest per-vertex face count found (> 64): the rows of such
+ * vertices are left empty.  Deterministic (no floating-point atomics).  ws: sn_mesh_ws_bytes(n_meshes, v_pad, f_pad).
+ * ---------------------------------------------------------------------------------------------- */
+size_t sn_mesh_ws_bytes(int64_t n_meshes, int64_t v_pad, int64_t f_pad);
+int sn_mesh_dirac_bsr4(const double* V, const int32_t* F, int64_t n_meshes, int64_t v_pad, int64_t f_pad,
+                       int32_t* d_browptr, int32_t* d_bcolind, float* d_bval, int32_t* da_browptr, int32_t* da_bcolind,
+                       float* da_bval, int32_t* status, void* ws, size_t ws_bytes, sn_stream_t stream);
+int sn_mesh_laplacian_csr(const double* V, const int32_t* F, int64_t n_meshes, int64_t v_pad, int64_t f_pad,
+                          int32_t* rowptr, int32_t* colind, float* val, int32_t* status, void* ws, size_t ws_bytes,
+                          sn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Operator application.
  *
  * sn_csr_spmm_f32 :  Y[n_rows x C] = S * X            (scalar Laplacian, utils_pt.py:167,176)

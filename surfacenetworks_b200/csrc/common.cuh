@@ -26,6 +26,11 @@ inline int launch_status() {
   return SN_OK;
 }
 
+// Device-wide exclusive scan (convert.cu): out[0..n) = exclusive prefix sums of counts, out[n] = total; out may alias
+// counts; tile_ws holds exclusive_scan_tiles(n) ints.
+int64_t exclusive_scan_tiles(int64_t n);
+int exclusive_scan(const int* counts, int64_t n, int* out, int* tile_ws, cudaStream_t st);
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ELU(alpha = 1), the activation in front of every operator application (utils_pt.py:161,172,195,208).

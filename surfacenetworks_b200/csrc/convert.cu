@@ -100,8 +100,10 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply(const int* __restrict
   }
 }
 
-// Exclusive scan of counts[0..n) into out[0..n], out[n] = total.  tile_ws: ceil(n / kScanTile) ints.
-static int exclusive_scan(const int* counts, int64_t n, int* out, int* tile_ws, cudaStream_t st) {
+int64_t exclusive_scan_tiles(int64_t n) { return ceil_div(n, kScanTile); }
+
+// Exclusive scan of counts[0..n) into out[0..n], out[n] = total.  tile_ws: exclusive_scan_tiles(n) ints.
+int exclusive_scan(const int* counts, int64_t n, int* out, int* tile_ws, cudaStream_t st) {
   const int64_t tiles = ceil_div(n, kScanTile);
   if (tiles > 0x7fffffffLL) return SN_ERR_OVERFLOW;
   scan_tile_sums<<<(unsigned)tiles, kScanThreads, 0, st>>>(counts, n, tile_ws);

@@ -323,6 +323,7 @@ int launch_lpr(const int32_t* rowptr, const int32_t* colind, const float* val, c
   const int sms = device_info().sms;
   const int64_t ws = LS::resident_warps(elu, sms), wm = LM::resident_warps(elu, sms), wl = LL::resident_warps(elu, sms);
   int pick = tile_mode;
+  if ((pick < 1 || pick > 3) && LPR == 32) pick = 1;   // C = 512: one row per warp pass; short tiles measured fastest
   if (pick < 1 || pick > 3) {
     const double es = LS::efficiency(n_rows, ws), em = LM::efficiency(n_rows, wm), el = LL::efficiency(n_rows, wl);
     // a tile length only qualifies when it gives every resident warp at least one tile

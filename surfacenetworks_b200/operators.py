@@ -17,7 +17,8 @@ import torch
 
 from . import _native as N
 
-__all__ = ["CsrOperator", "Bsr4Operator", "as_csr", "as_bsr4", "clear_cache", "MeshOperatorCache"]
+__all__ = ["CsrOperator", "Bsr4Operator", "as_csr", "as_bsr4", "clear_cache", "MeshOperatorCache",
+           "build_dirac_operators", "build_laplacian_operator", "pack_meshes"]
 
 
 def _ptr(t):
@@ -282,6 +283,118 @@ class Bsr4Operator:
             N.call("sn_bsr4_spmm_f32", _ptr(self.browptr), _ptr(self.bcolind), _ptr(self.bval),
                    _ptr(X), X.stride(0), _ptr(out), out.stride(0), self.n_brows, C, flags, _stream())
         return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU operator construction: padded mesh batch -> batch operators, no scipy / COO round trip.
+class _StructureSource:
+    """Stand-in for the COO source of an operator that was built directly in CSR32 / BSR4 form: expands the stored
+    structure to scalar COO on the device the first time the transpose is requested."""
+
+    def __init__(self, kind, ptr, ind, val, n_rows, n_cols, n_entries):
+        self.kind, self.ptr, self.ind, self.val = kind, ptr, ind, val
+        self.n_rows, self.n_cols, self.n_entries = n_rows, n_cols, n_entries
+
+    def _coo(self):
+        n = self.n_entries
+        counts = (self.ptr[1:] - self.ptr[:-1]).to(torch.int64)
+        major = torch.repeat_interleave(torch.arange(counts.numel(), device=self.ptr.device), counts, output_size=n)
+        minor = self.ind[:n].to(torch.int64)
+        if self.kind == "csr":
+            return major, minor, self.val[:n].contiguous()
+        # bval[16 k + 4 q + s] = B_k[(q + s) % 4][q]
+        q = torch.arange(4, device=self.ptr.device).view(1, 4, 1)
+        sft = torch.arange(4, device=self.ptr.device).view(1, 1, 4)
+        row = (4 * major.view(-1, 1, 1) + (q + sft) % 4).reshape(-1)
+        col = (4 * minor.view(-1, 1, 1) + q + 0 * sft).reshape(-1)
+        return row, col, self.val[:16 * n].contiguous()
+
+    def transposed(self):
+        row, col, val = self._coo()
+        return _CooSource(None, col, row, val, 0, 0, self.n_cols, self.n_rows, False)
+
+
+def _check_mesh_batch(V, F):
+    _require_cuda(V, "V")
+    _require_cuda(F, "F")
+    if V.dim() != 3 or V.size(2) != 3 or F.dim() != 3 or F.size(2) != 3 or V.size(0) != F.size(0):
+        raise ValueError("expected V [B, v_pad, 3] and F [B, f_pad, 3], got %s and %s" % (tuple(V.shape), tuple(F.shape)))
+    return V.to(torch.float64).contiguous(), F.to(torch.int32).contiguous()
+
+
+def _mesh_ws(n, v_pad, f_pad, dev):
+    nbytes = N.lib.sn_mesh_ws_bytes(n, v_pad, f_pad)
+    return torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev), nbytes
+
+
+def _check_mesh_status(status):
+    worst = int(status.item())
+    if worst:
+        raise ValueError("a vertex belongs to %d faces; GPU operator construction supports at most 64" % worst)
+
+
+def build_dirac_operators(V, F):
+    """Batch Dirac operator ``D`` [B*f_pad x B*v_pad] and adjoint ``D*`` [B*v_pad x B*f_pad] (block rows x block
+    columns) built on the GPU from padded positions ``V`` [B, v_pad, 3] and faces ``F`` [B, f_pad, 3] (local vertex
+    indices, padding faces = -1).  Same values as the reference's mesh.dirac (src/utils/mesh.py:35-64) after its
+    ``.astype('float32')``; replaces the offline numpy construction + sparse_diag_cat + upload."""
+    V, F = _check_mesh_batch(V, F)
+    n, v_pad, f_pad = V.size(0), V.size(1), F.size(1)
+    dev = V.device
+    cap = max(3 * n * f_pad, 1)
+    i32 = dict(dtype=torch.int32, device=dev)
+    d_ptr, d_ind = torch.empty(n * f_pad + 1, **i32), torch.empty(cap, **i32)
+    a_ptr, a_ind = torch.empty(n * v_pad + 1, **i32), torch.empty(cap, **i32)
+    d_val = torch.empty(16 * cap, dtype=torch.float32, device=dev)
+    a_val = torch.empty(16 * cap, dtype=torch.float32, device=dev)
+    status = torch.zeros(1, **i32)
+    ws, nbytes = _mesh_ws(n, v_pad, f_pad, dev)
+    with torch.cuda.device(dev):
+        N.call("sn_mesh_dirac_bsr4", _ptr(V), _ptr(F), n, v_pad, f_pad, _ptr(d_ptr), _ptr(d_ind), _ptr(d_val),
+               _ptr(a_ptr), _ptr(a_ind), _ptr(a_val), _ptr(status), _ptr(ws), nbytes, _stream())
+    _check_mesh_status(status)
+    nb = int(d_ptr[-1].item())                       # one read-back per construction, like from_source
+    max_a = int((a_ptr[1:] - a_ptr[:-1]).max().item()) if n * v_pad else 0
+    D = Bsr4Operator(d_ptr, d_ind[:max(nb, 1)], d_val[:16 * max(nb, 1)], n * f_pad, n * v_pad,
+                     _StructureSource("bsr4", d_ptr, d_ind, d_val, 4 * n * f_pad, 4 * n * v_pad, nb), nb, 3 if nb else 0)
+    DA = Bsr4Operator(a_ptr, a_ind[:max(nb, 1)], a_val[:16 * max(nb, 1)], n * v_pad, n * f_pad,
+                      _StructureSource("bsr4", a_ptr, a_ind, a_val, 4 * n * v_pad, 4 * n * f_pad, nb), nb, max_a)
+    return D, DA
+
+
+def build_laplacian_operator(V, F):
+    """Batch cotangent Laplacian ``A^-1 (D - W)`` [B*v_pad x B*v_pad] built on the GPU (reference recipe
+    src/as_rigid_as_possible/add_laplacian.py:50-56 over mesh.py:17-26,67-80,102-112 and graph.py:40-49)."""
+    V, F = _check_mesh_batch(V, F)
+    n, v_pad, f_pad = V.size(0), V.size(1), F.size(1)
+    dev = V.device
+    cap = max(n * (v_pad + 6 * f_pad), 1)
+    rowptr = torch.empty(n * v_pad + 1, dtype=torch.int32, device=dev)
+    colind = torch.empty(cap, dtype=torch.int32, device=dev)
+    val = torch.empty(cap, dtype=torch.float32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws, nbytes = _mesh_ws(n, v_pad, f_pad, dev)
+    with torch.cuda.device(dev):
+        N.call("sn_mesh_laplacian_csr", _ptr(V), _ptr(F), n, v_pad, f_pad, _ptr(rowptr), _ptr(colind), _ptr(val),
+               _ptr(status), _ptr(ws), nbytes, _stream())
+    _check_mesh_status(status)
+    nnz = int(rowptr[-1].item())
+    return CsrOperator(rowptr, colind[:max(nnz, 1)], val[:max(nnz, 1)], n * v_pad, n * v_pad,
+                       _StructureSource("csr", rowptr, colind, val, n * v_pad, n * v_pad, nnz), nnz)
+
+
+def pack_meshes(meshes, device, v_pad=None, f_pad=None):
+    """List of (V [nv, 3], F [nf, 3]) numpy meshes -> padded device tensors (V [B, v_pad, 3] fp64 zero-padded,
+    F [B, f_pad, 3] int32 padded with -1) for build_dirac_operators / build_laplacian_operator."""
+    import numpy as np
+    v_pad = v_pad or max(v.shape[0] for v, _ in meshes)
+    f_pad = f_pad or max(f.shape[0] for _, f in meshes)
+    Vp = np.zeros((len(meshes), v_pad, 3), dtype=np.float64)
+    Fp = np.full((len(meshes), f_pad, 3), -1, dtype=np.int32)
+    for i, (v, f) in enumerate(meshes):
+        Vp[i, :v.shape[0]] = v
+        Fp[i, :f.shape[0]] = f
+    return torch.from_numpy(Vp).to(device), torch.from_numpy(Fp).to(device)
 
 
 # ---------------------------------------------------------------------------------------------------
