@@ -13,5 +13,5 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:rowg
   python tools/spmm_bench.py --reps 1 --ops D,Dstar --variants rg > $O/e_ncu.log 2>&1
 echo "ncu exit $?"
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $O/e_launches.csv \
-  python bench.py --steps 1 --warmup 1 --no-e2e > $O/e_launch_bench.log 2>&1
+  python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-spmm-sweep > $O/e_launch_bench.log 2>&1
 echo "launch list exit $?"; wc -l $O/e_launches.csv
