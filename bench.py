@@ -193,15 +193,15 @@ def measured_peaks():
 
 def ncu_traffic():
     """DRAM bytes per launch of the Dirac kernel from the committed ncu --set full capture (profiles/), or None."""
-    path = os.path.join(ROOT, "profiles", "r1_bsr4_ncu_summary.json")
+    path = os.path.join(ROOT, "profiles", "r1_rowgroup_ncu_summary.json")
     try:
         with open(path) as fh:
-            d = json.load(fh)
-        row = d["r1f_stream (current hot kernel)"][0]
+            recs = [r for r in json.load(fh) if "rowgroup_spmm_kernel" in r["kernel"]]
+        row = recs[0]                                  # first capture: D (faces <- vertices) at the cfg3 size, C = 128
         rd = float(row["dram__bytes_read.sum"].split()[0]) * 1e6
         wr = float(row["dram__bytes_write.sum"].split()[0]) * 1e6
-        return rd + wr, ("ncu --set full, bsr4_spmm_stream_kernel D at cfg3 size: dram__bytes_read.sum %.1f MB + "
-                         "dram__bytes_write.sum %.1f MB (profiles/r1_bsr4_ncu_summary.json; part of Y is still "
+        return rd + wr, ("ncu --set full, rowgroup_spmm_kernel D at cfg3 size: dram__bytes_read.sum %.1f MB + "
+                         "dram__bytes_write.sum %.1f MB (profiles/r1_rowgroup_ncu_summary.json; part of Y is still "
                          "dirty in L2 when the kernel ends)" % (rd / 1e6, wr / 1e6))
     except Exception:
         return None, None
@@ -230,8 +230,9 @@ def spmm_sweep(dev):
 
     def entry(op, X, C):
         ms = time_op(op, X)
-        return {"us": ms * 1e3, "GBps": op.algorithmic_bytes(C) / ms / 1e6, "GFLOPs": op.flops(C) / ms / 1e6,
-                "alg_MB": op.algorithmic_bytes(C) / 1e6}
+        gbps = op.algorithmic_bytes(C) / ms / 1e6
+        return {"us": ms * 1e3, "GBps": gbps, "frac_of_hbm_peak": gbps / measured_peaks()[0],
+                "GFLOPs": op.flops(C) / ms / 1e6, "alg_MB": op.algorithmic_bytes(C) / 1e6}
 
     # cfg2: mesh_mnist Laplacian, 32 meshes x 500 V, C=128
     meshes = W.make_mesh_ops(500, range(32))
@@ -385,7 +386,7 @@ def run_b200(args):
     bsr_launches = sum(v["launches"] for v in bsr)
     achieved = bsr_bytes / (bsr_ms / 1e3) / 1e9 if bsr_ms > 0 else 0.0
     traffic, traffic_src = ncu_traffic()
-    roofline = {"kernel": "bsr4_spmm_stream_kernel (sn_bsr4_spmm_f32: D, D*, D^T, D*^T at C=128)", "bound": "hbm",
+    roofline = {"kernel": "rowgroup_spmm_kernel (sn_bsr4_spmm_f32: D, D*, D^T, D*^T at C=128)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src,
                 "peak_source": peak_src, "launches_timed": bsr_launches,

@@ -77,6 +77,7 @@ def spmm_flags(elu_input=False, direct_gather=False, smem_stream=False, variant=
 
 
 SN_GEMM_SINGLE_PASS = 1
+SN_GEMM_NO_L2_PREFETCH = 2
 
 
 class SurfnetError(RuntimeError):

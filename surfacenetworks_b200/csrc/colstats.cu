@@ -67,7 +67,23 @@ colstats_final_kernel(const float* __restrict__ partial, int n_partials, int64_t
   const int c = blockIdx.x * 32 + lc;
   double s = 0.0, q = 0.0;
   if (c < C) {
-    for (int i = g; i < n_partials; i += 32) {
+    // 8 independent loads in flight per statistic, accumulated in the same fixed order as a plain loop (the launch is
+    // pure latency: ~28 dependent L2 round trips per thread otherwise, 14 us measured)
+    int i = g;
+    for (; i + 7 * 32 < n_partials; i += 8 * 32) {
+      float a[8], b[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        a[u] = __ldg(partial + (size_t)(i + u * 32) * 2 * C + c);
+        b[u] = __ldg(partial + (size_t)(i + u * 32) * 2 * C + C + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        s += (double)a[u];
+        q += (double)b[u];
+      }
+    }
+    for (; i < n_partials; i += 32) {
       s += (double)__ldg(partial + (size_t)i * 2 * C + c);
       q += (double)__ldg(partial + (size_t)i * 2 * C + C + c);
     }

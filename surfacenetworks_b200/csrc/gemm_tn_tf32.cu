@@ -44,6 +44,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   }
 }
+constexpr int kPrefetchDist = 4;       // k-blocks of L2 prefetch distance
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
@@ -97,6 +101,7 @@ struct Params {
   int kb_per_cta;        // 32-row blocks per CTA
   int n_kb;
   int split;
+  int l2_prefetch;
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -146,6 +151,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_arrive_expect_tx(full_bar + stage, a_bytes + b_bytes);
         for (int i = 0; i < a_boxes; ++i) tma_load_2d(sa + i * kBoxBytes, &map_a, i * 32, kb * kBlockK, full_bar + stage);
         for (int i = 0; i < b_boxes; ++i) tma_load_2d(sb + i * kBoxBytes, &map_b, i * 32, kb * kBlockK, full_bar + stage);
+        // two-stage ring (the hi/lo twins fill shared memory): too shallow for DRAM latency, so the k-blocks this CTA
+        // loads kPrefetchDist iterations from now are pulled into L2 here
+        if (p.l2_prefetch && kb + kPrefetchDist < kb1) {
+          for (int i = 0; i < a_boxes; ++i) tma_prefetch_l2_2d(&map_a, i * 32, (kb + kPrefetchDist) * kBlockK);
+          for (int i = 0; i < b_boxes; ++i) tma_prefetch_l2_2d(&map_b, i * 32, (kb + kPrefetchDist) * kBlockK);
+        }
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     }
@@ -301,6 +312,7 @@ SN_API int sn_gemm_tn_tf32_f32(const float* A, int64_t lda, const float* B, int6
   p.n_kb = (int)((R + kBlockK - 1) / kBlockK);
   const int grid = grid_for(p.n_kb, &p.kb_per_cta);
   p.split = (flags & SN_GEMM_SINGLE_PASS) ? 0 : 1;
+  p.l2_prefetch = (flags & SN_GEMM_NO_L2_PREFETCH) ? 0 : 1;
   const size_t stage_bytes = 2 * ((size_t)(kM / 32) * kBoxBytes + (size_t)(N / 32) * kBoxBytes);
   const size_t smem = 2 * stage_bytes + 1024;
   cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -46,6 +46,8 @@ def main():
         out = {"M": M, "N": Nn, "K": K}
         for name, fn in (("sn_3xtf32", lambda: ours(0)), ("sn_tf32", lambda: ours(N.SN_GEMM_SINGLE_PASS)),
                          ("sn_3xtf32_nores", lambda: ours(0, False)),
+                         ("sn_3xtf32_nopf", lambda: ours(N.SN_GEMM_NO_L2_PREFETCH)),
+                         ("sn_3xtf32_nores_nopf", lambda: ours(N.SN_GEMM_NO_L2_PREFETCH, False)),
                          ("torch_fp32_addmm", lambda: torch.addmm(bias, A, B.t(), out=C).add_(R))):
             ms = time_it(fn)
             out[name] = {"us": ms * 1e3, "TFLOPs": flops / ms / 1e9, "GBps": bytes_ / ms / 1e6}
@@ -53,6 +55,26 @@ def main():
         ms = time_it(lambda: torch.addmm(bias, A, B.t(), out=C).add_(R))
         torch.backends.cuda.matmul.allow_tf32 = False
         out["torch_tf32_addmm"] = {"us": ms * 1e3, "TFLOPs": flops / ms / 1e9}
+        print(json.dumps(out), flush=True)
+
+    # weight-gradient product G = dY^T Z (split-K over the SMs)
+    for R, Nn in ((128000, 256), (255168, 256), (128000, 128)):
+        A = torch.randn(R, 128, device=dev)
+        B = torch.randn(R, Nn, device=dev)
+        G = torch.empty(128, Nn, device=dev)
+        nb = N.lib.sn_gemm_tn_tf32_ws_bytes(R, Nn)
+        WS = torch.empty(max(nb, 1), dtype=torch.uint8, device=dev)
+        st = torch.cuda.current_stream().cuda_stream
+
+        def tn(flags=0):
+            N.call("sn_gemm_tn_tf32_f32", A.data_ptr(), 128, B.data_ptr(), Nn, G.data_ptr(), Nn, R, 128, Nn, flags,
+                   WS.data_ptr(), nb, st)
+
+        out = {"op": "gemm_tn", "R": R, "M": 128, "N": Nn, "alg_MB": 4.0 * R * (128 + Nn) / 1e6}
+        for name, fn in (("sn_3xtf32", lambda: tn(0)), ("sn_3xtf32_nopf", lambda: tn(N.SN_GEMM_NO_L2_PREFETCH)),
+                         ("sn_tf32", lambda: tn(N.SN_GEMM_SINGLE_PASS)), ("torch_fp32", lambda: torch.mm(A.t(), B, out=G))):
+            ms = time_it(fn)
+            out[name] = {"us": ms * 1e3, "GBps": out["alg_MB"] / ms / 1e3}
         print(json.dumps(out), flush=True)
 
 
