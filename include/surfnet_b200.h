@@ -182,7 +182,7 @@ int sn_elu_bwd_group_f32(const float* A, int64_t lda, const float* G, int64_t ld
  * Supported: N in {64, 128, 256}, K % 32 == 0, 16-byte aligned pointers, leading dimensions % 4 == 0.
  * ---------------------------------------------------------------------------------------------- */
 #define SN_GEMM_SINGLE_PASS 1
-#define SN_GEMM_NO_L2_PREFETCH 2 /* A/B switch: disable the TMA / prefetch.global L2 prefetch of the next tile's operands */
+#define SN_GEMM_NO_L2_PREFETCH 2 /* A/B switch: disable the L2 prefetch of upcoming operands (residual rows / split-K boxes) */
 size_t sn_gemm_tf32_ws_bytes(int64_t N, int64_t K); /* workspace for the pre-split weights (3xTF32 mode) */
 int sn_gemm_tf32_f32(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, const float* R,
                      int64_t ldr, const float* rscale, const float* group_bias, int64_t rows_per_group, float* C,

@@ -68,11 +68,6 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-// TMA prefetch of one box into L2 only (no shared-memory destination, no barrier): hides the DRAM latency of a box
-// that this CTA will load for real one tile later
-__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
-}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // K-major, 128-byte-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), version 1
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
@@ -130,7 +125,7 @@ struct Params {
   int M, N, K;
   int stages;
   int split;             // 1: 3xTF32 (hi/lo split), 0: single-pass TF32
-  int l2_prefetch;       // 1: prefetch the next tile's A boxes / residual rows into L2 while this tile is processed
+  int l2_prefetch;       // 1: prefetch the next tile's residual rows into L2 while this tile is processed
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -187,10 +182,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           tma_load_2d(sa, &map_a, kb * kBlockK, tile * kBlockM, full_bar + stage);
           tma_load_2d(sb, &map_b, kb * kBlockK, 0, full_bar + stage);
           if (p.split) tma_load_2d(sb + b_bytes, &map_blo, kb * kBlockK, 0, full_bar + stage);   // pre-split weights
-          // the ring holds only 2-3 k-blocks (shared memory is spent on the hi/lo twins), too shallow for DRAM latency:
-          // pull the same k-block of this CTA's NEXT tile into L2 now, so that its real load is an L2 hit
-          if (p.l2_prefetch && tile + (int)gridDim.x < n_tiles)
-            tma_prefetch_l2_2d(&map_a, kb * kBlockK, (tile + (int)gridDim.x) * kBlockM);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -425,7 +416,11 @@ SN_API int sn_gemm_tf32_f32(const float* A, int64_t lda, const float* B, int64_t
   p.gbias = group_bias; p.rows_per_group = group_bias ? (int)rows_per_group : 1;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
   p.split = split ? 1 : 0;
-  p.l2_prefetch = (flags & SN_GEMM_NO_L2_PREFETCH) ? 0 : 1;
+  // Measured (tools/gemm_bench.py, profiles/r1_gemm_notes.md): prefetching the next tile's residual rows into L2 gains
+  // 6-9 % at N = 256 (the dZ product, whose epilogue streams a 1 KB residual row per output row) and costs a few % at
+  // N = 128; an L2 prefetch of the A boxes changed nothing (the mainloop is bound by shared-memory bandwidth, not by
+  // DRAM latency) and was removed.
+  p.l2_prefetch = (!(flags & SN_GEMM_NO_L2_PREFETCH) && R && N >= 256) ? 1 : 0;
   int dev = 0, sms = 148, smem_optin = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
