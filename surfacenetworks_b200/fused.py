@@ -314,5 +314,21 @@ def bn_linear(z, bn, fc, residual=None):
             left = None
         return _BnLinear.apply(z, bn.weight, bn.bias, fc.weight, fc.bias, residual, bn.running_mean, bn.running_var,
                                training, momentum, bn.eps, left)
+    # Output widths between the tensor-core shapes (the 128 -> 120 head of the ARAP / dense_correspondence models,
+    # conv2 at as_rigid_as_possible/models.py:121): zero-pad the Linear to the next supported width and slice -- the
+    # cuBLAS fp32 SIMT GEMMs it replaces were 0.6 ms of the 19 ms step (profiles/r1b_launches_bench_summary.json)
+    n_out, k = fc.weight.shape
+    n_pad = next((n for n in _GEMM_N if n >= n_out), None)
+    if residual is None and n_pad is not None and n_pad != n_out and n_out >= 64 and fc.bias is not None:
+        w_pad = torch.cat([fc.weight, fc.weight.new_zeros(n_pad - n_out, k)], 0)
+        if fused_supported(z, w_pad):
+            b_pad = torch.cat([fc.bias, fc.bias.new_zeros(n_pad - n_out)])
+            training = bn.training or bn.running_mean is None
+            if training and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+            momentum = 0.1 if bn.momentum is None else bn.momentum
+            y = _BnLinear.apply(z, bn.weight, bn.bias, w_pad, b_pad, None, bn.running_mean, bn.running_var, training,
+                                momentum, bn.eps, None)
+            return y[:, :n_out]
     y = fc(bn(z))
     return y if residual is None else y + residual
