@@ -8,7 +8,8 @@ Workload (BASELINE.json configs[2], "cfg3" in SURVEY.md 8(d)): per GPU a batch o
 vertices (~3970 faces), the reference's DirModel (src/as_rigid_as_possible/models.py:108-152: 8 DirResNet2 +
 7 AvgResNet2 blocks, 128 features).  One STEP = the training step of src/as_rigid_as_possible/main.py:219-230 on
 one batch: forward, masked smooth-L1 loss, backward, (N > 1: one flat NCCL gradient all-reduce), Adam update.
-Every Dirac application D v / D* f (16 forward + 16 backward per step) runs through sn_bsr4_spmm_f32.
+Every Dirac application D v / D* f (16 forward + 16 backward per step) runs through sn_bsr4_spmm_f32 /
+sn_bsr4_spmm_epilogue_f32 (backward: the activation derivative rides in the store path).
 Weak scaling: 64 meshes per GPU.  metric = meshes/s over all ranks.
 
   value     : device-timed, batch resident in HBM (operators already converted to BSR4)
@@ -364,7 +365,7 @@ def run_b200(args):
 
     # ---- per-kernel timing pass (eager: a graph replay hides individual launches from CUDA events): the same K
     #      steps with events around every sn_* launch on the launching stream
-    N.TIMER = N.KernelTimer(["sn_bsr4_spmm_f32", "sn_csr_spmm_f32", "sn_elu_f32", "sn_elu_bwd_f32", "sn_gemm_tf32_f32",
+    N.TIMER = N.KernelTimer(["sn_bsr4_spmm_f32", "sn_csr_spmm_f32", "sn_bsr4_spmm_epilogue_f32", "sn_csr_spmm_epilogue_f32", "sn_elu_f32", "sn_elu_bwd_f32", "sn_gemm_tf32_f32",
                              "sn_gemm_tn_tf32_f32", "sn_colstats_f32", "sn_elu_colstats_f32", "sn_segment_sum_f32", "sn_elu_bwd_group_f32", "sn_bn_fold_fwd_f32", "sn_bn_fold_bwd_f32"])
     counts0 = dict(N.CALL_COUNTS)
     barrier()
@@ -380,13 +381,13 @@ def run_b200(args):
     # ---- live roofline of the Dirac SpMM + per-kernel shares
     ksum = timer.summary()
     peak, peak_src = measured_peaks()
-    bsr = [v for (name, _), v in ksum.items() if name == "sn_bsr4_spmm_f32"]
+    bsr = [v for (name, _), v in ksum.items() if name in ("sn_bsr4_spmm_f32", "sn_bsr4_spmm_epilogue_f32")]
     bsr_ms = sum(v["ms"] for v in bsr)
     bsr_bytes = sum(v["bytes"] for v in bsr)
     bsr_launches = sum(v["launches"] for v in bsr)
     achieved = bsr_bytes / (bsr_ms / 1e3) / 1e9 if bsr_ms > 0 else 0.0
     traffic, traffic_src = ncu_traffic()
-    roofline = {"kernel": "rowgroup_spmm_kernel (sn_bsr4_spmm_f32: D, D*, D^T, D*^T at C=128)", "bound": "hbm",
+    roofline = {"kernel": "rowgroup_spmm_kernel (sn_bsr4_spmm_f32: D, D* forward; sn_bsr4_spmm_epilogue_f32: D^T, D*^T backward with elu' in the store path; C=128)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src,
                 "peak_source": peak_src, "launches_timed": bsr_launches,

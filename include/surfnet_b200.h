@@ -144,6 +144,21 @@ int sn_bsr4_spmm_f32(const int32_t* browptr, const int32_t* bcolind, const float
                      const float* X, int64_t ldx, float* Y, int64_t ldy,
                      int64_t n_brows, int64_t C, int flags, sn_stream_t stream);
 
+/* Backward-pass SpMM with the activation derivative in its store path:
+ *     Y = (S * X + G) .* elu'(A)        G, A optional (NULL: no addend / no derivative), [n_rows x C] with ldg / lda
+ * A holds ACTIVATED values a = elu(x), so elu' = 1 for a > 0 and a + 1 otherwise (as sn_elu_bwd_f32 with a_is_raw = 0).
+ * With S = the transposed operator, X = the gradient of the gathered half and G = the gradient of the un-gathered half
+ * this is the whole backward of "elu, then [x | S x]" (src/utils/utils_pt.py:161-168,195-216 through autograd in the
+ * reference) in one launch instead of an SpMM plus an elementwise pass.  Y may alias G.  Row-group kernel only:
+ * returns SN_ERR_UNSUPPORTED for C not in {32, 64, 128, 256, 512} or unaligned operands (callers then run
+ * sn_*_spmm_f32 followed by sn_elu_bwd_f32). */
+int sn_csr_spmm_epilogue_f32(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X,
+                             int64_t ldx, float* Y, int64_t ldy, int64_t n_rows, int64_t C, const float* G, int64_t ldg,
+                             const float* A, int64_t lda, int flags, sn_stream_t stream);
+int sn_bsr4_spmm_epilogue_f32(const int32_t* browptr, const int32_t* bcolind, const float* bval, const float* X,
+                              int64_t ldx, float* Y, int64_t ldy, int64_t n_brows, int64_t C, const float* G, int64_t ldg,
+                              const float* A, int64_t lda, int flags, sn_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Activation pass in front of each operator application (F.elu at utils_pt.py:161,172,195,208).
  * sn_elu_f32     : Y = elu(X), strided in/out so the result lands in the left half of the stage's
@@ -182,6 +197,7 @@ int sn_elu_bwd_group_f32(const float* A, int64_t lda, const float* G, int64_t ld
  * Supported: N in {64, 128, 256}, K % 32 == 0, 16-byte aligned pointers, leading dimensions % 4 == 0.
  * ---------------------------------------------------------------------------------------------- */
 #define SN_GEMM_SINGLE_PASS 1
+#define SN_GEMM_ELU_BWD_LEFT 4  /* multiply output columns [0, N/2) by elu'(R) (R = activated values: 1 if R > 0 else R + 1); needs R */
 #define SN_GEMM_NO_L2_PREFETCH 2 /* A/B switch: disable the L2 prefetch of upcoming operands (residual rows / split-K boxes) */
 size_t sn_gemm_tf32_ws_bytes(int64_t N, int64_t K); /* workspace for the pre-split weights (3xTF32 mode) */
 int sn_gemm_tf32_f32(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, const float* R,

@@ -48,6 +48,8 @@ SIGNATURES = {
     "sn_gemm_tf32_ws_bytes": (_sz, [_i64, _i64]),
     "sn_gemm_tf32_f32": (_int, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _int,
                                 _ptr, _sz, _ptr]),
+    "sn_csr_spmm_epilogue_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _int, _ptr]),
+    "sn_bsr4_spmm_epilogue_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _int, _ptr]),
     "sn_mesh_ws_bytes": (_sz, [_i64, _i64, _i64]),
     "sn_mesh_dirac_bsr4": (_int, [_ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),
     "sn_mesh_laplacian_csr": (_int, [_ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),
@@ -78,6 +80,7 @@ def spmm_flags(elu_input=False, direct_gather=False, smem_stream=False, variant=
 
 SN_GEMM_SINGLE_PASS = 1
 SN_GEMM_NO_L2_PREFETCH = 2
+SN_GEMM_ELU_BWD_LEFT = 4
 
 
 class SurfnetError(RuntimeError):
@@ -123,21 +126,29 @@ class KernelTimer:
         return out
 
 
-def call(name, *args):
-    """Call an int-returning entry point and raise SurfnetError on a non-zero status."""
+def call(name, *args, soft_unsupported=False):
+    """Call an int-returning entry point and raise SurfnetError on a non-zero status.  With ``soft_unsupported`` a
+    SN_ERR_UNSUPPORTED status (nothing was launched) is returned to the caller instead, who then takes another path."""
     t = TIMER
     if t is not None and name in t.names:
         import torch
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        check(name, getattr(lib, name)(*args))
+        rc = getattr(lib, name)(*args)
         e1.record()
-        tag, nbytes, flops = t._meta or ("", 0, 0)
-        t._meta = None
+        meta, t._meta = t._meta, None
+        if soft_unsupported and rc == SN_ERR_UNSUPPORTED:
+            return rc
+        check(name, rc)
+        tag, nbytes, flops = meta or ("", 0, 0)
         t.records.append((name, tag, nbytes, flops, e0, e1))
     else:
-        check(name, getattr(lib, name)(*args))
+        rc = getattr(lib, name)(*args)
+        if soft_unsupported and rc == SN_ERR_UNSUPPORTED:
+            return rc
+        check(name, rc)
     CALL_COUNTS[name] = CALL_COUNTS.get(name, 0) + 1
+    return SN_OK
 
 
 def version():

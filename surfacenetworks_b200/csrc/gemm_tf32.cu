@@ -126,6 +126,7 @@ struct Params {
   int stages;
   int split;             // 1: 3xTF32 (hi/lo split), 0: single-pass TF32
   int l2_prefetch;       // 1: prefetch the next tile's residual rows into L2 while this tile is processed
+  int elu_left;          // 1: multiply output columns [0, N/2) by elu'(R) (backward of the activated left half of Z)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -314,6 +315,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             if (p.R) {
               o.x = fmaf(rs.x, rr[i].x, o.x); o.y = fmaf(rs.y, rr[i].y, o.y);
               o.z = fmaf(rs.z, rr[i].z, o.z); o.w = fmaf(rs.w, rr[i].w, o.w);
+              if (p.elu_left && c0 < (N >> 1)) {   // chunk-uniform: 16-column chunks never straddle N/2
+                o.x *= rr[i].x > 0.f ? 1.f : rr[i].x + 1.f; o.y *= rr[i].y > 0.f ? 1.f : rr[i].y + 1.f;
+                o.z *= rr[i].z > 0.f ? 1.f : rr[i].z + 1.f; o.w *= rr[i].w > 0.f ? 1.f : rr[i].w + 1.f;
+              }
             }
             st_stream_f4(p.C + (int64_t)row * p.ldc + c0 + tc, o);
           }
@@ -399,6 +404,7 @@ SN_API int sn_gemm_tf32_f32(const float* A, int64_t lda, const float* B, int64_t
       (R && !aligned16(R)) || (bias && !aligned16(bias)) || (rscale && !aligned16(rscale)))
     return SN_ERR_UNSUPPORTED;
   const bool split = !(flags & SN_GEMM_SINGLE_PASS);
+  if ((flags & SN_GEMM_ELU_BWD_LEFT) && !R) return SN_ERR_ARG;
   CUtensorMap map_a, map_b, map_blo;
   if (!make_map(&map_a, A, M, K, lda, kBlockM)) return SN_ERR_UNSUPPORTED;
   if (split) {
@@ -421,6 +427,7 @@ SN_API int sn_gemm_tf32_f32(const float* A, int64_t lda, const float* B, int64_t
   // N = 128; an L2 prefetch of the A boxes changed nothing (the mainloop is bound by shared-memory bandwidth, not by
   // DRAM latency) and was removed.
   p.l2_prefetch = (!(flags & SN_GEMM_NO_L2_PREFETCH) && R && N >= 256) ? 1 : 0;
+  p.elu_left = (flags & SN_GEMM_ELU_BWD_LEFT) ? 1 : 0;
   int dev = 0, sms = 148, smem_optin = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

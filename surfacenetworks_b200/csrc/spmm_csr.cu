@@ -120,7 +120,8 @@ static int launch_vec4(const int32_t* rowptr, const int32_t* colind, const float
 }
 
 int launch_csr_rowgroup(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X, int64_t ldx,
-                        float* Y, int64_t ldy, int64_t n_rows, int64_t C, bool elu, int variant, cudaStream_t st);
+                        float* Y, int64_t ldy, int64_t n_rows, int64_t C, bool elu, int variant, const float* G,
+                        int64_t ldg, const float* A, int64_t lda, cudaStream_t st);
 
 }  // namespace sn
 
@@ -145,7 +146,8 @@ SN_API int sn_csr_spmm_f32(const int32_t* rowptr, const int32_t* colind, const f
     return launch_status();
   }
   if (!(flags & SN_SPMM_DIRECT_GATHER)) {  // row-group kernel: C = 16 ... 512
-    const int rc = launch_csr_rowgroup(rowptr, colind, val, X, ldx, Y, ldy, n_rows, C, elu, (flags >> 8) & 15, st);
+    const int rc = launch_csr_rowgroup(rowptr, colind, val, X, ldx, Y, ldy, n_rows, C, elu, (flags >> 8) & 15, nullptr, 0, nullptr,
+                                       0, st);
     if (rc != SN_ERR_UNSUPPORTED) return rc;
   }
   const int64_t v = C / 4;  // float4 columns
@@ -155,4 +157,19 @@ SN_API int sn_csr_spmm_f32(const int32_t* rowptr, const int32_t* colind, const f
   if (v <= 8) return launch_vec4<8>(rowptr, colind, val, X, ldx, Y, ldy, n_rows, (int)C, elu, st);
   if (v <= 16) return launch_vec4<16>(rowptr, colind, val, X, ldx, Y, ldy, n_rows, (int)C, elu, st);
   return launch_vec4<32>(rowptr, colind, val, X, ldx, Y, ldy, n_rows, (int)C, elu, st);
+}
+
+// Y = (S X + G) .* elu'(A), see sn_bsr4_spmm_epilogue_f32.
+SN_API int sn_csr_spmm_epilogue_f32(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X,
+                                    int64_t ldx, float* Y, int64_t ldy, int64_t n_rows, int64_t C, const float* G,
+                                    int64_t ldg, const float* A, int64_t lda, int flags, sn_stream_t stream) {
+  using namespace sn;
+  if (n_rows < 0 || C < 0 || C > 0x7fffffffLL) return SN_ERR_ARG;
+  if (n_rows == 0 || C == 0) return SN_OK;
+  if (!rowptr || !colind || !val || !X || !Y || ldx < C || ldy < C || (G && ldg < C) || (A && lda < C)) return SN_ERR_ARG;
+  if (flags & (SN_SPMM_DIRECT_GATHER | SN_SPMM_ELU_INPUT)) return SN_ERR_UNSUPPORTED;
+  if (C % 16 || ldx % 4 || ldy % 4 || ldg % 4 || lda % 4 || !aligned16(X) || !aligned16(Y) || !aligned16(G) || !aligned16(A))
+    return SN_ERR_UNSUPPORTED;
+  return launch_csr_rowgroup(rowptr, colind, val, X, ldx, Y, ldy, n_rows, C, false, (flags >> 8) & 15, G, ldg, A, lda,
+                             (cudaStream_t)stream);
 }

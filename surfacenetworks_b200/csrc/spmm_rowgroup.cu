@@ -60,17 +60,27 @@ struct Geo {
   static constexpr size_t kSmem = (size_t)kWarps * WARP_WORDS * 4;
 };
 
+// Optional output epilogue Y = (S X + G) .* elu'(A) (backward of "elu, then gather": the activation derivative and the
+// gradient of the un-gathered half are applied where the row is stored instead of in a separate pass).
+struct Epilogue {
+  const float* G;     // [n_rows x C], leading dimension ldgb bytes, or null
+  const float* A;     // activated values elu(x) [n_rows x C], leading dimension ldab bytes, or null
+  uint32_t ldgb, ldab;
+};
+
 }  // namespace
 
 // LPR lanes per row (C = 16 LPR); RPG rows per row group per warp-tile; BLK = 4: BSR4 (16 values per entry, rotated
 // column-major, see sn_csr32_to_bsr4_fill), BLK = 1: CSR (one value per entry); PD = pipeline depth in stages of EPS
 // consecutive entries per row group; MINB = CTAs per SM the register allocation is tuned for.
-template <int LPR, int RPG, int BLK, bool ELU, int PD, int EPS, int MINB>
+template <int LPR, int RPG, int BLK, int MODE, int PD, int EPS, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB)
 rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
                      const float* __restrict__ val, const float* __restrict__ X, uint32_t ldxb,
-                     float* __restrict__ Y, uint32_t ldyb, int n_rows, int n_wtiles) {
+                     float* __restrict__ Y, uint32_t ldyb, int n_rows, int n_wtiles, const Epilogue epi) {
   using Gm = Geo<LPR, RPG, BLK, PD, EPS>;
+  constexpr bool ELU = MODE == 1;      // ELU on the gathered operand
+  constexpr bool EPI = MODE == 2;      // output epilogue (G, elu')
   constexpr int C = 16 * LPR;
   constexpr int kQuarterBytes = C;             // (C/4 floats) * 4 bytes
   constexpr int G = Gm::G, WR = Gm::WR, CAP = Gm::CAP, BPS = Gm::BPS;
@@ -160,6 +170,23 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
         const uint32_t grow = grow0 + r;
         if (grow < (uint32_t)n_rows) {
           char* yrow = const_cast<char*>(ptr_mad(Yl, grow, ldyb));
+          if (EPI && epi.G != nullptr) {        // Y = S X + G
+            const char* grow_p = ptr_mad(reinterpret_cast<const char*>(epi.G) + t * 16, grow, epi.ldgb);
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+              acc[p] = add4(acc[p], __ldg(reinterpret_cast<const float4*>(grow_p + p * kQuarterBytes)));
+          }
+          if (EPI && epi.A != nullptr) {        // ... times elu'(x) taken from the activated values a = elu(x): 1 or a + 1
+            const char* arow_p = ptr_mad(reinterpret_cast<const char*>(epi.A) + t * 16, grow, epi.ldab);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(arow_p + p * kQuarterBytes));
+              acc[p].x *= a.x > 0.f ? 1.f : a.x + 1.f;
+              acc[p].y *= a.y > 0.f ? 1.f : a.y + 1.f;
+              acc[p].z *= a.z > 0.f ? 1.f : a.z + 1.f;
+              acc[p].w *= a.w > 0.f ? 1.f : a.w + 1.f;
+            }
+          }
 #pragma unroll
           for (int p = 0; p < 4; ++p) st_stream_f4(reinterpret_cast<float*>(yrow + p * kQuarterBytes), acc[p]);
         }
@@ -260,21 +287,22 @@ template <int LPR, int RPG, int BLK, int PD, int EPS, int MINB>
 struct Launcher {
   using Gm = Geo<LPR, RPG, BLK, PD, EPS>;
   // persistent warps resident on the device for this instantiation (0: kernel cannot run)
-  static int64_t resident_warps(bool elu, int sms) {
+  static int64_t resident_warps(int mode, int sms) {
     // occupancy is a property of (kernel, device model): queried once per process and device ordinal (a benign race:
     // concurrent first calls compute the same value)
-    static int64_t cached[2][32] = {};
+    static int64_t cached[3][32] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     const bool cacheable = dev >= 0 && dev < 32;
-    if (cacheable && cached[elu][dev] != 0) return cached[elu][dev] < 0 ? 0 : cached[elu][dev];
-    const int64_t w = query_resident_warps(elu, sms);
-    if (cacheable) cached[elu][dev] = w > 0 ? w : -1;
+    if (cacheable && cached[mode][dev] != 0) return cached[mode][dev] < 0 ? 0 : cached[mode][dev];
+    const int64_t w = query_resident_warps(mode, sms);
+    if (cacheable) cached[mode][dev] = w > 0 ? w : -1;
     return w;
   }
-  static int64_t query_resident_warps(bool elu, int sms) {
-    auto kern = elu ? rowgroup_spmm_kernel<LPR, RPG, BLK, true, PD, EPS, MINB>
-                    : rowgroup_spmm_kernel<LPR, RPG, BLK, false, PD, EPS, MINB>;
+  static int64_t query_resident_warps(int mode, int sms) {
+    auto kern = mode == 1 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 1, PD, EPS, MINB>
+                : mode == 2 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 2, PD, EPS, MINB>
+                            : rowgroup_spmm_kernel<LPR, RPG, BLK, 0, PD, EPS, MINB>;
     if (Gm::kSmem > 48 * 1024 &&
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::kSmem) != cudaSuccess) {
       cudaGetLastError();
@@ -295,15 +323,17 @@ struct Launcher {
     return (double)tiles / (double)(ceil_div(tiles, w) * warps);
   }
   static int launch(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X, int64_t ldx,
-                    float* Y, int64_t ldy, int64_t n_rows, bool elu, int64_t warps, cudaStream_t st) {
+                    float* Y, int64_t ldy, int64_t n_rows, int mode, int64_t warps, const Epilogue& epi,
+                    cudaStream_t st) {
     if (warps <= 0) return SN_ERR_UNSUPPORTED;
-    auto kern = elu ? rowgroup_spmm_kernel<LPR, RPG, BLK, true, PD, EPS, MINB>
-                    : rowgroup_spmm_kernel<LPR, RPG, BLK, false, PD, EPS, MINB>;
+    auto kern = mode == 1 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 1, PD, EPS, MINB>
+                : mode == 2 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 2, PD, EPS, MINB>
+                            : rowgroup_spmm_kernel<LPR, RPG, BLK, 0, PD, EPS, MINB>;
     const int64_t n_wtiles = ceil_div(n_rows, Gm::WR);
     const int64_t ctas = ceil_div(n_wtiles, kWarps);
     const int64_t grid = ctas < warps / kWarps ? ctas : warps / kWarps;
     kern<<<(unsigned)grid, kThreads, Gm::kSmem, st>>>(rowptr, colind, val, X, (uint32_t)(ldx * 4), Y,
-                                                      (uint32_t)(ldy * 4), (int)n_rows, (int)n_wtiles);
+                                                      (uint32_t)(ldy * 4), (int)n_rows, (int)n_wtiles, epi);
     return launch_status();
   }
 };
@@ -314,14 +344,14 @@ struct Launcher {
 // most efficient one.  tile_mode 1 / 2 / 3 force short / medium / long (benchmarks).
 template <int LPR, int BLK, int PD, int EPS, int MINB>
 int launch_lpr(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X, int64_t ldx, float* Y,
-               int64_t ldy, int64_t n_rows, bool elu, int tile_mode, cudaStream_t st) {
+               int64_t ldy, int64_t n_rows, int mode, int tile_mode, const Epilogue& epi, cudaStream_t st) {
   constexpr int G = 32 / LPR;
   constexpr int RS = G >= 4 ? 1 : 4 / G;      // short tile: >= 4 rows per warp
   using LS = Launcher<LPR, RS, BLK, PD, EPS, MINB>;
   using LM = Launcher<LPR, 2 * RS, BLK, PD, EPS, MINB>;
   using LL = Launcher<LPR, 4 * RS, BLK, PD, EPS, MINB>;
   const int sms = device_info().sms;
-  const int64_t ws = LS::resident_warps(elu, sms), wm = LM::resident_warps(elu, sms), wl = LL::resident_warps(elu, sms);
+  const int64_t ws = LS::resident_warps(mode, sms), wm = LM::resident_warps(mode, sms), wl = LL::resident_warps(mode, sms);
   int pick = tile_mode;
   if ((pick < 1 || pick > 3) && LPR == 32) pick = 1;   // C = 512: one row per warp pass; short tiles measured fastest
   if (pick < 1 || pick > 3) {
@@ -334,14 +364,17 @@ int launch_lpr(const int32_t* rowptr, const int32_t* colind, const float* val, c
     else if (qm && em >= es) pick = 2;
     else pick = 1;
   }
-  if (pick == 3) return LL::launch(rowptr, colind, val, X, ldx, Y, ldy, n_rows, elu, wl, st);
-  if (pick == 2) return LM::launch(rowptr, colind, val, X, ldx, Y, ldy, n_rows, elu, wm, st);
-  return LS::launch(rowptr, colind, val, X, ldx, Y, ldy, n_rows, elu, ws, st);
+  if (pick == 3) return LL::launch(rowptr, colind, val, X, ldx, Y, ldy, n_rows, mode, wl, epi, st);
+  if (pick == 2) return LM::launch(rowptr, colind, val, X, ldx, Y, ldy, n_rows, mode, wm, epi, st);
+  return LS::launch(rowptr, colind, val, X, ldx, Y, ldy, n_rows, mode, ws, epi, st);
 }
 
 template <int BLK>
 int launch_family(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X, int64_t ldx,
-                  float* Y, int64_t ldy, int64_t n_rows, int64_t C, bool elu, int variant, cudaStream_t st) {
+                  float* Y, int64_t ldy, int64_t n_rows, int64_t C, bool elu, int variant, const Epilogue& epi,
+                  cudaStream_t st) {
+  const int mode = (epi.G || epi.A) ? 2 : (elu ? 1 : 0);
+  if (mode == 2 && (elu || variant >= 4)) return SN_ERR_UNSUPPORTED;   // the epilogue exists for the default shape only
   // ldx / ldy in bytes and entry offsets (64 B per block) must fit 32 bits
   if (n_rows >= 0x7fffff00LL || ldx >= (1LL << 30) || ldy >= (1LL << 30)) return SN_ERR_UNSUPPORTED;
   // tuning variants (tools/spmm_bench.py --variants rgN): 1 / 2 / 3 force short / medium / long warp-tiles;
@@ -350,7 +383,7 @@ int launch_family(const int32_t* rowptr, const int32_t* colind, const float* val
   // (1, 1, 4) = 32 warps per SM with one entry in flight per row group is the fastest shape at every width.
   const int tile_mode = variant >= 1 && variant <= 3 ? variant : 0;
 #define SN_RG(LPR, PD, EPS, MINB) \
-  launch_lpr<LPR, BLK, PD, EPS, MINB>(rowptr, colind, val, X, ldx, Y, ldy, n_rows, elu, tile_mode, st)
+  launch_lpr<LPR, BLK, PD, EPS, MINB>(rowptr, colind, val, X, ldx, Y, ldy, n_rows, mode, tile_mode, epi, st)
 #define SN_RG_TUNE(LPR)                          \
   switch (variant) {                             \
     case 4: return SN_RG(LPR, 1, 2, 3);          \
@@ -373,14 +406,20 @@ int launch_family(const int32_t* rowptr, const int32_t* colind, const float* val
 
 // Both return SN_ERR_UNSUPPORTED when the kernel does not apply (C not in {32,...,512}); callers fall back to the
 // direct-gather kernels (at C = 16 a row is one 64-byte segment and a lane per row has nothing left to share).
+// G / A (optional, null = none): output epilogue Y = (S X + G) .* elu'(A), leading dimensions ldg / lda in floats.
 int launch_bsr4_rowgroup(const int32_t* browptr, const int32_t* bcolind, const float* bval, const float* X,
                          int64_t ldx, float* Y, int64_t ldy, int64_t n_brows, int64_t C, bool elu, int variant,
-                         cudaStream_t st) {
-  return launch_family<4>(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C, elu, variant, st);
+                         const float* G, int64_t ldg, const float* A, int64_t lda, cudaStream_t st) {
+  if (ldg >= (1LL << 30) || lda >= (1LL << 30)) return SN_ERR_UNSUPPORTED;
+  const Epilogue epi{G, A, (uint32_t)(ldg * 4), (uint32_t)(lda * 4)};
+  return launch_family<4>(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C, elu, variant, epi, st);
 }
 int launch_csr_rowgroup(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X, int64_t ldx,
-                        float* Y, int64_t ldy, int64_t n_rows, int64_t C, bool elu, int variant, cudaStream_t st) {
-  return launch_family<1>(rowptr, colind, val, X, ldx, Y, ldy, n_rows, C, elu, variant, st);
+                        float* Y, int64_t ldy, int64_t n_rows, int64_t C, bool elu, int variant, const float* G,
+                        int64_t ldg, const float* A, int64_t lda, cudaStream_t st) {
+  if (ldg >= (1LL << 30) || lda >= (1LL << 30)) return SN_ERR_UNSUPPORTED;
+  const Epilogue epi{G, A, (uint32_t)(ldg * 4), (uint32_t)(lda * 4)};
+  return launch_family<1>(rowptr, colind, val, X, ldx, Y, ldy, n_rows, C, elu, variant, epi, st);
 }
 
 }  // namespace sn

@@ -76,7 +76,8 @@ def elu_colstats_supported(X, out):
             X.data_ptr() % 16 == 0 and out.data_ptr() % 16 == 0 and X.shape[0] > 0)
 
 
-def gemm_tf32(A, B, bias=None, R=None, rscale=None, out=None, single_pass=False, group_bias=None, rows_per_group=0):
+def gemm_tf32(A, B, bias=None, R=None, rscale=None, out=None, single_pass=False, group_bias=None, rows_per_group=0,
+              elu_bwd_left=False):
     """out[M, N] = A[M, K] @ B[N, K]^T + bias + group_bias[row // rows_per_group] + rscale * R
     (3xTF32 tensor-core GEMM; N > 256 is split in column blocks; B may be a row-strided view)."""
     M, K = A.shape
@@ -90,6 +91,10 @@ def gemm_tf32(A, B, bias=None, R=None, rscale=None, out=None, single_pass=False,
     step = Nn if Nn in _GEMM_N else 256
     nb = N.lib.sn_gemm_tf32_ws_bytes(step, K)
     flags = N.SN_GEMM_SINGLE_PASS if single_pass else 0
+    if elu_bwd_left:
+        if R is None or step != Nn:
+            raise ValueError("elu_bwd_left needs the residual operand and a single column block")
+        flags |= N.SN_GEMM_ELU_BWD_LEFT
     with torch.cuda.device(A.device):
         for n0 in range(0, Nn, step):
             ws = _ws(nb, A.device)
@@ -125,7 +130,8 @@ def gemm_tn_tf32(A, B, single_pass=False):
 
 class _BnLinear(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, Z, gamma, beta, W, b, residual, running_mean, running_var, training, momentum, eps, left_stats):
+    def forward(ctx, Z, gamma, beta, W, b, residual, running_mean, running_var, training, momentum, eps, left_stats,
+                elu_bwd_left=False):
         rows, K = Z.shape
         Nn = W.shape[0]
         dev = Z.device
@@ -150,13 +156,14 @@ class _BnLinear(torch.autograd.Function):
         res = None if residual is None else residual.contiguous()
         Y = gemm_tf32(Z, Wf, bias=bf, R=res)
         ctx.save_for_backward(Z, W, stk, mean)
-        ctx.training, ctx.has_res = training, residual is not None
+        ctx.training, ctx.has_res, ctx.elu_bwd_left = training, residual is not None, elu_bwd_left
         return Y
 
     @staticmethod
     def backward(ctx, dY):
         Z, W, stk, mean = ctx.saved_tensors
-        dY = dY.contiguous()
+        if dY.stride(1) != 1 or dY.stride(0) % 4 or dY.data_ptr() % 16:     # row-strided views (halves of a dZ) are fine
+            dY = dY.contiguous()
         rows, K = Z.shape
         Nn = W.shape[0]
         dev = Z.device
@@ -175,10 +182,12 @@ class _BnLinear(torch.autograd.Function):
                    Nn, K, rows, 1 if ctx.training else 0, _ptr(dW), _ptr(db), _ptr(vec[0]), _ptr(vec[1]), _ptr(vec[2]),
                    _ptr(vec[3]), _ptr(WsT), _stream())
         if ctx.training:
-            dZ = gemm_tf32(dY, WsT, bias=vec[3], R=Z, rscale=vec[2])
+            # elu_bwd_left: the left half of Z holds activated values elu(x_self); its gradient leaves the epilogue
+            # already multiplied by elu'(x_self) (ops._StageConcat.backward then skips its elementwise pass)
+            dZ = gemm_tf32(dY, WsT, bias=vec[3], R=Z, rscale=vec[2], elu_bwd_left=ctx.elu_bwd_left)
         else:
             dZ = gemm_tf32(dY, WsT)
-        return dZ, vec[0], vec[1], dW, db, (dY if ctx.has_res else None), None, None, None, None, None, None
+        return dZ, vec[0], vec[1], dW, db, (dY if ctx.has_res else None), None, None, None, None, None, None, None
 
 
 def segment_sum(X, rows_per_seg, n_seg, weight=None):
@@ -312,8 +321,12 @@ def bn_linear(z, bn, fc, residual=None):
         left = getattr(z, "_sn_left_stats", None) if training else None
         if left is not None and not (z.shape[1] - left[0].numel()) % 4 == 0:
             left = None
+        cell = getattr(z, "_sn_stage_cell", None)
+        fold = bool(cell is not None and training and torch.is_grad_enabled() and fc.weight.shape[1] in _GEMM_N)
+        if fold:
+            cell["left_premultiplied"] = True
         return _BnLinear.apply(z, bn.weight, bn.bias, fc.weight, fc.bias, residual, bn.running_mean, bn.running_var,
-                               training, momentum, bn.eps, left)
+                               training, momentum, bn.eps, left, fold)
     # Output widths between the tensor-core shapes (the 128 -> 120 head of the ARAP / dense_correspondence models,
     # conv2 at as_rigid_as_possible/models.py:121): zero-pad the Linear to the next supported width and slice -- the
     # cuBLAS fp32 SIMT GEMMs it replaces were 0.6 ms of the 19 ms step (profiles/r1b_launches_bench_summary.json)

@@ -72,7 +72,7 @@ class _StageConcat(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x_self, x_gather, op, same, want_stats):
+    def forward(ctx, x_self, x_gather, op, same, want_stats, cell):
         xs = x_self.contiguous()
         rows_out, C = xs.shape
         Z = torch.empty(rows_out, 2 * C, dtype=torch.float32, device=xs.device)
@@ -91,7 +91,7 @@ class _StageConcat(torch.autograd.Function):
             elu_into(xg, act)
             op.apply(act, out=right)
             ctx.save_for_backward(Z, act)
-        ctx.op, ctx.same, ctx.C = op, same, C
+        ctx.op, ctx.same, ctx.C, ctx.cell = op, same, C, cell
         if stats is None:
             empty = Z.new_empty(0)
             stats = (empty, empty.clone())
@@ -105,15 +105,22 @@ class _StageConcat(torch.autograd.Function):
         g_left, g_right = gZ[:, :C], gZ[:, C:]
         if ctx.same:
             (Z,) = ctx.saved_tensors
-            t = op.T.apply(g_right)                       # S^T g
-            _elu_bwd(Z[:, :C], False, g_left, t, t)       # (g_left + S^T g) * elu'(x), in place
-            return t, None, None, None, None
+            t = op.T.apply_epilogue(g_right, G=g_left, A=Z[:, :C])     # (g_left + S^T g) * elu'(x) in the store path
+            if t is None:
+                t = op.T.apply(g_right)                   # S^T g
+                _elu_bwd(Z[:, :C], False, g_left, t, t)   # (g_left + S^T g) * elu'(x), in place
+            return t, None, None, None, None, None
         Z, act = ctx.saved_tensors
-        g_self = torch.empty(gZ.shape[0], C, dtype=torch.float32, device=gZ.device)
-        _elu_bwd(Z[:, :C], False, g_left, None, g_self)
-        t = op.T.apply(g_right)
-        _elu_bwd(act, False, t, None, t)
-        return g_self, t, None, None, None
+        if ctx.cell is not None and ctx.cell.get("left_premultiplied"):
+            g_self = g_left                               # the dZ GEMM already applied elu'(x_self) (SN_GEMM_ELU_BWD_LEFT)
+        else:
+            g_self = torch.empty(gZ.shape[0], C, dtype=torch.float32, device=gZ.device)
+            _elu_bwd(Z[:, :C], False, g_left, None, g_self)
+        t = op.T.apply_epilogue(g_right, A=act)           # (S^T g) * elu'(x_gather) in the store path
+        if t is None:
+            t = op.T.apply(g_right)
+            _elu_bwd(act, False, t, None, t)
+        return g_self, t, None, None, None, None
 
 
 def stage_concat(op, x_self, x_gather=None, want_stats=True):
@@ -122,7 +129,12 @@ def stage_concat(op, x_self, x_gather=None, want_stats=True):
     With ``want_stats`` the activation pass also reduces the left half's BatchNorm statistics; they ride on the
     returned tensor (``Z._sn_left_stats``) and ``fused.bn_linear`` then only reduces the right half."""
     same = x_gather is None
-    Z, mean_l, var_l = _StageConcat.apply(x_self, x_self if same else x_gather, op, same, want_stats)
+    # not-same stages: the consumer (fused.bn_linear) may fold elu'(x_self) into its dZ GEMM epilogue; it says so
+    # through this cell, which the backward above reads (default: not folded, run the elementwise pass)
+    cell = None if same else {"left_premultiplied": False}
+    Z, mean_l, var_l = _StageConcat.apply(x_self, x_self if same else x_gather, op, same, want_stats, cell)
     if mean_l.numel():
         Z._sn_left_stats = (mean_l, var_l)
+    if cell is not None:
+        Z._sn_stage_cell = cell
     return Z

@@ -253,3 +253,24 @@ def test_gemm_tn_matches_fp64(R, N):
     assert torch.equal(G, run_gemm_tn(A, B))          # deterministic split-K reduction
     G1 = run_gemm_tn(A, B, single_pass=True)
     assert torch.all((G1.double() - G64).abs() <= 2e-3 * mag)
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 256, 128), (777, 64, 32), (4096, 128, 64)])
+def test_gemm_elu_bwd_left_epilogue(M, N, K):
+    """SN_GEMM_ELU_BWD_LEFT: columns [0, N/2) of dZ = dY Ws + p.*Z + q leave the epilogue multiplied by elu'(Z) (Z holds
+    activated values) -- identical bits to the unfused product followed by the elementwise multiply."""
+    from surfacenetworks_b200 import fused
+    g = torch.Generator(device=DEV).manual_seed(M + N)
+    dY = torch.randn(M, K, device=DEV, generator=g)
+    Ws = torch.randn(N, K, device=DEV, generator=g) / K ** 0.5
+    Z = torch.randn(M, N, device=DEV, generator=g)
+    Z[:, :N // 2] = torch.nn.functional.elu(Z[:, :N // 2])                 # activated left half, as in the stage buffer
+    p, q = torch.randn(N, device=DEV, generator=g), torch.randn(N, device=DEV, generator=g)
+    plain = fused.gemm_tf32(dY, Ws, bias=q, R=Z, rscale=p)
+    fusedz = fused.gemm_tf32(dY, Ws, bias=q, R=Z, rscale=p, elu_bwd_left=True)
+    a = Z[:, :N // 2]
+    expect = plain.clone()
+    expect[:, :N // 2] = plain[:, :N // 2] * torch.where(a > 0, torch.ones_like(a), a + 1)
+    assert torch.equal(fusedz, expect)
+    with pytest.raises(ValueError):
+        fused.gemm_tf32(dY, Ws, bias=q, elu_bwd_left=True)                 # needs the residual operand

@@ -296,6 +296,38 @@ def test_rowgroup_persistent_warps(C, n_rows):
     within_bound(y.cpu().numpy(), y64, bound, "csr persistent")
 
 
+@pytest.mark.parametrize("C", [32, 64, 128, 256, 512, 48])
+def test_spmm_epilogue_matches_separate_passes(C):
+    """sn_*_spmm_epilogue_f32: Y = (S X + G) .* elu'(A) in the store path == SpMM, add, elementwise derivative as three
+    steps (same fp32 operations in the same order: bit-identical); unsupported widths report None."""
+    O = ops_mod()
+    rng = np.random.default_rng(C)
+    n_rows, n_cols = 500, 300
+    row, col, val = random_coo(rng, n_rows, n_cols, 3000, empty_rows=(0, 7, 8, 9, 499))
+    opc = O.CsrOperator.from_torch_coo(coo_cuda(np.stack([row, col]), val, (n_rows, n_cols), False))
+    brow, bcol, bvals = random_coo(rng, 4 * n_rows, 4 * n_cols, 9000, empty_rows=range(16, 40))
+    opb = O.Bsr4Operator.from_torch_coo(coo_cuda(np.stack([brow, bcol]), bvals, (4 * n_rows, 4 * n_cols), False))
+    X = torch.from_numpy(det_array((n_cols, C), 1)).to(DEV)
+    Gbuf = torch.from_numpy(det_array((n_rows, 2 * C), 2)).to(DEV)
+    G = Gbuf[:, :C]                                                          # row-strided, like the halves of a dZ
+    A = torch.nn.functional.elu(torch.from_numpy(det_array((n_rows, C), 3)).to(DEV))
+    dA = torch.where(A > 0, torch.ones_like(A), A + 1)
+    for op in (opc, opb):
+        plain = op.apply(X)
+        for g_, a_ in ((G, A), (None, A), (G, None)):
+            y = op.apply_epilogue(X, G=g_, A=a_)
+            if C == 48:
+                assert y is None
+                continue
+            expect = plain if g_ is None else plain + g_
+            expect = expect if a_ is None else expect * dA
+            assert torch.equal(y, expect), (op.kind, g_ is None, a_ is None)
+        if C != 48:                                                          # Y may alias G
+            Gc = G.clone()
+            y = op.apply_epilogue(X, G=Gc, A=A, out=Gc)
+            assert torch.equal(y, (plain + G) * dA)
+
+
 def test_elu_kernels():
     from surfacenetworks_b200 import ops
     x = np.concatenate([-np.logspace(-6, 1.2, 300), np.logspace(-6, 1.2, 300), [0.0, -0.0]]).astype(np.float32)
