@@ -111,7 +111,9 @@ int sn_assemble_block_diag(const int64_t* parts, int64_t n_parts, int64_t rows_p
  * the reference's operation order and rounded to fp32 once (the reference's .astype('float32')):
  *   sn_mesh_dirac_bsr4   : D  [n*f_pad x n*v_pad] block rows/cols: d_browptr [n*f_pad + 1], d_bcolind [<= 3 n f_pad],
  *                          d_bval [<= 48 n f_pad];  D* [n*v_pad x n*f_pad]: da_browptr [n*v_pad + 1], da_bcolind /
- *                          da_bval with the same capacities.  Block counts = the last row pointers.
+ *                          da_bval with the same capacities.  Block counts = the last row pointers.  Optionally
+ *                          (non-NULL pairs) the transposes used by backward: D^T = (da_browptr, dt_bcolind, dt_bval)
+ *                          shares D*'s structure, (D*)^T = (d_browptr, dat_bcolind, dat_bval) shares D's.
  *   sn_mesh_laplacian_csr: L  [n*v_pad x n*v_pad]: rowptr [n*v_pad + 1], colind / val [<= n (v_pad + 6 f_pad)].
  * status: one device int32, 0 on success, otherwise the largest per-vertex face count found (> 64): the rows of such
  * vertices are left empty.  Deterministic (no floating-point atomics).  ws: sn_mesh_ws_bytes(n_meshes, v_pad, f_pad).
@@ -119,7 +121,8 @@ int sn_assemble_block_diag(const int64_t* parts, int64_t n_parts, int64_t rows_p
 size_t sn_mesh_ws_bytes(int64_t n_meshes, int64_t v_pad, int64_t f_pad);
 int sn_mesh_dirac_bsr4(const double* V, const int32_t* F, int64_t n_meshes, int64_t v_pad, int64_t f_pad,
                        int32_t* d_browptr, int32_t* d_bcolind, float* d_bval, int32_t* da_browptr, int32_t* da_bcolind,
-                       float* da_bval, int32_t* status, void* ws, size_t ws_bytes, sn_stream_t stream);
+                       float* da_bval, int32_t* dt_bcolind, float* dt_bval, int32_t* dat_bcolind, float* dat_bval,
+                       int32_t* status, void* ws, size_t ws_bytes, sn_stream_t stream);
 int sn_mesh_laplacian_csr(const double* V, const int32_t* F, int64_t n_meshes, int64_t v_pad, int64_t f_pad,
                           int32_t* rowptr, int32_t* colind, float* val, int32_t* status, void* ws, size_t ws_bytes,
                           sn_stream_t stream);

@@ -144,8 +144,9 @@ __device__ __forceinline__ void store_block(float* out, const double (&B)[4][4])
 // D: one thread per face row; its three blocks in ascending vertex order
 __global__ void __launch_bounds__(128)
 dirac_rows_kernel(const double* __restrict__ V, const int32_t* __restrict__ F, const double* __restrict__ area,
-                  int n_meshes, int v_pad, int f_pad, const int* __restrict__ browptr, int32_t* __restrict__ bcolind,
-                  float* __restrict__ bval) {
+                  const double* __restrict__ varea, int n_meshes, int v_pad, int f_pad, const int* __restrict__ browptr,
+                  int32_t* __restrict__ bcolind, float* __restrict__ bval, int32_t* __restrict__ at_bcolind,
+                  float* __restrict__ at_bval) {
   const int64_t bf = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (bf >= (int64_t)n_meshes * f_pad || area[bf] < 0.0) return;
   const int b = (int)(bf / f_pad);
@@ -166,6 +167,16 @@ dirac_rows_kernel(const double* __restrict__ V, const int32_t* __restrict__ F, c
     dirac_block(P, f, c, area[bf], M);
     bcolind[k0 + i] = b * v_pad + f[c];
     store_block(bval + (int64_t)(k0 + i) * 16, M);
+    if (at_bval != nullptr) {        // (D*)^T has D's structure: block (f, j) = block*(j, f)^T = M A_f / A_v[j]
+      const double av = varea[(int64_t)b * v_pad + f[c]];
+      double T[4][4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) T[p][q] = __ddiv_rn(__dmul_rn(M[p][q], area[bf]), av);
+      at_bcolind[k0 + i] = b * v_pad + f[c];
+      store_block(at_bval + (int64_t)(k0 + i) * 16, T);
+    }
   }
 }
 
@@ -173,7 +184,8 @@ dirac_rows_kernel(const double* __restrict__ V, const int32_t* __restrict__ F, c
 __global__ void __launch_bounds__(128)
 adjoint_rows_kernel(const double* __restrict__ V, const int32_t* __restrict__ F, const double* __restrict__ area,
                     const double* __restrict__ varea, int v_pad, int f_pad, int64_t n_vert, const int* __restrict__ vptr,
-                    const int* __restrict__ inc, int32_t* __restrict__ bcolind, float* __restrict__ bval) {
+                    const int* __restrict__ inc, int32_t* __restrict__ bcolind, float* __restrict__ bval,
+                    int32_t* __restrict__ dt_bcolind, float* __restrict__ dt_bval) {
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n_vert) return;
   const int b = (int)(v / v_pad);
@@ -194,6 +206,15 @@ adjoint_rows_kernel(const double* __restrict__ V, const int32_t* __restrict__ F,
       for (int q = 0; q < 4; ++q) T[p][q] = __ddiv_rn(__dmul_rn(M[q][p], af), av);   // mat^T * A_f / A_v, mesh.py:59
     bcolind[k0 + i] = (int)bf;
     store_block(bval + (int64_t)(k0 + i) * 16, T);
+    if (dt_bval != nullptr) {        // D^T has D*'s structure: block (j, f) = block(f, j)^T
+      double Mt[4][4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) Mt[p][q] = M[q][p];
+      dt_bcolind[k0 + i] = (int)bf;
+      store_block(dt_bval + (int64_t)(k0 + i) * 16, Mt);
+    }
   }
 }
 
@@ -385,24 +406,28 @@ SN_API size_t sn_mesh_ws_bytes(int64_t n_meshes, int64_t v_pad, int64_t f_pad) {
 
 SN_API int sn_mesh_dirac_bsr4(const double* V, const int32_t* F, int64_t n_meshes, int64_t v_pad, int64_t f_pad,
                               int32_t* d_browptr, int32_t* d_bcolind, float* d_bval, int32_t* da_browptr,
-                              int32_t* da_bcolind, float* da_bval, int32_t* status, void* ws, size_t ws_bytes,
+                              int32_t* da_bcolind, float* da_bval, int32_t* dt_bcolind, float* dt_bval,
+                              int32_t* dat_bcolind, float* dat_bval, int32_t* status, void* ws, size_t ws_bytes,
                               sn_stream_t stream) {
   using namespace sn;
   using namespace sn::mesh;
   int rc = check_args(V, F, n_meshes, v_pad, f_pad, status, ws, ws_bytes);
   if (rc != SN_OK || n_meshes == 0) return rc;
   if (!d_browptr || !d_bcolind || !d_bval || !da_browptr || !da_bcolind || !da_bval) return SN_ERR_ARG;
-  if (!aligned16(d_bval) || !aligned16(da_bval)) return SN_ERR_UNSUPPORTED;
+  if (!aligned16(d_bval) || !aligned16(da_bval) || !aligned16(dt_bval) || !aligned16(dat_bval)) return SN_ERR_UNSUPPORTED;
+  if ((dt_bval == nullptr) != (dt_bcolind == nullptr) || (dat_bval == nullptr) != (dat_bcolind == nullptr)) return SN_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const Workspace w = carve(ws, n_meshes, v_pad, f_pad);
   const int64_t nv = n_meshes * v_pad, nf = n_meshes * f_pad;
   rc = front_end(V, F, n_meshes, v_pad, f_pad, status, w, d_browptr, st);
   if (rc != SN_OK) return rc;
-  dirac_rows_kernel<<<(unsigned)ceil_div(nf, 128), 128, 0, st>>>(V, F, w.area, (int)n_meshes, (int)v_pad, (int)f_pad,
-                                                                  d_browptr, d_bcolind, d_bval);
+  dirac_rows_kernel<<<(unsigned)ceil_div(nf, 128), 128, 0, st>>>(V, F, w.area, w.varea, (int)n_meshes, (int)v_pad,
+                                                                  (int)f_pad, d_browptr, d_bcolind, d_bval, dat_bcolind,
+                                                                  dat_bval);
   cudaMemcpyAsync(da_browptr, w.vcount, sizeof(int) * (nv + 1), cudaMemcpyDeviceToDevice, st);
   adjoint_rows_kernel<<<(unsigned)ceil_div(nv, 128), 128, 0, st>>>(V, F, w.area, w.varea, (int)v_pad, (int)f_pad, nv,
-                                                                    w.vcount, w.inc, da_bcolind, da_bval);
+                                                                    w.vcount, w.inc, da_bcolind, da_bval, dt_bcolind,
+                                                                    dt_bval);
   return launch_status();
 }
 

@@ -369,11 +369,16 @@ def _check_mesh_status(status):
         raise ValueError("a vertex belongs to %d faces; GPU operator construction supports at most 64" % worst)
 
 
-def build_dirac_operators(V, F):
+def build_dirac_operators(V, F, with_transposes=True, sync=True):
     """Batch Dirac operator ``D`` [B*f_pad x B*v_pad] and adjoint ``D*`` [B*v_pad x B*f_pad] (block rows x block
     columns) built on the GPU from padded positions ``V`` [B, v_pad, 3] and faces ``F`` [B, f_pad, 3] (local vertex
     indices, padding faces = -1).  Same values as the reference's mesh.dirac (src/utils/mesh.py:35-64) after its
-    ``.astype('float32')``; replaces the offline numpy construction + sparse_diag_cat + upload."""
+    ``.astype('float32')``; replaces the offline numpy construction + sparse_diag_cat + upload.
+
+    ``with_transposes``: D^T and (D*)^T (what backward applies) come out of the same kernels and are attached as
+    ``D.T`` / ``DA.T``.  ``sync=False`` skips the two small read-backs (status check, block count): the operators then
+    carry the capacity 3*B*f_pad as their block count (only the accounting of ``algorithmic_bytes`` is affected), so
+    the whole construction is stream-ordered -- for per-step geometry inside a pipelined training loop."""
     V, F = _check_mesh_batch(V, F)
     n, v_pad, f_pad = V.size(0), V.size(1), F.size(1)
     dev = V.device
@@ -385,16 +390,33 @@ def build_dirac_operators(V, F):
     a_val = torch.empty(16 * cap, dtype=torch.float32, device=dev)
     status = torch.zeros(1, **i32)
     ws, nbytes = _mesh_ws(n, v_pad, f_pad, dev)
+    dt_ind = dt_val = at_ind = at_val = None
+    if with_transposes:
+        dt_ind, at_ind = torch.empty(cap, **i32), torch.empty(cap, **i32)
+        dt_val = torch.empty(16 * cap, dtype=torch.float32, device=dev)
+        at_val = torch.empty(16 * cap, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         N.call("sn_mesh_dirac_bsr4", _ptr(V), _ptr(F), n, v_pad, f_pad, _ptr(d_ptr), _ptr(d_ind), _ptr(d_val),
-               _ptr(a_ptr), _ptr(a_ind), _ptr(a_val), _ptr(status), _ptr(ws), nbytes, _stream())
-    _check_mesh_status(status)
-    nb = int(d_ptr[-1].item())                       # one read-back per construction, like from_source
-    max_a = int((a_ptr[1:] - a_ptr[:-1]).max().item()) if n * v_pad else 0
-    D = Bsr4Operator(d_ptr, d_ind[:max(nb, 1)], d_val[:16 * max(nb, 1)], n * f_pad, n * v_pad,
-                     _StructureSource("bsr4", d_ptr, d_ind, d_val, 4 * n * f_pad, 4 * n * v_pad, nb), nb, 3 if nb else 0)
-    DA = Bsr4Operator(a_ptr, a_ind[:max(nb, 1)], a_val[:16 * max(nb, 1)], n * v_pad, n * f_pad,
-                      _StructureSource("bsr4", a_ptr, a_ind, a_val, 4 * n * v_pad, 4 * n * f_pad, nb), nb, max_a)
+               _ptr(a_ptr), _ptr(a_ind), _ptr(a_val), _ptr(dt_ind), _ptr(dt_val), _ptr(at_ind), _ptr(at_val),
+               _ptr(status), _ptr(ws), nbytes, _stream())
+    if sync:
+        _check_mesh_status(status)
+        nb = int(d_ptr[-1].item())                   # one read-back per construction, like from_source
+        max_a = int((a_ptr[1:] - a_ptr[:-1]).max().item()) if n * v_pad else 0
+    else:
+        nb, max_a = cap, 0
+    keep = max(nb, 1)
+    D = Bsr4Operator(d_ptr, d_ind[:keep], d_val[:16 * keep], n * f_pad, n * v_pad,
+                     _StructureSource("bsr4", d_ptr, d_ind, d_val, 4 * n * f_pad, 4 * n * v_pad, nb) if sync else None,
+                     nb, 3 if nb else 0)
+    DA = Bsr4Operator(a_ptr, a_ind[:keep], a_val[:16 * keep], n * v_pad, n * f_pad,
+                      _StructureSource("bsr4", a_ptr, a_ind, a_val, 4 * n * v_pad, 4 * n * f_pad, nb) if sync else None,
+                      nb, max_a)
+    if with_transposes:
+        D._T = Bsr4Operator(a_ptr, dt_ind[:keep], dt_val[:16 * keep], n * v_pad, n * f_pad, None, nb, max_a)
+        DA._T = Bsr4Operator(d_ptr, at_ind[:keep], at_val[:16 * keep], n * f_pad, n * v_pad, None, nb, 3 if nb else 0)
+        D._T._T, DA._T._T = D, DA
+    D.status = DA.status = status                    # device int32: 0, or the largest per-vertex face count (> 64)
     return D, DA
 
 

@@ -84,6 +84,13 @@ def test_ragged_batch_matches_host_builder(sizes):
     check_bsr4(D.T, Dr.T, "D^T")
     check_bsr4(DA.T, DAr.T, "D*^T")
     check_csr(L.T, Lr.T, "L^T")
+    # stream-ordered construction (no read-backs): same arrays, capacity-sized block count
+    D2, DA2 = O.build_dirac_operators(Vg, Fg, sync=False)
+    nb = D.n_blocks
+    assert int(D2.status.item()) == 0 and D2.n_blocks == 3 * len(sizes) * nf
+    for got, ref in ((D2, D), (DA2, DA), (D2.T, D.T), (DA2.T, DA.T)):
+        assert torch.equal(got.browptr, ref.browptr) and torch.equal(got.bcolind[:nb], ref.bcolind[:nb])
+        assert torch.equal(got.bval[:16 * nb], ref.bval[:16 * nb])
     # and the operators drive the layers: one DirResNet2 forward on GPU-built vs host-built operators
     from det import det_fill
     C = 32
