@@ -74,7 +74,7 @@ struct Epilogue {
 // column-major, see sn_csr32_to_bsr4_fill), BLK = 1: CSR (one value per entry); PD = pipeline depth in stages of EPS
 // consecutive entries per row group; MINB = CTAs per SM the register allocation is tuned for.
 template <int LPR, int RPG, int BLK, int MODE, int PD, int EPS, int MINB>
-__global__ void __launch_bounds__(kThreads, (MODE == 2 && MINB > 3) ? 3 : MINB)   // the epilogue keeps 16 more registers
+__global__ void __launch_bounds__(kThreads, MINB)
 rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
                      const float* __restrict__ val, const float* __restrict__ X, uint32_t ldxb,
                      float* __restrict__ Y, uint32_t ldyb, int n_rows, int n_wtiles, const Epilogue epi) {
@@ -164,17 +164,6 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
 #pragma unroll
     for (int p = 0; p < 4; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    // epilogue operand elu(x) of the row being accumulated: fetched when the row STARTS, consumed when it ends, so its
-    // latency hides behind the row's gathers
-    float4 ea[4];
-    auto load_epi = [&]() {
-      if (EPI && epi.A != nullptr && r < RPG && grow0 + r < (uint32_t)n_rows) {
-        const char* arow_p = ptr_mad(reinterpret_cast<const char*>(epi.A) + t * 16, grow0 + r, epi.ldab);
-#pragma unroll
-        for (int p = 0; p < 4; ++p) ea[p] = __ldg(reinterpret_cast<const float4*>(arow_p + p * kQuarterBytes));
-      }
-    };
-    load_epi();
     // store every row that ends at entry k (the current one, then the empty rows behind it)
     auto flush = [&]() {
       while (r < RPG && k == next_end) {
@@ -187,10 +176,13 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
             for (int p = 0; p < 4; ++p)
               acc[p] = add4(acc[p], __ldg(reinterpret_cast<const float4*>(grow_p + p * kQuarterBytes)));
           }
+          // (fetching this operand when the row STARTS, 16 more registers and 3 CTAs/SM, was measured slower: 104 / 92 us
+          // against 96 / 89 us for D^T / (D*)^T at the cfg3 size)
           if (EPI && epi.A != nullptr) {        // ... times elu'(x) taken from the activated values a = elu(x): 1 or a + 1
+            const char* arow_p = ptr_mad(reinterpret_cast<const char*>(epi.A) + t * 16, grow, epi.ldab);
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
-              const float4 a = ea[p];
+              const float4 a = __ldg(reinterpret_cast<const float4*>(arow_p + p * kQuarterBytes));
               acc[p].x *= a.x > 0.f ? 1.f : a.x + 1.f;
               acc[p].y *= a.y > 0.f ? 1.f : a.y + 1.f;
               acc[p].z *= a.z > 0.f ? 1.f : a.z + 1.f;
@@ -204,7 +196,6 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
         for (int p = 0; p < 4; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
         ++r;
         next_end = bp[rl0 + r + 1];
-        load_epi();
       }
     };
     // stage s <- entries kk .. kk + EPS - 1 of this group's run: X rows to registers; BSR4 values (64 bytes per
