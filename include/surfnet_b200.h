@@ -148,19 +148,20 @@ int sn_bsr4_spmm_f32(const int32_t* browptr, const int32_t* bcolind, const float
                      int64_t n_brows, int64_t C, int flags, sn_stream_t stream);
 
 /* Backward-pass SpMM with the activation derivative in its store path:
- *     Y = (S * X + G) .* elu'(A)        G, A optional (NULL: no addend / no derivative), [n_rows x C] with ldg / lda
+ *     Y = (S * X + G) .* elu'(A) + G2   G, A, G2 optional (NULL: absent), each [n_rows x C] with its leading dimension
  * A holds ACTIVATED values a = elu(x), so elu' = 1 for a > 0 and a + 1 otherwise (as sn_elu_bwd_f32 with a_is_raw = 0).
  * With S = the transposed operator, X = the gradient of the gathered half and G = the gradient of the un-gathered half
  * this is the whole backward of "elu, then [x | S x]" (src/utils/utils_pt.py:161-168,195-216 through autograd in the
- * reference) in one launch instead of an SpMM plus an elementwise pass.  Y may alias G.  Row-group kernel only:
+ * reference) in one launch instead of an SpMM plus an elementwise pass; G2 carries a gradient that bypasses the
+ * activation (the block residual, utils_pt.py:180,220), so autograd's accumulation adds disappear too.  Y may alias G / G2.  Row-group kernel only:
  * returns SN_ERR_UNSUPPORTED for C not in {32, 64, 128, 256, 512} or unaligned operands (callers then run
  * sn_*_spmm_f32 followed by sn_elu_bwd_f32). */
 int sn_csr_spmm_epilogue_f32(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X,
                              int64_t ldx, float* Y, int64_t ldy, int64_t n_rows, int64_t C, const float* G, int64_t ldg,
-                             const float* A, int64_t lda, int flags, sn_stream_t stream);
+                             const float* A, int64_t lda, const float* G2, int64_t ldg2, int flags, sn_stream_t stream);
 int sn_bsr4_spmm_epilogue_f32(const int32_t* browptr, const int32_t* bcolind, const float* bval, const float* X,
                               int64_t ldx, float* Y, int64_t ldy, int64_t n_brows, int64_t C, const float* G, int64_t ldg,
-                              const float* A, int64_t lda, int flags, sn_stream_t stream);
+                              const float* A, int64_t lda, const float* G2, int64_t ldg2, int flags, sn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Activation pass in front of each operator application (F.elu at utils_pt.py:161,172,195,208).

@@ -48,8 +48,10 @@ SIGNATURES = {
     "sn_gemm_tf32_ws_bytes": (_sz, [_i64, _i64]),
     "sn_gemm_tf32_f32": (_int, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _int,
                                 _ptr, _sz, _ptr]),
-    "sn_csr_spmm_epilogue_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _int, _ptr]),
-    "sn_bsr4_spmm_epilogue_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _int, _ptr]),
+    "sn_csr_spmm_epilogue_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64,
+                                        _int, _ptr]),
+    "sn_bsr4_spmm_epilogue_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64,
+                                         _int, _ptr]),
     "sn_mesh_ws_bytes": (_sz, [_i64, _i64, _i64]),
     "sn_mesh_dirac_bsr4": (_int, [_ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
                                   _ptr, _sz, _ptr]),

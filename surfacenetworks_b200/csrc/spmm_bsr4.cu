@@ -130,7 +130,7 @@ int launch_bsr4_stream(const int32_t* browptr, const int32_t* bcolind, const flo
                        float* Y, int64_t ldy, int64_t n_brows, int64_t C, bool elu, cudaStream_t st);
 int launch_bsr4_rowgroup(const int32_t* browptr, const int32_t* bcolind, const float* bval, const float* X,
                          int64_t ldx, float* Y, int64_t ldy, int64_t n_brows, int64_t C, bool elu, int variant,
-                         const float* G, int64_t ldg, const float* A, int64_t lda, cudaStream_t st);
+                         const float* G, int64_t ldg, const float* A, int64_t lda, const float* G2, int64_t ldg2, cudaStream_t st);
 
 }  // namespace sn
 
@@ -161,7 +161,7 @@ SN_API int sn_bsr4_spmm_f32(const int32_t* browptr, const int32_t* bcolind, cons
     if (rc != SN_ERR_UNSUPPORTED) return rc;
   } else if (!(flags & SN_SPMM_DIRECT_GATHER)) {  // row-group kernel: C = 16 ... 512 (powers of two)
     const int rc = launch_bsr4_rowgroup(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C, elu, (flags >> 8) & 15, nullptr, 0,
-                                        nullptr, 0, st);
+                                        nullptr, 0, nullptr, 0, st);
     if (rc != SN_ERR_UNSUPPORTED) return rc;
   }
   const int v = C4 / 4;  // float4 columns per quaternion component
@@ -171,19 +171,22 @@ SN_API int sn_bsr4_spmm_f32(const int32_t* browptr, const int32_t* bcolind, cons
   return launch_vec4<8>(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C4, elu, st);
 }
 
-// Y = (S X + G) .* elu'(A): the SpMM of a backward pass with the activation derivative (and the gradient of the
+// Y = (S X + G) .* elu'(A) + G2: the SpMM of a backward pass with the activation derivative (and the gradient of the
 // un-gathered half, G) applied in the store path -- replaces op.T.apply + sn_elu_bwd_f32.  Row-group kernel only.
 SN_API int sn_bsr4_spmm_epilogue_f32(const int32_t* browptr, const int32_t* bcolind, const float* bval, const float* X,
                                      int64_t ldx, float* Y, int64_t ldy, int64_t n_brows, int64_t C, const float* G,
-                                     int64_t ldg, const float* A, int64_t lda, int flags, sn_stream_t stream) {
+                                     int64_t ldg, const float* A, int64_t lda, const float* G2, int64_t ldg2, int flags,
+                                     sn_stream_t stream) {
   using namespace sn;
   if (n_brows < 0 || C < 0 || C > 0x7fffffffLL) return SN_ERR_ARG;
   if (n_brows == 0 || C == 0) return SN_OK;
-  if (!browptr || !bcolind || !bval || !X || !Y || ldx < C || ldy < C || (G && ldg < C) || (A && lda < C)) return SN_ERR_ARG;
+  if (!browptr || !bcolind || !bval || !X || !Y || ldx < C || ldy < C || (G && ldg < C) || (A && lda < C) ||
+      (G2 && ldg2 < C))
+    return SN_ERR_ARG;
   if (flags & (SN_SPMM_DIRECT_GATHER | SN_SPMM_SMEM_STREAM | SN_SPMM_ELU_INPUT)) return SN_ERR_UNSUPPORTED;
-  if (C % 16 || ldx % 4 || ldy % 4 || ldg % 4 || lda % 4 || !aligned16(X) || !aligned16(Y) || !aligned16(bval) ||
+  if (C % 16 || ldx % 4 || ldy % 4 || ldg % 4 || lda % 4 || ldg2 % 4 || !aligned16(G2) || !aligned16(X) || !aligned16(Y) || !aligned16(bval) ||
       !aligned16(G) || !aligned16(A))
     return SN_ERR_UNSUPPORTED;
-  return launch_bsr4_rowgroup(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C, false, (flags >> 8) & 15, G, ldg, A, lda,
+  return launch_bsr4_rowgroup(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C, false, (flags >> 8) & 15, G, ldg, A, lda, G2, ldg2,
                               (cudaStream_t)stream);
 }

@@ -121,7 +121,7 @@ static int launch_vec4(const int32_t* rowptr, const int32_t* colind, const float
 
 int launch_csr_rowgroup(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X, int64_t ldx,
                         float* Y, int64_t ldy, int64_t n_rows, int64_t C, bool elu, int variant, const float* G,
-                        int64_t ldg, const float* A, int64_t lda, cudaStream_t st);
+                        int64_t ldg, const float* A, int64_t lda, const float* G2, int64_t ldg2, cudaStream_t st);
 
 }  // namespace sn
 
@@ -147,7 +147,7 @@ SN_API int sn_csr_spmm_f32(const int32_t* rowptr, const int32_t* colind, const f
   }
   if (!(flags & SN_SPMM_DIRECT_GATHER)) {  // row-group kernel: C = 16 ... 512
     const int rc = launch_csr_rowgroup(rowptr, colind, val, X, ldx, Y, ldy, n_rows, C, elu, (flags >> 8) & 15, nullptr, 0, nullptr,
-                                       0, st);
+                                       0, nullptr, 0, st);
     if (rc != SN_ERR_UNSUPPORTED) return rc;
   }
   const int64_t v = C / 4;  // float4 columns
@@ -162,14 +162,17 @@ SN_API int sn_csr_spmm_f32(const int32_t* rowptr, const int32_t* colind, const f
 // Y = (S X + G) .* elu'(A), see sn_bsr4_spmm_epilogue_f32.
 SN_API int sn_csr_spmm_epilogue_f32(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X,
                                     int64_t ldx, float* Y, int64_t ldy, int64_t n_rows, int64_t C, const float* G,
-                                    int64_t ldg, const float* A, int64_t lda, int flags, sn_stream_t stream) {
+                                    int64_t ldg, const float* A, int64_t lda, const float* G2, int64_t ldg2, int flags,
+                                     sn_stream_t stream) {
   using namespace sn;
   if (n_rows < 0 || C < 0 || C > 0x7fffffffLL) return SN_ERR_ARG;
   if (n_rows == 0 || C == 0) return SN_OK;
-  if (!rowptr || !colind || !val || !X || !Y || ldx < C || ldy < C || (G && ldg < C) || (A && lda < C)) return SN_ERR_ARG;
+  if (!rowptr || !colind || !val || !X || !Y || ldx < C || ldy < C || (G && ldg < C) || (A && lda < C) ||
+      (G2 && ldg2 < C))
+    return SN_ERR_ARG;
   if (flags & (SN_SPMM_DIRECT_GATHER | SN_SPMM_ELU_INPUT)) return SN_ERR_UNSUPPORTED;
-  if (C % 16 || ldx % 4 || ldy % 4 || ldg % 4 || lda % 4 || !aligned16(X) || !aligned16(Y) || !aligned16(G) || !aligned16(A))
+  if (C % 16 || ldx % 4 || ldy % 4 || ldg % 4 || lda % 4 || ldg2 % 4 || !aligned16(G2) || !aligned16(X) || !aligned16(Y) || !aligned16(G) || !aligned16(A))
     return SN_ERR_UNSUPPORTED;
-  return launch_csr_rowgroup(rowptr, colind, val, X, ldx, Y, ldy, n_rows, C, false, (flags >> 8) & 15, G, ldg, A, lda,
+  return launch_csr_rowgroup(rowptr, colind, val, X, ldx, Y, ldy, n_rows, C, false, (flags >> 8) & 15, G, ldg, A, lda, G2, ldg2,
                              (cudaStream_t)stream);
 }

@@ -60,12 +60,13 @@ struct Geo {
   static constexpr size_t kSmem = (size_t)kWarps * WARP_WORDS * 4;
 };
 
-// Optional output epilogue Y = (S X + G) .* elu'(A) (backward of "elu, then gather": the activation derivative and the
+// Optional output epilogue Y = (S X + G) .* elu'(A) + G2 (backward of "elu, then gather": the activation derivative and the
 // gradient of the un-gathered half are applied where the row is stored instead of in a separate pass).
 struct Epilogue {
   const float* G;     // [n_rows x C], leading dimension ldgb bytes, or null
   const float* A;     // activated values elu(x) [n_rows x C], leading dimension ldab bytes, or null
-  uint32_t ldgb, ldab;
+  const float* G2;    // [n_rows x C] added AFTER the derivative (a residual-path gradient), or null
+  uint32_t ldgb, ldab, ldg2b;
 };
 
 }  // namespace
@@ -188,6 +189,12 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
               acc[p].z *= a.z > 0.f ? 1.f : a.z + 1.f;
               acc[p].w *= a.w > 0.f ? 1.f : a.w + 1.f;
             }
+          }
+          if (EPI && epi.G2 != nullptr) {       // ... + G2
+            const char* g2row_p = ptr_mad(reinterpret_cast<const char*>(epi.G2) + t * 16, grow, epi.ldg2b);
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+              acc[p] = add4(acc[p], __ldg(reinterpret_cast<const float4*>(g2row_p + p * kQuarterBytes)));
           }
 #pragma unroll
           for (int p = 0; p < 4; ++p) st_stream_f4(reinterpret_cast<float*>(yrow + p * kQuarterBytes), acc[p]);
@@ -375,7 +382,7 @@ template <int BLK>
 int launch_family(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X, int64_t ldx,
                   float* Y, int64_t ldy, int64_t n_rows, int64_t C, bool elu, int variant, const Epilogue& epi,
                   cudaStream_t st) {
-  const int mode = (epi.G || epi.A) ? 2 : (elu ? 1 : 0);
+  const int mode = (epi.G || epi.A || epi.G2) ? 2 : (elu ? 1 : 0);
   if (mode == 2 && (elu || variant >= 4)) return SN_ERR_UNSUPPORTED;   // the epilogue exists for the default shape only
   // ldx / ldy in bytes and entry offsets (64 B per block) must fit 32 bits
   if (n_rows >= 0x7fffff00LL || ldx >= (1LL << 30) || ldy >= (1LL << 30)) return SN_ERR_UNSUPPORTED;
@@ -408,19 +415,20 @@ int launch_family(const int32_t* rowptr, const int32_t* colind, const float* val
 
 // Both return SN_ERR_UNSUPPORTED when the kernel does not apply (C not in {32,...,512}); callers fall back to the
 // direct-gather kernels (at C = 16 a row is one 64-byte segment and a lane per row has nothing left to share).
-// G / A (optional, null = none): output epilogue Y = (S X + G) .* elu'(A), leading dimensions ldg / lda in floats.
+// G / A / G2 (optional, null = none): output epilogue Y = (S X + G) .* elu'(A) + G2, leading dimensions in floats.
 int launch_bsr4_rowgroup(const int32_t* browptr, const int32_t* bcolind, const float* bval, const float* X,
                          int64_t ldx, float* Y, int64_t ldy, int64_t n_brows, int64_t C, bool elu, int variant,
-                         const float* G, int64_t ldg, const float* A, int64_t lda, cudaStream_t st) {
-  if (ldg >= (1LL << 30) || lda >= (1LL << 30)) return SN_ERR_UNSUPPORTED;
-  const Epilogue epi{G, A, (uint32_t)(ldg * 4), (uint32_t)(lda * 4)};
+                         const float* G, int64_t ldg, const float* A, int64_t lda, const float* G2, int64_t ldg2,
+                         cudaStream_t st) {
+  if (ldg >= (1LL << 30) || lda >= (1LL << 30) || ldg2 >= (1LL << 30)) return SN_ERR_UNSUPPORTED;
+  const Epilogue epi{G, A, G2, (uint32_t)(ldg * 4), (uint32_t)(lda * 4), (uint32_t)(ldg2 * 4)};
   return launch_family<4>(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C, elu, variant, epi, st);
 }
 int launch_csr_rowgroup(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X, int64_t ldx,
                         float* Y, int64_t ldy, int64_t n_rows, int64_t C, bool elu, int variant, const float* G,
-                        int64_t ldg, const float* A, int64_t lda, cudaStream_t st) {
-  if (ldg >= (1LL << 30) || lda >= (1LL << 30)) return SN_ERR_UNSUPPORTED;
-  const Epilogue epi{G, A, (uint32_t)(ldg * 4), (uint32_t)(lda * 4)};
+                        int64_t ldg, const float* A, int64_t lda, const float* G2, int64_t ldg2, cudaStream_t st) {
+  if (ldg >= (1LL << 30) || lda >= (1LL << 30) || ldg2 >= (1LL << 30)) return SN_ERR_UNSUPPORTED;
+  const Epilogue epi{G, A, G2, (uint32_t)(ldg * 4), (uint32_t)(lda * 4), (uint32_t)(ldg2 * 4)};
   return launch_family<1>(rowptr, colind, val, X, ldx, Y, ldy, n_rows, C, elu, variant, epi, st);
 }
 

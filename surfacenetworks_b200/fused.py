@@ -128,66 +128,80 @@ def gemm_tn_tf32(A, B, single_pass=False):
     return G
 
 
+def bn_linear_forward(Z, gamma, beta, W, b, residual, running_mean, running_var, training, momentum, eps, left_stats):
+    """Forward of GraphConv1x1(batch_norm="pre") on rows (no autograd): statistics pass, BN folded into the weights,
+    tcgen05 GEMM with the residual in its epilogue.  Returns (Y, saved) with ``saved`` = what bn_linear_backward needs."""
+    rows, K = Z.shape
+    Nn = W.shape[0]
+    dev = Z.device
+    if training:
+        if left_stats is not None:                # left half already reduced by the fused ELU pass
+            Cl = left_stats[0].numel()
+            mr, vr = colstats(Z[:, Cl:])
+            mean, var = torch.cat([left_stats[0], mr]), torch.cat([left_stats[1], vr])
+        else:
+            mean, var = colstats(Z)
+    else:
+        mean, var = running_mean, running_var
+    W = W.contiguous()
+    Wf = torch.empty_like(W)                    # [C, 2C]: BatchNorm folded into the Linear
+    bf = torch.empty(Nn, dtype=torch.float32, device=dev)
+    stk = torch.empty(3, K, dtype=torch.float32, device=dev)          # s, t, rstd
+    update = training and running_mean is not None
+    with torch.cuda.device(dev):
+        N.call("sn_bn_fold_fwd_f32", _ptr(mean), _ptr(var), _ptr(gamma), _ptr(beta), _ptr(W), _ptr(b), Nn, K, float(eps),
+               _ptr(Wf), _ptr(bf), _ptr(stk[0]), _ptr(stk[1]), _ptr(stk[2]), _ptr(running_mean) if update else 0,
+               _ptr(running_var) if update else 0, float(momentum), rows, _stream())
+    res = None if residual is None else residual.contiguous()
+    Y = gemm_tf32(Z, Wf, bias=bf, R=res)
+    return Y, (Z, W, stk, mean)
+
+
+def bn_linear_backward(saved, dY, training, elu_bwd_left=False):
+    """Backward of bn_linear_forward: returns (dZ, dgamma, dbeta, dW, db).  ``elu_bwd_left``: the left half of Z holds
+    activated values elu(x); its gradient leaves the dZ GEMM epilogue already multiplied by elu'(x)."""
+    Z, W, stk, mean = saved
+    if dY.stride(1) != 1 or dY.stride(0) % 4 or dY.data_ptr() % 16:     # row-strided views (halves of a dZ) are fine
+        dY = dY.contiguous()
+    rows, K = Z.shape
+    Nn = W.shape[0]
+    dev = Z.device
+    if gemm_tn_supported(Nn, K):
+        G = gemm_tn_tf32(dY, Z)                 # [C, 2C] = dY^T Z: split-K tcgen05 (MN-major operands)
+        sdY = colstats(dY)[0] * rows            # colsum(dY) from the same deterministic statistics kernel
+    else:
+        G = torch.mm(dY.t(), Z)
+        sdY = dY.sum(0)
+    dW = torch.empty_like(W)
+    db = torch.empty(Nn, dtype=torch.float32, device=dev)
+    vec = torch.empty(4, K, dtype=torch.float32, device=dev)          # dgamma, dbeta, p, q
+    WsT = torch.empty(K, Nn, dtype=torch.float32, device=dev)         # (W diag(s))^T
+    with torch.cuda.device(dev):
+        N.call("sn_bn_fold_bwd_f32", _ptr(G), _ptr(sdY), _ptr(W), _ptr(stk[0]), _ptr(stk[1]), _ptr(stk[2]), _ptr(mean),
+               Nn, K, rows, 1 if training else 0, _ptr(dW), _ptr(db), _ptr(vec[0]), _ptr(vec[1]), _ptr(vec[2]),
+               _ptr(vec[3]), _ptr(WsT), _stream())
+    if training:
+        dZ = gemm_tf32(dY, WsT, bias=vec[3], R=Z, rscale=vec[2], elu_bwd_left=elu_bwd_left)
+    else:
+        dZ = gemm_tf32(dY, WsT)
+    return dZ, vec[0], vec[1], dW, db
+
+
 class _BnLinear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, Z, gamma, beta, W, b, residual, running_mean, running_var, training, momentum, eps, left_stats,
                 elu_bwd_left=False):
-        rows, K = Z.shape
-        Nn = W.shape[0]
-        dev = Z.device
-        if training:
-            if left_stats is not None:                # left half already reduced by the fused ELU pass (ops.stage_concat)
-                Cl = left_stats[0].numel()
-                mr, vr = colstats(Z[:, Cl:])
-                mean, var = torch.cat([left_stats[0], mr]), torch.cat([left_stats[1], vr])
-            else:
-                mean, var = colstats(Z)
-        else:
-            mean, var = running_mean, running_var
-        W = W.contiguous()
-        Wf = torch.empty_like(W)                    # [C, 2C]: BatchNorm folded into the Linear
-        bf = torch.empty(Nn, dtype=torch.float32, device=dev)
-        stk = torch.empty(3, K, dtype=torch.float32, device=dev)          # s, t, rstd
-        update = training and running_mean is not None
-        with torch.cuda.device(dev):
-            N.call("sn_bn_fold_fwd_f32", _ptr(mean), _ptr(var), _ptr(gamma), _ptr(beta), _ptr(W), _ptr(b), Nn, K, float(eps),
-                   _ptr(Wf), _ptr(bf), _ptr(stk[0]), _ptr(stk[1]), _ptr(stk[2]), _ptr(running_mean) if update else 0,
-                   _ptr(running_var) if update else 0, float(momentum), rows, _stream())
-        res = None if residual is None else residual.contiguous()
-        Y = gemm_tf32(Z, Wf, bias=bf, R=res)
-        ctx.save_for_backward(Z, W, stk, mean)
+        Y, saved = bn_linear_forward(Z, gamma, beta, W, b, residual, running_mean, running_var, training, momentum, eps,
+                                     left_stats)
+        ctx.save_for_backward(*saved)
         ctx.training, ctx.has_res, ctx.elu_bwd_left = training, residual is not None, elu_bwd_left
         return Y
 
     @staticmethod
     def backward(ctx, dY):
-        Z, W, stk, mean = ctx.saved_tensors
-        if dY.stride(1) != 1 or dY.stride(0) % 4 or dY.data_ptr() % 16:     # row-strided views (halves of a dZ) are fine
-            dY = dY.contiguous()
-        rows, K = Z.shape
-        Nn = W.shape[0]
-        dev = Z.device
-        if gemm_tn_supported(Nn, K):
-            G = gemm_tn_tf32(dY, Z)                 # [C, 2C] = dY^T Z: split-K tcgen05 (MN-major operands)
-            sdY = colstats(dY)[0] * rows            # colsum(dY) from the same deterministic statistics kernel
-        else:
-            G = torch.mm(dY.t(), Z)
-            sdY = dY.sum(0)
-        dW = torch.empty_like(W)
-        db = torch.empty(Nn, dtype=torch.float32, device=dev)
-        vec = torch.empty(4, K, dtype=torch.float32, device=dev)          # dgamma, dbeta, p, q
-        WsT = torch.empty(K, Nn, dtype=torch.float32, device=dev)         # (W diag(s))^T
-        with torch.cuda.device(dev):
-            N.call("sn_bn_fold_bwd_f32", _ptr(G), _ptr(sdY), _ptr(W), _ptr(stk[0]), _ptr(stk[1]), _ptr(stk[2]), _ptr(mean),
-                   Nn, K, rows, 1 if ctx.training else 0, _ptr(dW), _ptr(db), _ptr(vec[0]), _ptr(vec[1]), _ptr(vec[2]),
-                   _ptr(vec[3]), _ptr(WsT), _stream())
-        if ctx.training:
-            # elu_bwd_left: the left half of Z holds activated values elu(x_self); its gradient leaves the epilogue
-            # already multiplied by elu'(x_self) (ops._StageConcat.backward then skips its elementwise pass)
-            dZ = gemm_tf32(dY, WsT, bias=vec[3], R=Z, rscale=vec[2], elu_bwd_left=ctx.elu_bwd_left)
-        else:
-            dZ = gemm_tf32(dY, WsT)
-        return dZ, vec[0], vec[1], dW, db, (dY if ctx.has_res else None), None, None, None, None, None, None, None
+        dZ, dgamma, dbeta, dW, db = bn_linear_backward(ctx.saved_tensors, dY, ctx.training,
+                                                       ctx.elu_bwd_left and ctx.training)
+        return dZ, dgamma, dbeta, dW, db, (dY if ctx.has_res else None), None, None, None, None, None, None, None
 
 
 def segment_sum(X, rows_per_seg, n_seg, weight=None):

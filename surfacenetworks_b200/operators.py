@@ -171,14 +171,14 @@ class CsrOperator:
                    _stream())
         return out
 
-    def apply_epilogue(self, X, G=None, A=None, out=None):
-        """``(S @ X + G) * elu'(A)`` (A = activated values) in one launch, or None if unsupported for this shape."""
+    def apply_epilogue(self, X, G=None, A=None, out=None, G2=None):
+        """``(S @ X + G) * elu'(A) + G2`` (A = activated values) in one launch, or None if unsupported for this shape."""
         return _apply_epilogue(self, "sn_csr_spmm_epilogue_f32", self.n_rows, self.n_cols,
-                               (_ptr(self.rowptr), _ptr(self.colind), _ptr(self.val)), X, G, A, out)
+                               (_ptr(self.rowptr), _ptr(self.colind), _ptr(self.val)), X, G, A, out, G2)
 
 
-def _apply_epilogue(op, entry, n_rows, n_cols, ptrs, X, G, A, out):
-    """``out = (op @ X + G) * elu'(A)`` in one launch (sn_*_spmm_epilogue_f32); returns None when the row-group kernel
+def _apply_epilogue(op, entry, n_rows, n_cols, ptrs, X, G, A, out, G2=None):
+    """``out = (op @ X + G) * elu'(A) + G2`` in one launch (sn_*_spmm_epilogue_f32); returns None when the row-group kernel
     does not cover the shape, so that the caller can run the separate passes."""
     _check_dense(X, "X")
     C = X.shape[1]
@@ -186,18 +186,18 @@ def _apply_epilogue(op, entry, n_rows, n_cols, ptrs, X, G, A, out):
         raise ValueError("X has %d rows, operator has %d columns" % (X.shape[0], n_cols))
     if out is None:
         out = torch.empty(n_rows, C, dtype=torch.float32, device=X.device)
-    for t, name in ((out, "out"), (G, "G"), (A, "A")):
+    for t, name in ((out, "out"), (G, "G"), (A, "A"), (G2, "G2")):
         if t is not None:
             _check_dense(t, name)
             if t.shape[0] != n_rows or t.shape[1] != C:
                 raise ValueError("%s must be [%d, %d], got %s" % (name, n_rows, C, tuple(t.shape)))
     if N.TIMER is not None:      # canonical SpMM bytes + the epilogue operands, each read once
-        extra = 4 * n_rows * C * ((G is not None) + (A is not None))
+        extra = 4 * n_rows * C * ((G is not None) + (A is not None) + (G2 is not None))
         N.TIMER.annotate("%s %dx%d C=%d +epilogue" % (op.kind, n_rows, n_cols, C), op.algorithmic_bytes(C) + extra, op.flops(C))
     with torch.cuda.device(X.device):
         rc = N.call(entry, *ptrs, _ptr(X), X.stride(0), _ptr(out), out.stride(0), n_rows, C, _ptr(G),
-                    0 if G is None else G.stride(0), _ptr(A), 0 if A is None else A.stride(0), 0, _stream(),
-                    soft_unsupported=True)
+                    0 if G is None else G.stride(0), _ptr(A), 0 if A is None else A.stride(0), _ptr(G2),
+                    0 if G2 is None else G2.stride(0), 0, _stream(), soft_unsupported=True)
     return None if rc == N.SN_ERR_UNSUPPORTED else out
 
 
@@ -313,12 +313,12 @@ class Bsr4Operator:
                    _ptr(X), X.stride(0), _ptr(out), out.stride(0), self.n_brows, C, flags, _stream())
         return out
 
-    def apply_epilogue(self, X, G=None, A=None, out=None):
-        """``(S @ X + G) * elu'(A)`` (A = activated values) in one launch, or None if unsupported for this shape."""
+    def apply_epilogue(self, X, G=None, A=None, out=None, G2=None):
+        """``(S @ X + G) * elu'(A) + G2`` (A = activated values) in one launch, or None if unsupported for this shape."""
         if X.shape[1] % 4:
             raise ValueError("feature width must be divisible by 4 for the quaternion view, got %d" % X.shape[1])
         return _apply_epilogue(self, "sn_bsr4_spmm_epilogue_f32", self.n_brows, self.n_bcols,
-                               (_ptr(self.browptr), _ptr(self.bcolind), _ptr(self.bval)), X, G, A, out)
+                               (_ptr(self.browptr), _ptr(self.bcolind), _ptr(self.bval)), X, G, A, out, G2)
 
 
 # ---------------------------------------------------------------------------------------------------

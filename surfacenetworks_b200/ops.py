@@ -138,3 +138,86 @@ def stage_concat(op, x_self, x_gather=None, want_stats=True):
     if cell is not None:
         Z._sn_stage_cell = cell
     return Z
+
+
+class _DirBlock(torch.autograd.Function):
+    """A whole DirResNet2 block (reference src/utils/utils_pt.py:191-220) as ONE autograd node:
+
+        f_out = fc0(BN[elu(f) | D elu(v)]),   v_new = v + fc1(BN[elu(v) | D* elu(f_out)])
+
+    Same kernels as the two-stage composition (stage_concat + fused.bn_linear); what the single node buys:
+      * elu(v) is materialised once (left half of the vertex stage's buffer; D gathers from it in place);
+      * backward: every gradient that autograd would accumulate with separate add kernels (v has three consumers,
+        f_out two) rides in an epilogue instead --
+            g_fout = (D*^T dZv_right) .* elu'(f_out) + g_f_downstream
+            g_v    = (D^T dZf_right + dZv_left) .* elu'(v) + g_vnew           (sn_bsr4_spmm_epilogue_f32)
+        and elu'(f) is applied by the dZ GEMM epilogue (SN_GEMM_ELU_BWD_LEFT).
+    Used in training mode at the widths both epilogues cover; otherwise DirResNet2 composes the stage functions."""
+
+    @staticmethod
+    def forward(ctx, v2, f2, g0, b0, W0, c0, g1, b1, W1, c1, D, DA, bn0, bn1):
+        C = v2.shape[1]
+        v2, f2 = v2.contiguous(), f2.contiguous()
+        Zv = torch.empty(v2.shape[0], 2 * C, dtype=torch.float32, device=v2.device)
+        Zf = torch.empty(f2.shape[0], 2 * C, dtype=torch.float32, device=v2.device)
+        stats_v = fused.elu_colstats(v2, Zv[:, :C])
+        stats_f = fused.elu_colstats(f2, Zf[:, :C])
+        D.apply(Zv[:, :C], out=Zf[:, C:])                       # faces <- vertices, gathers the activated rows in place
+        f_out, saved0 = fused.bn_linear_forward(Zf, g0, b0, W0, c0, None, bn0.running_mean, bn0.running_var, True,
+                                                0.1 if bn0.momentum is None else bn0.momentum, bn0.eps, stats_f)
+        act_f = torch.empty_like(f_out)
+        elu_into(f_out, act_f)
+        DA.apply(act_f, out=Zv[:, C:])                          # vertices <- faces
+        v_new, saved1 = fused.bn_linear_forward(Zv, g1, b1, W1, c1, v2, bn1.running_mean, bn1.running_var, True,
+                                                0.1 if bn1.momentum is None else bn1.momentum, bn1.eps, stats_v)
+        ctx.save_for_backward(act_f, *saved0, *saved1)
+        ctx.D, ctx.DA, ctx.C = D, DA, C
+        ctx.set_materialize_grads(False)
+        return v_new, f_out
+
+    @staticmethod
+    def backward(ctx, g_vnew, g_fdown):
+        act_f, Zf, W0, stk0, mean0, Zv, W1, stk1, mean1 = ctx.saved_tensors
+        C, D, DA = ctx.C, ctx.D, ctx.DA
+
+        def dense(g):
+            if g is not None and (g.stride(1) != 1 or g.stride(0) % 4 or g.data_ptr() % 16):
+                g = g.contiguous()
+            return g
+        g_vnew, g_fdown = dense(g_vnew), dense(g_fdown)
+        if g_vnew is None:
+            g_vnew = torch.zeros(Zv.shape[0], C, dtype=torch.float32, device=Zv.device)
+        dZv, dg1, db1, dW1, dc1 = fused.bn_linear_backward((Zv, W1, stk1, mean1), g_vnew, True, False)
+        g_fout = DA.T.apply_epilogue(dZv[:, C:], A=act_f, G2=g_fdown)
+        dZf, dg0, db0, dW0, dc0 = fused.bn_linear_backward((Zf, W0, stk0, mean0), g_fout, True, True)
+        g_v = D.T.apply_epilogue(dZf[:, C:], G=dZv[:, :C], A=Zv[:, :C], G2=g_vnew)
+        return g_v, dZf[:, :C], dg0, db0, dW0, dc0, dg1, db1, dW1, dc1, None, None, None, None
+
+
+_DIR_BLOCK_WIDTHS = (64, 128)          # C and 2C both tensor-core GEMM widths, C covered by the row-group epilogue
+
+
+def dir_block_supported(v2, f2, conv0, conv1):
+    """True when the single-node Dirac block applies: CUDA fp32 rows, training-mode BatchNorm on both stages, widths
+    covered by the epilogues, gradients enabled."""
+    C = v2.shape[1]
+    if not (torch.is_grad_enabled() and v2.is_cuda and v2.dtype == torch.float32 and f2.dtype == torch.float32):
+        return False
+    if C not in _DIR_BLOCK_WIDTHS or f2.shape[1] != C or v2.shape[0] == 0 or f2.shape[0] == 0:
+        return False
+    for conv in (conv0, conv1):
+        bn, fc = conv.bn, conv.fc
+        if not (bn.training or bn.running_mean is None) or fc.bias is None or bn.weight is None:
+            return False
+        if tuple(fc.weight.shape) != (C, 2 * C) or fc.weight.dtype != torch.float32:
+            return False
+    return True
+
+
+def dir_block(D, DA, v2, f2, conv0, conv1):
+    """(v_new, f_out) of one DirResNet2 block on rows; conv0 / conv1 are its two GraphConv1x1(2C -> C, "pre")."""
+    for conv in (conv0, conv1):
+        if conv.bn.num_batches_tracked is not None:
+            conv.bn.num_batches_tracked += 1
+    return _DirBlock.apply(v2, f2, conv0.bn.weight, conv0.bn.bias, conv0.fc.weight, conv0.fc.bias, conv1.bn.weight,
+                           conv1.bn.bias, conv1.fc.weight, conv1.fc.bias, D, DA, conv0.bn, conv1.bn)

@@ -188,6 +188,9 @@ class DirResNet2(_TwoStageBlock):
         D, DA = as_bsr4(Di), as_bsr4(DiA)
         v2 = v.reshape(batch_size * num_nodes, num_inputs)
         f2 = f.reshape(batch_size * num_faces, num_inputs)
+        if ops.dir_block_supported(v2, f2, self.bn_fc0, self.bn_fc1):       # training: the whole block is one node
+            v_new, f_out = ops.dir_block(D, DA, v2, f2, self.bn_fc0, self.bn_fc1)
+            return v_new.view(batch_size, num_nodes, num_inputs), f_out.view(batch_size, num_faces, num_inputs)
         f_out = self.bn_fc0.forward_rows(ops.stage_concat(D, f2, v2))
         v_new = self.bn_fc1.forward_rows(ops.stage_concat(DA, v2, f_out), residual=v2)   # v + v_out in the epilogue
         return v_new.view(batch_size, num_nodes, num_inputs), f_out.view(batch_size, num_faces, num_inputs)

@@ -326,6 +326,10 @@ def test_spmm_epilogue_matches_separate_passes(C):
             Gc = G.clone()
             y = op.apply_epilogue(X, G=Gc, A=A, out=Gc)
             assert torch.equal(y, (plain + G) * dA)
+            G2 = Gbuf[:, C:]                                                 # addend behind the derivative
+            assert torch.equal(op.apply_epilogue(X, G=G, A=A, G2=G2), (plain + G) * dA + G2)
+            assert torch.equal(op.apply_epilogue(X, A=A, G2=G2), plain * dA + G2)
+            assert torch.equal(op.apply_epilogue(X, G2=G2), plain + G2)
 
 
 def test_elu_kernels():
