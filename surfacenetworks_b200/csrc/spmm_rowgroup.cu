@@ -362,6 +362,12 @@ int launch_lpr(const int32_t* rowptr, const int32_t* colind, const float* val, c
   const int sms = device_info().sms;
   const int64_t ws = LS::resident_warps(mode, sms), wm = LM::resident_warps(mode, sms), wl = LL::resident_warps(mode, sms);
   int pick = tile_mode;
+  // small operators at C >= 256 (one mesh of a few thousand rows, BASELINE cfg5): a single row per row group, so the
+  // serial chain of a warp is one row's entries instead of RS rows'
+  if ((pick < 1 || pick > 3) && RS > 1 && ceil_div(n_rows, G * RS) < ws) {
+    using LT = Launcher<LPR, 1, BLK, PD, EPS, MINB>;
+    return LT::launch(rowptr, colind, val, X, ldx, Y, ldy, n_rows, mode, LT::resident_warps(mode, sms), epi, st);
+  }
   if ((pick < 1 || pick > 3) && LPR == 32) pick = 1;   // C = 512: one row per warp pass; short tiles measured fastest
   if (pick < 1 || pick > 3) {
     const double es = LS::efficiency(n_rows, ws), em = LM::efficiency(n_rows, wm), el = LL::efficiency(n_rows, wl);
