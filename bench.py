@@ -249,6 +249,68 @@ def spmm_sweep(dev):
     return out
 
 
+def breakdown(dev, model, res, Dop, DAop, host, B):
+    """The remaining rows of SURVEY.md 8(d): cfg3 one Dirac block (forward, forward + backward), full forward, and the
+    cfg2 mesh_mnist encoder (5 x LapResNet2(128), 32 x 500 V) training pass; beside them the reference's own calls on the
+    host cores for the same batch -- torch.mm(Di_coo, x) as at utils_pt.py:202 and sparse_diag_cat (utils_pt.py:41-53)."""
+    import time
+    from surfacenetworks_b200 import models as M, operators as OP, utils_pt as U, workloads as W
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def gpu_ms(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    out = {}
+    nv, nf = host["num_vertices"], host["num_faces"]
+    blk = model.rn0
+    v = torch.randn(B, nv, 128, device=dev)
+    f = torch.randn(B, nf, 128, device=dev)
+    with torch.no_grad():
+        out["cfg3_dir_block_forward_ms"] = gpu_ms(lambda: blk(Dop, DAop, v, f))
+        out["cfg3_model_forward_ms"] = gpu_ms(lambda: model(Dop, DAop, res["mask"], res["inputs"]))
+    vg, fg = v.clone().requires_grad_(True), f.clone().requires_grad_(True)
+
+    def block_train():
+        a, b = blk(Dop, DAop, vg, fg)
+        (a.sum() + b.sum()).backward()
+    out["cfg3_dir_block_forward_backward_ms"] = gpu_ms(block_train)
+    # cfg2: mesh_mnist VAE encoder
+    meshes2 = W.make_mesh_ops(500, range(32))
+    lb = W.lap_batch(meshes2)
+    L2 = OP.as_csr(lb["L"].to(dev))
+    L2.T
+    enc = M.LapEncoder().to(dev).train()
+    x2 = torch.randn(32, lb["num_vertices"], 3, device=dev)
+    m2 = lb["mask"].to(dev)
+
+    def enc_train():
+        mu, lv = enc(x2, L2, m2)
+        (mu.sum() + lv.sum()).backward()
+    out["cfg2_lap_encoder_forward_backward_ms"] = gpu_ms(enc_train)
+    # the reference's own calls on the host (bounded: 3 repetitions each)
+    torch.set_num_threads(os.cpu_count() or 1)
+    Di = host["Di"]
+    xh = torch.randn(Di.shape[1], 32)                       # [4 * B * V, C / 4]: the view of utils_pt.py:201
+    t0 = time.perf_counter()
+    for _ in range(3):
+        torch.mm(Di, xh)
+    out["cpu_torch_mm_Di_ms"] = (time.perf_counter() - t0) / 3 * 1e3
+    per = [U.sp_sparse_to_pt_sparse(m.Di) for m in W.make_mesh_ops(host["num_vertices"], range(4))]
+    t0 = time.perf_counter()
+    U.sparse_diag_cat([per[i % 4] for i in range(B)], 4 * nf, 4 * nv)
+    out["cpu_sparse_diag_cat_Di_ms"] = (time.perf_counter() - t0) * 1e3
+    out["cpu_threads"] = torch.get_num_threads()
+    return out
+
+
 def run_b200(args):
     from surfacenetworks_b200 import _native as N
     from surfacenetworks_b200 import dist as D
@@ -593,6 +655,8 @@ def run_b200(args):
             "grad_allreduce_bytes": grads.nbytes}
     if not args.no_spmm_sweep and world == 1:
         line["spmm"] = spmm_sweep(dev)
+    if not args.no_spmm_sweep and world == 1:
+        line["breakdown"] = breakdown(dev, model, res, Dop, DAop, host, B)
     if not args.no_cpu_baseline and world == 1:
         cb = time_cpu(args, 3, 1)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
