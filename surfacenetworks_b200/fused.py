@@ -45,11 +45,13 @@ def fused_supported(z, weight):
             and z.data_ptr() % 16 == 0)
 
 
-def colstats(Z):
-    """Per-column mean and biased variance over all rows of Z [rows, C] (sn_colstats_f32)."""
+def colstats(Z, mean=None, var=None):
+    """Per-column mean and biased variance over all rows of Z [rows, C] (sn_colstats_f32); ``mean`` / ``var`` may be
+    given as contiguous [C] views (e.g. halves of a stage's full-width statistics vectors)."""
     rows, C = Z.shape
-    mean = torch.empty(C, dtype=torch.float32, device=Z.device)
-    var = torch.empty(C, dtype=torch.float32, device=Z.device)
+    if mean is None:
+        mean = torch.empty(C, dtype=torch.float32, device=Z.device)
+        var = torch.empty(C, dtype=torch.float32, device=Z.device)
     nb = N.lib.sn_colstats_ws_bytes(C)
     ws = _ws(nb, Z.device)
     with torch.cuda.device(Z.device):
@@ -57,11 +59,12 @@ def colstats(Z):
     return mean, var
 
 
-def elu_colstats(X, out):
+def elu_colstats(X, out, mean=None, var=None):
     """out = elu(X) and the column statistics (mean, biased variance) of out in ONE pass (sn_elu_colstats_f32)."""
     rows, C = X.shape
-    mean = torch.empty(C, dtype=torch.float32, device=X.device)
-    var = torch.empty(C, dtype=torch.float32, device=X.device)
+    if mean is None:
+        mean = torch.empty(C, dtype=torch.float32, device=X.device)
+        var = torch.empty(C, dtype=torch.float32, device=X.device)
     nb = N.lib.sn_colstats_ws_bytes(C)
     ws = _ws(nb, X.device)
     with torch.cuda.device(X.device):
@@ -145,7 +148,12 @@ def bn_linear_forward(Z, gamma, beta, W, b, residual, running_mean, running_var,
     Nn = W.shape[0]
     dev = Z.device
     if training:
-        if left_stats is not None:                # left half already reduced by the fused ELU pass
+        if left_stats is not None and len(left_stats) == 3:
+            # (mean, var, Cl): full-width vectors whose first Cl entries the fused ELU pass has already written; the
+            # statistics of the remaining columns land in place -- no concatenation kernels
+            mean, var, Cl = left_stats
+            colstats(Z[:, Cl:], mean[Cl:], var[Cl:])
+        elif left_stats is not None:              # left half already reduced by the fused ELU pass
             Cl = left_stats[0].numel()
             mr, vr = colstats(Z[:, Cl:])
             mean, var = torch.cat([left_stats[0], mr]), torch.cat([left_stats[1], vr])

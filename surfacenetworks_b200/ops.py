@@ -160,8 +160,10 @@ class _DirBlock(torch.autograd.Function):
         v2, f2 = v2.contiguous(), f2.contiguous()
         Zv = torch.empty(v2.shape[0], 2 * C, dtype=torch.float32, device=v2.device)
         Zf = torch.empty(f2.shape[0], 2 * C, dtype=torch.float32, device=v2.device)
-        stats_v = fused.elu_colstats(v2, Zv[:, :C])
-        stats_f = fused.elu_colstats(f2, Zf[:, :C])
+        st = torch.empty(4, 2 * C, dtype=torch.float32, device=v2.device)      # mean / var of Zv, mean / var of Zf
+        fused.elu_colstats(v2, Zv[:, :C], st[0, :C], st[1, :C])
+        fused.elu_colstats(f2, Zf[:, :C], st[2, :C], st[3, :C])
+        stats_v, stats_f = (st[0], st[1], C), (st[2], st[3], C)
         D.apply(Zv[:, :C], out=Zf[:, C:])                       # faces <- vertices, gathers the activated rows in place
         act_f = torch.empty(f2.shape[0], C, dtype=torch.float32, device=v2.device)     # elu(f_out), from the GEMM epilogue
         f_out, saved0 = fused.bn_linear_forward(Zf, g0, b0, W0, c0, None, bn0.running_mean, bn0.running_var, True,
