@@ -209,13 +209,6 @@ int sn_gemm_tf32_f32(const float* A, int64_t lda, const float* B, int64_t ldb, c
                      int64_t ldc, int64_t M, int64_t N, int64_t K, int flags, void* ws, size_t ws_bytes,
                      sn_stream_t stream);
 
-/* sn_gemm_tf32_f32 with a second output E[M x N] = elu(C) (leading dimension lde): the activated copy that the next
- * operator application gathers (F.elu(f_out), utils_pt.py:208) is written by the epilogue instead of a pass over C. */
-int sn_gemm_tf32_elu_f32(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, const float* R,
-                         int64_t ldr, const float* rscale, const float* group_bias, int64_t rows_per_group, float* C,
-                         int64_t ldc, float* E, int64_t lde, int64_t M, int64_t N, int64_t K, int flags, void* ws,
-                         size_t ws_bytes, sn_stream_t stream);
-
 /* Weight-gradient product of a stage, reduction over the rows (split-K over the SMs, deterministic):
  *
  *   G[M x N] = A[R x M]^T * B[R x N]        M = 128, N % 32 == 0, 32 <= N <= 256

@@ -48,8 +48,6 @@ SIGNATURES = {
     "sn_gemm_tf32_ws_bytes": (_sz, [_i64, _i64]),
     "sn_gemm_tf32_f32": (_int, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _int,
                                 _ptr, _sz, _ptr]),
-    "sn_gemm_tf32_elu_f32": (_int, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64,
-                                    _i64, _int, _ptr, _sz, _ptr]),
     "sn_csr_spmm_epilogue_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64,
                                         _int, _ptr]),
     "sn_bsr4_spmm_epilogue_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64,

@@ -121,8 +121,7 @@ struct Params {
   const float* gbias;    // [ceil(M / rows_per_group) x N] or null: per-row-group bias (AvgResNet2's per-mesh term)
   int rows_per_group;
   float* C;
-  float* E;              // optional second output: E = elu(C) (the activated copy the next operator application gathers)
-  int64_t ldr, ldc, lde;
+  int64_t ldr, ldc;
   int M, N, K;
   int stages;
   int split;             // 1: 3xTF32 (hi/lo split), 0: single-pass TF32
@@ -322,7 +321,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               }
             }
             st_stream_f4(p.C + (int64_t)row * p.ldc + c0 + tc, o);
-            if (p.E) *reinterpret_cast<float4*>(p.E + (int64_t)row * p.lde + c0 + tc) = elu4(o);   // re-read soon: no streaming hint
           }
         }
         __syncwarp();
@@ -391,13 +389,12 @@ SN_API size_t sn_gemm_tf32_ws_bytes(int64_t N, int64_t K) {
   return (N <= 0 || K <= 0) ? 0 : (size_t)(2 * N * K) * sizeof(float) + 256;
 }
 
-static int gemm_tf32_impl(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, const float* R,
-                          int64_t ldr, const float* rscale, const float* group_bias, int64_t rows_per_group, float* C,
-                          int64_t ldc, float* E, int64_t lde, int64_t M, int64_t N, int64_t K, int flags, void* ws,
-                          size_t ws_bytes, sn_stream_t stream) {
+SN_API int sn_gemm_tf32_f32(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, const float* R,
+                            int64_t ldr, const float* rscale, const float* group_bias, int64_t rows_per_group, float* C,
+                            int64_t ldc, int64_t M, int64_t N, int64_t K, int flags, void* ws, size_t ws_bytes,
+                            sn_stream_t stream) {
   using namespace sn;
   using namespace sn::gemm;
-  if (E && (lde < N || lde % 4 || !aligned16(E))) return lde < N ? SN_ERR_ARG : SN_ERR_UNSUPPORTED;
   if (M < 0 || N <= 0 || K <= 0) return SN_ERR_ARG;
   if (M == 0) return SN_OK;
   if (!A || !B || !C || lda < K || ldb < K || ldc < N || (R && ldr < N)) return SN_ERR_ARG;
@@ -421,7 +418,7 @@ static int gemm_tf32_impl(const float* A, int64_t lda, const float* B, int64_t l
     map_blo = map_b;
   }
   Params p;
-  p.bias = bias; p.R = R; p.rscale = rscale; p.C = C; p.ldr = ldr; p.ldc = ldc; p.E = E; p.lde = lde;
+  p.bias = bias; p.R = R; p.rscale = rscale; p.C = C; p.ldr = ldr; p.ldc = ldc;
   p.gbias = group_bias; p.rows_per_group = group_bias ? (int)rows_per_group : 1;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
   p.split = split ? 1 : 0;
@@ -447,23 +444,4 @@ static int gemm_tf32_impl(const float* A, int64_t lda, const float* B, int64_t l
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
   gemm_tf32_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, map_blo, p);
   return launch_status();
-}
-
-SN_API int sn_gemm_tf32_f32(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, const float* R,
-                            int64_t ldr, const float* rscale, const float* group_bias, int64_t rows_per_group, float* C,
-                            int64_t ldc, int64_t M, int64_t N, int64_t K, int flags, void* ws, size_t ws_bytes,
-                            sn_stream_t stream) {
-  return gemm_tf32_impl(A, lda, B, ldb, bias, R, ldr, rscale, group_bias, rows_per_group, C, ldc, nullptr, 0, M, N, K, flags,
-                        ws, ws_bytes, stream);
-}
-
-// Same product with a second output E = elu(C): the activated copy of a stage's result that the next operator
-// application gathers (utils_pt.py:208 F.elu(f_out)) leaves the epilogue instead of costing a pass over C.
-SN_API int sn_gemm_tf32_elu_f32(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, const float* R,
-                                int64_t ldr, const float* rscale, const float* group_bias, int64_t rows_per_group,
-                                float* C, int64_t ldc, float* E, int64_t lde, int64_t M, int64_t N, int64_t K, int flags,
-                                void* ws, size_t ws_bytes, sn_stream_t stream) {
-  if (!E) return SN_ERR_ARG;
-  return gemm_tf32_impl(A, lda, B, ldb, bias, R, ldr, rscale, group_bias, rows_per_group, C, ldc, E, lde, M, N, K, flags, ws,
-                        ws_bytes, stream);
 }

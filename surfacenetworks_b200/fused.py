@@ -80,7 +80,7 @@ def elu_colstats_supported(X, out):
 
 
 def gemm_tf32(A, B, bias=None, R=None, rscale=None, out=None, single_pass=False, group_bias=None, rows_per_group=0,
-              elu_bwd_left=False, elu_out=None):
+              elu_bwd_left=False):
     """out[M, N] = A[M, K] @ B[N, K]^T + bias + group_bias[row // rows_per_group] + rscale * R
     (3xTF32 tensor-core GEMM; N > 256 is split in column blocks; B may be a row-strided view)."""
     M, K = A.shape
@@ -98,15 +98,6 @@ def gemm_tf32(A, B, bias=None, R=None, rscale=None, out=None, single_pass=False,
         if R is None or step != Nn:
             raise ValueError("elu_bwd_left needs the residual operand and a single column block")
         flags |= N.SN_GEMM_ELU_BWD_LEFT
-    if elu_out is not None:            # second output elu(out) from the same epilogue (sn_gemm_tf32_elu_f32)
-        if step != Nn or elu_out.shape != out.shape or elu_out.stride(1) != 1:
-            raise ValueError("elu_out needs a single column block and the output's shape")
-        ws = _ws(nb, A.device)
-        with torch.cuda.device(A.device):
-            N.call("sn_gemm_tf32_elu_f32", _ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(bias), _ptr(R),
-                   0 if R is None else R.stride(0), _ptr(rscale), _ptr(group_bias), rows_per_group, _ptr(out), out.stride(0),
-                   _ptr(elu_out), elu_out.stride(0), M, Nn, K, flags, _ptr(ws), nb, _stream())
-        return out
     with torch.cuda.device(A.device):
         for n0 in range(0, Nn, step):
             ws = _ws(nb, A.device)
@@ -140,8 +131,7 @@ def gemm_tn_tf32(A, B, single_pass=False):
     return G
 
 
-def bn_linear_forward(Z, gamma, beta, W, b, residual, running_mean, running_var, training, momentum, eps, left_stats,
-                      elu_out=None):
+def bn_linear_forward(Z, gamma, beta, W, b, residual, running_mean, running_var, training, momentum, eps, left_stats):
     """Forward of GraphConv1x1(batch_norm="pre") on rows (no autograd): statistics pass, BN folded into the weights,
     tcgen05 GEMM with the residual in its epilogue.  Returns (Y, saved) with ``saved`` = what bn_linear_backward needs."""
     rows, K = Z.shape
@@ -171,7 +161,7 @@ def bn_linear_forward(Z, gamma, beta, W, b, residual, running_mean, running_var,
                _ptr(Wf), _ptr(bf), _ptr(stk[0]), _ptr(stk[1]), _ptr(stk[2]), _ptr(running_mean) if update else 0,
                _ptr(running_var) if update else 0, float(momentum), rows, _stream())
     res = None if residual is None else residual.contiguous()
-    Y = gemm_tf32(Z, Wf, bias=bf, R=res, elu_out=elu_out)      # elu_out: elu(Y) from the same epilogue
+    Y = gemm_tf32(Z, Wf, bias=bf, R=res)
     return Y, (Z, W, stk, mean)
 
 

@@ -165,10 +165,10 @@ class _DirBlock(torch.autograd.Function):
         fused.elu_colstats(f2, Zf[:, :C], st[2, :C], st[3, :C])
         stats_v, stats_f = (st[0], st[1], C), (st[2], st[3], C)
         D.apply(Zv[:, :C], out=Zf[:, C:])                       # faces <- vertices, gathers the activated rows in place
-        act_f = torch.empty(f2.shape[0], C, dtype=torch.float32, device=v2.device)     # elu(f_out), from the GEMM epilogue
         f_out, saved0 = fused.bn_linear_forward(Zf, g0, b0, W0, c0, None, bn0.running_mean, bn0.running_var, True,
-                                                0.1 if bn0.momentum is None else bn0.momentum, bn0.eps, stats_f,
-                                                elu_out=act_f)
+                                                0.1 if bn0.momentum is None else bn0.momentum, bn0.eps, stats_f)
+        act_f = torch.empty_like(f_out)
+        elu_into(f_out, act_f)
         DA.apply(act_f, out=Zv[:, C:])                          # vertices <- faces
         v_new, saved1 = fused.bn_linear_forward(Zv, g1, b1, W1, c1, v2, bn1.running_mean, bn1.running_var, True,
                                                 0.1 if bn1.momentum is None else bn1.momentum, bn1.eps, stats_v)

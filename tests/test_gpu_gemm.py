@@ -274,20 +274,3 @@ def test_gemm_elu_bwd_left_epilogue(M, N, K):
     assert torch.equal(fusedz, expect)
     with pytest.raises(ValueError):
         fused.gemm_tf32(dY, Ws, bias=q, elu_bwd_left=True)                 # needs the residual operand
-
-
-def test_gemm_second_output_elu():
-    """sn_gemm_tf32_elu_f32: E = elu(C) from the same epilogue, bit-identical to sn_elu_f32 applied to C."""
-    from surfacenetworks_b200 import fused, ops
-    g = torch.Generator(device=DEV).manual_seed(77)
-    M, N, K = 5000, 128, 256
-    A = torch.randn(M, K, device=DEV, generator=g)
-    B = torch.randn(N, K, device=DEV, generator=g) / 16
-    bias = torch.randn(N, device=DEV, generator=g)
-    E = torch.empty(M, N, device=DEV)
-    C = fused.gemm_tf32(A, B, bias=bias, elu_out=E)
-    assert torch.equal(C, fused.gemm_tf32(A, B, bias=bias))
-    ref = torch.empty_like(C)
-    ops.elu_into(C, ref)
-    assert torch.equal(E, ref)
-    assert (C < 0).any() and (C > 0).any()
