@@ -10,40 +10,41 @@
 namespace sn {
 
 constexpr int kFoldCols = 32;      // columns per CTA
-constexpr int kFoldRowGroups = 8;  // row groups per CTA (256 threads)
+constexpr int kFoldRowGroups = 32; // row groups per CTA of the backward kernel (1024 threads: 4 rows per thread at N = 128)
 
-// grid = ceil(K / 32) CTAs; thread (rg, c) handles rows rg, rg + 8, ... of column blockIdx.x * 32 + c
-__global__ void __launch_bounds__(kFoldCols * kFoldRowGroups)
-bn_fold_fwd_kernel(const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ gamma,
-                   const float* __restrict__ beta, const float* __restrict__ W, int N, int K, float eps,
-                   float* __restrict__ Wf, float* __restrict__ s_out, float* __restrict__ t_out, float* __restrict__ rstd_out,
-                   float* running_mean, float* running_var, float momentum, float unbias) {
-  const int c = threadIdx.x % kFoldCols, rg = threadIdx.x / kFoldCols;
-  const int k = blockIdx.x * kFoldCols + c;
-  if (k >= K) return;
-  const float m = mean[k], v = var[k];
-  const float rstd = rsqrtf(v + eps);
-  const float s = gamma[k] * rstd;
-  if (rg == 0) {
-    s_out[k] = s;
-    t_out[k] = beta[k] - m * s;
-    rstd_out[k] = rstd;
-    if (running_mean) {
-      running_mean[k] = (1.f - momentum) * running_mean[k] + momentum * m;
-      running_var[k] = (1.f - momentum) * running_var[k] + momentum * v * unbias;
-    }
-  }
-  for (int n = rg; n < N; n += kFoldRowGroups) Wf[(size_t)n * K + k] = W[(size_t)n * K + k] * s;
-}
-
-// b'[n] = b[n] + sum_k W[n,k] t[k]: one warp per output row, fixed-order lane partials + shuffle tree
+// ONE launch for the forward fold: one warp per output row n (8 rows per CTA).  Every warp recomputes s_k / t_k for its
+// lanes' columns from the statistics (a few flops) instead of waiting for a first kernel to publish them, writes its row
+// of W' = W diag(s) and reduces b'[n] = b[n] + sum_k W[n,k] t[k] (fixed-order lane partials + shuffle tree).  Warp 0 of
+// CTA 0 also publishes s, t, rstd and updates the running statistics.  (Was two dependent launches, 22 us; the work is
+// O(N K) = 32 k elements.)
 __global__ void __launch_bounds__(256)
-bn_fold_bias_kernel(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ t, int N, int K,
-                    float* __restrict__ bf) {
+bn_fold_fwd_kernel(const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, const float* __restrict__ W, const float* __restrict__ b, int N, int K,
+                   float eps, float* __restrict__ Wf, float* __restrict__ bf, float* __restrict__ s_out,
+                   float* __restrict__ t_out, float* __restrict__ rstd_out, float* running_mean, float* running_var,
+                   float momentum, float unbias) {
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const bool publish = blockIdx.x == 0 && threadIdx.x < 32;
   if (n >= N) return;
   float acc = 0.f;
-  for (int kk = lane; kk < K; kk += 32) acc = fmaf(W[(size_t)n * K + kk], t[kk], acc);
+  for (int k = lane; k < K; k += 32) {
+    const float m = mean[k], v = var[k];
+    const float rstd = rsqrtf(v + eps);
+    const float s = gamma[k] * rstd;
+    const float t = beta[k] - m * s;
+    const float w = W[(size_t)n * K + k];
+    Wf[(size_t)n * K + k] = w * s;
+    acc = fmaf(w, t, acc);
+    if (publish) {
+      s_out[k] = s;
+      t_out[k] = t;
+      rstd_out[k] = rstd;
+      if (running_mean) {
+        running_mean[k] = (1.f - momentum) * running_mean[k] + momentum * m;
+        running_var[k] = (1.f - momentum) * running_var[k] + momentum * v * unbias;
+      }
+    }
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) bf[n] = b[n] + acc;
@@ -101,9 +102,8 @@ SN_API int sn_bn_fold_fwd_f32(const float* mean, const float* var, const float* 
   if (N <= 0 || K <= 0 || !mean || !var || !gamma || !beta || !W || !b || !Wf || !bf || !s || !t || !rstd) return SN_ERR_ARG;
   const float unbias = rows > 1 ? (float)((double)rows / (double)(rows - 1)) : 1.f;
   cudaStream_t st = (cudaStream_t)stream;
-  bn_fold_fwd_kernel<<<(unsigned)ceil_div(K, kFoldCols), kFoldCols * kFoldRowGroups, 0, st>>>(
-      mean, var, gamma, beta, W, (int)N, (int)K, eps, Wf, s, t, rstd, running_mean, running_var, momentum, unbias);
-  bn_fold_bias_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(W, b, t, (int)N, (int)K, bf);
+  bn_fold_fwd_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(mean, var, gamma, beta, W, b, (int)N, (int)K, eps, Wf, bf, s, t,
+                                                              rstd, running_mean, running_var, momentum, unbias);
   return launch_status();
 }
 
