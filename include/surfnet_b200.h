@@ -178,13 +178,15 @@ int sn_elu_bwd_f32(const float* A, int64_t lda, int a_is_raw, const float* G, in
 /* Per-mesh (segment) column sums: out[s, c] = sum over the rows_per_seg rows of segment s of w[r] * X[r, c]
  * (w NULL = 1).  With w = mask this is the numerator of global_average (utils_pt.py:120-122); unweighted it is the
  * per-mesh gradient sum of its backward.  Deterministic (8 row slices per segment, fixed-order reductions).
- * sn_elu_bwd_group_f32: Y = (G + w[r] * GB[r / rows_per_seg]) * elu'(x) -- the backward of elu followed by
- * global_average's broadcast term, A holding the activated values as in sn_elu_bwd_f32 (a_is_raw = 0). */
+ * sn_elu_bwd_group_f32: Y = (G + w[r] * GB[r / rows_per_seg]) * elu'(x) + G3 -- the backward of elu followed by
+ * global_average's broadcast term, A holding the activated values as in sn_elu_bwd_f32 (a_is_raw = 0); G3 (may be NULL)
+ * is a gradient that bypasses the activation: the residual of AvgResNet2 (utils_pt.py:243). */
 size_t sn_segment_sum_ws_bytes(int64_t n_seg, int64_t C);
 int sn_segment_sum_f32(const float* X, int64_t ldx, const float* w, int64_t rows_per_seg, int64_t n_seg, int64_t C,
                        float* out, void* ws, size_t ws_bytes, sn_stream_t stream);
 int sn_elu_bwd_group_f32(const float* A, int64_t lda, const float* G, int64_t ldg, const float* GB, const float* w,
-                         int64_t rows_per_seg, float* Y, int64_t ldy, int64_t rows, int64_t C, sn_stream_t stream);
+                         int64_t rows_per_seg, const float* G3, int64_t ldg3, float* Y, int64_t ldy, int64_t rows, int64_t C,
+                         sn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Dense half of a stage on the tensor cores (tcgen05, kind::tf32, accumulators in TMEM):

@@ -58,7 +58,7 @@ SIGNATURES = {
     "sn_mesh_laplacian_csr": (_int, [_ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),
     "sn_segment_sum_ws_bytes": (_sz, [_i64, _i64]),
     "sn_segment_sum_f32": (_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _ptr, _sz, _ptr]),
-    "sn_elu_bwd_group_f32": (_int, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr]),
+    "sn_elu_bwd_group_f32": (_int, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr]),
     "sn_elu_bwd_f32": (_int, [_ptr, _i64, _int, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr]),
 }
 

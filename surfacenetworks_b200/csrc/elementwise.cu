@@ -107,8 +107,8 @@ __global__ void segment_sum_final_kernel(const float* __restrict__ partial, int6
 
 __global__ void __launch_bounds__(256)
 elu_bwd_group_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ G, int64_t ldg,
-                     const float* __restrict__ GB, const float* __restrict__ w, int rows_per_seg, float* __restrict__ Y,
-                     int64_t ldy, int64_t rows, int C4) {
+                     const float* __restrict__ GB, const float* __restrict__ w, int rows_per_seg,
+                     const float* __restrict__ G3, int64_t ldg3, float* __restrict__ Y, int64_t ldy, int64_t rows, int C4) {
   const int64_t total = rows * C4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / C4;
@@ -123,6 +123,10 @@ elu_bwd_group_kernel(const float* __restrict__ A, int64_t lda, const float* __re
     y.y = g.y * (a.y > 0.f ? 1.f : a.y + 1.f);
     y.z = g.z * (a.z > 0.f ? 1.f : a.z + 1.f);
     y.w = g.w * (a.w > 0.f ? 1.f : a.w + 1.f);
+    if (G3) {                     // gradient that bypasses the activation (the block residual)
+      const float4 g3 = __ldcs(reinterpret_cast<const float4*>(G3 + r * ldg3 + c));
+      y.x += g3.x; y.y += g3.y; y.z += g3.z; y.w += g3.w;
+    }
     *reinterpret_cast<float4*>(Y + r * ldy + c) = y;
   }
 }
@@ -151,16 +155,19 @@ SN_API int sn_segment_sum_f32(const float* X, int64_t ldx, const float* w, int64
 }
 
 SN_API int sn_elu_bwd_group_f32(const float* A, int64_t lda, const float* G, int64_t ldg, const float* GB, const float* w,
-                                int64_t rows_per_seg, float* Y, int64_t ldy, int64_t rows, int64_t C, sn_stream_t stream) {
+                                int64_t rows_per_seg, const float* G3, int64_t ldg3, float* Y, int64_t ldy, int64_t rows,
+                                int64_t C, sn_stream_t stream) {
   using namespace sn;
-  if (rows < 0 || C <= 0 || rows_per_seg <= 0 || !A || !G || !GB || !Y || lda < C || ldg < C || ldy < C) return SN_ERR_ARG;
+  if (rows < 0 || C <= 0 || rows_per_seg <= 0 || !A || !G || !GB || !Y || lda < C || ldg < C || ldy < C || (G3 && ldg3 < C))
+    return SN_ERR_ARG;
   if (rows == 0) return SN_OK;
   if (C % 4 || lda % 4 || ldg % 4 || ldy % 4 || !aligned16(A) || !aligned16(G) || !aligned16(GB) || !aligned16(Y) ||
-      rows_per_seg > 0x7fffffffLL)
+      rows_per_seg > 0x7fffffffLL || (G3 && (ldg3 % 4 || !aligned16(G3))))
     return SN_ERR_UNSUPPORTED;
   const int64_t work = rows * (C / 4);
   const unsigned grid = (unsigned)(ceil_div(work, 256) < 148 * 16 ? ceil_div(work, 256) : 148 * 16);
-  elu_bwd_group_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, lda, G, ldg, GB, w, (int)rows_per_seg, Y, ldy, rows, (int)(C / 4));
+  elu_bwd_group_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, lda, G, ldg, GB, w, (int)rows_per_seg, G3, ldg3, Y, ldy, rows,
+                                                               (int)(C / 4));
   return launch_status();
 }
 

@@ -239,7 +239,7 @@ class _AvgStage(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, maskw, inv_cnt, gamma, beta, W, b, residual, running_mean, running_var, training, momentum, eps,
-                n_seg, rows_per_seg):
+                n_seg, rows_per_seg, in_cell=None, res_cell=None):
         rows, C = x.shape
         Nn = W.shape[0]
         dev = x.device
@@ -271,6 +271,10 @@ class _AvgStage(torch.autograd.Function):
         Y = gemm_tf32(a, Wf[:, :C], R=res, group_bias=u, rows_per_group=rows_per_seg)
         ctx.save_for_backward(a, avg, W, stk, mean, maskw, inv_cnt)
         ctx.training, ctx.has_res, ctx.n_seg, ctx.rps = training, residual is not None, n_seg, rows_per_seg
+        # in_cell / res_cell: the two stages of one AvgResNet2 block share a cell.  The stage that holds the block
+        # residual (x + ...) leaves its gradient there instead of returning it, and the stage whose INPUT is that same x
+        # adds it inside its ELU-backward kernel -- autograd's separate accumulation add disappears.
+        ctx.in_cell, ctx.res_cell = in_cell, res_cell
         return Y
 
     @staticmethod
@@ -300,11 +304,15 @@ class _AvgStage(torch.autograd.Function):
         gsum = torch.mm(SdY, WsT[C:].t()) + ctx.rps * (p[C:] * avg + q[C:])       # [B, C]
         gb = (gsum * inv_cnt).contiguous()
         dx = torch.empty_like(a)
+        g3 = ctx.in_cell.pop("residual_grad", None) if ctx.in_cell is not None else None
         with torch.cuda.device(dev):
             N.call("sn_elu_bwd_group_f32", _ptr(a), a.stride(0), _ptr(dZl), dZl.stride(0), _ptr(gb), _ptr(maskw), ctx.rps,
-                   _ptr(dx), dx.stride(0), rows, C, _stream())
-        return (dx, None, None, vec[0], vec[1], dW, db, (dY if ctx.has_res else None), None, None, None, None, None,
-                None, None)
+                   _ptr(g3), 0 if g3 is None else g3.stride(0), _ptr(dx), dx.stride(0), rows, C, _stream())
+        g_res = dY if ctx.has_res else None
+        if g_res is not None and ctx.res_cell is not None:
+            ctx.res_cell["residual_grad"] = dY           # picked up by the block's first stage (runs later in backward)
+            g_res = None
+        return (dx, None, None, vec[0], vec[1], dW, db, g_res, None, None, None, None, None, None, None, None, None)
 
 
 def avg_stage_supported(x, weight):
@@ -315,7 +323,7 @@ def avg_stage_supported(x, weight):
             x.data_ptr() % 16 == 0)
 
 
-def avg_stage(x, mask, bn, fc, residual=None):
+def avg_stage(x, mask, bn, fc, residual=None, in_cell=None, res_cell=None):
     """elu -> [x | global_average] -> BatchNorm -> Linear (+ residual) for x [B, V, C] (AvgResNet2 stage); returns
     [B*V, C_out] rows, or None when the shapes are outside the fused path."""
     B, V, C = x.shape
@@ -330,7 +338,7 @@ def avg_stage(x, mask, bn, fc, residual=None):
     momentum = 0.1 if bn.momentum is None else bn.momentum
     res2 = None if residual is None else residual.reshape(B * V, -1)
     return _AvgStage.apply(x2, maskw, inv_cnt, bn.weight, bn.bias, fc.weight, fc.bias, res2, bn.running_mean,
-                           bn.running_var, training, momentum, bn.eps, B, V)
+                           bn.running_var, training, momentum, bn.eps, B, V, in_cell, res_cell)
 
 
 def bn_linear(z, bn, fc, residual=None):

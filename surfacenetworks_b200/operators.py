@@ -369,7 +369,7 @@ def _check_mesh_status(status):
         raise ValueError("a vertex belongs to %d faces; GPU operator construction supports at most 64" % worst)
 
 
-def build_dirac_operators(V, F, with_transposes=True, sync=True):
+def build_dirac_operators(V, F, with_transposes=True, sync=True, buffers=None):
     """Batch Dirac operator ``D`` [B*f_pad x B*v_pad] and adjoint ``D*`` [B*v_pad x B*f_pad] (block rows x block
     columns) built on the GPU from padded positions ``V`` [B, v_pad, 3] and faces ``F`` [B, f_pad, 3] (local vertex
     indices, padding faces = -1).  Same values as the reference's mesh.dirac (src/utils/mesh.py:35-64) after its
@@ -378,23 +378,33 @@ def build_dirac_operators(V, F, with_transposes=True, sync=True):
     ``with_transposes``: D^T and (D*)^T (what backward applies) come out of the same kernels and are attached as
     ``D.T`` / ``DA.T``.  ``sync=False`` skips the two small read-backs (status check, block count): the operators then
     carry the capacity 3*B*f_pad as their block count (only the accounting of ``algorithmic_bytes`` is affected), so
-    the whole construction is stream-ordered -- for per-step geometry inside a pipelined training loop."""
+    the whole construction is stream-ordered -- for per-step geometry inside a pipelined training loop.  ``buffers``:
+    a dict that keeps the output / workspace tensors between calls (same batch shape), so a per-step rebuild allocates
+    nothing."""
     V, F = _check_mesh_batch(V, F)
     n, v_pad, f_pad = V.size(0), V.size(1), F.size(1)
     dev = V.device
     cap = max(3 * n * f_pad, 1)
     i32 = dict(dtype=torch.int32, device=dev)
-    d_ptr, d_ind = torch.empty(n * f_pad + 1, **i32), torch.empty(cap, **i32)
-    a_ptr, a_ind = torch.empty(n * v_pad + 1, **i32), torch.empty(cap, **i32)
-    d_val = torch.empty(16 * cap, dtype=torch.float32, device=dev)
-    a_val = torch.empty(16 * cap, dtype=torch.float32, device=dev)
-    status = torch.zeros(1, **i32)
-    ws, nbytes = _mesh_ws(n, v_pad, f_pad, dev)
+    store = buffers if buffers is not None else {}
+    if store.get("shape") != (n, v_pad, f_pad, bool(with_transposes), str(dev)):
+        store.clear()
+        store["shape"] = (n, v_pad, f_pad, bool(with_transposes), str(dev))
+
+    def buf(name, numel, dtype):
+        if name not in store:
+            store[name] = torch.empty(numel, dtype=dtype, device=dev)
+        return store[name]
+    d_ptr, d_ind = buf("d_ptr", n * f_pad + 1, torch.int32), buf("d_ind", cap, torch.int32)
+    a_ptr, a_ind = buf("a_ptr", n * v_pad + 1, torch.int32), buf("a_ind", cap, torch.int32)
+    d_val, a_val = buf("d_val", 16 * cap, torch.float32), buf("a_val", 16 * cap, torch.float32)
+    status = buf("status", 1, torch.int32)
+    nbytes = N.lib.sn_mesh_ws_bytes(n, v_pad, f_pad)
+    ws = buf("ws", max(nbytes, 1), torch.uint8)
     dt_ind = dt_val = at_ind = at_val = None
     if with_transposes:
-        dt_ind, at_ind = torch.empty(cap, **i32), torch.empty(cap, **i32)
-        dt_val = torch.empty(16 * cap, dtype=torch.float32, device=dev)
-        at_val = torch.empty(16 * cap, dtype=torch.float32, device=dev)
+        dt_ind, at_ind = buf("dt_ind", cap, torch.int32), buf("at_ind", cap, torch.int32)
+        dt_val, at_val = buf("dt_val", 16 * cap, torch.float32), buf("at_val", 16 * cap, torch.float32)
     with torch.cuda.device(dev):
         N.call("sn_mesh_dirac_bsr4", _ptr(V), _ptr(F), n, v_pad, f_pad, _ptr(d_ptr), _ptr(d_ind), _ptr(d_val),
                _ptr(a_ptr), _ptr(a_ind), _ptr(a_val), _ptr(dt_ind), _ptr(dt_val), _ptr(at_ind), _ptr(at_val),

@@ -206,9 +206,12 @@ class AvgResNet2(_TwoStageBlock):
 
     def forward(self, L, mask, inputs):
         B, V, C = inputs.size()
-        y = fused.avg_stage(inputs, mask, self.bn_fc0.bn, self.bn_fc0.fc) if inputs.is_cuda else None
+        # the residual's gradient travels through this cell into the first stage's ELU-backward kernel (fused.py);
+        # only when autograd will really run both stages' backward in one pass over the same `inputs`
+        cell = {} if (torch.is_grad_enabled() and inputs.requires_grad) else None
+        y = fused.avg_stage(inputs, mask, self.bn_fc0.bn, self.bn_fc0.fc, in_cell=cell) if inputs.is_cuda else None
         if y is not None:
-            y = fused.avg_stage(y.view(B, V, -1), mask, self.bn_fc1.bn, self.bn_fc1.fc, residual=inputs)
+            y = fused.avg_stage(y.view(B, V, -1), mask, self.bn_fc1.bn, self.bn_fc1.fc, residual=inputs, res_cell=cell)
         if y is not None:
             return y.view(B, V, -1)
         x = F.elu(inputs)
