@@ -198,18 +198,25 @@ def bn_linear_backward(saved, dY, training, elu_bwd_left=False):
 class _BnLinear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, Z, gamma, beta, W, b, residual, running_mean, running_var, training, momentum, eps, left_stats,
-                elu_bwd_left=False):
+                elu_bwd_left=False, res_cell=None):
         Y, saved = bn_linear_forward(Z, gamma, beta, W, b, residual, running_mean, running_var, training, momentum, eps,
                                      left_stats)
         ctx.save_for_backward(*saved)
         ctx.training, ctx.has_res, ctx.elu_bwd_left = training, residual is not None, elu_bwd_left
+        ctx.res_cell = res_cell           # see ops.stage_concat(in_cell=...): where the residual's gradient goes instead
         return Y
 
     @staticmethod
     def backward(ctx, dY):
         dZ, dgamma, dbeta, dW, db = bn_linear_backward(ctx.saved_tensors, dY, ctx.training,
                                                        ctx.elu_bwd_left and ctx.training)
-        return dZ, dgamma, dbeta, dW, db, (dY if ctx.has_res else None), None, None, None, None, None, None, None
+        g_res = dY if ctx.has_res else None
+        if g_res is not None and ctx.res_cell is not None:
+            if g_res.stride(1) != 1 or g_res.stride(0) % 4 or g_res.data_ptr() % 16:
+                g_res = g_res.contiguous()
+            ctx.res_cell["residual_grad"] = g_res
+            g_res = None
+        return dZ, dgamma, dbeta, dW, db, g_res, None, None, None, None, None, None, None, None
 
 
 def segment_sum(X, rows_per_seg, n_seg, weight=None):
@@ -341,8 +348,18 @@ def avg_stage(x, mask, bn, fc, residual=None, in_cell=None, res_cell=None):
                            bn.running_var, training, momentum, bn.eps, B, V, in_cell, res_cell)
 
 
-def bn_linear(z, bn, fc, residual=None):
-    """GraphConv1x1(batch_norm="pre") on rows: fused path when the shapes allow it, torch composite otherwise."""
+def bn_linear_is_fused(rows_like, fc, residual_cols=None):
+    """Will bn_linear take the fused path for a [rows, 2C] buffer made from ``rows_like`` [rows, C]?  (Same conditions as
+    fused_supported, evaluated before the buffer exists.)"""
+    n_out, k = fc.weight.shape
+    return (rows_like.is_cuda and rows_like.dtype == torch.float32 and rows_like.dim() == 2 and k == 2 * rows_like.shape[1]
+            and gemm_supported(n_out, k) and gemm_supported(k, n_out) and k % 4 == 0 and 256 % (k // 4) == 0
+            and (residual_cols is None or residual_cols == n_out))
+
+
+def bn_linear(z, bn, fc, residual=None, res_cell=None):
+    """GraphConv1x1(batch_norm="pre") on rows: fused path when the shapes allow it, torch composite otherwise.
+    ``res_cell``: honoured by the fused path only -- callers must check ``bn_linear_is_fused`` before handing one over."""
     if fused_supported(z, fc.weight) and (residual is None or (residual.shape == (z.shape[0], fc.weight.shape[0]))):
         training = bn.training or bn.running_mean is None
         if training and bn.num_batches_tracked is not None:
@@ -356,7 +373,7 @@ def bn_linear(z, bn, fc, residual=None):
         if fold:
             cell["left_premultiplied"] = True
         return _BnLinear.apply(z, bn.weight, bn.bias, fc.weight, fc.bias, residual, bn.running_mean, bn.running_var,
-                               training, momentum, bn.eps, left, fold)
+                               training, momentum, bn.eps, left, fold, res_cell)
     # Output widths between the tensor-core shapes (the 128 -> 120 head of the ARAP / dense_correspondence models,
     # conv2 at as_rigid_as_possible/models.py:121): zero-pad the Linear to the next supported width and slice -- the
     # cuBLAS fp32 SIMT GEMMs it replaces were 0.6 ms of the 19 ms step (profiles/r1b_launches_bench_summary.json)

@@ -105,10 +105,14 @@ class _StageConcat(torch.autograd.Function):
         g_left, g_right = gZ[:, :C], gZ[:, C:]
         if ctx.same:
             (Z,) = ctx.saved_tensors
-            t = op.T.apply_epilogue(g_right, G=g_left, A=Z[:, :C])     # (g_left + S^T g) * elu'(x) in the store path
+            g_res = ctx.cell.pop("residual_grad", None) if ctx.cell is not None else None
+            # (g_left + S^T g) * elu'(x) + residual gradient, all in the store path
+            t = op.T.apply_epilogue(g_right, G=g_left, A=Z[:, :C], G2=g_res)
             if t is None:
                 t = op.T.apply(g_right)                   # S^T g
                 _elu_bwd(Z[:, :C], False, g_left, t, t)   # (g_left + S^T g) * elu'(x), in place
+                if g_res is not None:
+                    t += g_res
             return t, None, None, None, None, None
         Z, act = ctx.saved_tensors
         if ctx.cell is not None and ctx.cell.get("left_premultiplied"):
@@ -123,7 +127,7 @@ class _StageConcat(torch.autograd.Function):
         return g_self, t, None, None, None, None
 
 
-def stage_concat(op, x_self, x_gather=None, want_stats=True):
+def stage_concat(op, x_self, x_gather=None, want_stats=True, in_cell=None):
     """``[elu(x_self) | op @ elu(x_gather)]`` as one [rows, 2C] buffer; ``x_gather=None`` means x_self.
 
     With ``want_stats`` the activation pass also reduces the left half's BatchNorm statistics; they ride on the
@@ -131,11 +135,13 @@ def stage_concat(op, x_self, x_gather=None, want_stats=True):
     same = x_gather is None
     # not-same stages: the consumer (fused.bn_linear) may fold elu'(x_self) into its dZ GEMM epilogue; it says so
     # through this cell, which the backward above reads (default: not folded, run the elementwise pass)
-    cell = None if same else {"left_premultiplied": False}
+    # in_cell (Laplacian blocks): the block's second stage leaves the residual's gradient there
+    # (fused.bn_linear(res_cell=...)); it is added in this stage's backward SpMM epilogue instead of by autograd
+    cell = in_cell if same else {"left_premultiplied": False}
     Z, mean_l, var_l = _StageConcat.apply(x_self, x_self if same else x_gather, op, same, want_stats, cell)
     if mean_l.numel():
         Z._sn_left_stats = (mean_l, var_l)
-    if cell is not None:
+    if cell is not None and not same:
         Z._sn_stage_cell = cell
     return Z
 

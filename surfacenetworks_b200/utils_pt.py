@@ -88,12 +88,12 @@ class GraphConv1x1(nn.Module):
             self.bn = nn.BatchNorm1d(num_outputs)
         self.fc = nn.Linear(num_inputs, num_outputs)
 
-    def forward_rows(self, z, residual=None):
+    def forward_rows(self, z, residual=None, res_cell=None):
         """z: [rows, num_inputs] -> [rows, num_outputs] (+ residual).  "pre" BatchNorm + Linear runs as the fused
         stage of ``fused.py`` (statistics pass, BN folded into the weights, tcgen05 GEMM with the residual in its
         epilogue) whenever the widths allow it."""
         if self.batch_norm == "pre":
-            return fused.bn_linear(z, self.bn, self.fc, residual)
+            return fused.bn_linear(z, self.bn, self.fc, residual, res_cell)
         z = self.fc(z)
         if self.batch_norm == "post":
             z = self.bn(z)
@@ -148,8 +148,13 @@ class LapResNet2(_TwoStageBlock):
             return _dense_lap_block(self, L, inputs)
         op = as_csr(L)
         x = inputs.reshape(batch * node, feat)
-        y = self.bn_fc0.forward_rows(ops.stage_concat(op, x))
-        y = self.bn_fc1.forward_rows(ops.stage_concat(op, y), residual=x)       # "+ inputs" rides in the epilogue
+        # training: the residual's gradient skips autograd's accumulation add -- the second stage leaves it in `cell`,
+        # the first stage's backward SpMM adds it in its store path (ops.stage_concat / fused.bn_linear)
+        cell = None
+        if torch.is_grad_enabled() and x.requires_grad and fused.bn_linear_is_fused(x, self.bn_fc1.fc, feat):
+            cell = {}
+        y = self.bn_fc0.forward_rows(ops.stage_concat(op, x, in_cell=cell))
+        y = self.bn_fc1.forward_rows(ops.stage_concat(op, y), residual=x, res_cell=cell)   # "+ inputs" rides in the epilogue
         return y.view(batch, node, feat)
 
 

@@ -138,3 +138,49 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(root, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "sn_oracle" not in text, f
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    """The round-1b entry points (row-group epilogue SpMM, mesh construction, GEMM flags) reject bad arguments on the
+    host before any CUDA call."""
+    from surfacenetworks_b200 import _native as N
+    L = N.lib
+    # epilogue SpMM: null operands / short leading dimensions / flags that select another kernel
+    assert L.sn_bsr4_spmm_epilogue_f32(0, 0, 0, 0, 128, 0, 128, 8, 128, 0, 0, 0, 0, 0, 0, 0, 0) == N.SN_ERR_ARG
+    assert L.sn_bsr4_spmm_epilogue_f32(16, 16, 16, 16, 128, 16, 128, 8, 128, 16, 64, 0, 0, 0, 0, 0, 0) == N.SN_ERR_ARG
+    assert L.sn_bsr4_spmm_epilogue_f32(16, 16, 16, 16, 128, 16, 128, 8, 128, 0, 0, 0, 0, 0, 0,
+                                       N.SN_SPMM_DIRECT_GATHER, 0) == N.SN_ERR_UNSUPPORTED
+    assert L.sn_csr_spmm_epilogue_f32(16, 16, 16, 16, 48, 16, 48, 8, 48, 0, 0, 16, 48, 0, 0, 0, 0) == N.SN_ERR_UNSUPPORTED
+    assert L.sn_csr_spmm_epilogue_f32(16, 16, 16, 16, 64, 16, 64, 0, 64, 0, 0, 0, 0, 0, 0, 0, 0) == N.SN_OK   # no rows
+    # mesh construction: sizes, workspace
+    assert L.sn_mesh_ws_bytes(0, 10, 10) == 0 and L.sn_mesh_ws_bytes(2, 100, 200) > 0
+    assert L.sn_mesh_dirac_bsr4(0, 0, 2, 100, 200, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0) == N.SN_ERR_ARG
+    assert L.sn_mesh_dirac_bsr4(16, 16, 2, 100, 200, 16, 16, 16, 16, 16, 16, 0, 0, 0, 0, 16, 16, 8, 0) == N.SN_ERR_WORKSPACE
+    assert L.sn_mesh_laplacian_csr(16, 16, 1 << 40, 100, 200, 16, 16, 16, 16, 16, 1 << 40, 0) == N.SN_ERR_OVERFLOW
+    assert L.sn_mesh_laplacian_csr(16, 16, 0, 100, 200, 16, 16, 16, 16, 16, 0, 0) == N.SN_OK                 # no meshes
+    # GEMM: the elu' epilogue needs the residual operand
+    assert L.sn_gemm_tf32_f32(16, 128, 16, 128, 0, 0, 0, 0, 0, 0, 16, 256, 128, 256, 128, N.SN_GEMM_ELU_BWD_LEFT, 0, 0, 0) \
+        == N.SN_ERR_ARG
+    assert N.spmm_flags(True, False, True, 3) == (N.SN_SPMM_ELU_INPUT | N.SN_SPMM_SMEM_STREAM | (3 << 8))
+
+
+def test_mesh_packing_and_reference_seam_surface():
+    """pack_meshes pads like the batch operators expect; the src/utils/cuda mirror exposes the reference's names and
+    refuses CPU tensors (no fallback)."""
+    from surfacenetworks_b200 import cuda as C, geometry, operators as O
+    V1, F1 = geometry.cube_mesh()
+    V2, F2 = geometry.synth_mesh(30, 3)
+    Vp, Fp = O.pack_meshes([(V1, F1), (V2, F2)], "cpu")
+    assert Vp.shape == (2, 30, 3) and Vp.dtype == torch.float64 and Fp.dtype == torch.int32
+    assert Fp.shape == (2, max(F1.shape[0], F2.shape[0]), 3)
+    assert torch.all(Fp[0, F1.shape[0]:] == -1) and torch.all(Vp[0, 8:] == 0)
+    assert np.array_equal(Fp[1, :F2.shape[0]].numpy(), F2) and np.array_equal(Vp[0, :8].numpy(), V1)
+    with pytest.raises(RuntimeError):
+        O.build_dirac_operators(Vp, Fp)                                  # CPU tensors: loud failure
+    assert callable(C.batch_csr) and callable(C.sparse_bmm) and hasattr(C.SparseBMMFunc, "apply")
+    idx = torch.zeros(3, 4, dtype=torch.int64)
+    with pytest.raises(RuntimeError):
+        C.batch_csr(idx, (1, 2, 2))
+    S = torch.sparse_coo_tensor(idx, torch.ones(4), (1, 2, 2))
+    with pytest.raises(RuntimeError):
+        C.SparseBMMFunc.apply(S, torch.zeros(1, 2, 3))
