@@ -17,7 +17,7 @@ import torch
 
 from . import _native as N
 
-__all__ = ["CsrOperator", "Bsr4Operator", "as_csr", "as_bsr4", "clear_cache", "MeshOperatorCache",
+__all__ = ["CsrOperator", "Bsr4Operator", "as_csr", "as_bsr4", "clear_cache", "MeshOperatorCache", "Arena",
            "build_dirac_operators", "build_laplacian_operator", "pack_meshes"]
 
 
@@ -45,15 +45,45 @@ def _check_dense(X, name):
                          % (name, tuple(X.shape), X.stride()))
 
 
-def _coo_to_csr32(batch, row, col, val, rows_per_batch, cols_per_batch, n_rows, n_cols, is_sorted):
+class Arena:
+    """Replays a fixed sequence of device allocations: the first pass allocates, later passes (after ``begin()``) hand
+    the same tensors back in the same order.  A per-step conversion pipeline run through an arena allocates nothing in
+    steady state -- no caching-allocator traffic across streams, no cudaMalloc stalls (measured: the per-step COO
+    conversion of bench.py's e2e path jittered between 20 and 230 ms per step without it)."""
+
+    def __init__(self):
+        self._bufs, self._i = [], 0
+
+    def begin(self):
+        self._i = 0
+
+    def empty(self, numel, dtype, device):
+        numel = int(numel)
+        if self._i < len(self._bufs):
+            t = self._bufs[self._i]
+            if t.numel() >= numel and t.dtype == dtype and t.device == torch.device(device):
+                self._i += 1
+                return t[:numel]
+            del self._bufs[self._i:]                 # the sequence changed: re-record from here
+        t = torch.empty(numel, dtype=dtype, device=device)
+        self._bufs.append(t)
+        self._i += 1
+        return t
+
+
+def _empty(arena, numel, dtype, device):
+    return torch.empty(numel, dtype=dtype, device=device) if arena is None else arena.empty(numel, dtype, device)
+
+
+def _coo_to_csr32(batch, row, col, val, rows_per_batch, cols_per_batch, n_rows, n_cols, is_sorted, arena=None):
     """COO (int64, device) -> (rowptr, colind, val) via sn_coo_to_csr32 (replaces batch_csr.cu:13-47)."""
     dev = val.device
     nnz = int(val.numel())
-    rowptr = torch.empty(n_rows + 1, dtype=torch.int32, device=dev)
-    colind = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
-    out_val = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)
+    rowptr = _empty(arena, n_rows + 1, torch.int32, dev)
+    colind = _empty(arena, max(nnz, 1), torch.int32, dev)
+    out_val = _empty(arena, max(nnz, 1), torch.float32, dev)
     ws_bytes = 0 if is_sorted else N.lib.sn_coo_to_csr32_ws_bytes(nnz, n_rows)
-    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    ws = _empty(arena, max(ws_bytes, 1), torch.uint8, dev)
     with torch.cuda.device(dev):
         N.call("sn_coo_to_csr32", _ptr(batch), _ptr(row), _ptr(col), _ptr(val), nnz, rows_per_batch, cols_per_batch,
                n_rows, n_cols, N.SN_COO_SORTED if is_sorted else 0, _ptr(rowptr), _ptr(colind), _ptr(out_val),
@@ -74,9 +104,9 @@ class _CooSource:
         return _CooSource(self.batch, self.col, self.row, self.val, self.cols_per_batch, self.rows_per_batch,
                           self.n_cols, self.n_rows, False)
 
-    def to_csr(self):
+    def to_csr(self, arena=None):
         return _coo_to_csr32(self.batch, self.row, self.col, self.val, self.rows_per_batch, self.cols_per_batch,
-                             self.n_rows, self.n_cols, self.is_sorted)
+                             self.n_rows, self.n_cols, self.is_sorted, arena)
 
     @staticmethod
     def from_torch(S):
@@ -232,24 +262,30 @@ class Bsr4Operator:
         return self.browptr.device
 
     @classmethod
-    def from_source(cls, src):
+    def from_source(cls, src, arena=None, block_capacity=None):
+        """``arena``: take every device buffer from a replayable Arena (per-step conversions allocate nothing);
+        ``block_capacity``: an upper bound of the block count known to the caller -- skips the read-back of the exact
+        count, so the whole conversion is stream-ordered (the operator then reports the capacity as ``n_blocks``)."""
         if src.n_rows % 4 or src.n_cols % 4:
             raise ValueError("Dirac operator shape must be a multiple of 4 in both dims, got %dx%d"
                              % (src.n_rows, src.n_cols))
-        rowptr, colind, val, _ = src.to_csr()
+        rowptr, colind, val, _ = src.to_csr(arena)
         dev = val.device
         n_brows = src.n_rows // 4
-        browptr = torch.empty(n_brows + 1, dtype=torch.int32, device=dev)
+        browptr = _empty(arena, n_brows + 1, torch.int32, dev)
         ws_bytes = N.lib.sn_csr32_to_bsr4_ws_bytes(src.n_rows)
-        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        ws = _empty(arena, max(ws_bytes, 1), torch.uint8, dev)
         with torch.cuda.device(dev):
             N.call("sn_csr32_to_bsr4_count", _ptr(rowptr), _ptr(colind), src.n_rows, _ptr(browptr), _ptr(ws),
                    ws_bytes, _stream())
-            # one small read-back per operator conversion (not per step): block count + densest block-row
-            stats = torch.stack([browptr[-1], (browptr[1:] - browptr[:-1]).max() if n_brows else browptr[-1]]).tolist()
-            nb, max_row_blocks = int(stats[0]), int(stats[1])
-            bcolind = torch.empty(max(nb, 1), dtype=torch.int32, device=dev)
-            bval = torch.empty(max(nb, 1) * 16, dtype=torch.float32, device=dev)
+            if block_capacity is None:
+                # one small read-back per operator conversion (not per step): block count + densest block-row
+                stats = torch.stack([browptr[-1], (browptr[1:] - browptr[:-1]).max() if n_brows else browptr[-1]]).tolist()
+                nb, max_row_blocks = int(stats[0]), int(stats[1])
+            else:
+                nb, max_row_blocks = int(block_capacity), 0
+            bcolind = _empty(arena, max(nb, 1), torch.int32, dev)
+            bval = _empty(arena, max(nb, 1) * 16, torch.float32, dev)
             N.call("sn_csr32_to_bsr4_fill", _ptr(rowptr), _ptr(colind), _ptr(val), src.n_rows, _ptr(browptr),
                    _ptr(bcolind), _ptr(bval), _stream())
         if nb:
@@ -257,15 +293,21 @@ class Bsr4Operator:
         return cls(browptr, bcolind, bval, n_brows, src.n_cols // 4, src, nb, max_row_blocks)
 
     @classmethod
-    def from_torch_coo(cls, S):
-        return cls.from_source(_CooSource.from_torch(S))
+    def from_torch_coo(cls, S, arena=None, block_capacity=None):
+        return cls.from_source(_CooSource.from_torch(S), arena, block_capacity)
 
     @property
     def T(self):
         if self._T is None:
+            self.build_transpose()
+        return self._T
+
+    def build_transpose(self, arena=None, block_capacity=None):
+        """Builds (once) the transposed operator backward applies; ``arena`` / ``block_capacity`` as in from_source."""
+        if self._T is None:
             if self._source is None:
                 raise RuntimeError("transpose unavailable: operator was built without its COO source")
-            self._T = Bsr4Operator.from_source(self._source.transposed())
+            self._T = Bsr4Operator.from_source(self._source.transposed(), arena, block_capacity)
             self._T._T = self
         return self._T
 
