@@ -184,3 +184,44 @@ def test_mesh_packing_and_reference_seam_surface():
     S = torch.sparse_coo_tensor(idx, torch.ones(4), (1, 2, 2))
     with pytest.raises(RuntimeError):
         C.SparseBMMFunc.apply(S, torch.zeros(1, 2, 3))
+
+
+def test_arena_replays_allocations_and_structure_source_expands_blocks():
+    """Host logic behind the allocation-free e2e path and the transposes of GPU-built operators (device-agnostic, so
+    checked here on CPU tensors): Arena hands back the same storage in the same order after begin(); the BSR4 -> COO
+    expansion follows the rotated block layout bval[16k + 4q + s] = B[(q + s) % 4][q]."""
+    from surfacenetworks_b200 import operators as O
+    ar = O.Arena()
+    a1, b1 = ar.empty(10, torch.float32, "cpu"), ar.empty(7, torch.int32, "cpu")
+    ar.begin()
+    a2, b2 = ar.empty(10, torch.float32, "cpu"), ar.empty(5, torch.int32, "cpu")          # smaller request: a prefix view
+    assert a2.data_ptr() == a1.data_ptr() and b2.data_ptr() == b1.data_ptr() and b2.numel() == 5
+    ar.begin()
+    c = ar.empty(10, torch.float64, "cpu")                                                 # sequence changed: re-recorded
+    assert c.dtype == torch.float64 and c.data_ptr() != a1.data_ptr()
+    ar.begin()
+    assert ar.empty(10, torch.float64, "cpu").data_ptr() == c.data_ptr()
+    # two block rows, three blocks: (0,1), (1,0), (1,2); dense random 4x4 blocks
+    rng = np.random.default_rng(0)
+    blocks = rng.standard_normal((3, 4, 4)).astype(np.float32)
+    ptr = torch.tensor([0, 1, 3], dtype=torch.int32)
+    ind = torch.tensor([1, 0, 2], dtype=torch.int32)
+    bval = np.empty((3, 16), np.float32)
+    for k in range(3):
+        for q in range(4):
+            for s_ in range(4):
+                bval[k, 4 * q + s_] = blocks[k, (q + s_) % 4, q]
+    src = O._StructureSource("bsr4", ptr, ind, torch.from_numpy(bval.ravel()), 8, 12, 3)
+    row, col, val = src._coo()
+    dense = np.zeros((8, 12), np.float32)
+    dense[row.numpy(), col.numpy()] = val.numpy()
+    expect = np.zeros((8, 12), np.float32)
+    for k, (br, bc) in enumerate([(0, 1), (1, 0), (1, 2)]):
+        expect[4 * br:4 * br + 4, 4 * bc:4 * bc + 4] = blocks[k]
+    assert np.array_equal(dense, expect)
+    t = src.transposed()
+    assert (t.n_rows, t.n_cols) == (12, 8) and torch.equal(t.row, col) and torch.equal(t.col, row)
+    csr = O._StructureSource("csr", torch.tensor([0, 2, 2, 3], dtype=torch.int32), torch.tensor([1, 3, 0], dtype=torch.int32),
+                             torch.tensor([1.0, 2.0, 3.0]), 3, 4, 3)
+    r, c_, v = csr._coo()
+    assert r.tolist() == [0, 0, 2] and c_.tolist() == [1, 3, 0] and v.tolist() == [1.0, 2.0, 3.0]
