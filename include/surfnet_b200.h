@@ -11,8 +11,12 @@
  *   torch.mm(sparse_coo, dense) at src/utils/utils_pt.py:202,214   sn_bsr4_spmm_f32  (Dirac / adjoint)
  *   src/utils/cuda/sparse_bmm_func.py:53-72 (backward = A^T grad)  same SpMM entry points on a
  *                                                                  transposed structure built once
- *   GraphConv1x1 "pre" BN + Linear, utils_pt.py:91-104             sn_colstats_*, sn_bn_fold_f32,
- *                                                                  sn_linear_* (fused stage)
+ *   GraphConv1x1 "pre" BN + Linear, utils_pt.py:91-104             sn_colstats_f32, sn_bn_fold_{fwd,bwd}_f32,
+ *                                                                  sn_gemm_tf32_f32, sn_gemm_tn_tf32_f32
+ *   autograd backward of elu + torch.mm + cat, utils_pt.py:161-216 sn_{csr,bsr4}_spmm_epilogue_f32
+ *   AvgResNet2 / global_average, utils_pt.py:120-122,230-243       sn_segment_sum_f32, sn_elu_bwd_group_f32
+ *   sparse_diag_cat + upload per step, utils_pt.py:41-53           sn_assemble_block_diag
+ *   mesh.dirac / cotangent_weights / graph.laplacian (offline)     sn_mesh_dirac_bsr4, sn_mesh_laplacian_csr
  *
  * Conventions (same as the reference's cupy launch seam, sparse_bmm.py:49-59, made explicit):
  *   - every pointer is a DEVICE pointer unless its name starts with host_;
