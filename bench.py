@@ -295,7 +295,19 @@ def breakdown(dev, model, res, Dop, DAop, host, B):
         mu, lv = enc(x2, L2, m2)
         (mu.sum() + lv.sum()).backward()
     out["cfg2_lap_encoder_forward_backward_ms"] = gpu_ms(enc_train)
-    # the reference's own calls on the host (bounded: 3 repetitions each)
+    out.update(host_reference_calls(host, B))
+    return out
+
+
+def host_reference_calls(host, B):
+    """The reference's own per-step calls on the host cores for the bench batch (bounded: 3 repetitions each):
+    torch.mm(Di_coo, x) as at utils_pt.py:202, and the block-diagonal batch assembly of utils_pt.py:41-53 done the
+    reference's way (offset, concatenate, .coalesce()) next to this package's sparse_diag_cat (same output, skips the
+    sort when the inputs are already in coalesced order)."""
+    import time
+    from surfacenetworks_b200 import utils_pt as U, workloads as W
+    out = {}
+    nv, nf = host["num_vertices"], host["num_faces"]
     torch.set_num_threads(os.cpu_count() or 1)
     Di = host["Di"]
     xh = torch.randn(Di.shape[1], 32)                       # [4 * B * V, C / 4]: the view of utils_pt.py:201
@@ -304,9 +316,17 @@ def breakdown(dev, model, res, Dop, DAop, host, B):
         torch.mm(Di, xh)
     out["cpu_torch_mm_Di_ms"] = (time.perf_counter() - t0) / 3 * 1e3
     per = [U.sp_sparse_to_pt_sparse(m.Di) for m in W.make_mesh_ops(host["num_vertices"], range(4))]
+    lst = [per[i % 4] for i in range(B)]
+    U.sparse_diag_cat(lst[:2], 4 * nf, 4 * nv)              # warm the allocator / thread pool
     t0 = time.perf_counter()
-    U.sparse_diag_cat([per[i % 4] for i in range(B)], 4 * nf, 4 * nv)
+    ours = U.sparse_diag_cat(lst, 4 * nf, 4 * nv)
     out["cpu_sparse_diag_cat_Di_ms"] = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter()
+    idx = torch.cat([t._indices() + torch.tensor([[i * 4 * nf], [i * 4 * nv]]) for i, t in enumerate(lst)], 1)
+    ref = torch.sparse_coo_tensor(idx, torch.cat([t._values() for t in lst]), (B * 4 * nf, B * 4 * nv)).coalesce()
+    out["cpu_reference_style_diag_cat_Di_ms"] = (time.perf_counter() - t0) * 1e3
+    out["cpu_diag_cat_identical"] = bool(torch.equal(ours._indices(), ref._indices()) and
+                                         torch.equal(ours._values(), ref._values()))
     out["cpu_threads"] = torch.get_num_threads()
     return out
 
