@@ -252,3 +252,28 @@ def test_dense_correspondence_siamese(golden, batch):
         out = O.siamese(P, (B["L"], B["mask"]), (B["L"], B["mask"]), xa, xb, 3, "lap")
         scale = float(np.abs(d["siamese_lap3/out0"]).max())
         assert_close(out.numpy(), d["siamese_lap3/out0"], 1e-4, 1e-5 * scale, "siamese lap3")
+
+
+def test_mesh_operator_restatement_matches_reference_built_operators(golden):
+    """oracle/mesh_ops.py (the per-entry arithmetic the GPU construction kernels replay) reproduces, bit for bit, the
+    operators the reference's mesh.py / graph.py built for cube.ply (tests/golden/operators.npz), and the host builder on a
+    generic synthetic mesh."""
+    from oracle import mesh_ops
+    from surfacenetworks_b200 import geometry
+    V, F = geometry.cube_mesh()
+    r, c, v, shape = golden.coo("operators", "cube_L")
+    rr, cc, vv = mesh_ops.laplacian_coo(V, F)
+    assert sorted(zip(r.tolist(), c.tolist(), v.tolist())) == sorted(zip(rr.tolist(), cc.tolist(), vv.tolist()))
+    D, DA = mesh_ops.dirac_entries(V, F)
+    for name, got in (("cube_Di", D), ("cube_DiA", DA)):
+        r, c, v, shape = golden.coo("operators", name)
+        ref = {(int(a), int(b)): np.float32(x) for a, b, x in zip(r, c, v)}
+        assert ref == got, name
+    V, F = geometry.synth_mesh(120, 5)
+    L = geometry.build_laplacian(V, F).tocoo()
+    rr, cc, vv = mesh_ops.laplacian_coo(V, F)
+    assert sorted(zip(L.row.tolist(), L.col.tolist(), L.data.tolist())) == sorted(zip(rr.tolist(), cc.tolist(), vv.tolist()))
+    Dh, DAh = [m.tocoo() for m in geometry.build_dirac(V, F)]
+    D, DA = mesh_ops.dirac_entries(V, F)
+    for S, got in ((Dh, D), (DAh, DA)):
+        assert {(int(a), int(b)): np.float32(x) for a, b, x in zip(S.row, S.col, S.data)} == got
