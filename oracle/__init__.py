@@ -8,5 +8,6 @@ against fixtures produced by RUNNING THE REFERENCE in the build container (``tes
 -> ``tests/golden/*.npz``); ``tests/test_oracle_golden.py`` checks every function here against them.
 
   c_oracle.py  ctypes wrappers of sn_oracle.c (plain C: COO x dense, batch_csr, sparse_bmm, Dirac view, ELU)
-  layers.py    functional torch-CPU restatement of utils_pt.py's layers and the ARAP model stacks
+  layers.py    functional torch-CPU restatement of utils_pt.py's layers and the ARAP / dense_correspondence model stacks
+  mesh_ops.py  per-entry restatement of the mesh operators (mesh.py / graph.py) in the reference's fp64 operation order
 """
