@@ -209,11 +209,22 @@ int sn_elu_bwd_group_f32(const float* A, int64_t lda, const float* G, int64_t ld
 #define SN_GEMM_SINGLE_PASS 1
 #define SN_GEMM_ELU_BWD_LEFT 4  /* multiply output columns [0, N/2) by elu'(R) (R = activated values: 1 if R > 0 else R + 1); needs R */
 #define SN_GEMM_NO_L2_PREFETCH 2 /* A/B switch: disable the L2 prefetch of upcoming operands (residual rows / split-K boxes) */
+#define SN_GEMM_LEGACY_SS 8      /* A/B switch: the round-1 kernel (both operands from shared memory) instead of the TS-mode one */
 size_t sn_gemm_tf32_ws_bytes(int64_t N, int64_t K); /* workspace for the pre-split weights (3xTF32 mode) */
 int sn_gemm_tf32_f32(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, const float* R,
                      int64_t ldr, const float* rscale, const float* group_bias, int64_t rows_per_group, float* C,
                      int64_t ldc, int64_t M, int64_t N, int64_t K, int flags, void* ws, size_t ws_bytes,
                      sn_stream_t stream);
+
+/* Same product with the weights ALREADY split by the caller: B_hi = tf32(B), B_lo = B - B_hi, both [N x K] with leading
+ * dimension ldb (sn_bn_fold_{fwd,bwd}_f32 emit them; sn_split_tf32_f32 splits any matrix).  No workspace, no per-launch
+ * split kernel -- the form the fused stages use.  3xTF32 only. */
+int sn_gemm_tf32_presplit_f32(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb,
+                              const float* bias, const float* R, int64_t ldr, const float* rscale, const float* group_bias,
+                              int64_t rows_per_group, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int flags,
+                              sn_stream_t stream);
+/* hi = tf32(X) (round to nearest), lo = X - hi; X [rows x cols] with leading dimension ldx, outputs contiguous. */
+int sn_split_tf32_f32(const float* X, int64_t ldx, int64_t rows, int64_t cols, float* hi, float* lo, sn_stream_t stream);
 
 /* Weight-gradient product of a stage, reduction over the rows (split-K over the SMs, deterministic):
  *
@@ -248,11 +259,11 @@ int sn_elu_colstats_f32(const float* X, int64_t ldx, float* Y, int64_t ldy, int6
 int sn_bn_fold_fwd_f32(const float* mean, const float* var, const float* gamma, const float* beta, const float* W,
                        const float* b, int64_t N, int64_t K, float eps, float* Wf, float* bf, float* s, float* t,
                        float* rstd, float* running_mean, float* running_var, float momentum, int64_t rows,
-                       sn_stream_t stream);
+                       float* Wf_hi, float* Wf_lo, sn_stream_t stream);
 int sn_bn_fold_bwd_f32(const float* G, const float* sdY, const float* W, const float* s, const float* t,
                        const float* rstd, const float* mean, int64_t N, int64_t K, int64_t rows, int training,
                        float* dW, float* db, float* dgamma, float* dbeta, float* p, float* q, float* WsT,
-                       sn_stream_t stream);
+                       float* WsT_hi, float* WsT_lo, sn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -39,15 +39,18 @@ SIGNATURES = {
     "sn_gemm_tn_tf32_ws_bytes": (_sz, [_i64, _i64]),
     "sn_gemm_tn_tf32_f32": (_int, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _int, _ptr, _sz, _ptr]),
     "sn_bn_fold_fwd_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _f32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
-                                  _f32, _i64, _ptr]),
+                                  _f32, _i64, _ptr, _ptr, _ptr]),
     "sn_bn_fold_bwd_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _int, _ptr, _ptr, _ptr, _ptr,
-                                  _ptr, _ptr, _ptr, _ptr]),
+                                  _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "sn_colstats_ws_bytes": (_sz, [_i64]),
     "sn_colstats_f32": (_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _sz, _ptr]),
     "sn_elu_colstats_f32": (_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _sz, _ptr]),
     "sn_gemm_tf32_ws_bytes": (_sz, [_i64, _i64]),
     "sn_gemm_tf32_f32": (_int, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _int,
                                 _ptr, _sz, _ptr]),
+    "sn_gemm_tf32_presplit_f32": (_int, [_ptr, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64,
+                                         _i64, _int, _ptr]),
+    "sn_split_tf32_f32": (_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr]),
     "sn_csr_spmm_epilogue_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64,
                                         _int, _ptr]),
     "sn_bsr4_spmm_epilogue_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64,
@@ -84,6 +87,7 @@ def spmm_flags(elu_input=False, direct_gather=False, smem_stream=False, variant=
 SN_GEMM_SINGLE_PASS = 1
 SN_GEMM_NO_L2_PREFETCH = 2
 SN_GEMM_ELU_BWD_LEFT = 4
+SN_GEMM_LEGACY_SS = 8
 
 
 class SurfnetError(RuntimeError):

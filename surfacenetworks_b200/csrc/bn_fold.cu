@@ -9,6 +9,12 @@
 
 namespace sn {
 
+__device__ __forceinline__ float tf32_round(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 constexpr int kFoldCols = 32;      // columns per CTA
 constexpr int kFoldRowGroups = 32; // row groups per CTA of the backward kernel (1024 threads: 4 rows per thread at N = 128)
 
@@ -22,7 +28,7 @@ bn_fold_fwd_kernel(const float* __restrict__ mean, const float* __restrict__ var
                    const float* __restrict__ beta, const float* __restrict__ W, const float* __restrict__ b, int N, int K,
                    float eps, float* __restrict__ Wf, float* __restrict__ bf, float* __restrict__ s_out,
                    float* __restrict__ t_out, float* __restrict__ rstd_out, float* running_mean, float* running_var,
-                   float momentum, float unbias) {
+                   float momentum, float unbias, float* __restrict__ Wf_hi, float* __restrict__ Wf_lo) {
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   const bool publish = blockIdx.x == 0 && threadIdx.x < 32;
   if (n >= N) return;
@@ -33,7 +39,13 @@ bn_fold_fwd_kernel(const float* __restrict__ mean, const float* __restrict__ var
     const float s = gamma[k] * rstd;
     const float t = beta[k] - m * s;
     const float w = W[(size_t)n * K + k];
-    Wf[(size_t)n * K + k] = w * s;
+    const float ws = w * s;
+    Wf[(size_t)n * K + k] = ws;
+    if (Wf_hi) {                         // the 3xTF32 GEMM's pre-split B operand (sn_gemm_tf32_presplit_f32)
+      const float h = tf32_round(ws);
+      Wf_hi[(size_t)n * K + k] = h;
+      Wf_lo[(size_t)n * K + k] = ws - h;
+    }
     acc = fmaf(w, t, acc);
     if (publish) {
       s_out[k] = s;
@@ -55,7 +67,8 @@ bn_fold_bwd_kernel(const float* __restrict__ G, const float* __restrict__ sdY, c
                    const float* __restrict__ s, const float* __restrict__ t, const float* __restrict__ rstd,
                    const float* __restrict__ mean, int N, int K, float inv_rows, int training, float* __restrict__ dW,
                    float* __restrict__ db, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ p_out,
-                   float* __restrict__ q_out, float* __restrict__ WsT) {
+                   float* __restrict__ q_out, float* __restrict__ WsT, float* __restrict__ WsT_hi,
+                   float* __restrict__ WsT_lo) {
   __shared__ float red[2][kFoldRowGroups][kFoldCols];
   const int c = threadIdx.x % kFoldCols, rg = threadIdx.x / kFoldCols;
   const int k = blockIdx.x * kFoldCols + c;
@@ -67,7 +80,13 @@ bn_fold_bwd_kernel(const float* __restrict__ G, const float* __restrict__ sdY, c
       dW[(size_t)n * K + k] = fmaf(g, sk, d * tk);
       dbeta_p = fmaf(w, d, dbeta_p);
       wg_p = fmaf(w, g, wg_p);
-      WsT[(size_t)k * N + n] = w * sk;
+      const float ws = w * sk;
+      WsT[(size_t)k * N + n] = ws;
+      if (WsT_hi) {
+        const float h = tf32_round(ws);
+        WsT_hi[(size_t)k * N + n] = h;
+        WsT_lo[(size_t)k * N + n] = ws - h;
+      }
     }
   }
   red[0][rg][c] = dbeta_p;
@@ -97,25 +116,28 @@ bn_fold_bwd_kernel(const float* __restrict__ G, const float* __restrict__ sdY, c
 SN_API int sn_bn_fold_fwd_f32(const float* mean, const float* var, const float* gamma, const float* beta, const float* W,
                               const float* b, int64_t N, int64_t K, float eps, float* Wf, float* bf, float* s, float* t,
                               float* rstd, float* running_mean, float* running_var, float momentum, int64_t rows,
-                              sn_stream_t stream) {
+                              float* Wf_hi, float* Wf_lo, sn_stream_t stream) {
   using namespace sn;
   if (N <= 0 || K <= 0 || !mean || !var || !gamma || !beta || !W || !b || !Wf || !bf || !s || !t || !rstd) return SN_ERR_ARG;
+  if ((Wf_hi == nullptr) != (Wf_lo == nullptr)) return SN_ERR_ARG;
   const float unbias = rows > 1 ? (float)((double)rows / (double)(rows - 1)) : 1.f;
   cudaStream_t st = (cudaStream_t)stream;
   bn_fold_fwd_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(mean, var, gamma, beta, W, b, (int)N, (int)K, eps, Wf, bf, s, t,
-                                                              rstd, running_mean, running_var, momentum, unbias);
+                                                              rstd, running_mean, running_var, momentum, unbias, Wf_hi,
+                                                              Wf_lo);
   return launch_status();
 }
 
 SN_API int sn_bn_fold_bwd_f32(const float* G, const float* sdY, const float* W, const float* s, const float* t,
                               const float* rstd, const float* mean, int64_t N, int64_t K, int64_t rows, int training,
                               float* dW, float* db, float* dgamma, float* dbeta, float* p, float* q, float* WsT,
-                              sn_stream_t stream) {
+                              float* WsT_hi, float* WsT_lo, sn_stream_t stream) {
   using namespace sn;
   if (N <= 0 || K <= 0 || rows <= 0 || !G || !sdY || !W || !s || !t || !rstd || !mean || !dW || !db || !dgamma || !dbeta ||
-      !p || !q || !WsT)
+      !p || !q || !WsT || (WsT_hi == nullptr) != (WsT_lo == nullptr))
     return SN_ERR_ARG;
   bn_fold_bwd_kernel<<<(unsigned)ceil_div(K, kFoldCols), kFoldCols * kFoldRowGroups, 0, (cudaStream_t)stream>>>(
-      G, sdY, W, s, t, rstd, mean, (int)N, (int)K, (float)(1.0 / (double)rows), training, dW, db, dgamma, dbeta, p, q, WsT);
+      G, sdY, W, s, t, rstd, mean, (int)N, (int)K, (float)(1.0 / (double)rows), training, dW, db, dgamma, dbeta, p, q, WsT,
+      WsT_hi, WsT_lo);
   return launch_status();
 }

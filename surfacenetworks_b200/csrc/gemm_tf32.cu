@@ -23,6 +23,15 @@
 //               the residual loads issued one chunk ahead, coalesced streaming stores; overlaps the next tile's
 //               MMAs through the second TMEM buffer
 // Bound: the fused stage is HBM-bound once on tensor cores (A read once, C written once; B stays in L2).
+//
+// Two generations live here.  `gemm_tf32_ss_kernel` (round 1, structure above) feeds BOTH operands from shared memory and was
+// bound by shared-memory bandwidth: per 32-wide k-block the A tile crossed shared memory five times (TMA write, split
+// read, hi + lo write-back, 12 operand reads by the MMAs).  `gemm_tf32_ts_kernel` (round 2, the default) takes A out of
+// shared memory for the tensor core: the split warps read the TMA-landed tile ONCE, and write hi / lo straight into
+// TENSOR MEMORY (tcgen05.st); the MMAs run in TS mode (A operand from TMEM, B from shared memory).  The A ring (16 KB
+// stages, freed as soon as the split warps hold the tile in registers) and the B ring (pre-split weights streamed from
+// L2) are decoupled, so TMA runs 6 A stages + 4 TMEM stages ahead of the tensor core instead of 3.  SN_GEMM_LEGACY_SS
+// selects the old kernel (A/B runs, tools/gemm_bench.py).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -130,7 +139,7 @@ struct Params {
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+gemm_tf32_ss_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_blo, const Params p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1024-byte alignment is required by the 128-byte swizzle (TMA and UMMA agree on address bits [7,10))
@@ -343,6 +352,305 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
 }
 
+// ====================================================================================================================
+// Round-2 kernel: A operand in TENSOR MEMORY (TS mode)
+// ====================================================================================================================
+constexpr int kATmemStages = 4;        // TMEM A stages: 64 columns each (32 hi | 32 lo) = one 32-wide k-block
+constexpr int kATmemCol0 = 256;        // accumulators live in columns [0, 256), A stages in [256, 512)
+constexpr int kMaxAStages = 8;         // shared-memory A ring (16 KB stages)
+constexpr int kMaxBStages = 4;         // shared-memory B ring (hi | lo, nmma x 128 B each)
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
+      "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+      "r"(v[31])
+      : "memory");
+}
+
+struct ParamsTS {
+  const float* bias;     // [N] or null
+  const float* R;        // [M x N] or null: out += rscale .* R
+  const float* rscale;   // [N] or null (= 1)
+  const float* gbias;    // per-row-group bias or null
+  int rows_per_group;
+  float* C;
+  int64_t ldr, ldc;
+  int M, N, K;
+  int nmma;              // accumulator width = columns per MMA: N for N <= 128, else 128
+  int n_halves;          // N / nmma column passes per row tile ("jobs")
+  int a_resident;        // n_halves > 1 and K / 32 <= kATmemStages: the tile's whole A extent stays in TMEM for both passes
+  int a_stages, b_stages;
+  int split;             // 1: 3xTF32, 0: single pass
+  int l2_prefetch;
+  int elu_left;
+};
+
+// Roles (16 warps): 0 = A producer (TMA), 3 = B producer (TMA), 1 = MMA issuer, 2 = TMEM allocation, 4-7 = A split into
+// TMEM (warp w owns TMEM lanes [32 (w - 4), +32) = tile rows), 8-15 = epilogue.
+// Barriers: a_full / a_free  (TMA -> split warps -> TMA)           shared-memory A ring
+//           a_ready / a_tfree (split warps -> MMA -> split warps)  TMEM A stages (tcgen05.st ... tcgen05.commit)
+//           b_full / b_free  (TMA -> MMA -> TMA)                   shared-memory B ring
+//           tmem_full / tmem_empty (MMA -> epilogue -> MMA)        two accumulators
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_blo, const ParamsTS p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int nmma = p.nmma;
+  constexpr uint32_t a_bytes = kBlockM * kBlockK * 4;       // 16 KB
+  const uint32_t b_bytes = (uint32_t)nmma * kBlockK * 4;    // 8 / 16 KB per half (hi or lo)
+  unsigned char* a_ring = smem;
+  unsigned char* b_ring = smem + (size_t)p.a_stages * a_bytes;
+  __shared__ uint64_t a_full[kMaxAStages], a_free[kMaxAStages], a_ready[kATmemStages], a_tfree[kATmemStages];
+  __shared__ uint64_t b_full[kMaxBStages], b_free[kMaxBStages], tmem_full[2], tmem_empty[2];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float epi_buf[kEpiWarps * 32 * 20];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (p.M + kBlockM - 1) / kBlockM;
+  const int n_kb = p.K / kBlockK;
+  const int n_halves = p.n_halves;
+  const int n_a_pass = p.a_resident ? 1 : n_halves;          // times the A tile is streamed per row tile
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.a_stages; ++s) {
+      mbar_init(a_full + s, 1);
+      mbar_init(a_free + s, 4);          // one arrival per split warp
+    }
+    for (int s = 0; s < kATmemStages; ++s) {
+      mbar_init(a_ready + s, 4);
+      mbar_init(a_tfree + s, 1);
+    }
+    for (int s = 0; s < p.b_stages; ++s) {
+      mbar_init(b_full + s, 1);
+      mbar_init(b_free + s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tmem_full + b, 1);
+      mbar_init(tmem_empty + b, kEpiWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {                       // all 512 TMEM columns: 2 accumulators + 4 A stages (one CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ A producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        for (int pass = 0; pass < n_a_pass; ++pass)
+          for (int kb = 0; kb < n_kb; ++kb) {
+            mbar_wait(a_free + stage, phase ^ 1u);
+            mbar_arrive_expect_tx(a_full + stage, a_bytes);
+            tma_load_2d(a_ring + (size_t)stage * a_bytes, &map_a, kb * kBlockK, tile * kBlockM, a_full + stage);
+            if (++stage == p.a_stages) { stage = 0; phase ^= 1u; }
+          }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ B producer (pre-split weights, L2-resident)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        for (int half = 0; half < n_halves; ++half)
+          for (int kb = 0; kb < n_kb; ++kb) {
+            mbar_wait(b_free + stage, phase ^ 1u);
+            unsigned char* sb = b_ring + (size_t)stage * 2 * b_bytes;
+            mbar_arrive_expect_tx(b_full + stage, (p.split ? 2u : 1u) * b_bytes);
+            tma_load_2d(sb, &map_b, kb * kBlockK, half * nmma, b_full + stage);
+            if (p.split) tma_load_2d(sb + b_bytes, &map_blo, kb * kBlockK, half * nmma, b_full + stage);
+            if (++stage == p.b_stages) { stage = 0; phase ^= 1u; }
+          }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nmma >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+    int bs = 0;
+    uint32_t bph = 0;
+    uint32_t a_cnt = 0;                  // TMEM A stages consumed so far (stage = a_cnt % 4, parity = (a_cnt / 4) & 1)
+    uint32_t job = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int half = 0; half < n_halves; ++half, ++job) {
+        const uint32_t buf = job & 1u;
+        mbar_wait(tmem_empty + buf, ((job >> 1) & 1u) ^ 1u);      // epilogue drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_d = tmem_base + buf * (uint32_t)nmma;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          const uint32_t cnt = p.a_resident ? a_cnt + (uint32_t)kb : a_cnt;
+          const uint32_t at = cnt % kATmemStages;
+          if (half == 0 || !p.a_resident) mbar_wait(a_ready + at, (cnt / kATmemStages) & 1u);
+          mbar_wait(b_full + bs, bph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (lane == 0) {
+            const uint32_t ta = tmem_base + (uint32_t)(kATmemCol0 + at * 64);
+            const uint32_t sb = smem_u32(b_ring + (size_t)bs * 2 * b_bytes), sbl = sb + b_bytes;
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              const uint32_t off = k * kUmmaK * 4;             // 32 bytes per k-step inside the swizzle row
+              const uint64_t db = umma_desc_sw128(sb + off);
+              umma_tf32_ts(tmem_d, ta + k * kUmmaK, db, idesc, (kb | k) != 0);
+              if (p.split) {
+                umma_tf32_ts(tmem_d, ta + k * kUmmaK, umma_desc_sw128(sbl + off), idesc, true);     // hi * lo
+                umma_tf32_ts(tmem_d, ta + 32 + k * kUmmaK, db, idesc, true);                        // lo * hi
+              }
+            }
+            umma_commit(b_free + bs);
+            if (!p.a_resident || half == n_halves - 1) umma_commit(a_tfree + at);
+            if (kb == n_kb - 1) umma_commit(tmem_full + buf);
+          }
+          __syncwarp();
+          if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
+          if (!p.a_resident) ++a_cnt;
+        }
+      }
+      if (p.a_resident) a_cnt += (uint32_t)n_kb;
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------------ A: shared memory -> hi / lo -> tensor memory
+    // Thread r (0..127) owns tile row r = TMEM lane r.  The TMA box is 128-byte swizzled: logical 16-byte chunk i of
+    // row r sits at chunk i ^ (r & 7), so the eight LDS.128 of a quarter-warp hit eight distinct bank groups.
+    const int r = threadIdx.x - 128;
+    const uint32_t lane_base = (uint32_t)((warp - 4) * 32) << 16;
+    int as = 0;
+    uint32_t aph = 0, t_cnt = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+      for (int pass = 0; pass < n_a_pass; ++pass)
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(a_full + as, aph);
+          const unsigned char* row = a_ring + (size_t)as * a_bytes + (size_t)r * 128;
+          uint32_t hi[32], lo[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 x = *reinterpret_cast<const float4*>(row + ((i ^ (r & 7)) << 4));
+            const float h0 = to_tf32(x.x), h1 = to_tf32(x.y), h2 = to_tf32(x.z), h3 = to_tf32(x.w);
+            hi[4 * i] = __float_as_uint(h0); hi[4 * i + 1] = __float_as_uint(h1);
+            hi[4 * i + 2] = __float_as_uint(h2); hi[4 * i + 3] = __float_as_uint(h3);
+            lo[4 * i] = __float_as_uint(x.x - h0); lo[4 * i + 1] = __float_as_uint(x.y - h1);
+            lo[4 * i + 2] = __float_as_uint(x.z - h2); lo[4 * i + 3] = __float_as_uint(x.w - h3);
+          }
+          __syncwarp();                                        // every lane has consumed its shared-memory row
+          if (lane == 0) mbar_arrive(a_free + as);             // the TMA producer may refill this slot
+          const uint32_t at = t_cnt % kATmemStages;
+          mbar_wait(a_tfree + at, ((t_cnt / kATmemStages) & 1u) ^ 1u);   // the MMAs that read this TMEM stage retired
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t ta = tmem_base + lane_base + (uint32_t)(kATmemCol0 + at * 64);
+          tmem_st32(ta, hi);
+          if (p.split) tmem_st32(ta + 32, lo);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_ready + at);
+          ++t_cnt;
+          if (++as == p.a_stages) { as = 0; aph ^= 1u; }
+        }
+  } else if (warp >= 8) {
+    // ------------------------------------------------------------------ epilogue (one job = one row tile x one column pass)
+    const int e = warp - 8;
+    const int quarter = e & 3, chalf = e >> 2;
+    float* tbuf = epi_buf + e * (32 * 20);
+    const int tr = lane >> 2, tc = (lane & 3) * 4;            // 4 lanes cover one row's 16 columns (64 bytes)
+    const int ncol = nmma / 2;                                 // columns owned by this warp inside the job
+    const int N = p.N;
+    auto load_r = [&](float4 (&rr)[4], int row0, int c0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = row0 + i * 8 + tr;
+        rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < p.M) rr[i] = __ldcs(reinterpret_cast<const float4*>(p.R + (int64_t)row * p.ldr + c0 + tc));
+      }
+    };
+    uint32_t job = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int half = 0; half < n_halves; ++half, ++job) {
+        const uint32_t buf = job & 1u;
+        const int row0 = tile * kBlockM + quarter * 32;
+        const int cbase = half * nmma + chalf * ncol;          // first global column of this warp's share
+        float4 rr[4], rn[4], rn2[4];
+        if (p.R) {                                             // prefetch before waiting for the accumulator
+          load_r(rr, row0, cbase);
+          load_r(rn, row0, cbase + 16);
+          if (p.l2_prefetch) {                                 // ... and the next job's residual rows into L2
+            const bool next_half = half + 1 < n_halves;
+            const int nrow0 = (next_half ? tile : tile + (int)gridDim.x) * kBlockM + quarter * 32;
+            const int ncb = (next_half ? (half + 1) * nmma : 0) + chalf * ncol;
+            const int lines = ncol / 32;
+            for (int i = lane; i < 32 * lines; i += 32) {
+              const int row = nrow0 + i / lines;
+              if (row < p.M) prefetch_l2(p.R + (int64_t)row * p.ldr + ncb + (i % lines) * 32);
+            }
+          }
+        }
+        mbar_wait(tmem_full + buf, (job >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int c0 = cbase; c0 < cbase + ncol; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * nmma + (c0 - half * nmma)), v);
+          if (p.R && c0 + 32 < cbase + ncol) load_r(rn2, row0, c0 + 32);   // residual two chunks ahead
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(tbuf + lane * 20 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                            __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          __syncwarp();
+          float4 bia = make_float4(0.f, 0.f, 0.f, 0.f), rs = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (p.bias) bia = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + tc));
+          if (p.rscale) rs = __ldg(reinterpret_cast<const float4*>(p.rscale + c0 + tc));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rl = i * 8 + tr;
+            const int row = row0 + rl;
+            if (row < p.M) {
+              float4 o = add4(*reinterpret_cast<const float4*>(tbuf + rl * 20 + tc), bia);
+              if (p.gbias)
+                o = add4(o, __ldg(reinterpret_cast<const float4*>(p.gbias + (int64_t)(row / p.rows_per_group) * N + c0 + tc)));
+              if (p.R) {
+                o.x = fmaf(rs.x, rr[i].x, o.x); o.y = fmaf(rs.y, rr[i].y, o.y);
+                o.z = fmaf(rs.z, rr[i].z, o.z); o.w = fmaf(rs.w, rr[i].w, o.w);
+                if (p.elu_left && c0 < (N >> 1)) {   // chunk-uniform: 16-column chunks never straddle N/2
+                  o.x *= rr[i].x > 0.f ? 1.f : rr[i].x + 1.f; o.y *= rr[i].y > 0.f ? 1.f : rr[i].y + 1.f;
+                  o.z *= rr[i].z > 0.f ? 1.f : rr[i].z + 1.f; o.w *= rr[i].w > 0.f ? 1.f : rr[i].w + 1.f;
+                }
+              }
+              st_stream_f4(p.C + (int64_t)row * p.ldc + c0 + tc, o);
+            }
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { rr[i] = rn[i]; rn[i] = rn2[i]; }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty + buf);
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------ teardown
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
 // B -> (tf32(B), B - tf32(B)) into the workspace, row-major with leading dimension K
 __global__ void split_weights_kernel(const float* __restrict__ B, int64_t ldb, float* __restrict__ hi, float* __restrict__ lo,
                                      int N, int K) {
@@ -389,12 +697,84 @@ SN_API size_t sn_gemm_tf32_ws_bytes(int64_t N, int64_t K) {
   return (N <= 0 || K <= 0) ? 0 : (size_t)(2 * N * K) * sizeof(float) + 256;
 }
 
-SN_API int sn_gemm_tf32_f32(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, const float* R,
-                            int64_t ldr, const float* rscale, const float* group_bias, int64_t rows_per_group, float* C,
-                            int64_t ldc, int64_t M, int64_t N, int64_t K, int flags, void* ws, size_t ws_bytes,
-                            sn_stream_t stream) {
-  using namespace sn;
-  using namespace sn::gemm;
+namespace sn {
+namespace gemm {
+
+// Shared launcher: B_hi / B_lo are the pre-split weights (B_lo null = single pass on B_hi as given).
+static int launch_gemm(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb, const float* bias,
+                       const float* R, int64_t ldr, const float* rscale, const float* group_bias, int64_t rows_per_group,
+                       float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int flags, cudaStream_t stream) {
+  const bool split = B_lo != nullptr;
+  int dev = 0, sms = 148, smem_optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const int64_t tiles = ceil_div(M, kBlockM);
+  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  const int l2_prefetch = (!(flags & SN_GEMM_NO_L2_PREFETCH) && R && N >= 256) ? 1 : 0;
+  CUtensorMap map_a, map_b, map_blo;
+  if (!make_map(&map_a, A, M, K, lda, kBlockM)) return SN_ERR_UNSUPPORTED;
+
+  if (flags & SN_GEMM_LEGACY_SS) {       // round-1 kernel: both operands from shared memory
+    if (!make_map(&map_b, B_hi, N, K, ldb, (int)N)) return SN_ERR_UNSUPPORTED;
+    if (split) {
+      if (!make_map(&map_blo, B_lo, N, K, ldb, (int)N)) return SN_ERR_UNSUPPORTED;
+    } else {
+      map_blo = map_b;
+    }
+    Params p;
+    p.bias = bias; p.R = R; p.rscale = rscale; p.C = C; p.ldr = ldr; p.ldc = ldc;
+    p.gbias = group_bias; p.rows_per_group = group_bias ? (int)rows_per_group : 1;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K;
+    p.split = split ? 1 : 0;
+    p.l2_prefetch = l2_prefetch;
+    p.elu_left = (flags & SN_GEMM_ELU_BWD_LEFT) ? 1 : 0;
+    const size_t stage_bytes = 2 * ((size_t)kBlockM * kBlockK * 4 + (size_t)N * kBlockK * 4);
+    int stages = (int)(((size_t)smem_optin - 2048 - 22 * 1024) / stage_bytes);   // static smem: barriers + transpose buffers
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) return SN_ERR_UNSUPPORTED;
+    p.stages = stages;
+    const size_t smem = stages * stage_bytes + 1024;
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_ss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    gemm_tf32_ss_kernel<<<grid, kThreads, smem, stream>>>(map_a, map_b, map_blo, p);
+    return launch_status();
+  }
+
+  ParamsTS p;
+  p.bias = bias; p.R = R; p.rscale = rscale; p.C = C; p.ldr = ldr; p.ldc = ldc;
+  p.gbias = group_bias; p.rows_per_group = group_bias ? (int)rows_per_group : 1;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.nmma = N <= 128 ? (int)N : 128;
+  p.n_halves = (int)N / p.nmma;
+  p.a_resident = (p.n_halves > 1 && K / kBlockK <= kATmemStages) ? 1 : 0;
+  p.split = split ? 1 : 0;
+  p.l2_prefetch = l2_prefetch;
+  p.elu_left = (flags & SN_GEMM_ELU_BWD_LEFT) ? 1 : 0;
+  if (!make_map(&map_b, B_hi, N, K, ldb, p.nmma)) return SN_ERR_UNSUPPORTED;
+  if (split) {
+    if (!make_map(&map_blo, B_lo, N, K, ldb, p.nmma)) return SN_ERR_UNSUPPORTED;
+  } else {
+    map_blo = map_b;
+  }
+  // shared memory: B ring of 3 stages (hi | lo; the weights come from L2), the rest goes to the A ring (HBM latency)
+  const size_t a_bytes = (size_t)kBlockM * kBlockK * 4, b_stage = 2 * (size_t)p.nmma * kBlockK * 4;
+  const size_t budget = (size_t)smem_optin - 22 * 1024 - 1024;   // static: transpose buffers + barriers; 1 KB alignment
+  p.b_stages = 3;
+  int a_stages = (int)((budget - p.b_stages * b_stage) / a_bytes);
+  if (a_stages > kMaxAStages) a_stages = kMaxAStages;
+  if (a_stages < 2) return SN_ERR_UNSUPPORTED;
+  p.a_stages = a_stages;
+  const size_t smem = a_stages * a_bytes + p.b_stages * b_stage + 1024;
+  cudaError_t e = cudaFuncSetAttribute(gemm_tf32_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  gemm_tf32_ts_kernel<<<grid, kThreads, smem, stream>>>(map_a, map_b, map_blo, p);
+  return launch_status();
+}
+
+static int check_gemm_args(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, const float* R,
+                           int64_t ldr, const float* rscale, const float* group_bias, int64_t rows_per_group, const float* C,
+                           int64_t ldc, int64_t M, int64_t N, int64_t K, int flags) {
   if (M < 0 || N <= 0 || K <= 0) return SN_ERR_ARG;
   if (M == 0) return SN_OK;
   if (!A || !B || !C || lda < K || ldb < K || ldc < N || (R && ldr < N)) return SN_ERR_ARG;
@@ -403,45 +783,49 @@ SN_API int sn_gemm_tf32_f32(const float* A, int64_t lda, const float* B, int64_t
   if (lda % 4 || ldb % 4 || ldc % 4 || (R && ldr % 4) || !aligned16(A) || !aligned16(B) || !aligned16(C) ||
       (R && !aligned16(R)) || (bias && !aligned16(bias)) || (rscale && !aligned16(rscale)))
     return SN_ERR_UNSUPPORTED;
-  const bool split = !(flags & SN_GEMM_SINGLE_PASS);
   if ((flags & SN_GEMM_ELU_BWD_LEFT) && !R) return SN_ERR_ARG;
-  CUtensorMap map_a, map_b, map_blo;
-  if (!make_map(&map_a, A, M, K, lda, kBlockM)) return SN_ERR_UNSUPPORTED;
-  if (split) {
-    if (!ws || ws_bytes < sn_gemm_tf32_ws_bytes(N, K)) return SN_ERR_WORKSPACE;
-    float* hi = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
-    float* lo = hi + N * K;
-    split_weights_kernel<<<(unsigned)ceil_div(N * K, 256), 256, 0, (cudaStream_t)stream>>>(B, ldb, hi, lo, (int)N, (int)K);
-    if (!make_map(&map_b, hi, N, K, K, (int)N) || !make_map(&map_blo, lo, N, K, K, (int)N)) return SN_ERR_UNSUPPORTED;
-  } else {
-    if (!make_map(&map_b, B, N, K, ldb, (int)N)) return SN_ERR_UNSUPPORTED;
-    map_blo = map_b;
-  }
-  Params p;
-  p.bias = bias; p.R = R; p.rscale = rscale; p.C = C; p.ldr = ldr; p.ldc = ldc;
-  p.gbias = group_bias; p.rows_per_group = group_bias ? (int)rows_per_group : 1;
-  p.M = (int)M; p.N = (int)N; p.K = (int)K;
-  p.split = split ? 1 : 0;
-  // Measured (tools/gemm_bench.py, profiles/r1_gemm_notes.md): prefetching the next tile's residual rows into L2 gains
-  // 6-9 % at N = 256 (the dZ product, whose epilogue streams a 1 KB residual row per output row) and costs a few % at
-  // N = 128; an L2 prefetch of the A boxes changed nothing (the mainloop is bound by shared-memory bandwidth, not by
-  // DRAM latency) and was removed.
-  p.l2_prefetch = (!(flags & SN_GEMM_NO_L2_PREFETCH) && R && N >= 256) ? 1 : 0;
-  p.elu_left = (flags & SN_GEMM_ELU_BWD_LEFT) ? 1 : 0;
-  int dev = 0, sms = 148, smem_optin = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  const size_t stage_bytes = 2 * ((size_t)kBlockM * kBlockK * 4 + (size_t)N * kBlockK * 4);
-  int stages = (int)(((size_t)smem_optin - 2048 - 22 * 1024) / stage_bytes);   // static smem: barriers + transpose buffers
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) return SN_ERR_UNSUPPORTED;
-  p.stages = stages;
-  const size_t smem = stages * stage_bytes + 1024;
-  cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  const int64_t tiles = ceil_div(M, kBlockM);
-  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  gemm_tf32_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, map_blo, p);
+  return SN_OK;
+}
+
+}  // namespace gemm
+}  // namespace sn
+
+SN_API int sn_gemm_tf32_f32(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, const float* R,
+                            int64_t ldr, const float* rscale, const float* group_bias, int64_t rows_per_group, float* C,
+                            int64_t ldc, int64_t M, int64_t N, int64_t K, int flags, void* ws, size_t ws_bytes,
+                            sn_stream_t stream) {
+  using namespace sn;
+  using namespace sn::gemm;
+  const int rc = check_gemm_args(A, lda, B, ldb, bias, R, ldr, rscale, group_bias, rows_per_group, C, ldc, M, N, K, flags);
+  if (rc != SN_OK || M == 0) return rc;
+  if (flags & SN_GEMM_SINGLE_PASS)
+    return launch_gemm(A, lda, B, nullptr, ldb, bias, R, ldr, rscale, group_bias, rows_per_group, C, ldc, M, N, K, flags,
+                       (cudaStream_t)stream);
+  if (!ws || ws_bytes < sn_gemm_tf32_ws_bytes(N, K)) return SN_ERR_WORKSPACE;
+  float* hi = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  float* lo = hi + N * K;
+  split_weights_kernel<<<(unsigned)ceil_div(N * K, 256), 256, 0, (cudaStream_t)stream>>>(B, ldb, hi, lo, (int)N, (int)K);
+  return launch_gemm(A, lda, hi, lo, K, bias, R, ldr, rscale, group_bias, rows_per_group, C, ldc, M, N, K, flags,
+                     (cudaStream_t)stream);
+}
+
+SN_API int sn_gemm_tf32_presplit_f32(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb,
+                                     const float* bias, const float* R, int64_t ldr, const float* rscale,
+                                     const float* group_bias, int64_t rows_per_group, float* C, int64_t ldc, int64_t M,
+                                     int64_t N, int64_t K, int flags, sn_stream_t stream) {
+  using namespace sn;
+  using namespace sn::gemm;
+  const int rc = check_gemm_args(A, lda, B_hi, ldb, bias, R, ldr, rscale, group_bias, rows_per_group, C, ldc, M, N, K, flags);
+  if (rc != SN_OK || M == 0) return rc;
+  if (!B_lo || !aligned16(B_lo) || (flags & SN_GEMM_SINGLE_PASS)) return SN_ERR_ARG;
+  return launch_gemm(A, lda, B_hi, B_lo, ldb, bias, R, ldr, rscale, group_bias, rows_per_group, C, ldc, M, N, K, flags,
+                     (cudaStream_t)stream);
+}
+
+SN_API int sn_split_tf32_f32(const float* X, int64_t ldx, int64_t rows, int64_t cols, float* hi, float* lo, sn_stream_t stream) {
+  using namespace sn;
+  using namespace sn::gemm;
+  if (rows <= 0 || cols <= 0 || !X || !hi || !lo || ldx < cols || rows * cols > 0x7fffffffLL) return SN_ERR_ARG;
+  split_weights_kernel<<<(unsigned)ceil_div(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(X, ldx, hi, lo, (int)rows, (int)cols);
   return launch_status();
 }

@@ -79,34 +79,43 @@ def elu_colstats_supported(X, out):
             X.data_ptr() % 16 == 0 and out.data_ptr() % 16 == 0 and X.shape[0] > 0)
 
 
+def _legacy_flag():
+    import os
+    return N.SN_GEMM_LEGACY_SS if os.environ.get("SN_GEMM_LEGACY_SS") == "1" else 0
+
+
 def gemm_tf32(A, B, bias=None, R=None, rscale=None, out=None, single_pass=False, group_bias=None, rows_per_group=0,
-              elu_bwd_left=False):
+              elu_bwd_left=False, B_lo=None):
     """out[M, N] = A[M, K] @ B[N, K]^T + bias + group_bias[row // rows_per_group] + rscale * R
-    (3xTF32 tensor-core GEMM; N > 256 is split in column blocks; B may be a row-strided view)."""
+    (3xTF32 tensor-core GEMM; N > 256 is split in column blocks; B may be a row-strided view).
+    ``B_lo``: B is already split (B = tf32(W), B_lo = W - B, same layout) -- no split kernel, no workspace."""
     M, K = A.shape
     Nn = B.shape[0]
     if out is None:
         out = torch.empty(M, Nn, dtype=torch.float32, device=A.device)
-    if B.stride(1) != 1 or B.stride(0) % 4 or B.data_ptr() % 16:
+    if B_lo is None and (B.stride(1) != 1 or B.stride(0) % 4 or B.data_ptr() % 16):
         B = B.contiguous()
     if group_bias is not None and Nn not in _GEMM_N:
         raise ValueError("group_bias needs N in %s" % (_GEMM_N,))
     step = Nn if Nn in _GEMM_N else 256
-    nb = N.lib.sn_gemm_tf32_ws_bytes(step, K)
-    flags = N.SN_GEMM_SINGLE_PASS if single_pass else 0
+    flags = (N.SN_GEMM_SINGLE_PASS if single_pass else 0) | _legacy_flag()
     if elu_bwd_left:
         if R is None or step != Nn:
             raise ValueError("elu_bwd_left needs the residual operand and a single column block")
         flags |= N.SN_GEMM_ELU_BWD_LEFT
     with torch.cuda.device(A.device):
         for n0 in range(0, Nn, step):
-            ws = _ws(nb, A.device)
             Bs = B[n0:n0 + step]
-            N.call("sn_gemm_tf32_f32", _ptr(A), A.stride(0), _ptr(Bs), Bs.stride(0),
-                   0 if bias is None else bias[n0:].data_ptr(), 0 if R is None else R[:, n0:].data_ptr(),
-                   0 if R is None else R.stride(0), 0 if rscale is None else rscale[n0:].data_ptr(),
-                   _ptr(group_bias), rows_per_group, out[:, n0:].data_ptr(), out.stride(0), M, step, K, flags, _ptr(ws), nb,
-                   _stream())
+            common = (0 if bias is None else bias[n0:].data_ptr(), 0 if R is None else R[:, n0:].data_ptr(),
+                      0 if R is None else R.stride(0), 0 if rscale is None else rscale[n0:].data_ptr(),
+                      _ptr(group_bias), rows_per_group, out[:, n0:].data_ptr(), out.stride(0), M, step, K, flags)
+            if B_lo is not None:
+                N.call("sn_gemm_tf32_presplit_f32", _ptr(A), A.stride(0), _ptr(Bs), B_lo[n0:n0 + step].data_ptr(),
+                       Bs.stride(0), *common, _stream())
+            else:
+                nb = N.lib.sn_gemm_tf32_ws_bytes(step, K)
+                ws = _ws(nb, A.device)
+                N.call("sn_gemm_tf32_f32", _ptr(A), A.stride(0), _ptr(Bs), Bs.stride(0), *common, _ptr(ws), nb, _stream())
     return out
 
 
@@ -152,16 +161,16 @@ def bn_linear_forward(Z, gamma, beta, W, b, residual, running_mean, running_var,
     else:
         mean, var = running_mean, running_var
     W = W.contiguous()
-    Wf = torch.empty_like(W)                    # [C, 2C]: BatchNorm folded into the Linear
+    Wf = torch.empty(3, Nn, K, dtype=torch.float32, device=dev)       # [C, 2C] x (folded W', tf32(W'), W' - tf32(W'))
     bf = torch.empty(Nn, dtype=torch.float32, device=dev)
     stk = torch.empty(3, K, dtype=torch.float32, device=dev)          # s, t, rstd
     update = training and running_mean is not None
     with torch.cuda.device(dev):
         N.call("sn_bn_fold_fwd_f32", _ptr(mean), _ptr(var), _ptr(gamma), _ptr(beta), _ptr(W), _ptr(b), Nn, K, float(eps),
-               _ptr(Wf), _ptr(bf), _ptr(stk[0]), _ptr(stk[1]), _ptr(stk[2]), _ptr(running_mean) if update else 0,
-               _ptr(running_var) if update else 0, float(momentum), rows, _stream())
+               _ptr(Wf[0]), _ptr(bf), _ptr(stk[0]), _ptr(stk[1]), _ptr(stk[2]), _ptr(running_mean) if update else 0,
+               _ptr(running_var) if update else 0, float(momentum), rows, _ptr(Wf[1]), _ptr(Wf[2]), _stream())
     res = None if residual is None else residual.contiguous()
-    Y = gemm_tf32(Z, Wf, bias=bf, R=res)
+    Y = gemm_tf32(Z, Wf[1], bias=bf, R=res, B_lo=Wf[2])
     return Y, (Z, W, stk, mean)
 
 
@@ -183,15 +192,15 @@ def bn_linear_backward(saved, dY, training, elu_bwd_left=False):
     dW = torch.empty_like(W)
     db = torch.empty(Nn, dtype=torch.float32, device=dev)
     vec = torch.empty(4, K, dtype=torch.float32, device=dev)          # dgamma, dbeta, p, q
-    WsT = torch.empty(K, Nn, dtype=torch.float32, device=dev)         # (W diag(s))^T
+    WsT = torch.empty(3, K, Nn, dtype=torch.float32, device=dev)      # (W diag(s))^T: full, tf32 hi, lo
     with torch.cuda.device(dev):
         N.call("sn_bn_fold_bwd_f32", _ptr(G), _ptr(sdY), _ptr(W), _ptr(stk[0]), _ptr(stk[1]), _ptr(stk[2]), _ptr(mean),
                Nn, K, rows, 1 if training else 0, _ptr(dW), _ptr(db), _ptr(vec[0]), _ptr(vec[1]), _ptr(vec[2]),
-               _ptr(vec[3]), _ptr(WsT), _stream())
+               _ptr(vec[3]), _ptr(WsT[0]), _ptr(WsT[1]), _ptr(WsT[2]), _stream())
     if training:
-        dZ = gemm_tf32(dY, WsT, bias=vec[3], R=Z, rscale=vec[2], elu_bwd_left=elu_bwd_left)
+        dZ = gemm_tf32(dY, WsT[1], bias=vec[3], R=Z, rscale=vec[2], elu_bwd_left=elu_bwd_left, B_lo=WsT[2])
     else:
-        dZ = gemm_tf32(dY, WsT)
+        dZ = gemm_tf32(dY, WsT[1], B_lo=WsT[2])
     return dZ, vec[0], vec[1], dW, db
 
 
@@ -265,17 +274,18 @@ class _AvgStage(torch.autograd.Function):
             mean, var = running_mean, running_var
         W = W.contiguous()
         K = 2 * C
-        Wf = torch.empty_like(W)
+        Wf3 = torch.empty(3, Nn, K, dtype=torch.float32, device=dev)              # folded W', tf32(W'), W' - tf32(W')
+        Wf = Wf3[0]
         bf = torch.empty(Nn, dtype=torch.float32, device=dev)
         stk = torch.empty(3, K, dtype=torch.float32, device=dev)
         update = training and running_mean is not None
         with torch.cuda.device(dev):
             N.call("sn_bn_fold_fwd_f32", _ptr(mean), _ptr(var), _ptr(gamma), _ptr(beta), _ptr(W), _ptr(b), Nn, K, float(eps),
                    _ptr(Wf), _ptr(bf), _ptr(stk[0]), _ptr(stk[1]), _ptr(stk[2]), _ptr(running_mean) if update else 0,
-                   _ptr(running_var) if update else 0, float(momentum), rows, _stream())
+                   _ptr(running_var) if update else 0, float(momentum), rows, _ptr(Wf3[1]), _ptr(Wf3[2]), _stream())
         u = torch.addmm(bf, avg, Wf[:, C:].t())                                   # per-mesh bias [B, Nn]
         res = None if residual is None else residual.contiguous()
-        Y = gemm_tf32(a, Wf[:, :C], R=res, group_bias=u, rows_per_group=rows_per_seg)
+        Y = gemm_tf32(a, Wf3[1][:, :C], R=res, group_bias=u, rows_per_group=rows_per_seg, B_lo=Wf3[2][:, :C])
         ctx.save_for_backward(a, avg, W, stk, mean, maskw, inv_cnt)
         ctx.training, ctx.has_res, ctx.n_seg, ctx.rps = training, residual is not None, n_seg, rows_per_seg
         # in_cell / res_cell: the two stages of one AvgResNet2 block share a cell.  The stage that holds the block
@@ -300,13 +310,14 @@ class _AvgStage(torch.autograd.Function):
         dW = torch.empty_like(W)
         db = torch.empty(Nn, dtype=torch.float32, device=dev)
         vec = torch.empty(4, K, dtype=torch.float32, device=dev)                  # dgamma, dbeta, p, q
-        WsT = torch.empty(K, Nn, dtype=torch.float32, device=dev)
+        WsT3 = torch.empty(3, K, Nn, dtype=torch.float32, device=dev)
+        WsT = WsT3[0]
         with torch.cuda.device(dev):
             N.call("sn_bn_fold_bwd_f32", _ptr(G), _ptr(sdY), _ptr(W), _ptr(stk[0]), _ptr(stk[1]), _ptr(stk[2]), _ptr(mean),
                    Nn, K, rows, 1 if ctx.training else 0, _ptr(dW), _ptr(db), _ptr(vec[0]), _ptr(vec[1]), _ptr(vec[2]),
-                   _ptr(vec[3]), _ptr(WsT), _stream())
+                   _ptr(vec[3]), _ptr(WsT), _ptr(WsT3[1]), _ptr(WsT3[2]), _stream())
         p, q = vec[2], vec[3]
-        dZl = gemm_tf32(dY, WsT[:C], bias=q[:C].contiguous(), R=a, rscale=p[:C].contiguous())
+        dZl = gemm_tf32(dY, WsT3[1][:C], bias=q[:C], R=a, rscale=p[:C], B_lo=WsT3[2][:C])
         # gradient reaching the per-mesh averages: sum over the mesh's rows of dZ_R
         gsum = torch.mm(SdY, WsT[C:].t()) + ctx.rps * (p[C:] * avg + q[C:])       # [B, C]
         gb = (gsum * inv_cnt).contiguous()

@@ -39,7 +39,8 @@ def reference(A, B, bias, R, rscale):
     return y, mag
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (1000, 128, 256), (4096 + 77, 256, 128), (300, 64, 64), (20000, 128, 128)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (1000, 128, 256), (4096 + 77, 256, 128), (300, 64, 64), (20000, 128, 128),
+                                   (1000, 256, 256), (3000, 256, 64), (700, 64, 128), (148 * 128 * 3 + 5, 128, 512)])
 @pytest.mark.parametrize("mode", ["plain", "bias", "full"])
 def test_gemm_matches_fp64(M, N, K, mode):
     g = torch.Generator(device=DEV).manual_seed(M + N + K)
@@ -62,6 +63,37 @@ def test_gemm_matches_fp64(M, N, K, mode):
         ref32 = ref32 + rscale * R
     e32 = float(((ref32.double() - y64).abs() / (mag + 1e-300)).max())
     assert float((err / (mag + 1e-300)).max()) <= max(8 * e32, 2e-6)
+
+
+@pytest.mark.parametrize("M,N,K", [(5000, 128, 256), (5000, 256, 128), (2000, 256, 256), (900, 64, 96)])
+def test_gemm_presplit_and_legacy_kernel_agree(M, N, K):
+    """sn_gemm_tf32_presplit_f32 (weights split by the caller / by sn_bn_fold_*) is bit-identical to sn_gemm_tf32_f32, and the
+    TS-mode kernel (A operand in tensor memory) matches the round-1 shared-memory kernel within the 3xTF32 bound."""
+    from surfacenetworks_b200 import _native as Nt
+    g = torch.Generator(device=DEV).manual_seed(M + 3 * N + K)
+    A = torch.randn(M, K, device=DEV, generator=g)
+    B = torch.randn(N, K, device=DEV, generator=g) / K ** 0.5
+    bias = torch.randn(N, device=DEV, generator=g)
+    R = torch.randn(M, N, device=DEV, generator=g)
+    rs = torch.randn(N, device=DEV, generator=g)
+    st = torch.cuda.current_stream().cuda_stream
+    C0 = run_gemm(A, B, bias, R, rs)
+    hi, lo = torch.empty_like(B), torch.empty_like(B)
+    Nt.call("sn_split_tf32_f32", B.data_ptr(), K, N, K, hi.data_ptr(), lo.data_ptr(), st)
+    assert torch.equal(hi + lo, B)
+    assert torch.all((hi.view(torch.int32) & 0x1fff) == 0)            # tf32: low 13 mantissa bits clear
+    C1 = torch.empty_like(C0)
+    Nt.call("sn_gemm_tf32_presplit_f32", A.data_ptr(), K, hi.data_ptr(), lo.data_ptr(), K, bias.data_ptr(), R.data_ptr(), N,
+            rs.data_ptr(), 0, 0, C1.data_ptr(), N, M, N, K, 0, st)
+    assert torch.equal(C0, C1)
+    C2 = torch.empty_like(C0)
+    wsb = Nt.lib.sn_gemm_tf32_ws_bytes(N, K)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+    Nt.call("sn_gemm_tf32_f32", A.data_ptr(), K, B.data_ptr(), K, bias.data_ptr(), R.data_ptr(), N, rs.data_ptr(), 0, 0,
+            C2.data_ptr(), N, M, N, K, Nt.SN_GEMM_LEGACY_SS, ws.data_ptr(), wsb, st)
+    y64, mag = reference(A, B, bias, R, rs)
+    assert torch.all((C2.double() - y64).abs() <= 2e-6 * mag)
+    assert torch.all((C0.double() - C2.double()).abs() <= 4e-6 * mag)
 
 
 def test_gemm_strided_operands_and_repeatability():

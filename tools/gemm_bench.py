@@ -12,6 +12,19 @@ import torch  # noqa: E402
 def main():
     from surfacenetworks_b200 import _native as N
     dev = torch.device("cuda", 0)
+    if "--ncu" in sys.argv:              # short run for ncu --set full: the two BASELINE dense-stage shapes, TS kernel only
+        st = torch.cuda.current_stream().cuda_stream
+        for M, Nn, K in ((255168, 128, 256), (128000, 256, 128)):
+            A = torch.randn(M, K, device=dev)
+            B = torch.randn(Nn, K, device=dev) / K ** 0.5
+            hi, lo = torch.empty_like(B), torch.empty_like(B)
+            N.call("sn_split_tf32_f32", B.data_ptr(), K, Nn, K, hi.data_ptr(), lo.data_ptr(), st)
+            bias, R, C = torch.randn(Nn, device=dev), torch.randn(M, Nn, device=dev), torch.empty(M, Nn, device=dev)
+            for _ in range(3):
+                N.call("sn_gemm_tf32_presplit_f32", A.data_ptr(), K, hi.data_ptr(), lo.data_ptr(), K, bias.data_ptr(),
+                       R.data_ptr(), Nn, 0, 0, 0, C.data_ptr(), Nn, M, Nn, K, 0, st)
+        torch.cuda.synchronize()
+        return
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
@@ -43,8 +56,18 @@ def main():
 
         flops = 2.0 * M * Nn * K
         bytes_ = 4.0 * (M * K + 2 * M * Nn + Nn * K)
-        out = {"M": M, "N": Nn, "K": K}
+        out = {"M": M, "N": Nn, "K": K, "hbm_floor_us": bytes_ / 6551e3, "hbm_floor_nores_us": (bytes_ - 4.0 * M * Nn) / 6551e3}
+        hi, lo = torch.empty_like(B), torch.empty_like(B)
+        N.call("sn_split_tf32_f32", B.data_ptr(), K, Nn, K, hi.data_ptr(), lo.data_ptr(), st)
+
+        def presplit(flags=0, res=True):
+            N.call("sn_gemm_tf32_presplit_f32", A.data_ptr(), K, hi.data_ptr(), lo.data_ptr(), K, bias.data_ptr(),
+                   R.data_ptr() if res else 0, Nn, 0, 0, 0, C.data_ptr(), Nn, M, Nn, K, flags, st)
+
         for name, fn in (("sn_3xtf32", lambda: ours(0)), ("sn_tf32", lambda: ours(N.SN_GEMM_SINGLE_PASS)),
+                         ("sn_3xtf32_presplit", lambda: presplit(0)), ("sn_3xtf32_presplit_nores", lambda: presplit(0, False)),
+                         ("legacy_ss_3xtf32", lambda: ours(N.SN_GEMM_LEGACY_SS)),
+                         ("legacy_ss_3xtf32_nores", lambda: ours(N.SN_GEMM_LEGACY_SS, False)),
                          ("sn_3xtf32_nores", lambda: ours(0, False)),
                          ("sn_3xtf32_nopf", lambda: ours(N.SN_GEMM_NO_L2_PREFETCH)),
                          ("sn_3xtf32_nores_nopf", lambda: ours(N.SN_GEMM_NO_L2_PREFETCH, False)),
