@@ -236,6 +236,12 @@ int sn_split_tf32_f32(const float* X, int64_t ldx, int64_t rows, int64_t cols, f
 size_t sn_gemm_tn_tf32_ws_bytes(int64_t R, int64_t N);
 int sn_gemm_tn_tf32_f32(const float* A, int64_t lda, const float* B, int64_t ldb, float* G, int64_t ldg, int64_t R,
                         int64_t M, int64_t N, int flags, void* ws, size_t ws_bytes, sn_stream_t stream);
+/* The same product plus colsum_A[M] = column sums of A over the R rows, from the same pass (the A tile crosses the
+ * registers of the warps that move it into tensor memory): with A = dY this is db of the Linear and the second reduction
+ * the BatchNorm backward needs -- no separate pass over dY.  Deterministic (per-CTA partials added in a fixed order). */
+int sn_gemm_tn_colsum_tf32_f32(const float* A, int64_t lda, const float* B, int64_t ldb, float* G, int64_t ldg,
+                               float* colsum_A, int64_t R, int64_t M, int64_t N, int flags, void* ws, size_t ws_bytes,
+                               sn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Batch statistics for the training-mode BatchNorm in front of the Linear (utils_pt.py:84,98): per-column mean and

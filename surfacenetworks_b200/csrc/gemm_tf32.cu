@@ -366,6 +366,31 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
+// One elected lane of a converged warp.  Code under `if (elect_one())` is compiled as single-thread, warp-uniform code:
+// UTCHMMA / UTMALDG / UTCBAR are emitted bare.  Under `if (lane == 0)` ptxas wraps every one of them in an
+// ELECT ... BRA.U.ANY loop (it must assume divergence), which made the MMA-issuing thread the bottleneck of the first
+// version of this kernel (ncu: ~200 dependent uniform-datapath instructions per k-block, 1750 clk against 768 clk of
+// tensor-pipe time -- profiles/r2_gemm_notes.md).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+// TS-mode MMA with the shared-memory descriptor given as (lo, hi) words: hi is a constant of the layout, lo advances by
+// (byte offset >> 4), so the issuing thread spends one integer add per MMA on descriptors.
+__device__ __forceinline__ void umma_tf32_ts_lohi(uint32_t tmem_d, uint32_t tmem_a, uint32_t bdesc_lo, uint32_t bdesc_hi,
+                                                  uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 d;\nsetp.ne.b32 p, %5, 0;\nmov.b64 d, {%2, %3};\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], d, %4, p;\n}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
@@ -452,7 +477,7 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
   if (warp == 0) {
     // ------------------------------------------------------------------ A producer
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
@@ -466,7 +491,7 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else if (warp == 3) {
     // ------------------------------------------------------------------ B producer (pre-split weights, L2-resident)
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
@@ -481,47 +506,49 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nmma >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
-    int bs = 0;
-    uint32_t bph = 0;
-    uint32_t a_cnt = 0;                  // TMEM A stages consumed so far (stage = a_cnt % 4, parity = (a_cnt / 4) & 1)
-    uint32_t job = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      for (int half = 0; half < n_halves; ++half, ++job) {
-        const uint32_t buf = job & 1u;
-        mbar_wait(tmem_empty + buf, ((job >> 1) & 1u) ^ 1u);      // epilogue drained this accumulator
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tmem_d = tmem_base + buf * (uint32_t)nmma;
-        for (int kb = 0; kb < n_kb; ++kb) {
-          const uint32_t cnt = p.a_resident ? a_cnt + (uint32_t)kb : a_cnt;
-          const uint32_t at = cnt % kATmemStages;
-          if (half == 0 || !p.a_resident) mbar_wait(a_ready + at, (cnt / kATmemStages) & 1u);
-          mbar_wait(b_full + bs, bph);
+    // ------------------------------------------------------------------ MMA issuer (one elected thread runs the whole role)
+    if (elect_one()) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nmma >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+      const uint64_t d0 = umma_desc_sw128(smem_u32(b_ring));
+      const uint32_t d_lo0 = (uint32_t)d0, d_hi = (uint32_t)(d0 >> 32);
+      const uint32_t stage_units = (2u * b_bytes) >> 4, lo_units = b_bytes >> 4;   // descriptor address units of 16 bytes
+      const uint32_t split = (uint32_t)p.split;
+      int bs = 0;
+      uint32_t bph = 0;
+      uint32_t a_cnt = 0;                // TMEM A stages consumed so far (stage = a_cnt % 4, parity = (a_cnt / 4) & 1)
+      uint32_t job = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int half = 0; half < n_halves; ++half, ++job) {
+          const uint32_t buf = job & 1u;
+          mbar_wait(tmem_empty + buf, ((job >> 1) & 1u) ^ 1u);    // epilogue drained this accumulator
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          if (lane == 0) {
+          const uint32_t tmem_d = tmem_base + buf * (uint32_t)nmma;
+          for (int kb = 0; kb < n_kb; ++kb) {
+            const uint32_t cnt = p.a_resident ? a_cnt + (uint32_t)kb : a_cnt;
+            const uint32_t at = cnt % kATmemStages;
+            if (half == 0 || !p.a_resident) mbar_wait(a_ready + at, (cnt / kATmemStages) & 1u);
+            mbar_wait(b_full + bs, bph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t ta = tmem_base + (uint32_t)(kATmemCol0 + at * 64);
-            const uint32_t sb = smem_u32(b_ring + (size_t)bs * 2 * b_bytes), sbl = sb + b_bytes;
+            const uint32_t dlo = d_lo0 + (uint32_t)bs * stage_units;
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              const uint32_t off = k * kUmmaK * 4;             // 32 bytes per k-step inside the swizzle row
-              const uint64_t db = umma_desc_sw128(sb + off);
-              umma_tf32_ts(tmem_d, ta + k * kUmmaK, db, idesc, (kb | k) != 0);
-              if (p.split) {
-                umma_tf32_ts(tmem_d, ta + k * kUmmaK, umma_desc_sw128(sbl + off), idesc, true);     // hi * lo
-                umma_tf32_ts(tmem_d, ta + 32 + k * kUmmaK, db, idesc, true);                        // lo * hi
+              // 32 bytes per k-step inside the swizzle row = 2 descriptor units; 8 TMEM columns per k-step of A
+              umma_tf32_ts_lohi(tmem_d, ta + k * kUmmaK, dlo + 2 * k, d_hi, idesc, (uint32_t)((kb | k) != 0));
+              if (split) {
+                umma_tf32_ts_lohi(tmem_d, ta + k * kUmmaK, dlo + lo_units + 2 * k, d_hi, idesc, 1u);      // hi * lo
+                umma_tf32_ts_lohi(tmem_d, ta + 32 + k * kUmmaK, dlo + 2 * k, d_hi, idesc, 1u);            // lo * hi
               }
             }
             umma_commit(b_free + bs);
             if (!p.a_resident || half == n_halves - 1) umma_commit(a_tfree + at);
             if (kb == n_kb - 1) umma_commit(tmem_full + buf);
+            if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
+            if (!p.a_resident) ++a_cnt;
           }
-          __syncwarp();
-          if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
-          if (!p.a_resident) ++a_cnt;
         }
+        if (p.a_resident) a_cnt += (uint32_t)n_kb;
       }
-      if (p.a_resident) a_cnt += (uint32_t)n_kb;
     }
   } else if (warp >= 4 && warp < 8) {
     // ------------------------------------------------------------------ A: shared memory -> hi / lo -> tensor memory
@@ -529,17 +556,18 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // row r sits at chunk i ^ (r & 7), so the eight LDS.128 of a quarter-warp hit eight distinct bank groups.
     const int r = threadIdx.x - 128;
     const uint32_t lane_base = (uint32_t)((warp - 4) * 32) << 16;
+    const uint32_t a_ring_s = smem_u32(a_ring);
     int as = 0;
     uint32_t aph = 0, t_cnt = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
       for (int pass = 0; pass < n_a_pass; ++pass)
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(a_full + as, aph);
-          const unsigned char* row = a_ring + (size_t)as * a_bytes + (size_t)r * 128;
+          const uint32_t row = a_ring_s + (uint32_t)as * a_bytes + (uint32_t)r * 128u;
           uint32_t hi[32], lo[32];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 x = *reinterpret_cast<const float4*>(row + ((i ^ (r & 7)) << 4));
+            const float4 x = lds_f4(row + (uint32_t)((i ^ (r & 7)) << 4));
             const float h0 = to_tf32(x.x), h1 = to_tf32(x.y), h2 = to_tf32(x.z), h3 = to_tf32(x.w);
             hi[4 * i] = __float_as_uint(h0); hi[4 * i + 1] = __float_as_uint(h1);
             hi[4 * i + 2] = __float_as_uint(h2); hi[4 * i + 3] = __float_as_uint(h3);
@@ -602,6 +630,9 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int c0 = cbase; c0 < cbase + ncol; c0 += 16) {
           uint32_t v[16];
+          float4 bia = make_float4(0.f, 0.f, 0.f, 0.f), rs = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (p.bias) bia = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + tc));      // latency hidden behind the TMEM load
+          if (p.rscale) rs = __ldg(reinterpret_cast<const float4*>(p.rscale + c0 + tc));
           tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * nmma + (c0 - half * nmma)), v);
           if (p.R && c0 + 32 < cbase + ncol) load_r(rn2, row0, c0 + 32);   // residual two chunks ahead
 #pragma unroll
@@ -609,9 +640,6 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             *reinterpret_cast<float4*>(tbuf + lane * 20 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
                                                                             __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
           __syncwarp();
-          float4 bia = make_float4(0.f, 0.f, 0.f, 0.f), rs = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (p.bias) bia = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + tc));
-          if (p.rscale) rs = __ldg(reinterpret_cast<const float4*>(p.rscale + c0 + tc));
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int rl = i * 8 + tr;

@@ -15,6 +15,8 @@
 
 #include "common.cuh"
 
+SN_API size_t sn_gemm_tn_tf32_ws_bytes(int64_t R, int64_t N);
+
 namespace sn {
 namespace gemm_tn {
 
@@ -105,7 +107,7 @@ struct Params {
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+gemm_tn_ss_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int N = p.N;
@@ -241,6 +243,298 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
+// ====================================================================================================================
+// Round-2 kernel: dY (the A operand, M = 128 columns of dY) goes through TENSOR MEMORY, and colsum(dY) comes for free
+// ====================================================================================================================
+// The round-1 kernel above split BOTH tiles in shared memory (48 KB read + 96 KB written per 32-row k-block) and fed both
+// operands to the tensor core from shared memory (144 KB of operand reads): 336 KB of shared-memory traffic per k-block
+// against 48 KB of HBM traffic, two pipeline stages.  Here the dY tile lands un-swizzled ([32 rows][128 columns]);
+// thread m of the four A-split warps reads column m (32 conflict-free LDS.32), which is exactly row m of the tensor
+// core's A operand, and writes hi / lo into tensor memory (tcgen05.st): A never returns to shared memory.  While the
+// column passes through its registers the thread also adds it up: colsum(dY) -- which the BatchNorm backward needs next
+// to G (fused.py) and which used to be a separate HBM pass over dY (sn_colstats_f32) -- costs one FADD per element.
+// Z (the B operand, MN-major) is still split in shared memory by eight warps.
+constexpr int kATmemStages = 4;
+constexpr int kATmemCol0 = 256;
+constexpr int kAStages = 4;            // shared-memory dY ring (16 KB stages)
+constexpr int kMaxBStages = 4;
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void umma_tf32_ts_lohi(uint32_t tmem_d, uint32_t tmem_a, uint32_t bdesc_lo, uint32_t bdesc_hi,
+                                                  uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 d;\nsetp.ne.b32 p, %5, 0;\nmov.b64 d, {%2, %3};\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], d, %4, p;\n}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
+      "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+      "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ float lds_f1(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t saddr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+struct ParamsTS {
+  float* partial;        // [grid][kM][N]
+  float* csum_partial;   // [grid][kM]   per-CTA column sums of A (dY)
+  int R, N;
+  int kb_per_cta;
+  int n_kb;
+  int b_stages;
+  int split;
+  int l2_prefetch;
+};
+
+// Roles: warp 0 = dY producer (TMA), warp 3 = Z producer (TMA + L2 prefetch), warp 1 = MMA issuer, warp 2 = TMEM
+// allocation, warps 4-7 = dY: shared memory -> column sums, hi / lo -> tensor memory; then the epilogue,
+// warps 8-15 = Z: hi / lo split in shared memory.
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tn_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const ParamsTS p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int N = p.N;
+  const int b_boxes = N / 32;
+  constexpr uint32_t a_bytes = kBlockK * kM * 4;               // 16 KB: [32 rows][128 columns], no swizzle
+  const uint32_t b_bytes = (uint32_t)b_boxes * kBoxBytes;      // hi (in place) or lo twin
+  unsigned char* b_ring = smem;                                // 1024-byte aligned boxes first
+  unsigned char* a_ring = smem + (size_t)p.b_stages * 2 * b_bytes;
+  __shared__ uint64_t a_full[kAStages], a_free[kAStages], a_ready[kATmemStages], a_tfree[kATmemStages];
+  __shared__ uint64_t b_full[kMaxBStages], b_ready[kMaxBStages], b_free[kMaxBStages], done_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb0 = blockIdx.x * p.kb_per_cta;
+  const int kb1 = min(kb0 + p.kb_per_cta, p.n_kb);
+  const int my_kb = max(kb1 - kb0, 0);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kAStages; ++s) {
+      mbar_init(a_full + s, 1);
+      mbar_init(a_free + s, 4);
+    }
+    for (int s = 0; s < kATmemStages; ++s) {
+      mbar_init(a_ready + s, 4);
+      mbar_init(a_tfree + s, 1);
+    }
+    for (int s = 0; s < p.b_stages; ++s) {
+      mbar_init(b_full + s, 1);
+      mbar_init(b_ready + s, 8);
+      mbar_init(b_free + s, 1);
+    }
+    mbar_init(&done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(a_free + stage, phase ^ 1u);
+        mbar_arrive_expect_tx(a_full + stage, a_bytes);
+        tma_load_2d(a_ring + (size_t)stage * a_bytes, &map_a, 0, kb * kBlockK, a_full + stage);
+        if (p.l2_prefetch && kb + 2 * kPrefetchDist < kb1) tma_prefetch_l2_2d(&map_a, 0, (kb + 2 * kPrefetchDist) * kBlockK);
+        if (++stage == kAStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 3) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(b_free + stage, phase ^ 1u);
+        unsigned char* sb = b_ring + (size_t)stage * 2 * b_bytes;
+        mbar_arrive_expect_tx(b_full + stage, b_bytes);
+        for (int i = 0; i < b_boxes; ++i) tma_load_2d(sb + i * kBoxBytes, &map_b, i * 32, kb * kBlockK, b_full + stage);
+        // the Z ring is shallow (the hi / lo twins fill shared memory): pull the boxes this CTA loads kPrefetchDist
+        // iterations from now into L2
+        if (p.l2_prefetch && kb + kPrefetchDist < kb1)
+          for (int i = 0; i < b_boxes; ++i) tma_prefetch_l2_2d(&map_b, i * 32, (kb + kPrefetchDist) * kBlockK);
+        if (++stage == p.b_stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // D = F32, A = B = TF32, A K-major (tensor memory), B MN-major (bit 16), N >> 3 at bit 17, M >> 4 at bit 24
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+      const uint64_t d0 = umma_desc_mn_sw128(smem_u32(b_ring));
+      const uint32_t d_lo0 = (uint32_t)d0, d_hi = (uint32_t)(d0 >> 32);
+      const uint32_t stage_units = (2u * b_bytes) >> 4, lo_units = b_bytes >> 4;
+      const uint32_t split = (uint32_t)p.split;
+      int bs = 0;
+      uint32_t bph = 0;
+      for (int kb = 0; kb < my_kb; ++kb) {
+        const uint32_t at = (uint32_t)kb % kATmemStages;
+        mbar_wait(a_ready + at, ((uint32_t)kb / kATmemStages) & 1u);
+        mbar_wait(b_ready + bs, bph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t ta = tmem_base + (uint32_t)(kATmemCol0 + at * 64);
+        const uint32_t dlo = d_lo0 + (uint32_t)bs * stage_units;
+#pragma unroll
+        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+          // 8 K rows = one 1 KB group inside every box = 64 descriptor units
+          umma_tf32_ts_lohi(tmem_base, ta + k * kUmmaK, dlo + 64 * k, d_hi, idesc, (uint32_t)((kb | k) != 0));
+          if (split) {
+            umma_tf32_ts_lohi(tmem_base, ta + k * kUmmaK, dlo + lo_units + 64 * k, d_hi, idesc, 1u);    // hi * lo
+            umma_tf32_ts_lohi(tmem_base, ta + 32 + k * kUmmaK, dlo + 64 * k, d_hi, idesc, 1u);          // lo * hi
+          }
+        }
+        umma_commit(b_free + bs);
+        umma_commit(a_tfree + at);
+        if (kb == my_kb - 1) umma_commit(&done_bar);
+        if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------------ dY: column m of the tile = row m of the A operand
+    const int m = threadIdx.x - 128;                           // 0..127 = TMEM lane
+    const uint32_t lane_base = (uint32_t)((warp - 4) * 32) << 16;
+    const uint32_t a_ring_s = smem_u32(a_ring);
+    float csum = 0.f;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int kb = 0; kb < my_kb; ++kb) {
+      mbar_wait(a_full + as, aph);
+      const uint32_t col = a_ring_s + (uint32_t)as * a_bytes + (uint32_t)m * 4u;
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {                           // lanes read consecutive words of one row: conflict-free
+        const float x = lds_f1(col + (uint32_t)k * (kM * 4));
+        csum += x;                                             // rows past R are zero-filled by TMA
+        const float h = to_tf32(x);
+        hi[k] = __float_as_uint(h);
+        lo[k] = __float_as_uint(x - h);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_free + as);
+      const uint32_t at = (uint32_t)kb % kATmemStages;
+      mbar_wait(a_tfree + at, (((uint32_t)kb / kATmemStages) & 1u) ^ 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t ta = tmem_base + lane_base + (uint32_t)(kATmemCol0 + at * 64);
+      tmem_st32(ta, hi);
+      if (p.split) tmem_st32(ta + 32, lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready + at);
+      if (++as == kAStages) { as = 0; aph ^= 1u; }
+    }
+    // ------------------------------------------------------------------ epilogue: this CTA's partial [128 x N] -> workspace
+    p.csum_partial[(size_t)blockIdx.x * kM + m] = csum;
+    float* out = p.partial + ((size_t)blockIdx.x * kM + m) * N;
+    if (my_kb > 0) {
+      mbar_wait(&done_bar, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + lane_base + (uint32_t)c0, v);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(out + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                  __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      }
+    } else {
+      for (int c0 = 0; c0 < N; c0 += 4) *reinterpret_cast<float4*>(out + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  } else if (warp >= 8) {
+    // ------------------------------------------------------------------ Z: hi in place, lo into the twin (elementwise)
+    const int t = threadIdx.x - 256;                           // 0..255
+    const uint32_t b_ring_s = smem_u32(b_ring);
+    const int n_f4 = (int)(b_bytes / 16);
+    int bs = 0;
+    uint32_t bph = 0;
+    for (int kb = 0; kb < my_kb; ++kb) {
+      mbar_wait(b_full + bs, bph);
+      const uint32_t sb = b_ring_s + (uint32_t)bs * 2u * b_bytes;
+      for (int i0 = t; i0 < n_f4; i0 += 4 * 256) {             // four independent 16-byte loads in flight per thread
+        float4 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (i0 + u * 256 < n_f4) x[u] = lds_f4(sb + (uint32_t)(i0 + u * 256) * 16u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (i0 + u * 256 < n_f4) {
+            const uint32_t a = sb + (uint32_t)(i0 + u * 256) * 16u;
+            float4 h;
+            h.x = to_tf32(x[u].x); h.y = to_tf32(x[u].y); h.z = to_tf32(x[u].z); h.w = to_tf32(x[u].w);
+            sts_f4(a, h);
+            if (p.split) sts_f4(a + b_bytes, make_float4(x[u].x - h.x, x[u].y - h.y, x[u].z - h.z, x[u].w - h.w));
+          }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_ready + bs);
+      if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+// G[m][n] = sum over CTAs of partial[cta][m][n] and colsum[m] = sum over CTAs of csum[cta][m], both in a fixed order:
+// four lanes share one output, lane j adds partials j, j + 4, ... (independent loads), the four sums are added in order.
+__global__ void __launch_bounds__(256)
+reduce_partials4_kernel(const float* __restrict__ partial, const float* __restrict__ csum_partial, int n_partials, int MN,
+                        float* __restrict__ G, int64_t ldg, int N, float* __restrict__ colsum, int M) {
+  const int gi = blockIdx.x * 64 + (threadIdx.x >> 2);
+  const int j = threadIdx.x & 3;
+  const bool is_g = gi < MN, is_c = !is_g && colsum != nullptr && gi < MN + M;
+  float acc = 0.f;
+  if (is_g || is_c) {
+    const float* src = is_g ? partial + gi : csum_partial + (gi - MN);
+    const size_t stride = is_g ? (size_t)MN : (size_t)M;
+    int c = j;
+    for (; c + 12 < n_partials; c += 16) {
+      const float a0 = src[(size_t)c * stride], a1 = src[(size_t)(c + 4) * stride], a2 = src[(size_t)(c + 8) * stride],
+                  a3 = src[(size_t)(c + 12) * stride];
+      acc += a0; acc += a1; acc += a2; acc += a3;
+    }
+    for (; c < n_partials; c += 4) acc += src[(size_t)c * stride];
+  }
+  const float s1 = __shfl_down_sync(0xffffffffu, acc, 1), s2 = __shfl_down_sync(0xffffffffu, acc, 2),
+              s3 = __shfl_down_sync(0xffffffffu, acc, 3);
+  if (j == 0) {
+    const float tot = ((acc + s1) + s2) + s3;
+    if (is_g) G[(int64_t)(gi / N) * ldg + (gi % N)] = tot;
+    else if (is_c) colsum[gi - MN] = tot;
+  }
+}
+
 // G[m][n] = sum over CTAs of partial[cta][m][n], fixed order
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int n_partials, int MN, float* __restrict__ G,
                                        int64_t ldg, int N) {
@@ -275,6 +569,19 @@ static bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t 
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// dY tile for the TS kernel: one un-swizzled box of 32 rows x 128 columns (row-major in shared memory)
+static bool make_map_plain(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)kM, (cuuint32_t)kBlockK};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int grid_for(int64_t n_kb, int* kb_per_cta) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -285,6 +592,64 @@ static int grid_for(int64_t n_kb, int* kb_per_cta) {
   return (int)((n_kb + per - 1) / per);
 }
 
+static int launch_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* G, int64_t ldg, float* colsum_A,
+                     int64_t R, int64_t M, int64_t N, int flags, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (R <= 0 || M <= 0 || N <= 0 || !A || !B || !G || lda < M || ldb < N || ldg < N) return SN_ERR_ARG;
+  if (M != kM || N % 32 != 0 || N > 256 || N < 32 || R >= 0x7fffffffLL - 64) return SN_ERR_UNSUPPORTED;
+  if (lda % 4 || ldb % 4 || !aligned16(A) || !aligned16(B)) return SN_ERR_UNSUPPORTED;
+  if (!ws || ws_bytes < sn_gemm_tn_tf32_ws_bytes(R, N)) return SN_ERR_WORKSPACE;
+  CUtensorMap map_a, map_b;
+  if (!make_map(&map_b, B, R, N, ldb)) return SN_ERR_UNSUPPORTED;
+  float* partial = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  const int n_kb = (int)((R + kBlockK - 1) / kBlockK);
+  int kb_per_cta;
+  const int grid = grid_for(n_kb, &kb_per_cta);
+  const int split = (flags & SN_GEMM_SINGLE_PASS) ? 0 : 1;
+  const int l2_prefetch = (flags & SN_GEMM_NO_L2_PREFETCH) ? 0 : 1;
+  const int MN = (int)(kM * N);
+  float* csum_partial = partial + (size_t)grid * MN;
+
+  if (flags & SN_GEMM_LEGACY_SS) {       // round-1 kernel (both operands split in and read from shared memory)
+    if (colsum_A) return SN_ERR_UNSUPPORTED;
+    if (!make_map(&map_a, A, R, M, lda)) return SN_ERR_UNSUPPORTED;
+    Params p;
+    p.partial = partial;
+    p.R = (int)R; p.N = (int)N;
+    p.n_kb = n_kb; p.kb_per_cta = kb_per_cta;
+    p.split = split; p.l2_prefetch = l2_prefetch;
+    const size_t stage_bytes = 2 * ((size_t)(kM / 32) * kBoxBytes + (size_t)(N / 32) * kBoxBytes);
+    const size_t smem = 2 * stage_bytes + 1024;
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_ss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    gemm_tn_ss_kernel<<<grid, kThreads, smem, st>>>(map_a, map_b, p);
+    reduce_partials_kernel<<<(MN + 255) / 256, 256, 0, st>>>(p.partial, grid, MN, G, ldg, (int)N);
+    return launch_status();
+  }
+
+  if (!make_map_plain(&map_a, A, R, M, lda)) return SN_ERR_UNSUPPORTED;
+  ParamsTS p;
+  p.partial = partial;
+  p.csum_partial = csum_partial;
+  p.R = (int)R; p.N = (int)N;
+  p.n_kb = n_kb; p.kb_per_cta = kb_per_cta;
+  p.split = split; p.l2_prefetch = l2_prefetch;
+  int dev = 0, smem_optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const size_t a_ring = (size_t)kAStages * kBlockK * kM * 4, b_stage = 2 * (size_t)(N / 32) * kBoxBytes;
+  int b_stages = (int)(((size_t)smem_optin - 2048 - 1024 - a_ring) / b_stage);
+  if (b_stages > kMaxBStages) b_stages = kMaxBStages;
+  if (b_stages < 2) return SN_ERR_UNSUPPORTED;
+  p.b_stages = b_stages;
+  const size_t smem = a_ring + b_stages * b_stage + 1024;
+  cudaError_t e = cudaFuncSetAttribute(gemm_tn_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  gemm_tn_ts_kernel<<<grid, kThreads, smem, st>>>(map_a, map_b, p);
+  const int outs = MN + (colsum_A ? (int)kM : 0);
+  reduce_partials4_kernel<<<(outs + 63) / 64, 256, 0, st>>>(partial, csum_partial, grid, MN, G, ldg, (int)N, colsum_A, (int)kM);
+  return launch_status();
+}
+
 }  // namespace gemm_tn
 }  // namespace sn
 
@@ -293,33 +658,17 @@ SN_API size_t sn_gemm_tn_tf32_ws_bytes(int64_t R, int64_t N) {
   if (R <= 0 || N <= 0) return 0;
   int per;
   const int grid = grid_for((R + kBlockK - 1) / kBlockK, &per);
-  return (size_t)grid * kM * (size_t)N * sizeof(float) + 256;
+  return (size_t)grid * kM * (size_t)(N + 1) * sizeof(float) + 256;      // partial products + partial column sums
 }
 
 SN_API int sn_gemm_tn_tf32_f32(const float* A, int64_t lda, const float* B, int64_t ldb, float* G, int64_t ldg, int64_t R,
                                int64_t M, int64_t N, int flags, void* ws, size_t ws_bytes, sn_stream_t stream) {
-  using namespace sn;
-  using namespace sn::gemm_tn;
-  if (R <= 0 || M <= 0 || N <= 0 || !A || !B || !G || lda < M || ldb < N || ldg < N) return SN_ERR_ARG;
-  if (M != kM || N % 32 != 0 || N > 256 || N < 32 || R >= 0x7fffffffLL - 64) return SN_ERR_UNSUPPORTED;
-  if (lda % 4 || ldb % 4 || !aligned16(A) || !aligned16(B)) return SN_ERR_UNSUPPORTED;
-  if (!ws || ws_bytes < sn_gemm_tn_tf32_ws_bytes(R, N)) return SN_ERR_WORKSPACE;
-  CUtensorMap map_a, map_b;
-  if (!make_map(&map_a, A, R, M, lda) || !make_map(&map_b, B, R, N, ldb)) return SN_ERR_UNSUPPORTED;
-  Params p;
-  p.partial = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
-  p.R = (int)R; p.N = (int)N;
-  p.n_kb = (int)((R + kBlockK - 1) / kBlockK);
-  const int grid = grid_for(p.n_kb, &p.kb_per_cta);
-  p.split = (flags & SN_GEMM_SINGLE_PASS) ? 0 : 1;
-  p.l2_prefetch = (flags & SN_GEMM_NO_L2_PREFETCH) ? 0 : 1;
-  const size_t stage_bytes = 2 * ((size_t)(kM / 32) * kBoxBytes + (size_t)(N / 32) * kBoxBytes);
-  const size_t smem = 2 * stage_bytes + 1024;
-  cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  cudaStream_t st = (cudaStream_t)stream;
-  gemm_tn_kernel<<<grid, kThreads, smem, st>>>(map_a, map_b, p);
-  const int MN = (int)(kM * N);
-  reduce_partials_kernel<<<(MN + 255) / 256, 256, 0, st>>>(p.partial, grid, MN, G, ldg, (int)N);
-  return launch_status();
+  return sn::gemm_tn::launch_tn(A, lda, B, ldb, G, ldg, nullptr, R, M, N, flags, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+SN_API int sn_gemm_tn_colsum_tf32_f32(const float* A, int64_t lda, const float* B, int64_t ldb, float* G, int64_t ldg,
+                                      float* colsum_A, int64_t R, int64_t M, int64_t N, int flags, void* ws, size_t ws_bytes,
+                                      sn_stream_t stream) {
+  if (!colsum_A) return SN_ERR_ARG;
+  return sn::gemm_tn::launch_tn(A, lda, B, ldb, G, ldg, colsum_A, R, M, N, flags, ws, ws_bytes, (cudaStream_t)stream);
 }

@@ -19,7 +19,9 @@
 namespace sn {
 namespace mesh {
 
-constexpr int kMaxInc = 64;      // incident faces per vertex supported (mesh valence; Delaunay meshes stay below 20)
+constexpr int kMaxInc = 64;      // incident faces per vertex handled in registers / local memory (Delaunay meshes stay
+                                 // below 20); vertices above it (poles of UV spheres, cone apexes) take the same code
+                                 // over global scratch -- any valence is supported, like the reference
 
 __device__ __forceinline__ double sqdist3(const double* a, const double* b) {
   const double d0 = __dsub_rn(a[0], b[0]), d1 = __dsub_rn(a[1], b[1]), d2 = __dsub_rn(a[2], b[2]);
@@ -88,9 +90,20 @@ vertex_sort_kernel(const int* __restrict__ vptr, int* __restrict__ inc, const do
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n_vert) return;
   const int k0 = vptr[v], n = vptr[v + 1] - k0;
-  if (n > kMaxInc) {
+  if (n > kMaxInc) {                     // rare: sort in place in global memory (status reports the largest valence seen)
     atomicMax(status, n);
-    varea[v] = 0.0;
+    for (int i = 1; i < n; ++i) {
+      const int x = inc[k0 + i];
+      int j = i - 1;
+      while (j >= 0 && inc[k0 + j] > x) {
+        inc[k0 + j + 1] = inc[k0 + j];
+        --j;
+      }
+      inc[k0 + j + 1] = x;
+    }
+    double a = 0.0;
+    for (int i = 0; i < n; ++i) a = __dadd_rn(a, __ddiv_rn(area[inc[k0 + i] >> 2], 3.0));
+    varea[v] = a;
     return;
   }
   int key[kMaxInc];
@@ -191,7 +204,6 @@ adjoint_rows_kernel(const double* __restrict__ V, const int32_t* __restrict__ F,
   const int b = (int)(v / v_pad);
   const double* P = V + (int64_t)b * v_pad * 3;
   const int k0 = vptr[v], n = vptr[v + 1] - k0;
-  if (n > kMaxInc) return;
   const double av = varea[v];
   for (int i = 0; i < n; ++i) {
     const int key = inc[k0 + i];
@@ -224,10 +236,9 @@ adjoint_rows_kernel(const double* __restrict__ V, const int32_t* __restrict__ F,
 template <typename Emit>
 __device__ __forceinline__ int laplacian_row(const double* __restrict__ P, const int32_t* __restrict__ F,
                                              const double* __restrict__ area, const int* __restrict__ inc, int k0, int n,
-                                             int vi /*local vertex index*/, Emit emit) {
-  int nb[2 * kMaxInc];          // neighbour (local vertex index)
-  double wij[2 * kMaxInc];      // contribution to W[i, j]
-  double wji[2 * kMaxInc];      // contribution to W[j, i]  (column i, feeds the degree d_i = sum_j W[j, i])
+                                             int vi /*local vertex index*/, int* nb, double* wij, double* wji, Emit emit) {
+  // nb: neighbour (local vertex index); wij / wji: contributions to W[i, j] / W[j, i] (column i, feeds the degree
+  // d_i = sum_j W[j, i]); 2 n entries each -- thread-local arrays up to kMaxInc faces, global scratch above
   double A = 0.0;
   int m = 0;
   for (int t = 0; t < n; ++t) {
@@ -303,34 +314,48 @@ __device__ __forceinline__ int laplacian_row(const double* __restrict__ P, const
 __global__ void __launch_bounds__(128)
 laplacian_count_kernel(const double* __restrict__ V, const int32_t* __restrict__ F, const double* __restrict__ area,
                        int v_pad, int f_pad, int64_t n_vert, const int* __restrict__ vptr, const int* __restrict__ inc,
-                       int* __restrict__ rowcount) {
+                       int* __restrict__ rowcount, int* s_nb, double* s_wij, double* s_wji) {
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n_vert) return;
   const int b = (int)(v / v_pad);
   const int k0 = vptr[v], n = vptr[v + 1] - k0;
   int cnt = 0;
-  if (n > 0 && n <= kMaxInc)
-    cnt = laplacian_row(V + (int64_t)b * v_pad * 3, F, area, inc, k0, n, (int)(v - (int64_t)b * v_pad),
+  if (n > 0 && n <= kMaxInc) {
+    int nb[2 * kMaxInc];
+    double wij[2 * kMaxInc], wji[2 * kMaxInc];
+    cnt = laplacian_row(V + (int64_t)b * v_pad * 3, F, area, inc, k0, n, (int)(v - (int64_t)b * v_pad), nb, wij, wji,
                         [](int, int, float) {});
+  } else if (n > 0) {
+    cnt = laplacian_row(V + (int64_t)b * v_pad * 3, F, area, inc, k0, n, (int)(v - (int64_t)b * v_pad), s_nb + 2 * (int64_t)k0,
+                        s_wij + 2 * (int64_t)k0, s_wji + 2 * (int64_t)k0, [](int, int, float) {});
+  }
   rowcount[v] = cnt;
 }
 
 __global__ void __launch_bounds__(128)
 laplacian_fill_kernel(const double* __restrict__ V, const int32_t* __restrict__ F, const double* __restrict__ area,
                       int v_pad, int f_pad, int64_t n_vert, const int* __restrict__ vptr, const int* __restrict__ inc,
-                      const int* __restrict__ rowptr, int32_t* __restrict__ colind, float* __restrict__ val) {
+                      const int* __restrict__ rowptr, int32_t* __restrict__ colind, float* __restrict__ val, int* s_nb,
+                      double* s_wij, double* s_wji) {
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n_vert) return;
   const int b = (int)(v / v_pad);
   const int k0 = vptr[v], n = vptr[v + 1] - k0;
-  if (n <= 0 || n > kMaxInc) return;
+  if (n <= 0) return;
   const int r0 = rowptr[v];
   const int cbase = b * v_pad;
-  laplacian_row(V + (int64_t)b * v_pad * 3, F, area, inc, k0, n, (int)(v - (int64_t)b * v_pad),
-                [&](int i, int j, float x) {
-                  colind[r0 + i] = cbase + j;
-                  val[r0 + i] = x;
-                });
+  auto emit = [&](int i, int j, float x) {
+    colind[r0 + i] = cbase + j;
+    val[r0 + i] = x;
+  };
+  if (n <= kMaxInc) {
+    int nb[2 * kMaxInc];
+    double wij[2 * kMaxInc], wji[2 * kMaxInc];
+    laplacian_row(V + (int64_t)b * v_pad * 3, F, area, inc, k0, n, (int)(v - (int64_t)b * v_pad), nb, wij, wji, emit);
+  } else {
+    laplacian_row(V + (int64_t)b * v_pad * 3, F, area, inc, k0, n, (int)(v - (int64_t)b * v_pad), s_nb + 2 * (int64_t)k0,
+                  s_wij + 2 * (int64_t)k0, s_wji + 2 * (int64_t)k0, emit);
+  }
 }
 
 struct Workspace {
@@ -341,6 +366,9 @@ struct Workspace {
   int* fblocks;     // [n f_pad + 1]
   int* inc;         // [3 n f_pad]
   int* tiles;       // scan scratch
+  int* s_nb;        // [6 n f_pad]  Laplacian rows of vertices with more than kMaxInc incident faces (2 entries per incidence)
+  double* s_wij;    // [6 n f_pad]
+  double* s_wji;    // [6 n f_pad]
   size_t bytes;
 };
 inline size_t align_up(size_t v) { return (v + 255) / 256 * 256; }
@@ -361,6 +389,9 @@ inline Workspace carve(void* ws, int64_t n, int64_t v_pad, int64_t f_pad) {
   w.fblocks = reinterpret_cast<int*>(take(sizeof(int) * (nf + 1)));
   w.inc = reinterpret_cast<int*>(take(sizeof(int) * 3 * nf));
   w.tiles = reinterpret_cast<int*>(take(sizeof(int) * (exclusive_scan_tiles(nv > nf ? nv : nf) + 1)));
+  w.s_nb = reinterpret_cast<int*>(take(sizeof(int) * 6 * nf));
+  w.s_wij = reinterpret_cast<double*>(take(sizeof(double) * 6 * nf));
+  w.s_wji = reinterpret_cast<double*>(take(sizeof(double) * 6 * nf));
   w.bytes = off;
   return w;
 }
@@ -445,10 +476,10 @@ SN_API int sn_mesh_laplacian_csr(const double* V, const int32_t* F, int64_t n_me
   rc = front_end(V, F, n_meshes, v_pad, f_pad, status, w, nullptr, st);
   if (rc != SN_OK) return rc;
   laplacian_count_kernel<<<(unsigned)ceil_div(nv, 128), 128, 0, st>>>(V, F, w.area, (int)v_pad, (int)f_pad, nv, w.vcount,
-                                                                       w.inc, w.cursor);
+                                                                       w.inc, w.cursor, w.s_nb, w.s_wij, w.s_wji);
   rc = exclusive_scan(w.cursor, nv, rowptr, w.tiles, st);
   if (rc != SN_OK) return rc;
   laplacian_fill_kernel<<<(unsigned)ceil_div(nv, 128), 128, 0, st>>>(V, F, w.area, (int)v_pad, (int)f_pad, nv, w.vcount,
-                                                                      w.inc, rowptr, colind, val);
+                                                                      w.inc, rowptr, colind, val, w.s_nb, w.s_wij, w.s_wji);
   return launch_status();
 }

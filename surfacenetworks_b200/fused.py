@@ -123,21 +123,29 @@ def gemm_tn_supported(m, n):
     return m % 128 == 0 and n % 32 == 0
 
 
-def gemm_tn_tf32(A, B, single_pass=False):
-    """G[M, N] = A[R, M]^T @ B[R, N] (split-K tcgen05 3xTF32, deterministic); M in 128-blocks, N in <=256-blocks."""
+def gemm_tn_tf32(A, B, single_pass=False, colsum=False):
+    """G[M, N] = A[R, M]^T @ B[R, N] (split-K tcgen05 3xTF32, deterministic); M in 128-blocks, N in <=256-blocks.
+    ``colsum``: also return the column sums of A [M] from the same pass (sn_gemm_tn_colsum_tf32_f32)."""
     R, M = A.shape
     Nn = B.shape[1]
     G = torch.empty(M, Nn, dtype=torch.float32, device=A.device)
-    flags = N.SN_GEMM_SINGLE_PASS if single_pass else 0
+    cs = torch.empty(M, dtype=torch.float32, device=A.device) if colsum else None
+    flags = (N.SN_GEMM_SINGLE_PASS if single_pass else 0) | _legacy_flag()
+    if colsum and _legacy_flag():
+        cs = colstats(A)[0] * R
     with torch.cuda.device(A.device):
         for m0 in range(0, M, 128):
             for n0 in range(0, Nn, 256):
                 n = min(256, Nn - n0)
                 nb = N.lib.sn_gemm_tn_tf32_ws_bytes(R, n)
                 ws = _ws(nb, A.device)
-                N.call("sn_gemm_tn_tf32_f32", A[:, m0:].data_ptr(), A.stride(0), B[:, n0:].data_ptr(), B.stride(0),
-                       G[m0:, n0:].data_ptr(), G.stride(0), R, 128, n, flags, _ptr(ws), nb, _stream())
-    return G
+                if colsum and n0 == 0 and not _legacy_flag():
+                    N.call("sn_gemm_tn_colsum_tf32_f32", A[:, m0:].data_ptr(), A.stride(0), B[:, n0:].data_ptr(), B.stride(0),
+                           G[m0:, n0:].data_ptr(), G.stride(0), cs[m0:].data_ptr(), R, 128, n, flags, _ptr(ws), nb, _stream())
+                else:
+                    N.call("sn_gemm_tn_tf32_f32", A[:, m0:].data_ptr(), A.stride(0), B[:, n0:].data_ptr(), B.stride(0),
+                           G[m0:, n0:].data_ptr(), G.stride(0), R, 128, n, flags, _ptr(ws), nb, _stream())
+    return (G, cs) if colsum else G
 
 
 def bn_linear_forward(Z, gamma, beta, W, b, residual, running_mean, running_var, training, momentum, eps, left_stats):
@@ -184,8 +192,9 @@ def bn_linear_backward(saved, dY, training, elu_bwd_left=False):
     Nn = W.shape[0]
     dev = Z.device
     if gemm_tn_supported(Nn, K):
-        G = gemm_tn_tf32(dY, Z)                 # [C, 2C] = dY^T Z: split-K tcgen05 (MN-major operands)
-        sdY = colstats(dY)[0] * rows            # colsum(dY) from the same deterministic statistics kernel
+        # [C, 2C] = dY^T Z: split-K tcgen05; colsum(dY) falls out of the same pass (dY crosses the registers of the warps
+        # that feed it to tensor memory)
+        G, sdY = gemm_tn_tf32(dY, Z, colsum=True)
     else:
         G = torch.mm(dY.t(), Z)
         sdY = dY.sum(0)

@@ -405,12 +405,6 @@ def _mesh_ws(n, v_pad, f_pad, dev):
     return torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev), nbytes
 
 
-def _check_mesh_status(status):
-    worst = int(status.item())
-    if worst:
-        raise ValueError("a vertex belongs to %d faces; GPU operator construction supports at most 64" % worst)
-
-
 def build_dirac_operators(V, F, with_transposes=True, sync=True, buffers=None):
     """Batch Dirac operator ``D`` [B*f_pad x B*v_pad] and adjoint ``D*`` [B*v_pad x B*f_pad] (block rows x block
     columns) built on the GPU from padded positions ``V`` [B, v_pad, 3] and faces ``F`` [B, f_pad, 3] (local vertex
@@ -452,7 +446,6 @@ def build_dirac_operators(V, F, with_transposes=True, sync=True, buffers=None):
                _ptr(a_ptr), _ptr(a_ind), _ptr(a_val), _ptr(dt_ind), _ptr(dt_val), _ptr(at_ind), _ptr(at_val),
                _ptr(status), _ptr(ws), nbytes, _stream())
     if sync:
-        _check_mesh_status(status)
         nb = int(d_ptr[-1].item())                   # one read-back per construction, like from_source
         max_a = int((a_ptr[1:] - a_ptr[:-1]).max().item()) if n * v_pad else 0
     else:
@@ -468,7 +461,8 @@ def build_dirac_operators(V, F, with_transposes=True, sync=True, buffers=None):
         D._T = Bsr4Operator(a_ptr, dt_ind[:keep], dt_val[:16 * keep], n * v_pad, n * f_pad, None, nb, max_a)
         DA._T = Bsr4Operator(d_ptr, at_ind[:keep], at_val[:16 * keep], n * f_pad, n * v_pad, None, nb, 3 if nb else 0)
         D._T._T, DA._T._T = D, DA
-    D.status = DA.status = status                    # device int32: 0, or the largest per-vertex face count (> 64)
+    D.status = DA.status = status                    # device int32: 0, or the largest per-vertex face count when some
+    #                                                  vertex exceeds 64 faces (informational: any valence is supported)
     return D, DA
 
 
@@ -487,7 +481,6 @@ def build_laplacian_operator(V, F):
     with torch.cuda.device(dev):
         N.call("sn_mesh_laplacian_csr", _ptr(V), _ptr(F), n, v_pad, f_pad, _ptr(rowptr), _ptr(colind), _ptr(val),
                _ptr(status), _ptr(ws), nbytes, _stream())
-    _check_mesh_status(status)
     nnz = int(rowptr[-1].item())
     return CsrOperator(rowptr, colind[:max(nnz, 1)], val[:max(nnz, 1)], n * v_pad, n * v_pad,
                        _StructureSource("csr", rowptr, colind, val, n * v_pad, n * v_pad, nnz), nnz)

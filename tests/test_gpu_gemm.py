@@ -287,6 +287,61 @@ def test_gemm_tn_matches_fp64(R, N):
     assert torch.all((G1.double() - G64).abs() <= 2e-3 * mag)
 
 
+@pytest.mark.parametrize("R,N", [(32, 256), (5, 32), (1000, 256), (4133, 128), (128000, 256), (255168, 128)])
+def test_gemm_tn_colsum_and_legacy_kernel(R, N):
+    """sn_gemm_tn_colsum_tf32_f32: same G bits as sn_gemm_tn_tf32_f32, column sums of A within the fp32 summation bound
+    of the fp64 sums, deterministic; the TS kernel (dY through tensor memory) agrees with the round-1 kernel."""
+    from surfacenetworks_b200 import _native as Nt
+    g = torch.Generator(device=DEV).manual_seed(7 * R + N)
+    A = torch.randn(R, 128, device=DEV, generator=g) + 0.25
+    B = torch.randn(R, N, device=DEV, generator=g)
+    G0 = run_gemm_tn(A, B)
+    wsb = Nt.lib.sn_gemm_tn_tf32_ws_bytes(R, N)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def with_colsum():
+        G, cs = torch.empty(128, N, device=DEV), torch.empty(128, device=DEV)
+        Nt.call("sn_gemm_tn_colsum_tf32_f32", A.data_ptr(), 128, B.data_ptr(), N, G.data_ptr(), N, cs.data_ptr(), R, 128, N, 0,
+                ws.data_ptr(), wsb, st)
+        return G, cs
+
+    G1, cs1 = with_colsum()
+    G2, cs2 = with_colsum()
+    assert torch.equal(G0, G1) and torch.equal(G1, G2) and torch.equal(cs1, cs2)
+    cs64 = A.double().sum(0)
+    mag = A.double().abs().sum(0)
+    # sequential fp32 summation of <= ceil(R / 148) rows per CTA, then <= 148 partials: error <= (n + 148) eps |A| / 2
+    n_seq = (R + 147) // 148 + 32 + 148
+    assert torch.all((cs1.double() - cs64).abs() <= n_seq * 6e-8 * mag + 1e-30), float(((cs1.double() - cs64).abs() / mag).max())
+    Gl = torch.empty(128, N, device=DEV)
+    Nt.call("sn_gemm_tn_tf32_f32", A.data_ptr(), 128, B.data_ptr(), N, Gl.data_ptr(), N, R, 128, N, Nt.SN_GEMM_LEGACY_SS,
+            ws.data_ptr(), wsb, st)
+    G64 = A.double().t() @ B.double()
+    magG = A.double().abs().t() @ B.double().abs()
+    assert torch.all((Gl.double() - G64).abs() <= 2e-6 * magG)
+    assert torch.all((G0.double() - Gl.double()).abs() <= 4e-6 * magG)
+
+
+def test_tf32_operand_truncation_probe():
+    """Records how the tensor core reads an fp32 container as tf32 (printed, not asserted): single-pass product with
+    raw operands vs operands with the low 13 mantissa bits cleared."""
+    from surfacenetworks_b200 import _native as Nt
+    g = torch.Generator(device=DEV).manual_seed(11)
+    M, N, K = 1024, 128, 128
+    A = torch.randn(M, K, device=DEV, generator=g)
+    B = torch.randn(N, K, device=DEV, generator=g)
+    trunc = lambda t: (t.view(torch.int32) & ~0x1fff).view(torch.float32)
+    outs = []
+    for a, b in ((A, B), (trunc(A), trunc(B))):
+        C = torch.empty(M, N, device=DEV)
+        Nt.call("sn_gemm_tf32_f32", a.data_ptr(), K, b.data_ptr(), K, 0, 0, 0, 0, 0, 0, C.data_ptr(), N, M, N, K,
+                Nt.SN_GEMM_SINGLE_PASS | Nt.SN_GEMM_LEGACY_SS, 0, 0, torch.cuda.current_stream().cuda_stream)
+        outs.append(C)
+    print("tf32 operand read == truncation:", bool(torch.equal(outs[0], outs[1])),
+          "max diff", float((outs[0] - outs[1]).abs().max()))
+
+
 @pytest.mark.parametrize("M,N,K", [(1000, 256, 128), (777, 64, 32), (4096, 128, 64)])
 def test_gemm_elu_bwd_left_epilogue(M, N, K):
     """SN_GEMM_ELU_BWD_LEFT: columns [0, N/2) of dZ = dY Ws + p.*Z + q leave the epilogue multiplied by elu'(Z) (Z holds

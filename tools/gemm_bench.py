@@ -23,6 +23,15 @@ def main():
             for _ in range(3):
                 N.call("sn_gemm_tf32_presplit_f32", A.data_ptr(), K, hi.data_ptr(), lo.data_ptr(), K, bias.data_ptr(),
                        R.data_ptr(), Nn, 0, 0, 0, C.data_ptr(), Nn, M, Nn, K, 0, st)
+        for R, Nn in ((255168, 256), (128000, 256)):
+            A = torch.randn(R, 128, device=dev)
+            B = torch.randn(R, Nn, device=dev)
+            G, cs = torch.empty(128, Nn, device=dev), torch.empty(128, device=dev)
+            nb = N.lib.sn_gemm_tn_tf32_ws_bytes(R, Nn)
+            WS = torch.empty(max(nb, 1), dtype=torch.uint8, device=dev)
+            for _ in range(3):
+                N.call("sn_gemm_tn_colsum_tf32_f32", A.data_ptr(), 128, B.data_ptr(), Nn, G.data_ptr(), Nn, cs.data_ptr(), R, 128,
+                       Nn, 0, WS.data_ptr(), nb, st)
         torch.cuda.synchronize()
         return
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -93,8 +102,16 @@ def main():
             N.call("sn_gemm_tn_tf32_f32", A.data_ptr(), 128, B.data_ptr(), Nn, G.data_ptr(), Nn, R, 128, Nn, flags,
                    WS.data_ptr(), nb, st)
 
-        out = {"op": "gemm_tn", "R": R, "M": 128, "N": Nn, "alg_MB": 4.0 * R * (128 + Nn) / 1e6}
-        for name, fn in (("sn_3xtf32", lambda: tn(0)), ("sn_3xtf32_nopf", lambda: tn(N.SN_GEMM_NO_L2_PREFETCH)),
+        cs = torch.empty(128, device=dev)
+
+        def tn_cs():
+            N.call("sn_gemm_tn_colsum_tf32_f32", A.data_ptr(), 128, B.data_ptr(), Nn, G.data_ptr(), Nn, cs.data_ptr(), R, 128, Nn, 0,
+                   WS.data_ptr(), nb, st)
+
+        out = {"op": "gemm_tn", "R": R, "M": 128, "N": Nn, "alg_MB": 4.0 * R * (128 + Nn) / 1e6,
+               "hbm_floor_us": 4.0 * R * (128 + Nn) / 6551e3}
+        for name, fn in (("sn_3xtf32", lambda: tn(0)), ("sn_3xtf32_colsum", tn_cs), ("legacy_ss_3xtf32", lambda: tn(N.SN_GEMM_LEGACY_SS)),
+                         ("sn_3xtf32_nopf", lambda: tn(N.SN_GEMM_NO_L2_PREFETCH)),
                          ("sn_tf32", lambda: tn(N.SN_GEMM_SINGLE_PASS)), ("torch_fp32", lambda: torch.mm(A.t(), B, out=G))):
             ms = time_it(fn)
             out[name] = {"us": ms * 1e3, "GBps": out["alg_MB"] / ms / 1e3}
