@@ -110,7 +110,8 @@ int sn_assemble_block_diag(const int64_t* parts, int64_t n_parts, int64_t rows_p
  *
  * A batch of n_meshes triangle meshes, every mesh padded to v_pad vertices and f_pad faces:
  *   V [n_meshes, v_pad, 3] fp64 positions;  F [n_meshes, f_pad, 3] int32 LOCAL vertex indices, a face with a negative
- *   (or >= v_pad) index is padding.  A vertex may belong to at most 64 faces (status reports the violation).
+ *   (or >= v_pad) index is padding.  A vertex may belong to any number of faces (the reference is dense O(V^2) numpy and
+ *   has no limit either); vertices in more than 64 faces are processed over global scratch instead of registers.
  * Outputs are the block-diagonal batch operators in the formats of the SpMM entry points, values computed in fp64 with
  * the reference's operation order and rounded to fp32 once (the reference's .astype('float32')):
  *   sn_mesh_dirac_bsr4   : D  [n*f_pad x n*v_pad] block rows/cols: d_browptr [n*f_pad + 1], d_bcolind [<= 3 n f_pad],
@@ -119,8 +120,9 @@ int sn_assemble_block_diag(const int64_t* parts, int64_t n_parts, int64_t rows_p
  *                          (non-NULL pairs) the transposes used by backward: D^T = (da_browptr, dt_bcolind, dt_bval)
  *                          shares D*'s structure, (D*)^T = (d_browptr, dat_bcolind, dat_bval) shares D's.
  *   sn_mesh_laplacian_csr: L  [n*v_pad x n*v_pad]: rowptr [n*v_pad + 1], colind / val [<= n (v_pad + 6 f_pad)].
- * status: one device int32, 0 on success, otherwise the largest per-vertex face count found (> 64): the rows of such
- * vertices are left empty.  Deterministic (no floating-point atomics).  ws: sn_mesh_ws_bytes(n_meshes, v_pad, f_pad).
+ * status: one device int32, informational: 0, or the largest per-vertex face count when some vertex exceeds 64 faces
+ * (its rows are complete and exact like every other row).  Deterministic (no floating-point atomics).
+ * ws: sn_mesh_ws_bytes(n_meshes, v_pad, f_pad).
  * ---------------------------------------------------------------------------------------------- */
 size_t sn_mesh_ws_bytes(int64_t n_meshes, int64_t v_pad, int64_t f_pad);
 int sn_mesh_dirac_bsr4(const double* V, const int32_t* F, int64_t n_meshes, int64_t v_pad, int64_t f_pad,

@@ -44,7 +44,7 @@ bn_fold_fwd_kernel(const float* __restrict__ mean, const float* __restrict__ var
     if (Wf_hi) {                         // the 3xTF32 GEMM's pre-split B operand (sn_gemm_tf32_presplit_f32)
       const float h = tf32_round(ws);
       Wf_hi[(size_t)n * K + k] = h;
-      Wf_lo[(size_t)n * K + k] = ws - h;
+      Wf_lo[(size_t)n * K + k] = tf32_round(ws - h);
     }
     acc = fmaf(w, t, acc);
     if (publish) {
@@ -85,7 +85,7 @@ bn_fold_bwd_kernel(const float* __restrict__ G, const float* __restrict__ sdY, c
       if (WsT_hi) {
         const float h = tf32_round(ws);
         WsT_hi[(size_t)k * N + n] = h;
-        WsT_lo[(size_t)k * N + n] = ws - h;
+        WsT_lo[(size_t)k * N + n] = tf32_round(ws - h);
       }
     }
   }

@@ -440,11 +440,16 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   __shared__ uint64_t b_full[kMaxBStages], b_free[kMaxBStages], tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float epi_buf[kEpiWarps * 32 * 20];
+  __shared__ __align__(16) float s_bias[256], s_rscale[256];   // epilogue vectors: LDS instead of an L1-missing __ldg per chunk
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.M + kBlockM - 1) / kBlockM;
   const int n_kb = p.K / kBlockK;
   const int n_halves = p.n_halves;
+  if (threadIdx.x < p.N) {
+    s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
+    s_rscale[threadIdx.x] = p.rscale ? p.rscale[threadIdx.x] : 1.f;
+  }
   const int n_a_pass = p.a_resident ? 1 : n_halves;          // times the A tile is streamed per row tile
 
   if (threadIdx.x == 0) {
@@ -571,8 +576,10 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const float h0 = to_tf32(x.x), h1 = to_tf32(x.y), h2 = to_tf32(x.z), h3 = to_tf32(x.w);
             hi[4 * i] = __float_as_uint(h0); hi[4 * i + 1] = __float_as_uint(h1);
             hi[4 * i + 2] = __float_as_uint(h2); hi[4 * i + 3] = __float_as_uint(h3);
-            lo[4 * i] = __float_as_uint(x.x - h0); lo[4 * i + 1] = __float_as_uint(x.y - h1);
-            lo[4 * i + 2] = __float_as_uint(x.z - h2); lo[4 * i + 3] = __float_as_uint(x.w - h3);
+            // lo is rounded to tf32 too: the tensor core TRUNCATES the low 13 mantissa bits of its operands (measured,
+            // tests/test_gpu_gemm.py::test_tf32_operand_truncation_probe), rounding here halves that error
+            lo[4 * i] = __float_as_uint(to_tf32(x.x - h0)); lo[4 * i + 1] = __float_as_uint(to_tf32(x.y - h1));
+            lo[4 * i + 2] = __float_as_uint(to_tf32(x.z - h2)); lo[4 * i + 3] = __float_as_uint(to_tf32(x.w - h3));
           }
           __syncwarp();                                        // every lane has consumed its shared-memory row
           if (lane == 0) mbar_arrive(a_free + as);             // the TMA producer may refill this slot
@@ -605,41 +612,56 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (row < p.M) rr[i] = __ldcs(reinterpret_cast<const float4*>(p.R + (int64_t)row * p.ldr + c0 + tc));
       }
     };
+    // The residual operand R does not depend on the accumulator: its loads run TWO 16-column chunks ahead of the chunk
+    // being finished, across job and tile boundaries (a flat chunk sequence), so their DRAM latency never sits between a
+    // completed accumulator and its stores.  (Round-2 first version restarted the prefetch at every tile: ncu showed the
+    // epilogue warps on a long-scoreboard stall at each tile start while the MMA warp waited for a free accumulator.)
+    const int nchunks = ncol / 16;
+    struct ChunkIt { int tile, half, c; };
+    auto advance = [&](ChunkIt& it) {
+      if (++it.c == nchunks) {
+        it.c = 0;
+        if (++it.half == n_halves) { it.half = 0; it.tile += (int)gridDim.x; }
+      }
+    };
+    auto load_chunk = [&](float4 (&rr)[4], const ChunkIt& it) {
+      if (it.tile < n_tiles) load_r(rr, it.tile * kBlockM + quarter * 32, it.half * nmma + chalf * ncol + it.c * 16);
+    };
+    float4 rr[4], rn[4], rn2[4];
+    ChunkIt pf = {(int)blockIdx.x, 0, 0};
+    if (p.R) {
+      load_chunk(rr, pf); advance(pf);
+      load_chunk(rn, pf); advance(pf);
+    }
     uint32_t job = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int half = 0; half < n_halves; ++half, ++job) {
         const uint32_t buf = job & 1u;
         const int row0 = tile * kBlockM + quarter * 32;
         const int cbase = half * nmma + chalf * ncol;          // first global column of this warp's share
-        float4 rr[4], rn[4], rn2[4];
-        if (p.R) {                                             // prefetch before waiting for the accumulator
-          load_r(rr, row0, cbase);
-          load_r(rn, row0, cbase + 16);
-          if (p.l2_prefetch) {                                 // ... and the next job's residual rows into L2
-            const bool next_half = half + 1 < n_halves;
-            const int nrow0 = (next_half ? tile : tile + (int)gridDim.x) * kBlockM + quarter * 32;
-            const int ncb = (next_half ? (half + 1) * nmma : 0) + chalf * ncol;
-            const int lines = ncol / 32;
-            for (int i = lane; i < 32 * lines; i += 32) {
-              const int row = nrow0 + i / lines;
-              if (row < p.M) prefetch_l2(p.R + (int64_t)row * p.ldr + ncb + (i % lines) * 32);
-            }
+        if (p.R && p.l2_prefetch) {                            // the next job's residual rows into L2
+          const bool next_half = half + 1 < n_halves;
+          const int nrow0 = (next_half ? tile : tile + (int)gridDim.x) * kBlockM + quarter * 32;
+          const int ncb = (next_half ? (half + 1) * nmma : 0) + chalf * ncol;
+          const int lines = ncol / 32;
+          for (int i = lane; i < 32 * lines; i += 32) {
+            const int row = nrow0 + i / lines;
+            if (row < p.M) prefetch_l2(p.R + (int64_t)row * p.ldr + ncb + (i % lines) * 32);
           }
         }
         mbar_wait(tmem_full + buf, (job >> 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int c0 = cbase; c0 < cbase + ncol; c0 += 16) {
           uint32_t v[16];
-          float4 bia = make_float4(0.f, 0.f, 0.f, 0.f), rs = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (p.bias) bia = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + tc));      // latency hidden behind the TMEM load
-          if (p.rscale) rs = __ldg(reinterpret_cast<const float4*>(p.rscale + c0 + tc));
+          if (p.R) { load_chunk(rn2, pf); advance(pf); }       // residual two chunks ahead
           tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * nmma + (c0 - half * nmma)), v);
-          if (p.R && c0 + 32 < cbase + ncol) load_r(rn2, row0, c0 + 32);   // residual two chunks ahead
 #pragma unroll
           for (int j = 0; j < 16; j += 4)
             *reinterpret_cast<float4*>(tbuf + lane * 20 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
                                                                             __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
           __syncwarp();
+          const float4 bia = *reinterpret_cast<const float4*>(s_bias + c0 + tc);
+          const float4 rs = *reinterpret_cast<const float4*>(s_rscale + c0 + tc);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int rl = i * 8 + tr;
@@ -688,7 +710,7 @@ __global__ void split_weights_kernel(const float* __restrict__ B, int64_t ldb, f
   const float x = B[(int64_t)n * ldb + k];
   const float h = to_tf32(x);
   hi[i] = h;
-  lo[i] = x - h;
+  lo[i] = to_tf32(x - h);     // rounded: the tensor core truncates its operands
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -787,7 +809,7 @@ static int launch_gemm(const float* A, int64_t lda, const float* B_hi, const flo
   }
   // shared memory: B ring of 3 stages (hi | lo; the weights come from L2), the rest goes to the A ring (HBM latency)
   const size_t a_bytes = (size_t)kBlockM * kBlockK * 4, b_stage = 2 * (size_t)p.nmma * kBlockK * 4;
-  const size_t budget = (size_t)smem_optin - 22 * 1024 - 1024;   // static: transpose buffers + barriers; 1 KB alignment
+  const size_t budget = (size_t)smem_optin - 24 * 1024 - 1024;   // static: transpose buffers, epilogue vectors, barriers; 1 KB alignment
   p.b_stages = 3;
   int a_stages = (int)((budget - p.b_stages * b_stage) / a_bytes);
   if (a_stages > kMaxAStages) a_stages = kMaxAStages;

@@ -256,8 +256,11 @@ gemm_tn_ss_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 // Z (the B operand, MN-major) is still split in shared memory by eight warps.
 constexpr int kATmemStages = 4;
 constexpr int kATmemCol0 = 256;
-constexpr int kAStages = 4;            // shared-memory dY ring (16 KB stages)
-constexpr int kMaxBStages = 4;
+constexpr int kMaxAStages = 4;         // shared-memory dY ring (16 KB stages)
+constexpr int kMaxRawStages = 6;
+constexpr int kMaxLoStages = 4;
+
+__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -302,14 +305,20 @@ struct ParamsTS {
   int R, N;
   int kb_per_cta;
   int n_kb;
-  int b_stages;
+  int raw_stages;        // Z tiles as TMA lands them (= the hi operand: the tensor core truncates fp32 to tf32)
+  int lo_stages;         // Z lo tiles written by the split warps
+  int a_stages;          // dY tiles
   int split;
-  int l2_prefetch;
 };
 
-// Roles: warp 0 = dY producer (TMA), warp 3 = Z producer (TMA + L2 prefetch), warp 1 = MMA issuer, warp 2 = TMEM
-// allocation, warps 4-7 = dY: shared memory -> column sums, hi / lo -> tensor memory; then the epilogue,
-// warps 8-15 = Z: hi / lo split in shared memory.
+// Z (the B operand) needs no hi copy: tcgen05 reads an fp32 container as tf32 by TRUNCATING the low 13 mantissa bits
+// (measured: tests/test_gpu_gemm.py::test_tf32_operand_truncation_probe), so the TMA-landed tile IS the hi operand and
+// the split warps only write lo = tf32(x - trunc(x)) into a second ring.  The raw ring (3 stages) is deeper than the lo
+// ring (2): TMA runs ahead of the split, which the in-place hi/lo scheme of the first TS version could not (ncu: the
+// split warps sat on the `full` barrier of a two-stage ring).
+//
+// Roles: warp 0 = dY producer (TMA), warp 3 = Z producer (TMA), warp 1 = MMA issuer, warp 2 = TMEM allocation,
+// warps 4-7 = dY: shared memory -> column sums, hi / lo -> tensor memory; then the epilogue, warps 8-15 = Z lo tiles.
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tn_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const ParamsTS p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -317,11 +326,12 @@ gemm_tn_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const int N = p.N;
   const int b_boxes = N / 32;
   constexpr uint32_t a_bytes = kBlockK * kM * 4;               // 16 KB: [32 rows][128 columns], no swizzle
-  const uint32_t b_bytes = (uint32_t)b_boxes * kBoxBytes;      // hi (in place) or lo twin
-  unsigned char* b_ring = smem;                                // 1024-byte aligned boxes first
-  unsigned char* a_ring = smem + (size_t)p.b_stages * 2 * b_bytes;
-  __shared__ uint64_t a_full[kAStages], a_free[kAStages], a_ready[kATmemStages], a_tfree[kATmemStages];
-  __shared__ uint64_t b_full[kMaxBStages], b_ready[kMaxBStages], b_free[kMaxBStages], done_bar;
+  const uint32_t b_bytes = (uint32_t)b_boxes * kBoxBytes;
+  unsigned char* raw_ring = smem;                              // 1024-byte aligned boxes first
+  unsigned char* lo_ring = raw_ring + (size_t)p.raw_stages * b_bytes;
+  unsigned char* a_ring = lo_ring + (size_t)p.lo_stages * b_bytes;
+  __shared__ uint64_t a_full[kMaxAStages], a_free[kMaxAStages], a_ready[kATmemStages], a_tfree[kATmemStages];
+  __shared__ uint64_t raw_full[kMaxRawStages], raw_free[kMaxRawStages], lo_ready[kMaxLoStages], lo_free[kMaxLoStages], done_bar;
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -330,7 +340,7 @@ gemm_tn_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const int my_kb = max(kb1 - kb0, 0);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kAStages; ++s) {
+    for (int s = 0; s < p.a_stages; ++s) {
       mbar_init(a_full + s, 1);
       mbar_init(a_free + s, 4);
     }
@@ -338,10 +348,13 @@ gemm_tn_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       mbar_init(a_ready + s, 4);
       mbar_init(a_tfree + s, 1);
     }
-    for (int s = 0; s < p.b_stages; ++s) {
-      mbar_init(b_full + s, 1);
-      mbar_init(b_ready + s, 8);
-      mbar_init(b_free + s, 1);
+    for (int s = 0; s < p.raw_stages; ++s) {
+      mbar_init(raw_full + s, 1);
+      mbar_init(raw_free + s, 1);
+    }
+    for (int s = 0; s < p.lo_stages; ++s) {
+      mbar_init(lo_ready + s, 8);
+      mbar_init(lo_free + s, 1);
     }
     mbar_init(&done_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -363,8 +376,7 @@ gemm_tn_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         mbar_wait(a_free + stage, phase ^ 1u);
         mbar_arrive_expect_tx(a_full + stage, a_bytes);
         tma_load_2d(a_ring + (size_t)stage * a_bytes, &map_a, 0, kb * kBlockK, a_full + stage);
-        if (p.l2_prefetch && kb + 2 * kPrefetchDist < kb1) tma_prefetch_l2_2d(&map_a, 0, (kb + 2 * kPrefetchDist) * kBlockK);
-        if (++stage == kAStages) { stage = 0; phase ^= 1u; }
+        if (++stage == p.a_stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 3) {
@@ -372,47 +384,47 @@ gemm_tn_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(b_free + stage, phase ^ 1u);
-        unsigned char* sb = b_ring + (size_t)stage * 2 * b_bytes;
-        mbar_arrive_expect_tx(b_full + stage, b_bytes);
-        for (int i = 0; i < b_boxes; ++i) tma_load_2d(sb + i * kBoxBytes, &map_b, i * 32, kb * kBlockK, b_full + stage);
-        // the Z ring is shallow (the hi / lo twins fill shared memory): pull the boxes this CTA loads kPrefetchDist
-        // iterations from now into L2
-        if (p.l2_prefetch && kb + kPrefetchDist < kb1)
-          for (int i = 0; i < b_boxes; ++i) tma_prefetch_l2_2d(&map_b, i * 32, (kb + kPrefetchDist) * kBlockK);
-        if (++stage == p.b_stages) { stage = 0; phase ^= 1u; }
+        mbar_wait(raw_free + stage, phase ^ 1u);
+        unsigned char* sb = raw_ring + (size_t)stage * b_bytes;
+        mbar_arrive_expect_tx(raw_full + stage, b_bytes);
+        for (int i = 0; i < b_boxes; ++i) tma_load_2d(sb + i * kBoxBytes, &map_b, i * 32, kb * kBlockK, raw_full + stage);
+        if (++stage == p.raw_stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
       // D = F32, A = B = TF32, A K-major (tensor memory), B MN-major (bit 16), N >> 3 at bit 17, M >> 4 at bit 24
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
-      const uint64_t d0 = umma_desc_mn_sw128(smem_u32(b_ring));
-      const uint32_t d_lo0 = (uint32_t)d0, d_hi = (uint32_t)(d0 >> 32);
-      const uint32_t stage_units = (2u * b_bytes) >> 4, lo_units = b_bytes >> 4;
+      const uint64_t d0 = umma_desc_mn_sw128(smem_u32(raw_ring));
+      const uint32_t d_raw0 = (uint32_t)d0, d_hi = (uint32_t)(d0 >> 32);
+      const uint32_t d_lo0 = (uint32_t)umma_desc_mn_sw128(smem_u32(lo_ring));
+      const uint32_t stage_units = b_bytes >> 4;
       const uint32_t split = (uint32_t)p.split;
-      int bs = 0;
-      uint32_t bph = 0;
+      int rs = 0, ls = 0;
+      uint32_t rph = 0, lph = 0;
       for (int kb = 0; kb < my_kb; ++kb) {
         const uint32_t at = (uint32_t)kb % kATmemStages;
         mbar_wait(a_ready + at, ((uint32_t)kb / kATmemStages) & 1u);
-        mbar_wait(b_ready + bs, bph);
+        mbar_wait(raw_full + rs, rph);
+        if (split) mbar_wait(lo_ready + ls, lph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t ta = tmem_base + (uint32_t)(kATmemCol0 + at * 64);
-        const uint32_t dlo = d_lo0 + (uint32_t)bs * stage_units;
+        const uint32_t dh = d_raw0 + (uint32_t)rs * stage_units, dl = d_lo0 + (uint32_t)ls * stage_units;
 #pragma unroll
         for (int k = 0; k < kBlockK / kUmmaK; ++k) {
           // 8 K rows = one 1 KB group inside every box = 64 descriptor units
-          umma_tf32_ts_lohi(tmem_base, ta + k * kUmmaK, dlo + 64 * k, d_hi, idesc, (uint32_t)((kb | k) != 0));
+          umma_tf32_ts_lohi(tmem_base, ta + k * kUmmaK, dh + 64 * k, d_hi, idesc, (uint32_t)((kb | k) != 0));   // hi * hi
           if (split) {
-            umma_tf32_ts_lohi(tmem_base, ta + k * kUmmaK, dlo + lo_units + 64 * k, d_hi, idesc, 1u);    // hi * lo
-            umma_tf32_ts_lohi(tmem_base, ta + 32 + k * kUmmaK, dlo + 64 * k, d_hi, idesc, 1u);          // lo * hi
+            umma_tf32_ts_lohi(tmem_base, ta + k * kUmmaK, dl + 64 * k, d_hi, idesc, 1u);                          // hi * lo
+            umma_tf32_ts_lohi(tmem_base, ta + 32 + k * kUmmaK, dh + 64 * k, d_hi, idesc, 1u);                     // lo * hi
           }
         }
-        umma_commit(b_free + bs);
+        umma_commit(raw_free + rs);
+        if (split) umma_commit(lo_free + ls);
         umma_commit(a_tfree + at);
         if (kb == my_kb - 1) umma_commit(&done_bar);
-        if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
+        if (++rs == p.raw_stages) { rs = 0; rph ^= 1u; }
+        if (++ls == p.lo_stages) { ls = 0; lph ^= 1u; }
       }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -433,7 +445,7 @@ gemm_tn_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         csum += x;                                             // rows past R are zero-filled by TMA
         const float h = to_tf32(x);
         hi[k] = __float_as_uint(h);
-        lo[k] = __float_as_uint(x - h);
+        lo[k] = __float_as_uint(to_tf32(x - h));
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(a_free + as);
@@ -447,7 +459,7 @@ gemm_tn_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready + at);
-      if (++as == kAStages) { as = 0; aph ^= 1u; }
+      if (++as == p.a_stages) { as = 0; aph ^= 1u; }
     }
     // ------------------------------------------------------------------ epilogue: this CTA's partial [128 x N] -> workspace
     p.csum_partial[(size_t)blockIdx.x * kM + m] = csum;
@@ -466,35 +478,36 @@ gemm_tn_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     } else {
       for (int c0 = 0; c0 < N; c0 += 4) *reinterpret_cast<float4*>(out + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-  } else if (warp >= 8) {
-    // ------------------------------------------------------------------ Z: hi in place, lo into the twin (elementwise)
+  } else if (warp >= 8 && p.split) {
+    // ------------------------------------------------------------------ Z: lo = tf32(x - trunc(x)) into the lo ring
     const int t = threadIdx.x - 256;                           // 0..255
-    const uint32_t b_ring_s = smem_u32(b_ring);
+    const uint32_t raw_s = smem_u32(raw_ring), lo_s = smem_u32(lo_ring);
     const int n_f4 = (int)(b_bytes / 16);
-    int bs = 0;
-    uint32_t bph = 0;
+    int rs = 0, ls = 0;
+    uint32_t rph = 0, lph = 0;
     for (int kb = 0; kb < my_kb; ++kb) {
-      mbar_wait(b_full + bs, bph);
-      const uint32_t sb = b_ring_s + (uint32_t)bs * 2u * b_bytes;
+      mbar_wait(raw_full + rs, rph);
+      mbar_wait(lo_free + ls, lph ^ 1u);
+      const uint32_t src = raw_s + (uint32_t)rs * b_bytes, dst = lo_s + (uint32_t)ls * b_bytes;
       for (int i0 = t; i0 < n_f4; i0 += 4 * 256) {             // four independent 16-byte loads in flight per thread
         float4 x[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-          if (i0 + u * 256 < n_f4) x[u] = lds_f4(sb + (uint32_t)(i0 + u * 256) * 16u);
+          if (i0 + u * 256 < n_f4) x[u] = lds_f4(src + (uint32_t)(i0 + u * 256) * 16u);
 #pragma unroll
         for (int u = 0; u < 4; ++u)
           if (i0 + u * 256 < n_f4) {
-            const uint32_t a = sb + (uint32_t)(i0 + u * 256) * 16u;
-            float4 h;
-            h.x = to_tf32(x[u].x); h.y = to_tf32(x[u].y); h.z = to_tf32(x[u].z); h.w = to_tf32(x[u].w);
-            sts_f4(a, h);
-            if (p.split) sts_f4(a + b_bytes, make_float4(x[u].x - h.x, x[u].y - h.y, x[u].z - h.z, x[u].w - h.w));
+            float4 l;
+            l.x = to_tf32(x[u].x - trunc_tf32(x[u].x)); l.y = to_tf32(x[u].y - trunc_tf32(x[u].y));
+            l.z = to_tf32(x[u].z - trunc_tf32(x[u].z)); l.w = to_tf32(x[u].w - trunc_tf32(x[u].w));
+            sts_f4(dst + (uint32_t)(i0 + u * 256) * 16u, l);
           }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
       __syncwarp();
-      if (lane == 0) mbar_arrive(b_ready + bs);
-      if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
+      if (lane == 0) mbar_arrive(lo_ready + ls);
+      if (++rs == p.raw_stages) { rs = 0; rph ^= 1u; }
+      if (++ls == p.lo_stages) { ls = 0; lph ^= 1u; }
     }
   }
 
@@ -632,16 +645,21 @@ static int launch_tn(const float* A, int64_t lda, const float* B, int64_t ldb, f
   p.csum_partial = csum_partial;
   p.R = (int)R; p.N = (int)N;
   p.n_kb = n_kb; p.kb_per_cta = kb_per_cta;
-  p.split = split; p.l2_prefetch = l2_prefetch;
+  p.split = split;
   int dev = 0, smem_optin = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  const size_t a_ring = (size_t)kAStages * kBlockK * kM * 4, b_stage = 2 * (size_t)(N / 32) * kBoxBytes;
-  int b_stages = (int)(((size_t)smem_optin - 2048 - 1024 - a_ring) / b_stage);
-  if (b_stages > kMaxBStages) b_stages = kMaxBStages;
-  if (b_stages < 2) return SN_ERR_UNSUPPORTED;
-  p.b_stages = b_stages;
-  const size_t smem = a_ring + b_stages * b_stage + 1024;
+  // shared memory: lo ring 2 stages, dY ring 3 stages, the rest (up to 6 stages) to the raw Z ring that TMA fills
+  const size_t a_stage = (size_t)kBlockK * kM * 4, b_stage = (size_t)(N / 32) * kBoxBytes;
+  p.lo_stages = 2;
+  p.a_stages = 3;
+  const size_t budget = (size_t)smem_optin - 2048 - 1024;
+  int raw_stages = (int)((budget - p.lo_stages * b_stage - p.a_stages * a_stage) / b_stage);
+  if (raw_stages > kMaxRawStages) raw_stages = kMaxRawStages;
+  if (raw_stages < 2) return SN_ERR_UNSUPPORTED;
+  p.raw_stages = raw_stages;
+  if (raw_stages >= 5 && p.a_stages < kMaxAStages) p.a_stages = kMaxAStages;
+  const size_t smem = (size_t)(p.raw_stages + p.lo_stages) * b_stage + p.a_stages * a_stage + 1024;
   cudaError_t e = cudaFuncSetAttribute(gemm_tn_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   gemm_tn_ts_kernel<<<grid, kThreads, smem, st>>>(map_a, map_b, p);
