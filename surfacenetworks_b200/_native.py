@@ -111,10 +111,12 @@ TIMER = None
 
 
 class KernelTimer:
-    """Collects (name, tag, bytes, flops, start_event, end_event) for calls whose name is in ``names``."""
+    """Collects (name, tag, bytes, flops, start_event, end_event) for calls whose name is in ``names`` (None: every
+    kernel-launching entry point)."""
 
-    def __init__(self, names):
-        self.names = set(names)
+    def __init__(self, names=None):
+        self.names = set(n for n in SIGNATURES if not n.endswith("_ws_bytes") and n not in ("sn_version", "sn_status_string")) \
+            if names is None else set(names)
         self.records = []
         self._meta = None
 

@@ -54,6 +54,8 @@ def colstats(Z, mean=None, var=None):
         var = torch.empty(C, dtype=torch.float32, device=Z.device)
     nb = N.lib.sn_colstats_ws_bytes(C)
     ws = _ws(nb, Z.device)
+    if N.TIMER is not None:
+        N.TIMER.annotate("colstats %dx%d" % (rows, C), 4 * rows * C, 3 * rows * C)
     with torch.cuda.device(Z.device):
         N.call("sn_colstats_f32", _ptr(Z), Z.stride(0), rows, C, _ptr(mean), _ptr(var), _ptr(ws), nb, _stream())
     return mean, var
@@ -67,6 +69,8 @@ def elu_colstats(X, out, mean=None, var=None):
         var = torch.empty(C, dtype=torch.float32, device=X.device)
     nb = N.lib.sn_colstats_ws_bytes(C)
     ws = _ws(nb, X.device)
+    if N.TIMER is not None:
+        N.TIMER.annotate("elu_colstats %dx%d" % (rows, C), 8 * rows * C, 4 * rows * C)
     with torch.cuda.device(X.device):
         N.call("sn_elu_colstats_f32", _ptr(X), X.stride(0), _ptr(out), out.stride(0), rows, C, _ptr(mean), _ptr(var),
                _ptr(ws), nb, _stream())
@@ -106,6 +110,9 @@ def gemm_tf32(A, B, bias=None, R=None, rscale=None, out=None, single_pass=False,
     with torch.cuda.device(A.device):
         for n0 in range(0, Nn, step):
             Bs = B[n0:n0 + step]
+            if N.TIMER is not None:   # canonical HBM bytes: A read once, C written once, R read once, (pre-split) weights
+                N.TIMER.annotate("gemm %dx%dx%d%s" % (M, step, K, "" if R is None else " +R"),
+                                 4 * (M * K + M * step * (1 if R is None else 2) + 2 * step * K), 2 * M * step * K)
             common = (0 if bias is None else bias[n0:].data_ptr(), 0 if R is None else R[:, n0:].data_ptr(),
                       0 if R is None else R.stride(0), 0 if rscale is None else rscale[n0:].data_ptr(),
                       _ptr(group_bias), rows_per_group, out[:, n0:].data_ptr(), out.stride(0), M, step, K, flags)
@@ -139,6 +146,8 @@ def gemm_tn_tf32(A, B, single_pass=False, colsum=False):
                 n = min(256, Nn - n0)
                 nb = N.lib.sn_gemm_tn_tf32_ws_bytes(R, n)
                 ws = _ws(nb, A.device)
+                if N.TIMER is not None:
+                    N.TIMER.annotate("gemm_tn R=%d %dx%d" % (R, 128, n), 4 * R * (128 + n), 2 * R * 128 * n)
                 if colsum and n0 == 0 and not _legacy_flag():
                     N.call("sn_gemm_tn_colsum_tf32_f32", A[:, m0:].data_ptr(), A.stride(0), B[:, n0:].data_ptr(), B.stride(0),
                            G[m0:, n0:].data_ptr(), G.stride(0), cs[m0:].data_ptr(), R, 128, n, flags, _ptr(ws), nb, _stream())

@@ -175,6 +175,20 @@ class CsrOperator:
     def release_source(self):
         self._source = None
 
+    def load_from(self, other, clamp=False):
+        """Overwrite this operator's device arrays with ``other``'s (same shape, nnz within capacity), keeping addresses
+        (see Bsr4Operator.load_from)."""
+        if (other.n_rows, other.n_cols) != (self.n_rows, self.n_cols):
+            raise ValueError("operator shapes differ")
+        if other.nnz > self.colind.numel() and not clamp:
+            raise ValueError("nnz %d exceeds the slot capacity %d" % (other.nnz, self.colind.numel()))
+        nnz = min(other.nnz, self.colind.numel())
+        self.rowptr.copy_(other.rowptr, non_blocking=True)
+        self.colind[:nnz].copy_(other.colind[:nnz], non_blocking=True)
+        self.val[:nnz].copy_(other.val[:nnz], non_blocking=True)
+        self._nnz = nnz
+        return self
+
     def algorithmic_bytes(self, C):
         """Canonical HBM bytes of one application at feature width C."""
         return 4 * (self.n_rows + 1) + 8 * self.nnz + 4 * self.n_cols * C + 4 * self.n_rows * C
@@ -314,14 +328,16 @@ class Bsr4Operator:
     def release_source(self):
         self._source = None
 
-    def load_from(self, other):
+    def load_from(self, other, clamp=False):
         """Overwrite this operator's device arrays with ``other``'s (same shape, block count within capacity), keeping
-        the buffers' addresses -- lets a captured CUDA graph be replayed on a new batch's operator."""
+        the buffers' addresses -- lets a captured CUDA graph be replayed on a new batch's operator.  ``clamp``: ``other``
+        was built without a read-back and reports its buffer CAPACITY as block count (``from_source(block_capacity=)``,
+        ``build_dirac_operators(sync=False)``); copy what fits the slot (the caller guarantees the real count does)."""
         if (other.n_brows, other.n_bcols) != (self.n_brows, self.n_bcols):
             raise ValueError("operator shapes differ")
-        if other.n_blocks > self.bcolind.numel():
+        if other.n_blocks > self.bcolind.numel() and not clamp:
             raise ValueError("block count %d exceeds the slot capacity %d" % (other.n_blocks, self.bcolind.numel()))
-        nb = other.n_blocks
+        nb = min(other.n_blocks, self.bcolind.numel())
         self.browptr.copy_(other.browptr, non_blocking=True)
         self.bcolind[:nb].copy_(other.bcolind[:nb], non_blocking=True)
         self.bval[:16 * nb].copy_(other.bval[:16 * nb], non_blocking=True)
@@ -513,7 +529,9 @@ def _cached(S, kind, builder):
             setattr(S, _ATTR, cache)
         except Exception:  # pragma: no cover - exotic tensor subclasses
             return builder(S)
-    key = (kind, S._values().data_ptr(), S._values()._version, S._nnz())
+    # values AND indices identify the operator: an in-place edit of either (or a reshape) must rebuild the structures
+    idx = S._indices()
+    key = (kind, S._values().data_ptr(), S._values()._version, idx.data_ptr(), idx._version, S._nnz(), tuple(S.shape))
     op = cache.get(key)
     if op is None:
         cache.clear()
@@ -587,6 +605,10 @@ class MeshOperatorCache:
             return op.rowptr, op.colind, op.val, op.n_rows, op.nnz
         return op.browptr, op.bcolind, op.bval, op.n_brows, op.n_blocks
 
+    @staticmethod
+    def _n_cols(op):
+        return op.n_cols if op.kind == "csr" else op.n_bcols
+
     def _assemble_one(self, parts, kind, rows_pad, cols_pad, out):
         dev = self.device
         table, off = [], 0
@@ -594,6 +616,8 @@ class MeshOperatorCache:
             rp, ci, va, n_rows, n_ent = self._arrays(op)
             if n_rows > rows_pad:
                 raise ValueError("mesh operator has %d rows, more than the padded size %d" % (n_rows, rows_pad))
+            if self._n_cols(op) > cols_pad:       # an oversized mesh would bleed into the next block's columns
+                raise ValueError("mesh operator has %d columns, more than the padded size %d" % (self._n_cols(op), cols_pad))
             table += [rp.data_ptr(), ci.data_ptr(), va.data_ptr(), n_rows, n_ent, off]
             off += n_ent
         table = torch.tensor(table, dtype=torch.int64).to(dev, non_blocking=True)

@@ -277,3 +277,43 @@ def test_mesh_operator_restatement_matches_reference_built_operators(golden):
     D, DA = mesh_ops.dirac_entries(V, F)
     for S, got in ((Dh, D), (DAh, DA)):
         assert {(int(a), int(b)): np.float32(x) for a, b, x in zip(S.row, S.col, S.data)} == got
+
+
+def test_cpu_arm_workload_is_pinned(golden):
+    """oracle/workload.py (what bench.py's CPU arms run on, independent of the product package): its Dirac operators
+    equal the reference-built cube operators and the per-entry restatement; meshes, batch operators and the parameter
+    layout equal the product's host-side builders, so both bench arms see the same workload."""
+    from oracle import mesh_ops, workload as W
+    from surfacenetworks_b200 import geometry, workloads as PW
+
+    def as_dict(m):
+        m = m.tocoo()
+        return {(int(r), int(c)): np.float32(v) for r, c, v in zip(m.row, m.col, m.data)}
+
+    V, F = geometry.cube_mesh()
+    D, DA = W.dirac_operators(V, F)
+    for name, m in (("cube_Di", D), ("cube_DiA", DA)):
+        r, c, v, shape = golden.coo("operators", name)
+        assert m.shape == shape
+        assert as_dict(m) == {(int(a), int(b)): np.float32(x) for a, b, x in zip(r, c, v)}, name
+    V, F = W.synth_mesh(120, 5)
+    Vp, Fp = geometry.synth_mesh(120, 5)
+    assert np.array_equal(V, Vp) and np.array_equal(F, Fp)
+    D, DA = W.dirac_operators(V, F)
+    De, DAe = mesh_ops.dirac_entries(V, F)
+    assert as_dict(D) == De and as_dict(DA) == DAe
+    # batch: same coalesced block-diagonal operators, inputs, targets and mask as the product's workload builder
+    meshes = [W.synth_mesh(n, s) for n, s in ((90, 1), (70, 2), (90, 3))]
+    b = W.arap_batch(meshes, seed=4)
+    pb = PW.arap_batch([PW.MeshOps(v, f) for v, f in meshes], seed=4)
+    for k in ("inputs", "targets", "mask"):
+        assert torch.equal(b[k], pb[k]), k
+    for k in ("Di", "DiA"):
+        assert b[k].shape == pb[k].shape
+        assert torch.equal(b[k]._indices(), pb[k]._indices()) and torch.equal(b[k]._values(), pb[k]._values()), k
+    # parameter dictionary: the reference DirModel's state_dict layout (= the product model's)
+    from surfacenetworks_b200 import models as M
+    sd = M.ArapDirModel().state_dict()
+    P = W.arap_dir_params(0)
+    assert list(P.keys()) == list(sd.keys())
+    assert all(P[k].shape == sd[k].shape and P[k].dtype == sd[k].dtype for k in sd)
