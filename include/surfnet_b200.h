@@ -225,6 +225,19 @@ int sn_gemm_tf32_presplit_f32(const float* A, int64_t lda, const float* B_hi, co
                               const float* bias, const float* R, int64_t ldr, const float* rscale, const float* group_bias,
                               int64_t rows_per_group, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int flags,
                               sn_stream_t stream);
+/* The dense stage with the NEXT stage's activation (utils_pt.py:161,172,195,208: F.elu in front of every operator
+ * application) and that stage's left-half BatchNorm statistics (utils_pt.py:98) fused into the epilogue:
+ *   raw   = A * (B_hi + B_lo)^T + bias + group_bias + rscale .* R          (C, may be NULL: raw value not stored)
+ *   C_act = elu(raw)                                                        (leading dimension ldc_act: any row-strided view)
+ *   act_mean / act_var = per-column mean / biased variance of C_act over the M rows (both NULL: no statistics)
+ * Statistics are deterministic: per-warp shared-memory accumulators, per-CTA partials in `ws`
+ * (sn_gemm_act_ws_bytes(N) bytes), fixed-order fp64 final reduction.  Flags must be 0. */
+size_t sn_gemm_act_ws_bytes(int64_t N);
+int sn_gemm_tf32_presplit_act_f32(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb,
+                                  const float* bias, const float* R, int64_t ldr, const float* rscale,
+                                  const float* group_bias, int64_t rows_per_group, float* C, int64_t ldc, float* C_act,
+                                  int64_t ldc_act, float* act_mean, float* act_var, int64_t M, int64_t N, int64_t K,
+                                  int flags, void* ws, size_t ws_bytes, sn_stream_t stream);
 /* hi = tf32(X) (round to nearest), lo = X - hi; X [rows x cols] with leading dimension ldx, outputs contiguous. */
 int sn_split_tf32_f32(const float* X, int64_t ldx, int64_t rows, int64_t cols, float* hi, float* lo, sn_stream_t stream);
 
@@ -258,6 +271,19 @@ int sn_colstats_f32(const float* X, int64_t ldx, int64_t rows, int64_t C, float*
  * (the left half of a stage's concat buffer needs no separate statistics pass).  Same workspace as sn_colstats_f32. */
 int sn_elu_colstats_f32(const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t rows, int64_t C, float* mean,
                         float* var_biased, void* ws, size_t ws_bytes, sn_stream_t stream);
+
+/* Y = S X together with the per-column mean / biased variance of Y over all rows, from ONE launch: the BatchNorm statistics
+ * of the right half of a stage's concat buffer (utils_pt.py:98 applied to the torch.cat of :168,177,204,216) are taken in
+ * the row-group kernel's store path (per-(warp, row group) shared-memory accumulators, per-CTA partials in `ws`,
+ * fixed-order fp64 final reduction: bit-reproducible).  Y is bit-identical to sn_{bsr4,csr}_spmm_f32.
+ * Row-group kernel only: C in {32, 64, 128, 256, 512}; SN_ERR_UNSUPPORTED otherwise (nothing launched). */
+size_t sn_spmm_stats_ws_bytes(int64_t C);
+int sn_bsr4_spmm_stats_f32(const int32_t* browptr, const int32_t* bcolind, const float* bval, const float* X, int64_t ldx,
+                           float* Y, int64_t ldy, int64_t n_brows, int64_t C, float* mean, float* var_biased, int flags,
+                           void* ws, size_t ws_bytes, sn_stream_t stream);
+int sn_csr_spmm_stats_f32(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X, int64_t ldx,
+                          float* Y, int64_t ldy, int64_t n_rows, int64_t C, float* mean, float* var_biased, int flags,
+                          void* ws, size_t ws_bytes, sn_stream_t stream);
 
 /* O(C^2) glue of the fused dense stage, one launch each way.
  * forward : s = gamma*rstd, t = beta - mean*s, Wf = W diag(s) [N x K], bf = b + W t, rstd = 1/sqrt(var+eps); when

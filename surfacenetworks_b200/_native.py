@@ -51,6 +51,12 @@ SIGNATURES = {
                                 _ptr, _sz, _ptr]),
     "sn_gemm_tf32_presplit_f32": (_int, [_ptr, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64,
                                          _i64, _int, _ptr]),
+    "sn_gemm_act_ws_bytes": (_sz, [_i64]),
+    "sn_gemm_tf32_presplit_act_f32": (_int, [_ptr, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64, _ptr,
+                                             _i64, _ptr, _ptr, _i64, _i64, _i64, _int, _ptr, _sz, _ptr]),
+    "sn_spmm_stats_ws_bytes": (_sz, [_i64]),
+    "sn_bsr4_spmm_stats_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _ptr, _int, _ptr, _sz, _ptr]),
+    "sn_csr_spmm_stats_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _ptr, _int, _ptr, _sz, _ptr]),
     "sn_split_tf32_f32": (_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr]),
     "sn_csr_spmm_epilogue_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64,
                                         _int, _ptr]),

@@ -101,7 +101,7 @@ colstats_final_kernel(const float* __restrict__ partial, int n_partials, int64_t
     const double m = s / (double)rows;            // mean of the shifted values
     double v = q / (double)rows - m * m;
     if (v < 0.0) v = 0.0;
-    mean[c] = (float)(m + (double)X[c]);
+    mean[c] = (float)(m + (X ? (double)X[c] : 0.0));      // X: the shift the partial sums were taken around (null: none)
     var[c] = (float)v;
   }
 }
@@ -149,6 +149,14 @@ elu_colstats_kernel(const float* __restrict__ X, int64_t ldx, float* __restrict_
     for (int g = 0; g < RG; ++g) a += red[(size_t)g * 2 * C + i];
     partial[(size_t)blockIdx.x * 2 * C + i] = a;
   }
+}
+
+// Final reduction for producers that emit the partial sums themselves (the GEMM's ACT epilogue, the row-group SpMM's
+// statistics store path): partial [n_partials][2][C] (sum | sum of squares of x - shift), shift [C] or null.
+int launch_colstats_final(const float* partial, int n_partials, int64_t rows, int C, const float* shift, float* mean,
+                          float* var, cudaStream_t st) {
+  colstats_final_kernel<<<(unsigned)ceil_div(C, 32), 1024, 0, st>>>(partial, n_partials, rows, C, shift, mean, var);
+  return launch_status();
 }
 
 static int stat_grid() {

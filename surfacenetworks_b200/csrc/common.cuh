@@ -31,6 +31,10 @@ inline int launch_status() {
 int64_t exclusive_scan_tiles(int64_t n);
 int exclusive_scan(const int* counts, int64_t n, int* out, int* tile_ws, cudaStream_t st);
 
+// colstats.cu: fixed-order fp64 reduction of per-CTA partial sums [n_partials][2][C] -> mean / biased variance
+int launch_colstats_final(const float* partial, int n_partials, int64_t rows, int C, const float* shift, float* mean,
+                          float* var, cudaStream_t st);
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ELU(alpha = 1), the activation in front of every operator application (utils_pt.py:161,172,195,208).

@@ -418,6 +418,13 @@ struct ParamsTS {
   int split;             // 1: 3xTF32, 0: single pass
   int l2_prefetch;
   int elu_left;
+  // ACT epilogue (template parameter of the kernel): C2 = elu(result) with leading dimension ldc2 -- the activated copy the
+  // NEXT stage gathers from / takes as the left half of its concat buffer (C may then be null: the raw value has no other
+  // consumer) -- and, when stat_partial is given, the per-CTA column sums / sums of squares of C2 [gridDim.x][2][N] for that
+  // stage's BatchNorm (finished by colstats_final_kernel in a fixed order: bit-reproducible).
+  float* C2;
+  int64_t ldc2;
+  float* stat_partial;
 };
 
 // Roles (16 warps): 0 = A producer (TMA), 3 = B producer (TMA), 1 = MMA issuer, 2 = TMEM allocation, 4-7 = A split into
@@ -426,6 +433,7 @@ struct ParamsTS {
 //           a_ready / a_tfree (split warps -> MMA -> split warps)  TMEM A stages (tcgen05.st ... tcgen05.commit)
 //           b_full / b_free  (TMA -> MMA -> TMA)                   shared-memory B ring
 //           tmem_full / tmem_empty (MMA -> epilogue -> MMA)        two accumulators
+template <bool ACT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_blo, const ParamsTS p) {
@@ -441,6 +449,7 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float epi_buf[kEpiWarps * 32 * 20];
   __shared__ __align__(16) float s_bias[256], s_rscale[256];   // epilogue vectors: LDS instead of an L1-missing __ldg per chunk
+  __shared__ __align__(16) float s_stat[ACT ? kEpiWarps : 1][2][128];   // ACT: per-epilogue-warp column sums / sums of squares
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.M + kBlockM - 1) / kBlockM;
@@ -633,6 +642,10 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       load_chunk(rr, pf); advance(pf);
       load_chunk(rn, pf); advance(pf);
     }
+    if (ACT) {
+      for (int i = lane; i < 2 * 128; i += 32) (&s_stat[e][0][0])[i] = 0.f;
+      __syncwarp();
+    }
     uint32_t job = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int half = 0; half < n_halves; ++half, ++job) {
@@ -662,6 +675,7 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           __syncwarp();
           const float4 bia = *reinterpret_cast<const float4*>(s_bias + c0 + tc);
           const float4 rs = *reinterpret_cast<const float4*>(s_rscale + c0 + tc);
+          float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), qsum = ssum;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int rl = i * 8 + tr;
@@ -673,12 +687,36 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               if (p.R) {
                 o.x = fmaf(rs.x, rr[i].x, o.x); o.y = fmaf(rs.y, rr[i].y, o.y);
                 o.z = fmaf(rs.z, rr[i].z, o.z); o.w = fmaf(rs.w, rr[i].w, o.w);
-                if (p.elu_left && c0 < (N >> 1)) {   // chunk-uniform: 16-column chunks never straddle N/2
+                if (!ACT && p.elu_left && c0 < (N >> 1)) {   // chunk-uniform: 16-column chunks never straddle N/2
                   o.x *= rr[i].x > 0.f ? 1.f : rr[i].x + 1.f; o.y *= rr[i].y > 0.f ? 1.f : rr[i].y + 1.f;
                   o.z *= rr[i].z > 0.f ? 1.f : rr[i].z + 1.f; o.w *= rr[i].w > 0.f ? 1.f : rr[i].w + 1.f;
                 }
               }
-              st_stream_f4(p.C + (int64_t)row * p.ldc + c0 + tc, o);
+              if (!ACT || p.C) st_stream_f4(p.C + (int64_t)row * p.ldc + c0 + tc, o);
+              if (ACT) {
+                // the activated copy is re-read soon (gathered by the next SpMM / A operand of the next GEMM): default
+                // store policy, not streaming
+                const float4 a = elu4(o);
+                *reinterpret_cast<float4*>(p.C2 + (int64_t)row * p.ldc2 + c0 + tc) = a;
+                ssum = add4(ssum, a);
+                qsum.x = fmaf(a.x, a.x, qsum.x); qsum.y = fmaf(a.y, a.y, qsum.y);
+                qsum.z = fmaf(a.z, a.z, qsum.z); qsum.w = fmaf(a.w, a.w, qsum.w);
+              }
+            }
+          }
+          if (ACT && p.stat_partial) {
+            // rows of the chunk: 4 per lane (above), then the 8 lanes that share tc (lane bits 2..4), fixed tree order
+#pragma unroll
+            for (int m = 4; m <= 16; m <<= 1) {
+              ssum = add4(ssum, shfl_xor4(ssum, m));
+              qsum = add4(qsum, shfl_xor4(qsum, m));
+            }
+            if (lane < 4) {
+              const int lc = half * ncol + (c0 - cbase) + tc;     // column inside this warp's share of the N columns
+              float4* sp = reinterpret_cast<float4*>(&s_stat[e][0][lc]);
+              float4* qp = reinterpret_cast<float4*>(&s_stat[e][1][lc]);
+              *sp = add4(*sp, ssum);
+              *qp = add4(*qp, qsum);
             }
           }
           __syncwarp();
@@ -688,6 +726,19 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(tmem_empty + buf);
+      }
+    }
+    if (ACT && p.stat_partial) {
+      // the CTA's partial: the four row-quarter warps that own a column, added in a fixed order
+      asm volatile("bar.sync 1, 256;" ::: "memory");           // the eight epilogue warps only
+      for (int i = threadIdx.x - 256; i < 2 * N; i += 256) {
+        const int stat = i / N, col = i - stat * N;
+        const int hf = col / nmma, within = col - hf * nmma;
+        const int ch = within / ncol, lc = hf * ncol + (within - ch * ncol);
+        float a = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a += s_stat[ch * 4 + q][stat][lc];
+        p.stat_partial[(size_t)blockIdx.x * 2 * N + i] = a;
       }
     }
   }
@@ -753,7 +804,8 @@ namespace gemm {
 // Shared launcher: B_hi / B_lo are the pre-split weights (B_lo null = single pass on B_hi as given).
 static int launch_gemm(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb, const float* bias,
                        const float* R, int64_t ldr, const float* rscale, const float* group_bias, int64_t rows_per_group,
-                       float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int flags, cudaStream_t stream) {
+                       float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int flags, cudaStream_t stream,
+                       float* C_act = nullptr, int64_t ldc_act = 0, float* stat_partial = nullptr) {
   const bool split = B_lo != nullptr;
   int dev = 0, sms = 148, smem_optin = 0;
   cudaGetDevice(&dev);
@@ -766,6 +818,7 @@ static int launch_gemm(const float* A, int64_t lda, const float* B_hi, const flo
   if (!make_map(&map_a, A, M, K, lda, kBlockM)) return SN_ERR_UNSUPPORTED;
 
   if (flags & SN_GEMM_LEGACY_SS) {       // round-1 kernel: both operands from shared memory
+    if (C_act) return SN_ERR_UNSUPPORTED;
     if (!make_map(&map_b, B_hi, N, K, ldb, (int)N)) return SN_ERR_UNSUPPORTED;
     if (split) {
       if (!make_map(&map_blo, B_lo, N, K, ldb, (int)N)) return SN_ERR_UNSUPPORTED;
@@ -801,6 +854,7 @@ static int launch_gemm(const float* A, int64_t lda, const float* B_hi, const flo
   p.split = split ? 1 : 0;
   p.l2_prefetch = l2_prefetch;
   p.elu_left = (flags & SN_GEMM_ELU_BWD_LEFT) ? 1 : 0;
+  p.C2 = C_act; p.ldc2 = ldc_act; p.stat_partial = stat_partial;
   if (!make_map(&map_b, B_hi, N, K, ldb, p.nmma)) return SN_ERR_UNSUPPORTED;
   if (split) {
     if (!make_map(&map_blo, B_lo, N, K, ldb, p.nmma)) return SN_ERR_UNSUPPORTED;
@@ -809,17 +863,28 @@ static int launch_gemm(const float* A, int64_t lda, const float* B_hi, const flo
   }
   // shared memory: B ring of 3 stages (hi | lo; the weights come from L2), the rest goes to the A ring (HBM latency)
   const size_t a_bytes = (size_t)kBlockM * kBlockK * 4, b_stage = 2 * (size_t)p.nmma * kBlockK * 4;
-  const size_t budget = (size_t)smem_optin - 24 * 1024 - 1024;   // static: transpose buffers, epilogue vectors, barriers; 1 KB alignment
+  // static: transpose buffers, epilogue vectors, barriers (+ 8 KB of statistics accumulators in the ACT kernel); 1 KB alignment
+  const size_t budget = (size_t)smem_optin - (C_act ? 32 : 24) * 1024 - 1024;
   p.b_stages = 3;
   int a_stages = (int)((budget - p.b_stages * b_stage) / a_bytes);
   if (a_stages > kMaxAStages) a_stages = kMaxAStages;
   if (a_stages < 2) return SN_ERR_UNSUPPORTED;
   p.a_stages = a_stages;
   const size_t smem = a_stages * a_bytes + p.b_stages * b_stage + 1024;
-  cudaError_t e = cudaFuncSetAttribute(gemm_tf32_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = C_act ? gemm_tf32_ts_kernel<true> : gemm_tf32_ts_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  gemm_tf32_ts_kernel<<<grid, kThreads, smem, stream>>>(map_a, map_b, map_blo, p);
+  kern<<<grid, kThreads, smem, stream>>>(map_a, map_b, map_blo, p);
   return launch_status();
+}
+
+// CTAs launch_gemm uses for M rows (= rows of the ACT kernel's statistics partials)
+static int64_t gemm_grid(int64_t M) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t tiles = ceil_div(M, kBlockM);
+  return tiles < sms ? tiles : sms;
 }
 
 static int check_gemm_args(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, const float* R,
@@ -870,6 +935,38 @@ SN_API int sn_gemm_tf32_presplit_f32(const float* A, int64_t lda, const float* B
   if (!B_lo || !aligned16(B_lo) || (flags & SN_GEMM_SINGLE_PASS)) return SN_ERR_ARG;
   return launch_gemm(A, lda, B_hi, B_lo, ldb, bias, R, ldr, rscale, group_bias, rows_per_group, C, ldc, M, N, K, flags,
                      (cudaStream_t)stream);
+}
+
+SN_API size_t sn_gemm_act_ws_bytes(int64_t N) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return N <= 0 ? 0 : (size_t)sms * 2 * (size_t)N * sizeof(float);
+}
+
+SN_API int sn_gemm_tf32_presplit_act_f32(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb,
+                                         const float* bias, const float* R, int64_t ldr, const float* rscale,
+                                         const float* group_bias, int64_t rows_per_group, float* C, int64_t ldc, float* C_act,
+                                         int64_t ldc_act, float* act_mean, float* act_var, int64_t M, int64_t N, int64_t K,
+                                         int flags, void* ws, size_t ws_bytes, sn_stream_t stream) {
+  using namespace sn;
+  using namespace sn::gemm;
+  if (!C_act || ldc_act < N || (act_mean == nullptr) != (act_var == nullptr)) return SN_ERR_ARG;
+  // the raw output is optional here: validate the shapes against the activated destination when it is absent
+  const int rc = check_gemm_args(A, lda, B_hi, ldb, bias, R, ldr, rscale, group_bias, rows_per_group, C ? C : C_act,
+                                 C ? ldc : ldc_act, M, N, K, flags);
+  if (rc != SN_OK || M == 0) return rc;
+  if (!B_lo || !aligned16(B_lo) || (flags & (SN_GEMM_SINGLE_PASS | SN_GEMM_ELU_BWD_LEFT | SN_GEMM_LEGACY_SS))) return SN_ERR_ARG;
+  if (ldc_act % 4 || !aligned16(C_act)) return SN_ERR_UNSUPPORTED;
+  float* partial = nullptr;
+  if (act_mean) {
+    if (!ws || ws_bytes < sn_gemm_act_ws_bytes(N) || !aligned16(ws)) return SN_ERR_WORKSPACE;
+    partial = reinterpret_cast<float*>(ws);
+  }
+  const int rc2 = launch_gemm(A, lda, B_hi, B_lo, ldb, bias, R, ldr, rscale, group_bias, rows_per_group, C, ldc, M, N, K, flags,
+                              (cudaStream_t)stream, C_act, ldc_act, partial);
+  if (rc2 != SN_OK || !act_mean) return rc2;
+  return launch_colstats_final(partial, (int)gemm_grid(M), M, (int)N, nullptr, act_mean, act_var, (cudaStream_t)stream);
 }
 
 SN_API int sn_split_tf32_f32(const float* X, int64_t ldx, int64_t rows, int64_t cols, float* hi, float* lo, sn_stream_t stream) {

@@ -130,7 +130,9 @@ int launch_bsr4_stream(const int32_t* browptr, const int32_t* bcolind, const flo
                        float* Y, int64_t ldy, int64_t n_brows, int64_t C, bool elu, cudaStream_t st);
 int launch_bsr4_rowgroup(const int32_t* browptr, const int32_t* bcolind, const float* bval, const float* X,
                          int64_t ldx, float* Y, int64_t ldy, int64_t n_brows, int64_t C, bool elu, int variant,
-                         const float* G, int64_t ldg, const float* A, int64_t lda, const float* G2, int64_t ldg2, cudaStream_t st);
+                         const float* G, int64_t ldg, const float* A, int64_t lda, const float* G2, int64_t ldg2, cudaStream_t st,
+                         float* stat_partial = nullptr, int* grid_out = nullptr);
+int64_t rowgroup_max_grid();
 
 }  // namespace sn
 
@@ -189,4 +191,29 @@ SN_API int sn_bsr4_spmm_epilogue_f32(const int32_t* browptr, const int32_t* bcol
     return SN_ERR_UNSUPPORTED;
   return launch_bsr4_rowgroup(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C, false, (flags >> 8) & 15, G, ldg, A, lda, G2, ldg2,
                               (cudaStream_t)stream);
+}
+
+// Y = S X and the per-column mean / biased variance of Y over all n_brows rows from the same pass (the BatchNorm
+// statistics of the right half of the stage's concat buffer, utils_pt.py:98 after :203): every row's values are added to
+// per-(warp, row group) accumulators in shared memory where the row is stored; per-CTA partials, fixed-order fp64 final
+// reduction.  Row-group kernel only (C in {32, ..., 512}); SN_ERR_UNSUPPORTED otherwise (nothing launched).
+SN_API size_t sn_spmm_stats_ws_bytes(int64_t C) {
+  return C <= 0 ? 0 : (size_t)sn::rowgroup_max_grid() * 2 * (size_t)C * sizeof(float);
+}
+
+SN_API int sn_bsr4_spmm_stats_f32(const int32_t* browptr, const int32_t* bcolind, const float* bval, const float* X,
+                                  int64_t ldx, float* Y, int64_t ldy, int64_t n_brows, int64_t C, float* mean,
+                                  float* var_biased, int flags, void* ws, size_t ws_bytes, sn_stream_t stream) {
+  using namespace sn;
+  if (n_brows <= 0 || C <= 0 || C > 0x7fffffffLL) return SN_ERR_ARG;
+  if (!browptr || !bcolind || !bval || !X || !Y || !mean || !var_biased || ldx < C || ldy < C) return SN_ERR_ARG;
+  if (flags & (SN_SPMM_DIRECT_GATHER | SN_SPMM_SMEM_STREAM | SN_SPMM_ELU_INPUT)) return SN_ERR_UNSUPPORTED;
+  if (C % 16 || ldx % 4 || ldy % 4 || !aligned16(X) || !aligned16(Y) || !aligned16(bval)) return SN_ERR_UNSUPPORTED;
+  if (!ws || ws_bytes < sn_spmm_stats_ws_bytes(C) || !aligned16(ws)) return SN_ERR_WORKSPACE;
+  int grid = 0;
+  const int rc = launch_bsr4_rowgroup(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C, false, (flags >> 8) & 3, nullptr, 0,
+                                      nullptr, 0, nullptr, 0, (cudaStream_t)stream, reinterpret_cast<float*>(ws), &grid);
+  if (rc != SN_OK) return rc;
+  return launch_colstats_final(reinterpret_cast<const float*>(ws), grid, n_brows, (int)C, nullptr, mean, var_biased,
+                               (cudaStream_t)stream);
 }

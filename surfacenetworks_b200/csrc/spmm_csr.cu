@@ -121,7 +121,9 @@ static int launch_vec4(const int32_t* rowptr, const int32_t* colind, const float
 
 int launch_csr_rowgroup(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X, int64_t ldx,
                         float* Y, int64_t ldy, int64_t n_rows, int64_t C, bool elu, int variant, const float* G,
-                        int64_t ldg, const float* A, int64_t lda, const float* G2, int64_t ldg2, cudaStream_t st);
+                        int64_t ldg, const float* A, int64_t lda, const float* G2, int64_t ldg2, cudaStream_t st,
+                        float* stat_partial = nullptr, int* grid_out = nullptr);
+int64_t rowgroup_max_grid();
 
 }  // namespace sn
 
@@ -175,4 +177,22 @@ SN_API int sn_csr_spmm_epilogue_f32(const int32_t* rowptr, const int32_t* colind
     return SN_ERR_UNSUPPORTED;
   return launch_csr_rowgroup(rowptr, colind, val, X, ldx, Y, ldy, n_rows, C, false, (flags >> 8) & 15, G, ldg, A, lda, G2, ldg2,
                              (cudaStream_t)stream);
+}
+
+// CSR twin of sn_bsr4_spmm_stats_f32 (Laplacian stages, utils_pt.py:98 after :167 / :176).
+SN_API int sn_csr_spmm_stats_f32(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X,
+                                 int64_t ldx, float* Y, int64_t ldy, int64_t n_rows, int64_t C, float* mean,
+                                 float* var_biased, int flags, void* ws, size_t ws_bytes, sn_stream_t stream) {
+  using namespace sn;
+  if (n_rows <= 0 || C <= 0 || C > 0x7fffffffLL) return SN_ERR_ARG;
+  if (!rowptr || !colind || !val || !X || !Y || !mean || !var_biased || ldx < C || ldy < C) return SN_ERR_ARG;
+  if (flags & (SN_SPMM_DIRECT_GATHER | SN_SPMM_ELU_INPUT)) return SN_ERR_UNSUPPORTED;
+  if (C % 16 || ldx % 4 || ldy % 4 || !aligned16(X) || !aligned16(Y)) return SN_ERR_UNSUPPORTED;
+  if (!ws || ws_bytes < (size_t)rowgroup_max_grid() * 2 * (size_t)C * sizeof(float) || !aligned16(ws)) return SN_ERR_WORKSPACE;
+  int grid = 0;
+  const int rc = launch_csr_rowgroup(rowptr, colind, val, X, ldx, Y, ldy, n_rows, C, false, (flags >> 8) & 3, nullptr, 0, nullptr,
+                                     0, nullptr, 0, (cudaStream_t)stream, reinterpret_cast<float*>(ws), &grid);
+  if (rc != SN_OK) return rc;
+  return launch_colstats_final(reinterpret_cast<const float*>(ws), grid, n_rows, (int)C, nullptr, mean, var_biased,
+                               (cudaStream_t)stream);
 }

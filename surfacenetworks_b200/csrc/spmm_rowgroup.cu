@@ -58,6 +58,9 @@ struct Geo {
   static constexpr int WRING = BLK == 4 ? PD * G * 16 * EPS : 0;   // floats: PD stages x G groups x EPS blocks
   static constexpr int WARP_WORDS = ((WRING + 3 * BPS + 2 * CAP + (BLK == 1 ? 2 * CAP : 0)) + 3) / 4 * 4;
   static constexpr size_t kSmem = (size_t)kWarps * WARP_WORDS * 4;
+  // MODE 3 (statistics in the store path): one [2][C] accumulator per (warp, row group) behind the per-warp regions
+  static constexpr size_t kStatSmem = (size_t)kWarps * G * 2 * (16 * LPR) * 4;
+  static constexpr size_t smem_bytes(int mode) { return kSmem + (mode == 3 ? kStatSmem : 0); }
 };
 
 // Optional output epilogue Y = (S X + G) .* elu'(A) + G2 (backward of "elu, then gather": the activation derivative and the
@@ -67,6 +70,10 @@ struct Epilogue {
   const float* A;     // activated values elu(x) [n_rows x C], leading dimension ldab bytes, or null
   const float* G2;    // [n_rows x C] added AFTER the derivative (a residual-path gradient), or null
   uint32_t ldgb, ldab, ldg2b;
+  // MODE 3: per-CTA column sums / sums of squares of Y [gridDim.x][2][C] -- the BatchNorm statistics of the right half of
+  // the stage's concat buffer, taken where the rows are stored instead of by a second pass over Y (sn_colstats_f32)
+  float* stat_partial;
+  int* host_grid_out; // HOST pointer (never dereferenced on the device): receives the grid size = number of partial rows
 };
 
 }  // namespace
@@ -82,6 +89,7 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
   using Gm = Geo<LPR, RPG, BLK, PD, EPS>;
   constexpr bool ELU = MODE == 1;      // ELU on the gathered operand
   constexpr bool EPI = MODE == 2;      // output epilogue (G, elu')
+  constexpr bool STATS = MODE == 3;    // column statistics of the output in the store path
   constexpr int C = 16 * LPR;
   constexpr int kQuarterBytes = C;             // (C/4 floats) * 4 bytes
   constexpr int G = Gm::G, WR = Gm::WR, CAP = Gm::CAP, BPS = Gm::BPS;
@@ -101,7 +109,16 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
   const float* wslot0 = wring + g * 16 * EPS;            // this group's blocks in stage 0
   const int wstride = gridDim.x * kWarps;
   int wt = blockIdx.x * kWarps + warp;
-  if (wt >= n_wtiles) return;                    // warps never synchronise with each other
+  if (!STATS && wt >= n_wtiles) return;          // warps never synchronise with each other (STATS: once, at the very end)
+  // STATS: this (warp, row group)'s accumulator; lane t owns columns q C/4 + 4t .. +3 (q = 0..3) of both statistics
+  float* wstat = reinterpret_cast<float*>(smem_i + kWarps * Gm::WARP_WORDS) + (warp * G + g) * 2 * C + 4 * t;
+  if (STATS) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      *reinterpret_cast<float4*>(wstat + p * (C / 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(wstat + C + p * (C / 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
 
   auto prefetch_bp = [&](int tile, int buf) {    // row pointers of warp-tile `tile`
     if (tile < n_wtiles) {
@@ -198,6 +215,18 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
           }
 #pragma unroll
           for (int p = 0; p < 4; ++p) st_stream_f4(reinterpret_cast<float*>(yrow + p * kQuarterBytes), acc[p]);
+          if (STATS) {                          // rows in the order this group stores them: fixed, run to run
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+              float4* sp = reinterpret_cast<float4*>(wstat + p * (C / 4));
+              float4* qp = reinterpret_cast<float4*>(wstat + C + p * (C / 4));
+              const float4 a = acc[p];
+              float4 sq = *qp;
+              sq.x = fmaf(a.x, a.x, sq.x); sq.y = fmaf(a.y, a.y, sq.y); sq.z = fmaf(a.z, a.z, sq.z); sq.w = fmaf(a.w, a.w, sq.w);
+              *sp = add4(*sp, a);
+              *qp = sq;
+            }
+          }
         }
 #pragma unroll
         for (int p = 0; p < 4; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -280,6 +309,17 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
     b3 = b3n;
     b2 ^= 1;
   }
+  if (STATS) {
+    // the CTA's partial: its kWarps * G accumulators added in a fixed order (idle warps hold zeros)
+    cp_async_wait<0>();
+    __syncthreads();
+    const float* all = reinterpret_cast<const float*>(smem_i + kWarps * Gm::WARP_WORDS);
+    for (int i = threadIdx.x; i < 2 * C; i += kThreads) {
+      float a = 0.f;
+      for (int w = 0; w < kWarps * G; ++w) a += all[w * 2 * C + i];
+      epi.stat_partial[(size_t)blockIdx.x * 2 * C + i] = a;
+    }
+  }
 }
 
 namespace {
@@ -299,7 +339,7 @@ struct Launcher {
   static int64_t resident_warps(int mode, int sms) {
     // occupancy is a property of (kernel, device model): queried once per process and device ordinal (a benign race:
     // concurrent first calls compute the same value)
-    static int64_t cached[3][32] = {};
+    static int64_t cached[4][32] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     const bool cacheable = dev >= 0 && dev < 32;
@@ -311,14 +351,16 @@ struct Launcher {
   static int64_t query_resident_warps(int mode, int sms) {
     auto kern = mode == 1 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 1, PD, EPS, MINB>
                 : mode == 2 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 2, PD, EPS, MINB>
+                : mode == 3 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 3, PD, EPS, MINB>
                             : rowgroup_spmm_kernel<LPR, RPG, BLK, 0, PD, EPS, MINB>;
-    if (Gm::kSmem > 48 * 1024 &&
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::kSmem) != cudaSuccess) {
+    const size_t smem = Gm::smem_bytes(mode);
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       cudaGetLastError();
       return 0;
     }
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, Gm::kSmem) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem) != cudaSuccess) {
       cudaGetLastError();
       return 0;
     }
@@ -337,12 +379,14 @@ struct Launcher {
     if (warps <= 0) return SN_ERR_UNSUPPORTED;
     auto kern = mode == 1 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 1, PD, EPS, MINB>
                 : mode == 2 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 2, PD, EPS, MINB>
+                : mode == 3 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 3, PD, EPS, MINB>
                             : rowgroup_spmm_kernel<LPR, RPG, BLK, 0, PD, EPS, MINB>;
     const int64_t n_wtiles = ceil_div(n_rows, Gm::WR);
     const int64_t ctas = ceil_div(n_wtiles, kWarps);
     const int64_t grid = ctas < warps / kWarps ? ctas : warps / kWarps;
-    kern<<<(unsigned)grid, kThreads, Gm::kSmem, st>>>(rowptr, colind, val, X, (uint32_t)(ldx * 4), Y,
-                                                      (uint32_t)(ldy * 4), (int)n_rows, (int)n_wtiles, epi);
+    if (mode == 3 && epi.host_grid_out) *epi.host_grid_out = (int)grid;
+    kern<<<(unsigned)grid, kThreads, Gm::smem_bytes(mode), st>>>(rowptr, colind, val, X, (uint32_t)(ldx * 4), Y,
+                                                                 (uint32_t)(ldy * 4), (int)n_rows, (int)n_wtiles, epi);
     return launch_status();
   }
 };
@@ -388,8 +432,9 @@ template <int BLK>
 int launch_family(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X, int64_t ldx,
                   float* Y, int64_t ldy, int64_t n_rows, int64_t C, bool elu, int variant, const Epilogue& epi,
                   cudaStream_t st) {
-  const int mode = (epi.G || epi.A || epi.G2) ? 2 : (elu ? 1 : 0);
-  if (mode == 2 && (elu || variant >= 4)) return SN_ERR_UNSUPPORTED;   // the epilogue exists for the default shape only
+  const int mode = (epi.G || epi.A || epi.G2) ? 2 : (epi.stat_partial ? 3 : (elu ? 1 : 0));
+  if (mode >= 2 && (elu || variant >= 4)) return SN_ERR_UNSUPPORTED;   // the epilogues exist for the default shape only
+  if (mode == 2 && epi.stat_partial) return SN_ERR_UNSUPPORTED;
   // ldx / ldy in bytes and entry offsets (64 B per block) must fit 32 bits
   if (n_rows >= 0x7fffff00LL || ldx >= (1LL << 30) || ldy >= (1LL << 30)) return SN_ERR_UNSUPPORTED;
   // tuning variants (tools/spmm_bench.py --variants rgN): 1 / 2 / 3 force short / medium / long warp-tiles;
@@ -425,17 +470,21 @@ int launch_family(const int32_t* rowptr, const int32_t* colind, const float* val
 int launch_bsr4_rowgroup(const int32_t* browptr, const int32_t* bcolind, const float* bval, const float* X,
                          int64_t ldx, float* Y, int64_t ldy, int64_t n_brows, int64_t C, bool elu, int variant,
                          const float* G, int64_t ldg, const float* A, int64_t lda, const float* G2, int64_t ldg2,
-                         cudaStream_t st) {
+                         cudaStream_t st, float* stat_partial, int* grid_out) {
   if (ldg >= (1LL << 30) || lda >= (1LL << 30) || ldg2 >= (1LL << 30)) return SN_ERR_UNSUPPORTED;
-  const Epilogue epi{G, A, G2, (uint32_t)(ldg * 4), (uint32_t)(lda * 4), (uint32_t)(ldg2 * 4)};
+  const Epilogue epi{G, A, G2, (uint32_t)(ldg * 4), (uint32_t)(lda * 4), (uint32_t)(ldg2 * 4), stat_partial, grid_out};
   return launch_family<4>(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C, elu, variant, epi, st);
 }
 int launch_csr_rowgroup(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X, int64_t ldx,
                         float* Y, int64_t ldy, int64_t n_rows, int64_t C, bool elu, int variant, const float* G,
-                        int64_t ldg, const float* A, int64_t lda, const float* G2, int64_t ldg2, cudaStream_t st) {
+                        int64_t ldg, const float* A, int64_t lda, const float* G2, int64_t ldg2, cudaStream_t st,
+                        float* stat_partial, int* grid_out) {
   if (ldg >= (1LL << 30) || lda >= (1LL << 30) || ldg2 >= (1LL << 30)) return SN_ERR_UNSUPPORTED;
-  const Epilogue epi{G, A, G2, (uint32_t)(ldg * 4), (uint32_t)(lda * 4), (uint32_t)(ldg2 * 4)};
+  const Epilogue epi{G, A, G2, (uint32_t)(ldg * 4), (uint32_t)(lda * 4), (uint32_t)(ldg2 * 4), stat_partial, grid_out};
   return launch_family<1>(rowptr, colind, val, X, ldx, Y, ldy, n_rows, C, elu, variant, epi, st);
 }
+
+// upper bound of the grid any instantiation launches (at most 2048 / 256 = 8 CTAs per SM): rows of the statistics workspace
+int64_t rowgroup_max_grid() { return (int64_t)device_info().sms * 8; }
 
 }  // namespace sn

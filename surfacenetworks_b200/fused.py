@@ -126,6 +126,38 @@ def gemm_tf32(A, B, bias=None, R=None, rscale=None, out=None, single_pass=False,
     return out
 
 
+def gemm_tf32_act(A, B_hi, B_lo, bias=None, R=None, rscale=None, out=None, act_out=None, mean=None, var=None,
+                  group_bias=None, rows_per_group=0, want_raw=True):
+    """The dense stage with the NEXT stage's activation fused into the epilogue (sn_gemm_tf32_presplit_act_f32):
+
+        raw = A @ (B_hi + B_lo)^T + bias + group_bias[row // rows_per_group] + rscale * R
+        act_out = elu(raw)                       (any row-strided [M, N] view, e.g. the left half of a concat buffer)
+        mean / var = column statistics of act_out (when given: contiguous [N] views)
+
+    ``want_raw=False`` skips the raw store entirely (the raw value has no other consumer).  Returns (raw | None, act_out)."""
+    M, K = A.shape
+    Nn = B_hi.shape[0]
+    if Nn not in _GEMM_N:
+        raise ValueError("gemm_tf32_act needs N in %s" % (_GEMM_N,))
+    if act_out is None:
+        act_out = torch.empty(M, Nn, dtype=torch.float32, device=A.device)
+    if want_raw and out is None:
+        out = torch.empty(M, Nn, dtype=torch.float32, device=A.device)
+    if not want_raw:
+        out = None
+    nb = N.lib.sn_gemm_act_ws_bytes(Nn) if mean is not None else 0
+    ws = _ws(nb, A.device) if nb else None
+    if N.TIMER is not None:
+        N.TIMER.annotate("gemm+act %dx%dx%d%s%s" % (M, Nn, K, "" if R is None else " +R", " raw+act" if want_raw else " act"),
+                         4 * (M * K + M * Nn * ((1 if want_raw else 0) + 1 + (0 if R is None else 1)) + 2 * Nn * K), 2 * M * Nn * K)
+    with torch.cuda.device(A.device):
+        N.call("sn_gemm_tf32_presplit_act_f32", _ptr(A), A.stride(0), _ptr(B_hi), _ptr(B_lo), B_hi.stride(0), _ptr(bias),
+               _ptr(R), 0 if R is None else R.stride(0), _ptr(rscale), _ptr(group_bias), rows_per_group, _ptr(out),
+               0 if out is None else out.stride(0), _ptr(act_out), act_out.stride(0), _ptr(mean), _ptr(var), M, Nn, K, 0,
+               _ptr(ws), nb, _stream())
+    return out, act_out
+
+
 def gemm_tn_supported(m, n):
     return m % 128 == 0 and n % 32 == 0
 
@@ -157,18 +189,23 @@ def gemm_tn_tf32(A, B, single_pass=False, colsum=False):
     return (G, cs) if colsum else G
 
 
-def bn_linear_forward(Z, gamma, beta, W, b, residual, running_mean, running_var, training, momentum, eps, left_stats):
+def bn_linear_forward(Z, gamma, beta, W, b, residual, running_mean, running_var, training, momentum, eps, left_stats,
+                      act=None):
     """Forward of GraphConv1x1(batch_norm="pre") on rows (no autograd): statistics pass, BN folded into the weights,
-    tcgen05 GEMM with the residual in its epilogue.  Returns (Y, saved) with ``saved`` = what bn_linear_backward needs."""
+    tcgen05 GEMM with the residual in its epilogue.  Returns (Y, saved) with ``saved`` = what bn_linear_backward needs.
+    ``act``: dict(act_out=, mean=, var=, want_raw=) -- the GEMM also emits elu(Y) (and its column statistics) for the next
+    stage (gemm_tf32_act); Y is None when ``want_raw`` is false."""
     rows, K = Z.shape
     Nn = W.shape[0]
     dev = Z.device
     if training:
         if left_stats is not None and len(left_stats) == 3:
             # (mean, var, Cl): full-width vectors whose first Cl entries the fused ELU pass has already written; the
-            # statistics of the remaining columns land in place -- no concatenation kernels
+            # statistics of the remaining columns land in place -- no concatenation kernels.  Cl == K: the producers
+            # of both halves (GEMM activation epilogue, SpMM store path) have written everything.
             mean, var, Cl = left_stats
-            colstats(Z[:, Cl:], mean[Cl:], var[Cl:])
+            if Cl < K:
+                colstats(Z[:, Cl:], mean[Cl:], var[Cl:])
         elif left_stats is not None:              # left half already reduced by the fused ELU pass
             Cl = left_stats[0].numel()
             mr, vr = colstats(Z[:, Cl:])
@@ -187,7 +224,11 @@ def bn_linear_forward(Z, gamma, beta, W, b, residual, running_mean, running_var,
                _ptr(Wf[0]), _ptr(bf), _ptr(stk[0]), _ptr(stk[1]), _ptr(stk[2]), _ptr(running_mean) if update else 0,
                _ptr(running_var) if update else 0, float(momentum), rows, _ptr(Wf[1]), _ptr(Wf[2]), _stream())
     res = None if residual is None else residual.contiguous()
-    Y = gemm_tf32(Z, Wf[1], bias=bf, R=res, B_lo=Wf[2])
+    if act is not None:
+        Y, _ = gemm_tf32_act(Z, Wf[1], Wf[2], bias=bf, R=res, act_out=act["act_out"], mean=act.get("mean"), var=act.get("var"),
+                             want_raw=act.get("want_raw", True))
+    else:
+        Y = gemm_tf32(Z, Wf[1], bias=bf, R=res, B_lo=Wf[2])
     return Y, (Z, W, stk, mean)
 
 

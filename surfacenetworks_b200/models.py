@@ -42,6 +42,26 @@ def _num_faces(Di, DiA, batch_size):
     return as_bsr4(DiA).n_bcols // batch_size
 
 
+def _dirac_stack(model, n_layers, D, DA, mask, v, f):
+    """The reference's block loop ``v, f = rn_i(Di, DiA, v, f)`` / ``v = rn_i(L, mask, v)`` (as_rigid_as_possible/models.py:
+    142-146 and its twins).  Returns v; the final f is discarded by every caller, as in the reference.  When the Dirac
+    blocks run their fused training path the face features are handed from block to block in ACTIVATED form (the only
+    form anybody reads): utils_pt.DirResNet2.forward_chained."""
+    blocks = [model._modules["rn{}".format(i)] for i in range(n_layers)]
+    dirac = [i for i, b in enumerate(blocks) if isinstance(b, utils.DirResNet2)]
+    chained = bool(dirac) and all(blocks[i].chain_supported(v, f) for i in dirac)
+    state = ops.face_chain_start(f.reshape(-1, f.size(2))) if chained else None
+    for i, blk in enumerate(blocks):
+        if isinstance(blk, utils.DirResNet2):
+            if chained:
+                v, state = blk.forward_chained(D, DA, v, state, last=(i == dirac[-1]))
+            else:
+                v, f = blk(D, DA, v, f)
+        else:
+            v = blk(None, mask, v)
+    return v
+
+
 class ArapLapModel(nn.Module):
     """as_rigid_as_possible ``Model(layer, dense)``: conv1(6->128), alternating Lap / Avg blocks, conv2(128->120)."""
 
@@ -104,11 +124,7 @@ class ArapDirModel(nn.Module):
         D, DA = as_bsr4(Di), as_bsr4(DiA)
         v = self.conv1(inputs)
         f = v.new_zeros(batch_size, _num_faces(Di, DiA, batch_size), 128)
-        for i in range(15):
-            if i % 2 == 0:
-                v, f = self._modules["rn{}".format(i)](D, DA, v, f)
-            else:
-                v = self._modules["rn{}".format(i)](None, mask, v)
+        v = _dirac_stack(self, 15, D, DA, mask, v, f)
         return self.conv2(F.elu(v)) + _last3_tiled(inputs, 40)
 
 
@@ -188,11 +204,7 @@ class DirDeepModel(nn.Module):
         D, DA = as_bsr4(Di), as_bsr4(DiA)
         v = self.conv1(inputs)
         f = v.new_zeros(batch_size, DA.n_bcols // batch_size, self.feature_width)
-        for i in range(self.layer_num):
-            if i % 2 == 0:
-                v, f = self._modules["rn{}".format(i)](D, DA, v, f)
-            else:
-                v = self._modules["rn{}".format(i)](None, mask, v)
+        v = _dirac_stack(self, self.layer_num, D, DA, mask, v, f)
         return F.elu(self.conv2(v))
 
     def fuzzy_load(self, pre_dict):
@@ -237,11 +249,7 @@ class DcDirModel(nn.Module):
         D, DA = as_bsr4(Di), as_bsr4(DiA)
         v = self.conv1(inputs)
         f = v.new_zeros(batch_size, DA.n_bcols // batch_size, 128)
-        for i in range(self.layer):
-            if i % 2 == 0:
-                v, f = self._modules["rn{}".format(i)](D, DA, v, f)
-            else:
-                v = self._modules["rn{}".format(i)](None, mask, v)
+        v = _dirac_stack(self, self.layer, D, DA, mask, v, f)
         return self.conv2(F.elu(v)) + _last3_tiled(inputs, 40)
 
 

@@ -215,10 +215,38 @@ class CsrOperator:
                    _stream())
         return out
 
+    def apply_stats(self, X, out, mean, var):
+        """``out = S @ X`` and the column statistics of ``out`` (mean, biased variance over all rows) in one launch, or
+        None if unsupported for this shape (then run ``apply`` + ``fused.colstats``)."""
+        return _apply_stats(self, "sn_csr_spmm_stats_f32", self.n_rows, self.n_cols,
+                            (_ptr(self.rowptr), _ptr(self.colind), _ptr(self.val)), X, out, mean, var)
+
     def apply_epilogue(self, X, G=None, A=None, out=None, G2=None):
         """``(S @ X + G) * elu'(A) + G2`` (A = activated values) in one launch, or None if unsupported for this shape."""
         return _apply_epilogue(self, "sn_csr_spmm_epilogue_f32", self.n_rows, self.n_cols,
                                (_ptr(self.rowptr), _ptr(self.colind), _ptr(self.val)), X, G, A, out, G2)
+
+
+def _apply_stats(op, entry, n_rows, n_cols, ptrs, X, out, mean, var):
+    """``out = op @ X`` plus the per-column mean / biased variance of ``out`` from the same launch
+    (sn_*_spmm_stats_f32); returns None when the row-group kernel does not cover the shape."""
+    _check_dense(X, "X")
+    _check_dense(out, "out")
+    C = X.shape[1]
+    if X.shape[0] < n_cols:
+        raise ValueError("X has %d rows, operator has %d columns" % (X.shape[0], n_cols))
+    if out.shape[0] != n_rows or out.shape[1] != C:
+        raise ValueError("out must be [%d, %d], got %s" % (n_rows, C, tuple(out.shape)))
+    if mean.numel() != C or var.numel() != C or not (mean.is_contiguous() and var.is_contiguous()):
+        raise ValueError("mean / var must be contiguous [%d] vectors" % C)
+    nb = N.lib.sn_spmm_stats_ws_bytes(C)
+    ws = torch.empty(max(int(nb), 1), dtype=torch.uint8, device=X.device)
+    if N.TIMER is not None:
+        N.TIMER.annotate("%s %dx%d C=%d +stats" % (op.kind, n_rows, n_cols, C), op.algorithmic_bytes(C), op.flops(C))
+    with torch.cuda.device(X.device):
+        rc = N.call(entry, *ptrs, _ptr(X), X.stride(0), _ptr(out), out.stride(0), n_rows, C, _ptr(mean), _ptr(var), 0,
+                    _ptr(ws), nb, _stream(), soft_unsupported=True)
+    return None if rc == N.SN_ERR_UNSUPPORTED else out
 
 
 def _apply_epilogue(op, entry, n_rows, n_cols, ptrs, X, G, A, out, G2=None):
@@ -370,6 +398,11 @@ class Bsr4Operator:
             N.call("sn_bsr4_spmm_f32", _ptr(self.browptr), _ptr(self.bcolind), _ptr(self.bval),
                    _ptr(X), X.stride(0), _ptr(out), out.stride(0), self.n_brows, C, flags, _stream())
         return out
+
+    def apply_stats(self, X, out, mean, var):
+        """``out = S @ X`` and the column statistics of ``out`` in one launch (see CsrOperator.apply_stats)."""
+        return _apply_stats(self, "sn_bsr4_spmm_stats_f32", self.n_brows, self.n_bcols,
+                            (_ptr(self.browptr), _ptr(self.bcolind), _ptr(self.bval)), X, out, mean, var)
 
     def apply_epilogue(self, X, G=None, A=None, out=None, G2=None):
         """``(S @ X + G) * elu'(A) + G2`` (A = activated values) in one launch, or None if unsupported for this shape."""

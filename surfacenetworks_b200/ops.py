@@ -196,10 +196,116 @@ class _DirBlock(torch.autograd.Function):
         if g_vnew is None:
             g_vnew = torch.zeros(Zv.shape[0], C, dtype=torch.float32, device=Zv.device)
         dZv, dg1, db1, dW1, dc1 = fused.bn_linear_backward((Zv, W1, stk1, mean1), g_vnew, True, False)
-        g_fout = DA.T.apply_epilogue(dZv[:, C:], A=act_f, G2=g_fdown)
+        g_fout = _epilogue_or_passes(DA.T, dZv[:, C:], None, act_f, g_fdown)
         dZf, dg0, db0, dW0, dc0 = fused.bn_linear_backward((Zf, W0, stk0, mean0), g_fout, True, True)
-        g_v = D.T.apply_epilogue(dZf[:, C:], G=dZv[:, :C], A=Zv[:, :C], G2=g_vnew)
+        g_v = _epilogue_or_passes(D.T, dZf[:, C:], dZv[:, :C], Zv[:, :C], g_vnew)
         return g_v, dZf[:, :C], dg0, db0, dW0, dc0, dg1, db1, dW1, dc1, None, None, None, None
+
+
+def _spmm_with_stats(op, X, out, mean, var):
+    """out = op @ X and the column statistics of out: one launch when the row-group kernel covers the shape."""
+    if op.apply_stats(X, out, mean, var) is None:
+        op.apply(X, out=out)
+        fused.colstats(out, mean, var)
+
+
+class _FaceChainStart(torch.autograd.Function):
+    """Entry of a chain of Dirac blocks: f [F, C] -> (Zf [F, 2C] whose LEFT half holds elu(f), st [2, 2C] whose first C
+    columns hold that half's mean / biased variance).  The right halves are written by the first block of the chain."""
+
+    @staticmethod
+    def forward(ctx, f2):
+        C = f2.shape[1]
+        f2 = f2.contiguous()
+        Zf = torch.empty(f2.shape[0], 2 * C, dtype=torch.float32, device=f2.device)
+        st = torch.empty(2, 2 * C, dtype=torch.float32, device=f2.device)
+        fused.elu_colstats(f2, Zf[:, :C], st[0, :C], st[1, :C])
+        ctx.C = C
+        ctx.mark_non_differentiable(st)
+        return Zf, st
+
+    @staticmethod
+    def backward(ctx, gZf, _gst=None):
+        # the consuming block's dZ GEMM has already applied elu'(f) to the left half (SN_GEMM_ELU_BWD_LEFT)
+        return None if gZf is None else gZf[:, :ctx.C]
+
+
+class _DirBlockChained(torch.autograd.Function):
+    """DirResNet2 (reference src/utils/utils_pt.py:191-220) inside a stack whose face features only ever travel from one
+    Dirac block to the next (as_rigid_as_possible/models.py:142-146, normal_predict/models.py:262-268,
+    dense_correspondence/models.py:170-176).  Nobody reads the raw f_out: the next block takes elu(f_out) as the left half
+    of its concat buffer and D* gathers elu(f_out).  So, compared with _DirBlock:
+
+      * the face stage's GEMM writes ONLY elu(f_out), straight into the left half of the NEXT block's concat buffer, and
+        reduces that half's BatchNorm statistics in its epilogue (sn_gemm_tf32_presplit_act_f32) -- the separate
+        sn_elu_f32 pass and the next block's sn_elu_colstats_f32 pass over the faces are gone;
+      * both SpMMs reduce the statistics of the right halves in their store path (sn_bsr4_spmm_stats_f32) -- the two
+        sn_colstats_f32 passes are gone.
+    Backward is _DirBlock's (the gradient w.r.t. raw f_out arrives as the left half of the next block's dZ, already
+    multiplied by elu'(f_out) by that block's dZ GEMM)."""
+
+    @staticmethod
+    def forward(ctx, v2, Zf, stf, g0, b0, W0, c0, g1, b1, W1, c1, D, DA, bn0, bn1, last):
+        C = v2.shape[1]
+        v2 = v2.contiguous()
+        dev = v2.device
+        Zv = torch.empty(v2.shape[0], 2 * C, dtype=torch.float32, device=dev)
+        stv = torch.empty(2, 2 * C, dtype=torch.float32, device=dev)
+        fused.elu_colstats(v2, Zv[:, :C], stv[0, :C], stv[1, :C])
+        _spmm_with_stats(D, Zv[:, :C], Zf[:, C:], stf[0, C:], stf[1, C:])        # faces <- vertices
+        if last:
+            Zf_next = st_next = None
+            act_f = torch.empty(Zf.shape[0], C, dtype=torch.float32, device=dev)
+            act = dict(act_out=act_f, want_raw=False)
+        else:
+            Zf_next = torch.empty_like(Zf)
+            st_next = torch.empty_like(stf)
+            act_f = Zf_next[:, :C]
+            act = dict(act_out=act_f, mean=st_next[0, :C], var=st_next[1, :C], want_raw=False)
+        _, saved0 = fused.bn_linear_forward(Zf, g0, b0, W0, c0, None, bn0.running_mean, bn0.running_var, True,
+                                            0.1 if bn0.momentum is None else bn0.momentum, bn0.eps, (stf[0], stf[1], 2 * C),
+                                            act=act)
+        _spmm_with_stats(DA, act_f, Zv[:, C:], stv[0, C:], stv[1, C:])           # vertices <- faces
+        v_new, saved1 = fused.bn_linear_forward(Zv, g1, b1, W1, c1, v2, bn1.running_mean, bn1.running_var, True,
+                                                0.1 if bn1.momentum is None else bn1.momentum, bn1.eps, (stv[0], stv[1], 2 * C))
+        ctx.save_for_backward(act_f, *saved0, *saved1)
+        ctx.D, ctx.DA, ctx.C = D, DA, C
+        ctx.set_materialize_grads(False)
+        if last:
+            Zf_next = Zf.new_empty(0)
+            st_next = Zf.new_empty(0)
+        ctx.mark_non_differentiable(st_next)
+        return v_new, Zf_next, st_next
+
+    @staticmethod
+    def backward(ctx, g_vnew, g_Zfnext, _gst=None):
+        act_f, Zf, W0, stk0, mean0, Zv, W1, stk1, mean1 = ctx.saved_tensors
+        C, D, DA = ctx.C, ctx.D, ctx.DA
+        g_fdown = None
+        if g_Zfnext is not None and g_Zfnext.numel():
+            g_fdown = g_Zfnext[:, :C]
+            if g_fdown.stride(1) != 1 or g_fdown.stride(0) % 4 or g_fdown.data_ptr() % 16:
+                g_fdown = g_fdown.contiguous()
+        if g_vnew is not None and (g_vnew.stride(1) != 1 or g_vnew.stride(0) % 4 or g_vnew.data_ptr() % 16):
+            g_vnew = g_vnew.contiguous()
+        if g_vnew is None:
+            g_vnew = torch.zeros(Zv.shape[0], C, dtype=torch.float32, device=Zv.device)
+        dZv, dg1, db1, dW1, dc1 = fused.bn_linear_backward((Zv, W1, stk1, mean1), g_vnew, True, False)
+        g_fout = _epilogue_or_passes(DA.T, dZv[:, C:], None, act_f, g_fdown)
+        dZf, dg0, db0, dW0, dc0 = fused.bn_linear_backward((Zf, W0, stk0, mean0), g_fout, True, True)
+        g_v = _epilogue_or_passes(D.T, dZf[:, C:], dZv[:, :C], Zv[:, :C], g_vnew)
+        return g_v, dZf, None, dg0, db0, dW0, dc0, dg1, db1, dW1, dc1, None, None, None, None, None
+
+
+def _epilogue_or_passes(opT, X, G, A, G2):
+    """(opT @ X + G) .* elu'(A) + G2: one launch (row-group epilogue) or, where that kernel does not apply, the passes."""
+    t = opT.apply_epilogue(X, G=G, A=A, G2=G2)
+    if t is None:
+        t = opT.apply(X)
+        _elu_bwd(A, False, t, G, t)               # (opT @ X + G) .* elu'(A), in place
+        if G2 is not None:
+            t += G2
+    return t
 
 
 _DIR_BLOCK_WIDTHS = (64, 128)          # C and 2C both tensor-core GEMM widths, C covered by the row-group epilogue
@@ -220,6 +326,21 @@ def dir_block_supported(v2, f2, conv0, conv1):
         if tuple(fc.weight.shape) != (C, 2 * C) or fc.weight.dtype != torch.float32:
             return False
     return True
+
+
+def face_chain_start(f2):
+    """(Zf, st) for the first block of a chain of Dirac blocks, see _DirBlockChained."""
+    return _FaceChainStart.apply(f2)
+
+
+def dir_block_chained(D, DA, v2, Zf, stf, conv0, conv1, last):
+    """One DirResNet2 block inside a chain: returns (v_new, Zf_next, st_next); ``last`` = no Dirac block follows (the
+    activated faces then go to a plain buffer, Zf_next / st_next come back empty)."""
+    for conv in (conv0, conv1):
+        if conv.bn.num_batches_tracked is not None:
+            conv.bn.num_batches_tracked += 1
+    return _DirBlockChained.apply(v2, Zf, stf, conv0.bn.weight, conv0.bn.bias, conv0.fc.weight, conv0.fc.bias, conv1.bn.weight,
+                                  conv1.bn.bias, conv1.fc.weight, conv1.fc.bias, D, DA, conv0.bn, conv1.bn, bool(last))
 
 
 def dir_block(D, DA, v2, f2, conv0, conv1):

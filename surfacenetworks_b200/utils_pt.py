@@ -220,6 +220,26 @@ class DirResNet2(_TwoStageBlock):
         return v_new.view(batch_size, num_nodes, num_inputs), f_out.view(batch_size, num_faces, num_inputs)
 
 
+    # ---- chained form (stacks where the face features only travel from one Dirac block to the next, see ops._DirBlockChained)
+    def chain_supported(self, v, f):
+        """True when ``forward_chained`` applies: training-mode fused block at a width both epilogues cover."""
+        if v.dim() != 3 or f.dim() != 3:
+            return False
+        v2 = v.reshape(-1, v.size(2))
+        f2 = f.reshape(-1, f.size(2))
+        return ops.dir_block_supported(v2, f2, self.bn_fc0, self.bn_fc1)
+
+    def forward_chained(self, Di, DiA, v, face_state, last=False):
+        """``forward`` with the face features handed over in activated form: ``face_state`` = ``ops.face_chain_start(f)``
+        or the state returned by the previous Dirac block.  Returns (v_out, next_face_state)."""
+        batch_size, num_nodes, num_inputs = v.size()
+        D, DA = as_bsr4(Di), as_bsr4(DiA)
+        v2 = v.reshape(batch_size * num_nodes, num_inputs)
+        Zf, stf = face_state
+        v_new, Zf_next, st_next = ops.dir_block_chained(D, DA, v2, Zf, stf, self.bn_fc0, self.bn_fc1, last)
+        return v_new.view(batch_size, num_nodes, num_inputs), (Zf_next, st_next)
+
+
 class AvgResNet2(_TwoStageBlock):
     """Global-average block, no sparse operator (utils_pt.py:222-243):
     x -> x + fc1(BN[e1 | avg(e1)]),  e1 = elu(fc0(BN[e0 | avg(e0)])),  e0 = elu(x), avg = masked mean over the mesh.
