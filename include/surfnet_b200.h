@@ -299,6 +299,33 @@ int sn_bn_fold_bwd_f32(const float* G, const float* sdY, const float* W, const f
                        float* dW, float* db, float* dgamma, float* dbeta, float* p, float* q, float* WsT,
                        float* WsT_hi, float* WsT_lo, sn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * AvgResNet2 stage (utils_pt.py:222-243): x -> elu -> [a | global_average(a, mask) broadcast] -> BatchNorm -> Linear.
+ * The broadcast half is never built (it is constant per mesh): the stage is a K = C GEMM plus a per-mesh bias.
+ *   sn_avg_stage_pre_f32  A = elu(X) [n_seg * rows_per_seg x C]; mean / var_biased [2C] = training-mode statistics of
+ *                         [A | avg broadcast]; avg [n_seg x C] = (sum_r w[r] A[r]) * inv_cnt[seg] (w NULL = 1).  One pass
+ *                         over X plus a tiny reduction; workspace sn_avg_stage_ws_bytes(n_seg, C).
+ *   sn_avg_fold_fwd_f32   sn_bn_fold_fwd_f32 for K = 2C (outputs only the tf32 hi / lo split of W' = W diag(s), [N x 2C])
+ *                         plus u [n_seg x N] = b' + W'[:, C:] avg_seg: the group_bias of sn_gemm_tf32_presplit_f32.
+ *   sn_avg_fold_bwd_f32   backward glue in one launch: with GL = dY^T A [N x C] and SdY [n_seg x N] = per-mesh sums of dY
+ *                         it forms G = [GL | SdY^T avg], runs the folded BatchNorm backward of sn_bn_fold_bwd_f32 on it
+ *                         (dW [N x 2C], db, dgamma, dbeta, p, q [2C], WsT hi / lo [2C x N]) and returns
+ *                         gb [n_seg x C] = inv_cnt (SdY (W_R diag(s_R)) + rows_per_seg (p_R avg + q_R)), the gradient that
+ *                         sn_elu_bwd_group_f32 hands back to every row of the mesh.
+ * ---------------------------------------------------------------------------------------------- */
+size_t sn_avg_stage_ws_bytes(int64_t n_seg, int64_t C);
+int sn_avg_stage_pre_f32(const float* X, int64_t ldx, const float* w, const float* inv_cnt, int64_t rows_per_seg,
+                         int64_t n_seg, int64_t C, float* A, int64_t lda, float* mean, float* var_biased, float* avg,
+                         void* ws, size_t ws_bytes, sn_stream_t stream);
+int sn_avg_fold_fwd_f32(const float* mean, const float* var, const float* gamma, const float* beta, const float* W,
+                        const float* b, int64_t N, int64_t C, float eps, float* Wf_hi, float* Wf_lo, float* s, float* t,
+                        float* rstd, float* running_mean, float* running_var, float momentum, int64_t rows,
+                        const float* avg, int64_t n_seg, float* u, sn_stream_t stream);
+int sn_avg_fold_bwd_f32(const float* GL, int64_t ldgl, const float* SdY, const float* avg, const float* W, const float* s,
+                        const float* t, const float* rstd, const float* mean, const float* inv_cnt, int64_t N, int64_t C,
+                        int64_t n_seg, int64_t rows_per_seg, int training, float* dW, float* db, float* dgamma,
+                        float* dbeta, float* p, float* q, float* WsT_hi, float* WsT_lo, float* gb, sn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

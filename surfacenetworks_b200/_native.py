@@ -57,6 +57,12 @@ SIGNATURES = {
     "sn_spmm_stats_ws_bytes": (_sz, [_i64]),
     "sn_bsr4_spmm_stats_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _ptr, _int, _ptr, _sz, _ptr]),
     "sn_csr_spmm_stats_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _ptr, _int, _ptr, _sz, _ptr]),
+    "sn_avg_stage_ws_bytes": (_sz, [_i64, _i64]),
+    "sn_avg_stage_pre_f32": (_int, [_ptr, _i64, _ptr, _ptr, _i64, _i64, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),
+    "sn_avg_fold_fwd_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _f32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
+                                   _f32, _i64, _ptr, _i64, _ptr, _ptr]),
+    "sn_avg_fold_bwd_f32": (_int, [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _int,
+                                   _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "sn_split_tf32_f32": (_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr]),
     "sn_csr_spmm_epilogue_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64,
                                         _int, _ptr]),

@@ -38,8 +38,29 @@ int launch_colstats_final(const float* partial, int n_partials, int64_t rows, in
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ELU(alpha = 1), the activation in front of every operator application (utils_pt.py:161,172,195,208).
-// torch's CPU kernel evaluates the negative branch with expm1; expm1f keeps us within 1 ulp of it.
-__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+// torch evaluates the negative branch with expm1.  expm1f from libdevice costs ~35 instructions with branches, which made
+// the GEMM's activation epilogue issue-bound (profiles/r2_fusion_notes.md); this branch-free Cody-Waite form is 18:
+//   n = rint(x log2 e),  r = x - n ln 2 (hi/lo),  e^r - 1 = r + r^2 (1/2 + r/6 + ... + r^5/7!)   (|r| <= 0.347),
+//   e^x - 1 = 2^n (e^r - 1) + (2^n - 1)            -- one FMA; 2^n - 1 is exact
+// Measured against float64 expm1 over [-100, 0] (tools/elu_accuracy.py): max error 0.87 ulp, i.e. as close to the
+// reference's activation as expm1f (1 ulp) is.
+__device__ __forceinline__ float expm1_nonpos(float x) {
+  const float xn = fmaxf(x, -30.f);                            // e^-30 - 1 rounds to -1
+  const float t = fmaf(xn, 1.4426950408889634f, 12582912.f);   // 1.5 * 2^23 + rint(x log2 e)
+  const float n = t - 12582912.f;
+  float r = fmaf(n, -0.693145751953125f, xn);
+  r = fmaf(n, -1.428606765330187045e-06f, r);
+  float p = 1.f / 5040.f;
+  p = fmaf(p, r, 1.f / 720.f);
+  p = fmaf(p, r, 1.f / 120.f);
+  p = fmaf(p, r, 1.f / 24.f);
+  p = fmaf(p, r, 1.f / 6.f);
+  p = fmaf(p, r, 0.5f);
+  const float pm1 = fmaf(p, r * r, r);
+  const float s = __int_as_float((__float_as_int(t) << 23) + 0x3f800000);   // 2^n, n in [-44, 0]
+  return fmaf(s, pm1, s - 1.f);
+}
+__device__ __forceinline__ float elu1(float x) { return x <= 0.f ? expm1_nonpos(x) : x; }   // NaN propagates
 __device__ __forceinline__ float4 elu4(float4 v) {
   return make_float4(elu1(v.x), elu1(v.y), elu1(v.z), elu1(v.w));
 }

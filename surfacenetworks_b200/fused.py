@@ -318,33 +318,30 @@ class _AvgStage(torch.autograd.Function):
         rows, C = x.shape
         Nn = W.shape[0]
         dev = x.device
-        a = torch.empty_like(x)
-        if training:
-            mean_l, var_l = elu_colstats(x, a)                                    # activation + statistics in one pass
-        else:
-            with torch.cuda.device(dev):
-                N.call("sn_elu_f32", _ptr(x), x.stride(0), _ptr(a), a.stride(0), rows, C, _stream())
-        avg = segment_sum(a, rows_per_seg, n_seg, maskw) * inv_cnt                # [B, C]
-        if training:
-            mean_r = avg.mean(0)
-            var_r = ((avg - mean_r) ** 2).mean(0)        # two-pass on [B, C]: the per-mesh averages are close together
-            mean, var = torch.cat([mean_l, mean_r]), torch.cat([var_l, var_r])
-        else:
-            mean, var = running_mean, running_var
-        W = W.contiguous()
         K = 2 * C
-        Wf3 = torch.empty(3, Nn, K, dtype=torch.float32, device=dev)              # folded W', tf32(W'), W' - tf32(W')
-        Wf = Wf3[0]
-        bf = torch.empty(Nn, dtype=torch.float32, device=dev)
+        a = torch.empty_like(x)
+        avg = torch.empty(n_seg, C, dtype=torch.float32, device=dev)
+        st = torch.empty(2, K, dtype=torch.float32, device=dev)                   # batch mean / biased variance of [a | avg]
+        nb = N.lib.sn_avg_stage_ws_bytes(n_seg, C)
+        ws = _ws(nb, dev)
+        if N.TIMER is not None:
+            N.TIMER.annotate("avg_pre %dx%d" % (rows, C), 8 * rows * C, 6 * rows * C)
+        with torch.cuda.device(dev):
+            # activation, left-half statistics and the masked per-mesh sums in ONE pass; then the tiny [B, C] reductions
+            N.call("sn_avg_stage_pre_f32", _ptr(x), x.stride(0), _ptr(maskw), _ptr(inv_cnt), rows_per_seg, n_seg, C, _ptr(a),
+                   a.stride(0), _ptr(st[0]), _ptr(st[1]), _ptr(avg), _ptr(ws), nb, _stream())
+        mean, var = (st[0], st[1]) if training else (running_mean, running_var)
+        W = W.contiguous()
+        Wf = torch.empty(2, Nn, K, dtype=torch.float32, device=dev)               # tf32(W'), W' - tf32(W')
         stk = torch.empty(3, K, dtype=torch.float32, device=dev)
+        u = torch.empty(n_seg, Nn, dtype=torch.float32, device=dev)               # per-mesh bias [B, Nn]
         update = training and running_mean is not None
         with torch.cuda.device(dev):
-            N.call("sn_bn_fold_fwd_f32", _ptr(mean), _ptr(var), _ptr(gamma), _ptr(beta), _ptr(W), _ptr(b), Nn, K, float(eps),
-                   _ptr(Wf), _ptr(bf), _ptr(stk[0]), _ptr(stk[1]), _ptr(stk[2]), _ptr(running_mean) if update else 0,
-                   _ptr(running_var) if update else 0, float(momentum), rows, _ptr(Wf3[1]), _ptr(Wf3[2]), _stream())
-        u = torch.addmm(bf, avg, Wf[:, C:].t())                                   # per-mesh bias [B, Nn]
+            N.call("sn_avg_fold_fwd_f32", _ptr(mean), _ptr(var), _ptr(gamma), _ptr(beta), _ptr(W), _ptr(b), Nn, C, float(eps),
+                   _ptr(Wf[0]), _ptr(Wf[1]), _ptr(stk[0]), _ptr(stk[1]), _ptr(stk[2]), _ptr(running_mean) if update else 0,
+                   _ptr(running_var) if update else 0, float(momentum), rows, _ptr(avg), n_seg, _ptr(u), _stream())
         res = None if residual is None else residual.contiguous()
-        Y = gemm_tf32(a, Wf3[1][:, :C], R=res, group_bias=u, rows_per_group=rows_per_seg, B_lo=Wf3[2][:, :C])
+        Y = gemm_tf32(a, Wf[0][:, :C], R=res, group_bias=u, rows_per_group=rows_per_seg, B_lo=Wf[1][:, :C])
         ctx.save_for_backward(a, avg, W, stk, mean, maskw, inv_cnt)
         ctx.training, ctx.has_res, ctx.n_seg, ctx.rps = training, residual is not None, n_seg, rows_per_seg
         # in_cell / res_cell: the two stages of one AvgResNet2 block share a cell.  The stage that holds the block
@@ -362,24 +359,20 @@ class _AvgStage(torch.autograd.Function):
         K = 2 * C
         dev = a.device
         SdY = segment_sum(dY, ctx.rps, ctx.n_seg)                                 # [B, Nn] per-mesh sums of dY
-        sdY = SdY.sum(0)
-        G = torch.empty(Nn, K, dtype=torch.float32, device=dev)
-        G[:, :C] = gemm_tn_tf32(dY, a)
-        G[:, C:] = torch.mm(SdY.t(), avg)
+        GL = gemm_tn_tf32(dY, a)                                                  # [Nn, C] = dY^T a
         dW = torch.empty_like(W)
         db = torch.empty(Nn, dtype=torch.float32, device=dev)
         vec = torch.empty(4, K, dtype=torch.float32, device=dev)                  # dgamma, dbeta, p, q
-        WsT3 = torch.empty(3, K, Nn, dtype=torch.float32, device=dev)
-        WsT = WsT3[0]
+        WsT = torch.empty(2, K, Nn, dtype=torch.float32, device=dev)              # (W diag(s))^T: tf32 hi, lo
+        gb = torch.empty(ctx.n_seg, C, dtype=torch.float32, device=dev)           # gradient of the per-mesh averages / count
         with torch.cuda.device(dev):
-            N.call("sn_bn_fold_bwd_f32", _ptr(G), _ptr(sdY), _ptr(W), _ptr(stk[0]), _ptr(stk[1]), _ptr(stk[2]), _ptr(mean),
-                   Nn, K, rows, 1 if ctx.training else 0, _ptr(dW), _ptr(db), _ptr(vec[0]), _ptr(vec[1]), _ptr(vec[2]),
-                   _ptr(vec[3]), _ptr(WsT), _ptr(WsT3[1]), _ptr(WsT3[2]), _stream())
+            # G_R = SdY^T avg, the folded BatchNorm backward on [G_L | G_R] and gb, one launch
+            N.call("sn_avg_fold_bwd_f32", _ptr(GL), GL.stride(0), _ptr(SdY), _ptr(avg), _ptr(W), _ptr(stk[0]), _ptr(stk[1]),
+                   _ptr(stk[2]), _ptr(mean), _ptr(inv_cnt), Nn, C, ctx.n_seg, ctx.rps, 1 if ctx.training else 0, _ptr(dW),
+                   _ptr(db), _ptr(vec[0]), _ptr(vec[1]), _ptr(vec[2]), _ptr(vec[3]), _ptr(WsT[0]), _ptr(WsT[1]), _ptr(gb),
+                   _stream())
         p, q = vec[2], vec[3]
-        dZl = gemm_tf32(dY, WsT3[1][:C], bias=q[:C], R=a, rscale=p[:C], B_lo=WsT3[2][:C])
-        # gradient reaching the per-mesh averages: sum over the mesh's rows of dZ_R
-        gsum = torch.mm(SdY, WsT[C:].t()) + ctx.rps * (p[C:] * avg + q[C:])       # [B, C]
-        gb = (gsum * inv_cnt).contiguous()
+        dZl = gemm_tf32(dY, WsT[0][:C], bias=q[:C], R=a, rscale=p[:C], B_lo=WsT[1][:C])
         dx = torch.empty_like(a)
         g3 = ctx.in_cell.pop("residual_grad", None) if ctx.in_cell is not None else None
         with torch.cuda.device(dev):
@@ -400,6 +393,25 @@ def avg_stage_supported(x, weight):
             x.data_ptr() % 16 == 0)
 
 
+_MASK_ATTR = "_sn_mask_info"
+
+
+def mask_info(mask, B, V):
+    """(row weights [B*V] fp32, 1 / per-mesh count [B, 1]) of a [B, V, 1] mask, computed once per mask tensor (every
+    AvgResNet2 stage of a forward pass sees the same mask: 14 stages in the as_rigid_as_possible DirModel)."""
+    key = (mask.data_ptr(), mask._version, tuple(mask.shape), mask.dtype)
+    info = getattr(mask, _MASK_ATTR, None)
+    if info is not None and info[0] == key:
+        return info[1], info[2]
+    maskw = mask.reshape(B * V).to(torch.float32).contiguous()
+    inv_cnt = (1.0 / mask.reshape(B, V).sum(1, keepdim=True).to(torch.float32)).contiguous()      # [B, 1]
+    try:
+        setattr(mask, _MASK_ATTR, (key, maskw, inv_cnt))
+    except Exception:  # pragma: no cover
+        pass
+    return maskw, inv_cnt
+
+
 def avg_stage(x, mask, bn, fc, residual=None, in_cell=None, res_cell=None):
     """elu -> [x | global_average] -> BatchNorm -> Linear (+ residual) for x [B, V, C] (AvgResNet2 stage); returns
     [B*V, C_out] rows, or None when the shapes are outside the fused path."""
@@ -407,8 +419,7 @@ def avg_stage(x, mask, bn, fc, residual=None, in_cell=None, res_cell=None):
     x2 = x.reshape(B * V, C)
     if not avg_stage_supported(x2, fc.weight) or mask.shape[0] != B or mask.shape[1] != V:
         return None
-    maskw = mask.reshape(B * V).to(torch.float32).contiguous()
-    inv_cnt = (1.0 / mask.reshape(B, V).sum(1, keepdim=True).to(torch.float32)).contiguous()      # [B, 1]
+    maskw, inv_cnt = mask_info(mask, B, V)
     training = bn.training or bn.running_mean is None
     if training and bn.num_batches_tracked is not None:
         bn.num_batches_tracked += 1

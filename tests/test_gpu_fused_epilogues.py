@@ -189,3 +189,44 @@ def test_chained_dirac_blocks_match_the_block_by_block_path(C):
             assert err <= 2e-4 * max(float(pa.grad.abs().max()), 1e-2 * gs), "grad %s: %g" % (k, err)
         for (k, xa), (_, xb) in zip(ba.named_buffers(), bb.named_buffers()):
             close(xb.float(), xa.float(), "buffer " + k)
+
+
+@pytest.mark.parametrize("C,B,nv", [(128, 3, 150), (256, 2, 90), (128, 70, 40)])
+def test_avg_block_fused_stage_vs_oracle(C, B, nv):
+    """AvgResNet2 (utils_pt.py:222-243) on the fused stage kernels (sn_avg_stage_pre_f32 / sn_avg_fold_{fwd,bwd}_f32) against
+    the oracle port on the CPU: forward, input and parameter gradients, BatchNorm buffers.  B = 70 exercises the 64-mesh
+    chunking of the fold kernels, ragged masks exercise the masked average.  Tolerance 2e-4 * (|ref| + max|ref|)."""
+    from det import det_fill, det_tensor
+    from oracle import layers as O
+    from surfacenetworks_b200 import utils_pt as U
+    block = det_fill(U.AvgResNet2(C), 5, gain=0.5)
+    P = {}
+    for k, v in block.state_dict().items():
+        v = v.clone()
+        if v.is_floating_point() and not k.endswith(("running_mean", "running_var")):
+            v.requires_grad_(True)
+        P[k] = v
+    x = det_tensor((B, nv, C), 1)
+    mask = torch.ones(B, nv, 1)
+    for b in range(B):
+        mask[b, nv - (b % 7):] = 0           # ragged meshes
+    x = x * mask
+    w = det_tensor((B, nv, C), 3)
+    xc = x.clone().requires_grad_(True)
+    ref = O.avg_resnet2(P, mask, xc)
+    (ref * w).sum().backward()
+    blk = block.to(DEV).train()
+    xg = x.to(DEV).requires_grad_(True)
+    out = blk(None, mask.to(DEV), xg)
+    (out * w.to(DEV)).sum().backward()
+
+    def close(a, b, what, tol=2e-4, floor=0.0):
+        a, b = a.detach().cpu().double(), b.detach().double()
+        err = (a - b).abs()
+        assert torch.all(err <= tol * (b.abs() + max(float(b.abs().max()), floor))), "%s: max err %g scale %g" % (what, float(err.max()), float(b.abs().max()))
+
+    close(out, ref, "out")
+    close(xg.grad, xc.grad, "dx")
+    gscale = max(float(P[k].grad.abs().max()) for k, _ in blk.named_parameters())
+    for k, p in blk.named_parameters():
+        close(p.grad, P[k].grad, "grad " + k, 1e-3, floor=1e-2 * gscale)
