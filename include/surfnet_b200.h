@@ -326,6 +326,35 @@ int sn_avg_fold_bwd_f32(const float* GL, int64_t ldgl, const float* SdY, const f
                         int64_t n_seg, int64_t rows_per_seg, int training, float* dW, float* db, float* dgamma,
                         float* dbeta, float* p, float* q, float* WsT_hi, float* WsT_lo, float* gb, sn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * The two ends of the model stacks.
+ * Input layer conv1 = GraphConv1x1(K -> N, no BatchNorm), K = 3 or 6 channels (as_rigid_as_possible/models.py:112,
+ * dense_correspondence/models.py:144, mesh_mnist/models_vae.py:26; nn.Linear at utils_pt.py:89,99):
+ *   sn_linear_smallk_fwd_f32   Y[rows x N] = X[rows x K] W[N x K]^T + b          (K in {3, 6}, N % 4 == 0; one pass, write-bound)
+ *   sn_linear_smallk_bwd_f32   dW[N x K] = dY^T X, db[N] = colsum(dY) (db may be NULL) from ONE pass over dY; K in {3, 6},
+ *                              N <= 256; deterministic (per-CTA partials, fixed-order fp64 final sum)
+ * as_rigid_as_possible output head and loss (models.py:152, main.py:225-226):
+ *   sn_head_add_tiled_f32      Out[r, j] = Y[r, j] + In[r, c_in - 3 + j % 3]     (`+ inputs[:, :, -3:].repeat(1, 1, 40)`)
+ *   sn_head_pad_grad_f32       dYp[r, j] = j < n_out ? G[r, j] : 0               (gradient of the first n_out columns of the
+ *                              zero-padded 128-wide conv2 output)
+ *   sn_masked_smooth_l1_*      loss[0] = scale * sum smooth_l1(Out .* M - T)   (M: one weight per row, beta = 1);
+ *                              dOut = grad_loss[0] * scale * M .* smooth_l1'(Out .* M - T)   (grad_loss NULL = 1)
+ * ---------------------------------------------------------------------------------------------- */
+int sn_linear_smallk_fwd_f32(const float* X, int64_t ldx, const float* W, const float* b, float* Y, int64_t ldy, int64_t rows,
+                             int64_t N, int64_t K, sn_stream_t stream);
+size_t sn_linear_smallk_bwd_ws_bytes(int64_t N, int64_t K);
+int sn_linear_smallk_bwd_f32(const float* dY, int64_t ldd, const float* X, int64_t ldx, int64_t rows, int64_t N, int64_t K,
+                             float* dW, float* db, void* ws, size_t ws_bytes, sn_stream_t stream);
+int sn_head_add_tiled_f32(const float* Y, int64_t ldy, const float* In, int64_t ldi, int64_t c_in, float* Out, int64_t ldo,
+                          int64_t rows, int64_t n_out, sn_stream_t stream);
+int sn_head_pad_grad_f32(const float* G, int64_t ldg, float* dYp, int64_t ldd, int64_t rows, int64_t n_out, int64_t n_pad,
+                         sn_stream_t stream);
+size_t sn_masked_smooth_l1_ws_bytes(void);
+int sn_masked_smooth_l1_fwd_f32(const float* Out, const float* T, const float* M, int64_t rows, int64_t C, float scale,
+                                float* loss, void* ws, size_t ws_bytes, sn_stream_t stream);
+int sn_masked_smooth_l1_bwd_f32(const float* Out, const float* T, const float* M, const float* grad_loss, int64_t rows,
+                                int64_t C, float scale, float* dOut, sn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

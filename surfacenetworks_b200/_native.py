@@ -63,6 +63,14 @@ SIGNATURES = {
                                    _f32, _i64, _ptr, _i64, _ptr, _ptr]),
     "sn_avg_fold_bwd_f32": (_int, [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _int,
                                    _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "sn_linear_smallk_fwd_f32": (_int, [_ptr, _i64, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr]),
+    "sn_linear_smallk_bwd_ws_bytes": (_sz, [_i64, _i64]),
+    "sn_linear_smallk_bwd_f32": (_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _sz, _ptr]),
+    "sn_head_add_tiled_f32": (_int, [_ptr, _i64, _ptr, _i64, _i64, _ptr, _i64, _i64, _i64, _ptr]),
+    "sn_head_pad_grad_f32": (_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _ptr]),
+    "sn_masked_smooth_l1_ws_bytes": (_sz, []),
+    "sn_masked_smooth_l1_fwd_f32": (_int, [_ptr, _ptr, _ptr, _i64, _i64, _f32, _ptr, _ptr, _sz, _ptr]),
+    "sn_masked_smooth_l1_bwd_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _i64, _f32, _ptr, _ptr]),
     "sn_split_tf32_f32": (_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr]),
     "sn_csr_spmm_epilogue_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64,
                                         _int, _ptr]),

@@ -429,6 +429,148 @@ def avg_stage(x, mask, bn, fc, residual=None, in_cell=None, res_cell=None):
                            bn.running_var, training, momentum, bn.eps, B, V, in_cell, res_cell)
 
 
+class _SmallKLinear(torch.autograd.Function):
+    """nn.Linear with 3 or 6 input channels on rows (the models' conv1): one write-bound pass forward, one pass over dY
+    backward (dW and db together) instead of a SIMT sgemm over 1e5 rows plus a column-sum."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        rows, K = x.shape
+        Nn = W.shape[0]
+        x = x.contiguous()
+        W = W.contiguous()
+        y = torch.empty(rows, Nn, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            N.call("sn_linear_smallk_fwd_f32", _ptr(x), x.stride(0), _ptr(W), _ptr(b), _ptr(y), y.stride(0), rows, Nn, K, _stream())
+        ctx.save_for_backward(x, W)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dY):
+        x, W = ctx.saved_tensors
+        rows, K = x.shape
+        Nn = W.shape[0]
+        if dY.stride(1) != 1 or dY.stride(0) % 4 or dY.data_ptr() % 16:
+            dY = dY.contiguous()
+        dW = torch.empty_like(W)
+        db = torch.empty(Nn, dtype=torch.float32, device=x.device) if ctx.has_bias else None
+        nb = N.lib.sn_linear_smallk_bwd_ws_bytes(Nn, K)
+        ws = _ws(nb, x.device)
+        with torch.cuda.device(x.device):
+            N.call("sn_linear_smallk_bwd_f32", _ptr(dY), dY.stride(0), _ptr(x), x.stride(0), rows, Nn, K, _ptr(dW), _ptr(db),
+                   _ptr(ws), nb, _stream())
+        dx = dY @ W if ctx.needs_input_grad[0] else None
+        return dx, dW, db
+
+
+def smallk_linear_supported(x, fc):
+    n_out, k = fc.weight.shape
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and k in (3, 6) and n_out % 4 == 0 and n_out <= 256
+            and 256 % (n_out // 4) == 0 and x.shape[0] > 0 and fc.weight.dtype == torch.float32)
+
+
+def smallk_linear(x, fc):
+    """fc(x) for the 3 / 6-channel input layers (see _SmallKLinear); caller checks ``smallk_linear_supported``."""
+    return _SmallKLinear.apply(x, fc.weight, fc.bias)
+
+
+class _SliceCols(torch.autograd.Function):
+    """y[:, :n] of a zero-padded [rows, n_pad] GEMM output; backward writes the padded gradient in one kernel
+    (sn_head_pad_grad_f32) instead of autograd's zeros + strided copy."""
+
+    @staticmethod
+    def forward(ctx, yp, n):
+        ctx.n, ctx.n_pad = n, yp.shape[1]
+        return yp[:, :n]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        rows = g.shape[0]
+        if g.stride(1) != 1 or g.stride(0) % 4 or g.data_ptr() % 16 or ctx.n % 4:
+            out = g.new_zeros(rows, ctx.n_pad)
+            out[:, :ctx.n] = g
+            return out, None
+        out = torch.empty(rows, ctx.n_pad, dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            N.call("sn_head_pad_grad_f32", _ptr(g), g.stride(0), _ptr(out), out.stride(0), rows, ctx.n, ctx.n_pad, _stream())
+        return out, None
+
+
+class _HeadAddTiled(torch.autograd.Function):
+    """``y + inputs[:, :, -3:].repeat(1, 1, n // 3)`` (as_rigid_as_possible/models.py:152 and twins) in one pass."""
+
+    @staticmethod
+    def forward(ctx, y, inputs):
+        B, V, n = y.shape
+        y2 = y.reshape(B * V, n)
+        in2 = inputs.reshape(B * V, inputs.shape[2])
+        out = torch.empty(B * V, n, dtype=torch.float32, device=y.device)
+        with torch.cuda.device(y.device):
+            N.call("sn_head_add_tiled_f32", _ptr(y2), y2.stride(0), _ptr(in2), in2.stride(0), in2.shape[1], _ptr(out),
+                   out.stride(0), B * V, n, _stream())
+        return out.view(B, V, n)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+def head_add_tiled(y, inputs, times):
+    """``y + inputs[:, :, -3:].repeat(1, 1, times)``; fused when y is fp32 CUDA with a 16-byte-aligned row layout."""
+    n = y.shape[2]
+    y2 = y.reshape(-1, n) if y.dim() == 3 else None
+    ok = (y.is_cuda and y.dtype == torch.float32 and y.dim() == 3 and n == 3 * times and n % 4 == 0 and not inputs.requires_grad
+          and inputs.dtype == torch.float32 and inputs.is_contiguous() and y2 is not None and y2.stride(1) == 1
+          and y2.stride(0) % 4 == 0 and y2.data_ptr() % 16 == 0 and y2.data_ptr() == y.data_ptr())
+    if ok:
+        return _HeadAddTiled.apply(y, inputs)
+    return y + inputs[:, :, -3:].repeat(1, 1, times)
+
+
+class _MaskedSmoothL1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, outputs, targets, maskw, scale):
+        rows = maskw.numel()
+        C = outputs.numel() // rows
+        loss = torch.empty((), dtype=torch.float32, device=outputs.device)
+        nb = N.lib.sn_masked_smooth_l1_ws_bytes()
+        ws = _ws(nb, outputs.device)
+        with torch.cuda.device(outputs.device):
+            N.call("sn_masked_smooth_l1_fwd_f32", _ptr(outputs), _ptr(targets), _ptr(maskw), rows, C, float(scale), _ptr(loss),
+                   _ptr(ws), nb, _stream())
+        ctx.save_for_backward(outputs, targets, maskw)
+        ctx.scale = float(scale)
+        return loss
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        outputs, targets, maskw = ctx.saved_tensors
+        rows = maskw.numel()
+        C = outputs.numel() // rows
+        g = g.contiguous().to(torch.float32)
+        d = torch.empty_like(outputs)
+        with torch.cuda.device(outputs.device):
+            N.call("sn_masked_smooth_l1_bwd_f32", _ptr(outputs), _ptr(targets), _ptr(maskw), _ptr(g), rows, C, ctx.scale, _ptr(d),
+                   _stream())
+        return d, None, None, None
+
+
+def masked_smooth_l1(outputs, targets, mask, scale):
+    """``scale * F.smooth_l1_loss(outputs * mask, targets, reduction="sum")`` (as_rigid_as_possible/main.py:225-226) as one
+    reduction pass forward and one elementwise pass backward; None when the layout is outside the fused path."""
+    if not (outputs.is_cuda and outputs.dtype == torch.float32 and targets.dtype == torch.float32 and outputs.dim() == 3
+            and outputs.shape == targets.shape and outputs.is_contiguous() and targets.is_contiguous()
+            and mask.shape[:2] == outputs.shape[:2] and mask.numel() == outputs.shape[0] * outputs.shape[1]
+            and outputs.shape[2] % 4 == 0 and not targets.requires_grad and not mask.requires_grad):
+        return None
+    maskw = mask_info(mask, outputs.shape[0], outputs.shape[1])[0]
+    return _MaskedSmoothL1.apply(outputs, targets, maskw, scale)
+
+
 def bn_linear_is_fused(rows_like, fc, residual_cols=None):
     """Will bn_linear take the fused path for a [rows, 2C] buffer made from ``rows_like`` [rows, C]?  (Same conditions as
     fused_supported, evaluated before the buffer exists.)"""
@@ -470,6 +612,6 @@ def bn_linear(z, bn, fc, residual=None, res_cell=None):
             momentum = 0.1 if bn.momentum is None else bn.momentum
             y = _BnLinear.apply(z, bn.weight, bn.bias, w_pad, b_pad, None, bn.running_mean, bn.running_var, training,
                                 momentum, bn.eps, None)
-            return y[:, :n_out]
+            return _SliceCols.apply(y, n_out)
     y = fc(bn(z))
     return y if residual is None else y + residual

@@ -19,6 +19,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import fused
 from . import ops
 from . import utils_pt as utils
 from .operators import as_bsr4, as_csr
@@ -34,6 +35,11 @@ def _add_blocks(model, kinds, width):
 
 def _last3_tiled(inputs, times):
     return inputs[:, :, -3:].repeat(1, 1, times)
+
+
+def _add_last3_tiled(y, inputs, times):
+    """``y + inputs[:, :, -3:].repeat(1, 1, times)`` (reference as_rigid_as_possible/models.py:152): one fused pass."""
+    return fused.head_add_tiled(y, inputs, times)
 
 
 def _num_faces(Di, DiA, batch_size):
@@ -77,7 +83,7 @@ class ArapLapModel(nn.Module):
         x = self.conv1(inputs)
         for i in range(self.layer):
             x = self._modules["rn{}".format(i)](L, mask, x)
-        return self.conv2(F.elu(x)) + _last3_tiled(inputs, 40)
+        return _add_last3_tiled(self.conv2(F.elu(x)), inputs, 40)
 
 
 class ArapAvgModel(nn.Module):
@@ -91,7 +97,7 @@ class ArapAvgModel(nn.Module):
         x = self.conv1(inputs)
         for i in range(15):
             x = self._modules["rn{}".format(i)](L, mask, x)
-        return self.conv2(F.elu(x)) + _last3_tiled(inputs, 40)
+        return _add_last3_tiled(self.conv2(F.elu(x)), inputs, 40)
 
 
 class ArapMlpModel(nn.Module):
@@ -125,11 +131,14 @@ class ArapDirModel(nn.Module):
         v = self.conv1(inputs)
         f = v.new_zeros(batch_size, _num_faces(Di, DiA, batch_size), 128)
         v = _dirac_stack(self, 15, D, DA, mask, v, f)
-        return self.conv2(F.elu(v)) + _last3_tiled(inputs, 40)
+        return _add_last3_tiled(self.conv2(F.elu(v)), inputs, 40)
 
 
 def arap_loss(outputs, targets, mask, batch_size):
     """Masked smooth-L1, summed, per mesh (src/as_rigid_as_possible/main.py:225-226)."""
+    loss = fused.masked_smooth_l1(outputs, targets, mask, 1.0 / batch_size) if outputs.is_cuda else None
+    if loss is not None:
+        return loss
     return F.smooth_l1_loss(outputs * mask.expand_as(outputs), targets, reduction="sum") / batch_size
 
 
@@ -228,7 +237,7 @@ class DcLapModel(nn.Module):
         x = self.conv1(inputs)
         for i in range(self.layer):
             x = self._modules["rn{}".format(i)](Lop, mask, x)
-        return self.conv2(F.elu(x)) + _last3_tiled(inputs, 40)
+        return _add_last3_tiled(self.conv2(F.elu(x)), inputs, 40)
 
 
 class DcDirModel(nn.Module):
@@ -250,7 +259,7 @@ class DcDirModel(nn.Module):
         v = self.conv1(inputs)
         f = v.new_zeros(batch_size, DA.n_bcols // batch_size, 128)
         v = _dirac_stack(self, self.layer, D, DA, mask, v, f)
-        return self.conv2(F.elu(v)) + _last3_tiled(inputs, 40)
+        return _add_last3_tiled(self.conv2(F.elu(v)), inputs, 40)
 
 
 class SiameseModel(nn.Module):

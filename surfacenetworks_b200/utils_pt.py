@@ -113,7 +113,10 @@ class GraphConv1x1(nn.Module):
         epilogue) whenever the widths allow it."""
         if self.batch_norm == "pre":
             return fused.bn_linear(z, self.bn, self.fc, residual, res_cell)
-        z = self.fc(z)
+        if fused.smallk_linear_supported(z, self.fc):          # the 3 / 6-channel input layers (conv1)
+            z = fused.smallk_linear(z, self.fc)
+        else:
+            z = self.fc(z)
         if self.batch_norm == "post":
             z = self.bn(z)
         return z if residual is None else z + residual
