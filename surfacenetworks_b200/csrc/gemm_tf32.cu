@@ -34,6 +34,8 @@
 // selects the old kernel (A/B runs, tools/gemm_bench.py).
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace sn {
@@ -425,6 +427,9 @@ struct ParamsTS {
   float* C2;
   int64_t ldc2;
   float* stat_partial;
+  int r_slots;           // residual boxes in flight per epilogue warp (1 or 2)
+  int epi_slots;         // 4 KB staging boxes per epilogue warp: output (+ residual slots / activated copy)
+  int debug;             // timing experiments only (SN_GEMM_DEBUG_*, tools/gemm_stage_bench.py): results are garbage
 };
 
 // Roles (16 warps): 0 = A producer (TMA), 3 = B producer (TMA), 1 = MMA issuer, 2 = TMEM allocation, 4-7 = A split into
@@ -436,7 +441,9 @@ struct ParamsTS {
 template <bool ACT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const __grid_constant__ CUtensorMap map_blo, const ParamsTS p) {
+                    const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_c,
+                    const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_c2,
+                    const ParamsTS p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int nmma = p.nmma;
@@ -444,10 +451,12 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const uint32_t b_bytes = (uint32_t)nmma * kBlockK * 4;    // 8 / 16 KB per half (hi or lo)
   unsigned char* a_ring = smem;
   unsigned char* b_ring = smem + (size_t)p.a_stages * a_bytes;
+  // epilogue staging, per epilogue warp: [output box 4 KB][p.epi_slots - 1 more 4 KB boxes: residual slots / activated copy]
+  unsigned char* epi_ring = b_ring + (size_t)p.b_stages * 2 * b_bytes;
   __shared__ uint64_t a_full[kMaxAStages], a_free[kMaxAStages], a_ready[kATmemStages], a_tfree[kATmemStages];
   __shared__ uint64_t b_full[kMaxBStages], b_free[kMaxBStages], tmem_full[2], tmem_empty[2];
+  __shared__ uint64_t r_full[kEpiWarps][2];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ __align__(16) float epi_buf[kEpiWarps * 32 * 20];
   __shared__ __align__(16) float s_bias[256], s_rscale[256];   // epilogue vectors: LDS instead of an L1-missing __ldg per chunk
   __shared__ __align__(16) float s_stat[ACT ? kEpiWarps : 1][2][128];   // ACT: per-epilogue-warp column sums / sums of squares
 
@@ -478,6 +487,10 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       mbar_init(tmem_full + b, 1);
       mbar_init(tmem_empty + b, kEpiWarps);
     }
+    for (int w = 0; w < kEpiWarps; ++w) {
+      mbar_init(&r_full[w][0], 1);
+      mbar_init(&r_full[w][1], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {                       // all 512 TMEM columns: 2 accumulators + 4 A stages (one CTA per SM)
@@ -505,7 +518,7 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else if (warp == 3) {
     // ------------------------------------------------------------------ B producer (pre-split weights, L2-resident)
-    if (elect_one()) {
+    if (elect_one() && !(p.debug & 16)) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
@@ -541,12 +554,12 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const uint32_t cnt = p.a_resident ? a_cnt + (uint32_t)kb : a_cnt;
             const uint32_t at = cnt % kATmemStages;
             if (half == 0 || !p.a_resident) mbar_wait(a_ready + at, (cnt / kATmemStages) & 1u);
-            mbar_wait(b_full + bs, bph);
+            if (!(p.debug & 16)) mbar_wait(b_full + bs, bph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t ta = tmem_base + (uint32_t)(kATmemCol0 + at * 64);
             const uint32_t dlo = d_lo0 + (uint32_t)bs * stage_units;
 #pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            for (int k = 0; k < kBlockK / kUmmaK && !(p.debug & 4); ++k) {
               // 32 bytes per k-step inside the swizzle row = 2 descriptor units; 8 TMEM columns per k-step of A
               umma_tf32_ts_lohi(tmem_d, ta + k * kUmmaK, dlo + 2 * k, d_hi, idesc, (uint32_t)((kb | k) != 0));
               if (split) {
@@ -554,7 +567,7 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 umma_tf32_ts_lohi(tmem_d, ta + 32 + k * kUmmaK, dlo + 2 * k, d_hi, idesc, 1u);            // lo * hi
               }
             }
-            umma_commit(b_free + bs);
+            if (!(p.debug & 16)) umma_commit(b_free + bs);
             if (!p.a_resident || half == n_halves - 1) umma_commit(a_tfree + at);
             if (kb == n_kb - 1) umma_commit(tmem_full + buf);
             if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
@@ -579,6 +592,10 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           mbar_wait(a_full + as, aph);
           const uint32_t row = a_ring_s + (uint32_t)as * a_bytes + (uint32_t)r * 128u;
           uint32_t hi[32], lo[32];
+          if (p.debug & 8) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) hi[i] = lo[i] = (uint32_t)i;
+          } else
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 x = lds_f4(row + (uint32_t)((i ^ (r & 7)) << 4));
@@ -607,25 +624,29 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
   } else if (warp >= 8) {
     // ------------------------------------------------------------------ epilogue (one job = one row tile x one column pass)
+    // Round-2 rewrite.  The first TS epilogue moved the tile through per-thread global accesses (register prefetch of the
+    // residual, transpose buffer, 64-byte store segments): ~375 instructions per 16-column chunk and warp, and it -- not
+    // HBM, not the tensor pipe -- set the kernel's period (tools/gemm_stage_bench.py: [128000 x 128] . [128 x 128] + R
+    // 54 us, 25 us with the epilogue switched off).  Now every global access of the epilogue is a TMA box:
+    //   * warp e owns tile rows [32 (e % 4), +32) (its TMEM lanes) and the column half e / 4 of the job; it works in
+    //     32-column chunks: tcgen05.ld gives lane r the 32 columns of row r = one 128-byte row of a [32 x 32] box;
+    //   * the residual box of that chunk was TMA-loaded (128-byte swizzle) into the warp's slot one or two chunks ahead
+    //     (flat chunk sequence across jobs and tiles: loads for the next job fly while the tensor core works on it);
+    //   * results go to the warp's output box with conflict-free swizzled STS.128 and leave with ONE
+    //     cp.async.bulk.tensor store (rows >= M are clipped by the tensor map): no address arithmetic, no predicates.
     const int e = warp - 8;
     const int quarter = e & 3, chalf = e >> 2;
-    float* tbuf = epi_buf + e * (32 * 20);
-    const int tr = lane >> 2, tc = (lane & 3) * 4;            // 4 lanes cover one row's 16 columns (64 bytes)
     const int ncol = nmma / 2;                                 // columns owned by this warp inside the job
+    const int nchunks = ncol / 32;                             // 2 (nmma = 128) or 1 (nmma = 64)
     const int N = p.N;
-    auto load_r = [&](float4 (&rr)[4], int row0, int c0) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int row = row0 + i * 8 + tr;
-        rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < p.M) rr[i] = __ldcs(reinterpret_cast<const float4*>(p.R + (int64_t)row * p.ldr + c0 + tc));
-      }
-    };
-    // The residual operand R does not depend on the accumulator: its loads run TWO 16-column chunks ahead of the chunk
-    // being finished, across job and tile boundaries (a flat chunk sequence), so their DRAM latency never sits between a
-    // completed accumulator and its stores.  (Round-2 first version restarted the prefetch at every tile: ncu showed the
-    // epilogue warps on a long-scoreboard stall at each tile start while the MMA warp waited for a free accumulator.)
-    const int nchunks = ncol / 16;
+    unsigned char* my_g = epi_ring + (size_t)e * p.epi_slots * 4096;
+    const uint32_t my_s = smem_u32(my_g);
+    const uint32_t out_s = my_s;                               // output box
+    const int r_slots = p.r_slots;                             // residual slots (ACT: the last box stages the activated copy)
+    const uint32_t r_s = my_s + 4096;
+    const uint32_t act_s = my_s + (uint32_t)(p.epi_slots - 1) * 4096;
+    const uint32_t row_off = (uint32_t)lane * 128u;
+    const uint32_t sw = (uint32_t)(lane & 7);
     struct ChunkIt { int tile, half, c; };
     auto advance = [&](ChunkIt& it) {
       if (++it.c == nchunks) {
@@ -633,15 +654,22 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (++it.half == n_halves) { it.half = 0; it.tile += (int)gridDim.x; }
       }
     };
-    auto load_chunk = [&](float4 (&rr)[4], const ChunkIt& it) {
-      if (it.tile < n_tiles) load_r(rr, it.tile * kBlockM + quarter * 32, it.half * nmma + chalf * ncol + it.c * 16);
-    };
-    float4 rr[4], rn[4], rn2[4];
     ChunkIt pf = {(int)blockIdx.x, 0, 0};
-    if (p.R) {
-      load_chunk(rr, pf); advance(pf);
-      load_chunk(rn, pf); advance(pf);
-    }
+    uint32_t r_issued = 0, r_used = 0;
+    auto issue_r = [&]() {                                     // TMA load of the residual box of chunk `pf` into the next slot
+      if (pf.tile < n_tiles) {
+        if (lane == 0) {
+          const uint32_t slot = r_issued % (uint32_t)r_slots;
+          mbar_arrive_expect_tx(&r_full[e][slot], 4096u);
+          tma_load_2d(my_g + 4096 + slot * 4096u, &map_r, pf.half * nmma + chalf * ncol + pf.c * 32,
+                      pf.tile * kBlockM + quarter * 32, &r_full[e][slot]);
+        }
+        ++r_issued;
+        advance(pf);
+      }
+    };
+    if (p.R)
+      for (int i = 0; i < r_slots; ++i) issue_r();
     if (ACT) {
       for (int i = lane; i < 2 * 128; i += 32) (&s_stat[e][0][0])[i] = 0.f;
       __syncwarp();
@@ -652,82 +680,101 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const uint32_t buf = job & 1u;
         const int row0 = tile * kBlockM + quarter * 32;
         const int cbase = half * nmma + chalf * ncol;          // first global column of this warp's share
-        if (p.R && p.l2_prefetch) {                            // the next job's residual rows into L2
-          const bool next_half = half + 1 < n_halves;
-          const int nrow0 = (next_half ? tile : tile + (int)gridDim.x) * kBlockM + quarter * 32;
-          const int ncb = (next_half ? (half + 1) * nmma : 0) + chalf * ncol;
-          const int lines = ncol / 32;
-          for (int i = lane; i < 32 * lines; i += 32) {
-            const int row = nrow0 + i / lines;
-            if (row < p.M) prefetch_l2(p.R + (int64_t)row * p.ldr + ncb + (i % lines) * 32);
-          }
-        }
+        const float* gb_row = p.gbias ? p.gbias + (int64_t)((row0 + lane < p.M ? row0 + lane : p.M - 1) / p.rows_per_group) * N : nullptr;
         mbar_wait(tmem_full + buf, (job >> 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int c0 = cbase; c0 < cbase + ncol; c0 += 16) {
-          uint32_t v[16];
-          if (p.R) { load_chunk(rn2, pf); advance(pf); }       // residual two chunks ahead
-          tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * nmma + (c0 - half * nmma)), v);
-#pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            *reinterpret_cast<float4*>(tbuf + lane * 20 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                                            __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        for (int ci = 0; ci < nchunks && !(p.debug & 1); ++ci) {
+          const int c0 = cbase + ci * 32;
+          uint32_t rslot_s = 0;
+          if (p.R) {
+            const uint32_t slot = r_used % (uint32_t)r_slots;
+            mbar_wait(&r_full[e][slot], (r_used / (uint32_t)r_slots) & 1u);
+            rslot_s = r_s + slot * 4096u;
+          }
+          // the previous bulk store(s) of this warp must have read the staging boxes before they are overwritten
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();
-          const float4 bia = *reinterpret_cast<const float4*>(s_bias + c0 + tc);
-          const float4 rs = *reinterpret_cast<const float4*>(s_rscale + c0 + tc);
-          float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), qsum = ssum;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rl = i * 8 + tr;
-            const int row = row0 + rl;
-            if (row < p.M) {
-              float4 o = add4(*reinterpret_cast<const float4*>(tbuf + rl * 20 + tc), bia);
-              if (p.gbias)
-                o = add4(o, __ldg(reinterpret_cast<const float4*>(p.gbias + (int64_t)(row / p.rows_per_group) * N + c0 + tc)));
+          for (int h = 0; h < 2; ++h) {                        // 16 accumulator columns per tcgen05.ld
+            uint32_t v[16];
+            if (p.debug & 2) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = (uint32_t)(c0 + j);
+            } else {
+              tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * nmma + (c0 - half * nmma) + h * 16), v);
+            }
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const int cidx = h * 4 + j4;                     // 16-byte chunk of the 128-byte box row
+              const int col = c0 + cidx * 4;
+              const uint32_t swz = row_off + (((uint32_t)cidx ^ sw) << 4);
+              float4 o = add4(make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]),
+                                          __uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])),
+                              *reinterpret_cast<const float4*>(s_bias + col));
+              if (p.gbias) o = add4(o, __ldg(reinterpret_cast<const float4*>(gb_row + col)));
               if (p.R) {
-                o.x = fmaf(rs.x, rr[i].x, o.x); o.y = fmaf(rs.y, rr[i].y, o.y);
-                o.z = fmaf(rs.z, rr[i].z, o.z); o.w = fmaf(rs.w, rr[i].w, o.w);
-                if (!ACT && p.elu_left && c0 < (N >> 1)) {   // chunk-uniform: 16-column chunks never straddle N/2
-                  o.x *= rr[i].x > 0.f ? 1.f : rr[i].x + 1.f; o.y *= rr[i].y > 0.f ? 1.f : rr[i].y + 1.f;
-                  o.z *= rr[i].z > 0.f ? 1.f : rr[i].z + 1.f; o.w *= rr[i].w > 0.f ? 1.f : rr[i].w + 1.f;
+                const float4 rr = lds_f4(rslot_s + swz);
+                const float4 rs = *reinterpret_cast<const float4*>(s_rscale + col);
+                o.x = fmaf(rs.x, rr.x, o.x); o.y = fmaf(rs.y, rr.y, o.y);
+                o.z = fmaf(rs.z, rr.z, o.z); o.w = fmaf(rs.w, rr.w, o.w);
+                if (!ACT && p.elu_left && c0 < (N >> 1)) {     // chunk-uniform: 32-column chunks never straddle N/2
+                  o.x *= rr.x > 0.f ? 1.f : rr.x + 1.f; o.y *= rr.y > 0.f ? 1.f : rr.y + 1.f;
+                  o.z *= rr.z > 0.f ? 1.f : rr.z + 1.f; o.w *= rr.w > 0.f ? 1.f : rr.w + 1.f;
                 }
               }
-              if (!ACT || p.C) st_stream_f4(p.C + (int64_t)row * p.ldc + c0 + tc, o);
+              if (!ACT || p.C)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(out_s + swz), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
               if (ACT) {
-                // the activated copy is re-read soon (gathered by the next SpMM / A operand of the next GEMM): default
-                // store policy, not streaming
                 const float4 a = elu4(o);
-                *reinterpret_cast<float4*>(p.C2 + (int64_t)row * p.ldc2 + c0 + tc) = a;
-                ssum = add4(ssum, a);
-                qsum.x = fmaf(a.x, a.x, qsum.x); qsum.y = fmaf(a.y, a.y, qsum.y);
-                qsum.z = fmaf(a.z, a.z, qsum.z); qsum.w = fmaf(a.w, a.w, qsum.w);
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(act_s + swz), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
               }
             }
           }
-          if (ACT && p.stat_partial) {
-            // rows of the chunk: 4 per lane (above), then the 8 lanes that share tc (lane bits 2..4), fixed tree order
-#pragma unroll
-            for (int m = 4; m <= 16; m <<= 1) {
-              ssum = add4(ssum, shfl_xor4(ssum, m));
-              qsum = add4(qsum, shfl_xor4(qsum, m));
-            }
-            if (lane < 4) {
-              const int lc = half * ncol + (c0 - cbase) + tc;     // column inside this warp's share of the N columns
-              float4* sp = reinterpret_cast<float4*>(&s_stat[e][0][lc]);
-              float4* qp = reinterpret_cast<float4*>(&s_stat[e][1][lc]);
-              *sp = add4(*sp, ssum);
-              *qp = add4(*qp, qsum);
-            }
+          if (ci == nchunks - 1) {                             // accumulator drained: hand it back before the stores
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty + buf);
           }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem accesses -> visible to TMA
           __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { rr[i] = rn[i]; rn[i] = rn2[i]; }
+          if (p.R) {                                           // every lane has read this slot: refill it
+            ++r_used;
+            issue_r();
+          }
+          if (lane == 0) {
+            if (!ACT || p.C)
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&map_c), "r"(c0),
+                           "r"(row0), "r"(out_s) : "memory");
+            if (ACT)
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&map_c2), "r"(c0),
+                           "r"(row0), "r"(act_s) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          if (ACT && p.stat_partial) {
+            // column sums of the activated box: lane L adds column L over the valid rows, in row order
+            const int nvalid = p.M - row0 < 32 ? (p.M - row0 > 0 ? p.M - row0 : 0) : 32;
+            float cs = 0.f, cq = 0.f;
+            const uint32_t cpos = (uint32_t)(lane >> 2), cin = (uint32_t)(lane & 3) * 4u;
+            for (int r = 0; r < nvalid; ++r) {
+              float a;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a) : "r"(act_s + (uint32_t)r * 128u + ((cpos ^ (uint32_t)(r & 7)) << 4) + cin));
+              cs += a;
+              cq = fmaf(a, a, cq);
+            }
+            const int lc = half * ncol + ci * 32 + lane;       // column inside this warp's share of the N columns
+            s_stat[e][0][lc] += cs;
+            s_stat[e][1][lc] += cq;
+          }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty + buf);
+        if (p.debug & 1) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty + buf);
+        }
       }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before the CTA exits
+    __syncwarp();
     if (ACT && p.stat_partial) {
       // the CTA's partial: the four row-quarter warps that own a column, added in a fixed order
       asm volatile("bar.sync 1, 256;" ::: "memory");           // the eight epilogue warps only
@@ -855,26 +902,45 @@ static int launch_gemm(const float* A, int64_t lda, const float* B_hi, const flo
   p.l2_prefetch = l2_prefetch;
   p.elu_left = (flags & SN_GEMM_ELU_BWD_LEFT) ? 1 : 0;
   p.C2 = C_act; p.ldc2 = ldc_act; p.stat_partial = stat_partial;
+  p.debug = (flags >> 8) & 0xff;
   if (!make_map(&map_b, B_hi, N, K, ldb, p.nmma)) return SN_ERR_UNSUPPORTED;
   if (split) {
     if (!make_map(&map_blo, B_lo, N, K, ldb, p.nmma)) return SN_ERR_UNSUPPORTED;
   } else {
     map_blo = map_b;
   }
-  // shared memory: B ring of 3 stages (hi | lo; the weights come from L2), the rest goes to the A ring (HBM latency)
+  // epilogue boxes: [32 rows x 32 columns], 128-byte swizzle, one tensor map per matrix the epilogue touches
+  CUtensorMap map_c, map_r, map_c2;
+  if (C && !make_map(&map_c, C, M, N, ldc, 32)) return SN_ERR_UNSUPPORTED;
+  if (C_act && !make_map(&map_c2, C_act, M, N, ldc_act, 32)) return SN_ERR_UNSUPPORTED;
+  if (!C) map_c = map_c2;
+  if (!C_act) map_c2 = map_c;
+  if (R) {
+    if (!make_map(&map_r, R, M, N, ldr, 32)) return SN_ERR_UNSUPPORTED;
+  } else {
+    map_r = map_c;
+  }
+  // shared memory: per epilogue warp one output box + the residual slots (+ the activated copy); a B ring of pre-split
+  // weights streamed from L2; everything else goes to the A ring (HBM latency)
+  static const int env_rslots = [] { const char* v = getenv("SN_GEMM_RSLOTS"); return v ? atoi(v) : 0; }();
+  static const int env_bstages = [] { const char* v = getenv("SN_GEMM_BSTAGES"); return v ? atoi(v) : 0; }();
+  p.r_slots = R ? ((env_rslots == 1 || env_rslots == 2) ? env_rslots : (C_act ? 1 : 2)) : 0;
+  if (C_act && p.r_slots > 1) p.r_slots = 1;
+  p.epi_slots = 1 + p.r_slots + (C_act ? 1 : 0);
   const size_t a_bytes = (size_t)kBlockM * kBlockK * 4, b_stage = 2 * (size_t)p.nmma * kBlockK * 4;
-  // static: transpose buffers, epilogue vectors, barriers (+ 8 KB of statistics accumulators in the ACT kernel); 1 KB alignment
-  const size_t budget = (size_t)smem_optin - (C_act ? 32 : 24) * 1024 - 1024;
-  p.b_stages = 3;
-  int a_stages = (int)((budget - p.b_stages * b_stage) / a_bytes);
+  const size_t epi_bytes = (size_t)kEpiWarps * p.epi_slots * 4096;
+  // static: epilogue vectors, barriers (+ 8 KB of statistics accumulators in the ACT kernel); 1 KB alignment
+  const size_t budget = (size_t)smem_optin - (C_act ? 12 : 4) * 1024 - 1024;
+  p.b_stages = (env_bstages >= 2 && env_bstages <= kMaxBStages) ? env_bstages : (epi_bytes <= 64 * 1024 ? 3 : 2);
+  int a_stages = (int)((budget - p.b_stages * b_stage - epi_bytes) / a_bytes);
   if (a_stages > kMaxAStages) a_stages = kMaxAStages;
   if (a_stages < 2) return SN_ERR_UNSUPPORTED;
   p.a_stages = a_stages;
-  const size_t smem = a_stages * a_bytes + p.b_stages * b_stage + 1024;
+  const size_t smem = a_stages * a_bytes + p.b_stages * b_stage + epi_bytes + 1024;
   auto kern = C_act ? gemm_tf32_ts_kernel<true> : gemm_tf32_ts_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  kern<<<grid, kThreads, smem, stream>>>(map_a, map_b, map_blo, p);
+  kern<<<grid, kThreads, smem, stream>>>(map_a, map_b, map_blo, map_c, map_r, map_c2, p);
   return launch_status();
 }
 
