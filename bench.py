@@ -266,23 +266,42 @@ def spmm_sweep(dev):
             total += e0.elapsed_time(e1)
         return total / reps
 
-    def entry(op, X, C):
+    def parity(op, S, X):
+        """CHECKER (not measured): the timed tensors against the double-precision oracle product, the bound of
+        tests/test_gpu_spmm.py: |y - y64| <= 32 eps_fp32 (|S||x|).  Returns the worst error in units of eps |S||x|."""
+        from oracle import c_oracle
+        idx, val = S._indices().numpy(), S._values().numpy()
+        y = op.apply(X).cpu().numpy().astype(np.float64)
+        xh = X.cpu().numpy()
+        if op.kind == "csr":
+            y64, bound = c_oracle.coo_mm_f64(idx[0], idx[1], val, S.shape[0], xh)
+        else:
+            y64, bound = c_oracle.dirac_view_mm_f64(idx[0], idx[1], val, S.shape[0] // 4, xh)
+        worst = float((np.abs(y - y64) / (np.finfo(np.float32).eps * bound + 1e-300)).max())
+        if not worst < 32:
+            raise AssertionError("SpMM parity against the oracle failed: worst error %.1f eps |S||x|" % worst)
+        return worst
+
+    def entry(op, S, X, C):
         ms = time_op(op, X)
         gbps = op.algorithmic_bytes(C) / ms / 1e6
         return {"us": ms * 1e3, "GBps": gbps, "frac_of_hbm_peak": gbps / measured_peaks()[0],
-                "GFLOPs": op.flops(C) / ms / 1e6, "alg_MB": op.algorithmic_bytes(C) / 1e6}
+                "GFLOPs": op.flops(C) / ms / 1e6, "alg_MB": op.algorithmic_bytes(C) / 1e6,
+                "parity_checked": True, "worst_err_eps_Sx": parity(op, S, X)}
 
     # cfg2: mesh_mnist Laplacian, 32 meshes x 500 V, C=128
     meshes = W.make_mesh_ops(500, range(32))
-    L = OP.as_csr(W.lap_batch(meshes)["L"].to(dev))
-    out["lap_cfg2_B32_V500_C128"] = entry(L, torch.randn(L.n_cols, 128, device=dev), 128)
+    Lc = W.lap_batch(meshes)["L"]
+    L = OP.as_csr(Lc.to(dev))
+    out["lap_cfg2_B32_V500_C128"] = entry(L, Lc, torch.randn(L.n_cols, 128, device=dev), 128)
     # cfg5: FAUST-size single mesh, Dirac sweep over feature width
     m = W.make_mesh_ops(7000, [0])
     b = W.arap_batch(m, 0)
     D, DA = OP.as_bsr4(b["Di"].to(dev)), OP.as_bsr4(b["DiA"].to(dev))
     for C in (16, 32, 64, 128, 256, 512):
-        out["dirac_D_cfg5_V7000_C%d" % C] = entry(D, torch.randn(D.n_bcols, C, device=dev), C)
-        out["dirac_Dstar_cfg5_V7000_C%d" % C] = entry(DA, torch.randn(DA.n_bcols, C, device=dev), C)
+        out["dirac_D_cfg5_V7000_C%d" % C] = entry(D, b["Di"], torch.randn(D.n_bcols, C, device=dev), C)
+        out["dirac_Dstar_cfg5_V7000_C%d" % C] = entry(DA, b["DiA"], torch.randn(DA.n_bcols, C, device=dev), C)
+    out["parity_bound"] = "|y - y64| <= 32 eps_fp32 (|S||x|) against oracle/sn_oracle.c (double precision), asserted on the timed tensors"
     return out
 
 
@@ -332,6 +351,21 @@ def breakdown(dev, model, res, Dop, DAop, host, B):
         mu, lv = enc(x2, L2, m2)
         (mu.sum() + lv.sum()).backward()
     out["cfg2_lap_encoder_forward_backward_ms"] = gpu_ms(enc_train)
+    # BASELINE configs[1] as a training step: the same encoder, Adam, captured once into a CUDA graph by the package
+    # (graph.CapturedTrainStep) -- 16 000-row problems are launch-bound when driven op by op
+    from surfacenetworks_b200 import graph as G
+    enc2 = M.LapEncoder().to(dev).train()
+    opt2 = torch.optim.Adam(enc2.parameters(), 1e-3, fused=True, capturable=True)
+
+    def enc_loss(m, t, o):
+        mu, lv = m(t["inputs"], o["L"], t["mask"])
+        return (mu.square().sum() + lv.square().sum()) / 32
+
+    st2 = G.CapturedTrainStep(enc2, enc_loss, opt2, tensors={"inputs": x2, "mask": m2}, operators={"L": L2}, warmup=3)
+    ms2 = gpu_ms(st2.replay, reps=20)
+    out["cfg2_lap_encoder_train_step_ms"] = ms2
+    out["cfg2_step_mode"] = st2.mode
+    out["mesh_mnist_lap_train_meshes_per_sec"] = 32 / (ms2 / 1e3)
     out.update(host_reference_calls(host, B))
     return out
 
@@ -722,6 +756,19 @@ def run_b200(args):
             "padded": {"num_vertices": nv, "num_faces": nf, "dirac_blocks": Dop.n_blocks},
             "grad_allreduce_bytes": step.grad_bytes}
     if not args.no_spmm_sweep and world == 1:
+        # CHECKER: the cfg3 operators the step above was timed on, against the double-precision oracle (same bound)
+        from oracle import c_oracle
+        worst = 0.0
+        for op, S in ((Dop, host["Di"]), (DAop, host["DiA"])):
+            X = torch.randn(op.n_bcols, 128, device=dev)
+            idx, val = S._indices().numpy(), S._values().numpy()
+            y64, bound = c_oracle.dirac_view_mm_f64(idx[0], idx[1], val, S.shape[0] // 4, X.cpu().numpy())
+            y = op.apply(X).cpu().numpy().astype(np.float64)
+            worst = max(worst, float((np.abs(y - y64) / (np.finfo(np.float32).eps * bound + 1e-300)).max()))
+        if not worst < 32:
+            raise AssertionError("cfg3 Dirac SpMM parity against the oracle failed: %.1f eps |S||x|" % worst)
+        line["roofline_spmm"]["parity_checked"] = True
+        line["roofline_spmm"]["worst_err_eps_Sx"] = worst
         line["spmm"] = spmm_sweep(dev)
     if not args.no_spmm_sweep and world == 1:
         line["breakdown"] = breakdown(dev, model, res, Dop, DAop, host, B)

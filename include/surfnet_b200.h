@@ -238,6 +238,14 @@ int sn_gemm_tf32_presplit_act_f32(const float* A, int64_t lda, const float* B_hi
                                   const float* group_bias, int64_t rows_per_group, float* C, int64_t ldc, float* C_act,
                                   int64_t ldc_act, float* act_mean, float* act_var, int64_t M, int64_t N, int64_t K,
                                   int flags, void* ws, size_t ws_bytes, sn_stream_t stream);
+/* All-pairs feature correlation of the dense_correspondence SiameseModel (dense_correspondence/models.py:199-203,
+ * torch.bmm(FA, FB^T) per shape pair): C[M x N] = A[M x K] * (B_hi + B_lo)[N x K]^T for WIDE N (thousands of columns),
+ * K <= 128, K % 4 == 0, N % 4 == 0 (K and N tails are zero-filled / clipped by the tensor maps: no padding copies).
+ * Same tcgen05 3xTF32 kernel as above; the A row tile is split once into tensor memory and stays resident while its
+ * column passes stream the B rows; (row tile, column group) work items fill all SMs; the result leaves through the
+ * TMA-store epilogue (the product is bound by writing M x N floats). */
+int sn_gemm_nt_wide_tf32_f32(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb, float* C,
+                             int64_t ldc, int64_t M, int64_t N, int64_t K, sn_stream_t stream);
 /* hi = tf32(X) (round to nearest), lo = X - hi; X [rows x cols] with leading dimension ldx, outputs contiguous. */
 int sn_split_tf32_f32(const float* X, int64_t ldx, int64_t rows, int64_t cols, float* hi, float* lo, sn_stream_t stream);
 
@@ -354,6 +362,43 @@ int sn_masked_smooth_l1_fwd_f32(const float* Out, const float* T, const float* M
                                 float* loss, void* ws, size_t ws_bytes, sn_stream_t stream);
 int sn_masked_smooth_l1_bwd_f32(const float* Out, const float* T, const float* M, const float* grad_loss, int64_t rows,
                                 int64_t C, float scale, float* dOut, sn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * One ResNet stage as ONE call (orchestration of the entry points above).  What the reference's cupy seam
+ * (src/utils/cuda/sparse_bmm_func.py:27-72) plus F.elu / torch.cat / GraphConv1x1 (utils_pt.py:161-169, 195-205, 208-218)
+ * do per stage:
+ *   forward   Y = Linear(BatchNorm_train([ elu(x_self) | S elu(x_gather) ])) (+ residual)
+ *             Dirac:     S = D (x_self = f, x_gather = v) or S = D* (x_self = v, x_gather = f_out)
+ *             Laplacian: S = L, x_gather = x_self (the SpMM gathers from the activated left half of Z)
+ *             saved for backward (caller-allocated): Z [rows_out x 2C], act_gather [rows_in x C] (Dirac), stk [3 x 2C]
+ *             (s | t | rstd), mean [2C]; var_biased [2C] is an output only.  running_mean / running_var may be NULL.
+ *   backward  dZ [rows_out x 2C] (scratch and result: for the Dirac stage its LEFT half is the gradient of x_self),
+ *             d_gather [rows_in x C] = gradient of x_gather (Laplacian: the full gradient of x) + g_extra (optional, e.g.
+ *             a residual-path gradient), dgamma / dbeta [2C], dW [C x 2C], db [C].  t_* = the TRANSPOSED operator's arrays.
+ * C in {64, 128}; workspaces from sn_stage_{fwd,bwd}_ws_bytes.
+ * ---------------------------------------------------------------------------------------------- */
+size_t sn_stage_fwd_ws_bytes(int64_t C);
+size_t sn_stage_bwd_ws_bytes(int64_t rows_out, int64_t C);
+int sn_dir_stage_fwd_f32(const int32_t* browptr, const int32_t* bcolind, const float* bval, int64_t n_brows, int64_t n_bcols,
+                         const float* x_self, int64_t ld_self, const float* x_gather, int64_t ld_gather, int64_t C,
+                         const float* gamma, const float* beta, const float* W, const float* b, const float* residual,
+                         int64_t ldr, float* running_mean, float* running_var, float momentum, float eps, float* Z,
+                         float* act_gather, float* stk, float* mean, float* var_biased, float* Y, int64_t ldy, void* ws,
+                         size_t ws_bytes, sn_stream_t stream);
+int sn_lap_stage_fwd_f32(const int32_t* rowptr, const int32_t* colind, const float* val, int64_t n_rows, const float* x,
+                         int64_t ldx, int64_t C, const float* gamma, const float* beta, const float* W, const float* b,
+                         const float* residual, int64_t ldr, float* running_mean, float* running_var, float momentum, float eps,
+                         float* Z, float* stk, float* mean, float* var_biased, float* Y, int64_t ldy, void* ws, size_t ws_bytes,
+                         sn_stream_t stream);
+int sn_dir_stage_bwd_f32(const int32_t* t_browptr, const int32_t* t_bcolind, const float* t_bval, int64_t rows_out,
+                         int64_t rows_in, const float* dY, int64_t ldd, const float* Z, const float* act_gather, const float* W,
+                         const float* stk, const float* mean, int64_t C, float* dZ, float* d_gather, int64_t ld_dg,
+                         const float* g_extra, int64_t ld_ge, float* dgamma, float* dbeta, float* dW, float* db, void* ws,
+                         size_t ws_bytes, sn_stream_t stream);
+int sn_lap_stage_bwd_f32(const int32_t* t_rowptr, const int32_t* t_colind, const float* t_val, int64_t n_rows, const float* dY,
+                         int64_t ldd, const float* Z, const float* W, const float* stk, const float* mean, int64_t C, float* dZ,
+                         float* dx, int64_t ld_dx, const float* g_extra, int64_t ld_ge, float* dgamma, float* dbeta, float* dW,
+                         float* db, void* ws, size_t ws_bytes, sn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -71,6 +71,17 @@ SIGNATURES = {
     "sn_masked_smooth_l1_ws_bytes": (_sz, []),
     "sn_masked_smooth_l1_fwd_f32": (_int, [_ptr, _ptr, _ptr, _i64, _i64, _f32, _ptr, _ptr, _sz, _ptr]),
     "sn_masked_smooth_l1_bwd_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _i64, _f32, _ptr, _ptr]),
+    "sn_gemm_nt_wide_tf32_f32": (_int, [_ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _ptr]),
+    "sn_stage_fwd_ws_bytes": (_sz, [_i64]),
+    "sn_stage_bwd_ws_bytes": (_sz, [_i64, _i64]),
+    "sn_dir_stage_fwd_f32": (_int, [_ptr, _ptr, _ptr, _i64, _i64, _ptr, _i64, _ptr, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64,
+                                    _ptr, _ptr, _f32, _f32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _sz, _ptr]),
+    "sn_lap_stage_fwd_f32": (_int, [_ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _f32,
+                                    _f32, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _sz, _ptr]),
+    "sn_dir_stage_bwd_f32": (_int, [_ptr, _ptr, _ptr, _i64, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _i64,
+                                    _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),
+    "sn_lap_stage_bwd_f32": (_int, [_ptr, _ptr, _ptr, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64,
+                                    _ptr, _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),
     "sn_split_tf32_f32": (_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr]),
     "sn_csr_spmm_epilogue_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64,
                                         _int, _ptr]),

@@ -414,7 +414,8 @@ struct ParamsTS {
   int64_t ldr, ldc;
   int M, N, K;
   int nmma;              // accumulator width = columns per MMA: N for N <= 128, else 128
-  int n_halves;          // N / nmma column passes per row tile ("jobs")
+  int n_halves;          // ceil(N / nmma) column passes per row tile ("jobs")
+  int n_groups, hpg;     // work items per row tile and column passes per item (1, n_halves unless N is wide)
   int a_resident;        // n_halves > 1 and K / 32 <= kATmemStages: the tile's whole A extent stays in TMEM for both passes
   int a_stages, b_stages;
   int split;             // 1: 3xTF32, 0: single pass
@@ -455,20 +456,28 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   unsigned char* epi_ring = b_ring + (size_t)p.b_stages * 2 * b_bytes;
   __shared__ uint64_t a_full[kMaxAStages], a_free[kMaxAStages], a_ready[kATmemStages], a_tfree[kATmemStages];
   __shared__ uint64_t b_full[kMaxBStages], b_free[kMaxBStages], tmem_full[2], tmem_empty[2];
-  __shared__ uint64_t r_full[kEpiWarps][2];
+  __shared__ uint64_t r_full[kEpiWarps * 2];                  // [epilogue warp][residual slot]
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float s_bias[256], s_rscale[256];   // epilogue vectors: LDS instead of an L1-missing __ldg per chunk
   __shared__ __align__(16) float s_stat[ACT ? kEpiWarps : 1][2][128];   // ACT: per-epilogue-warp column sums / sums of squares
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles = (p.M + kBlockM - 1) / kBlockM;
-  const int n_kb = p.K / kBlockK;
-  const int n_halves = p.n_halves;
-  if (threadIdx.x < p.N) {
+  // Work items.  Standard case (N <= 256): one item per 128-row tile, p.n_halves column passes each.  Wide-N case (the
+  // dense_correspondence correlation FA . FB^T, N ~ 7000): the column passes of a row tile are split into p.n_groups
+  // groups so that every SM gets items; an item = (row tile, group) runs p.hpg passes (the last group what is left).
+  const int n_groups = p.n_groups;
+  const int n_tiles = ((p.M + kBlockM - 1) / kBlockM) * n_groups;
+  const int n_kb = (p.K + kBlockK - 1) / kBlockK;              // a K tail is zero-filled by TMA
+  auto item_row = [&](int item) { return (item / n_groups) * kBlockM; };
+  auto item_half0 = [&](int item) { return (item % n_groups) * p.hpg; };
+  auto item_nh = [&](int item) {
+    const int left = p.n_halves - (item % n_groups) * p.hpg;
+    return left < p.hpg ? left : p.hpg;
+  };
+  if (threadIdx.x < p.N && threadIdx.x < 256) {
     s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
     s_rscale[threadIdx.x] = p.rscale ? p.rscale[threadIdx.x] : 1.f;
   }
-  const int n_a_pass = p.a_resident ? 1 : n_halves;          // times the A tile is streamed per row tile
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.a_stages; ++s) {
@@ -488,8 +497,8 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       mbar_init(tmem_empty + b, kEpiWarps);
     }
     for (int w = 0; w < kEpiWarps; ++w) {
-      mbar_init(&r_full[w][0], 1);
-      mbar_init(&r_full[w][1], 1);
+      mbar_init(r_full + 2 * w, 1);
+      mbar_init(r_full + 2 * w + 1, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -507,14 +516,16 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int n_a_pass = p.a_resident ? 1 : item_nh(tile);   // times the A tile is streamed per item
         for (int pass = 0; pass < n_a_pass; ++pass)
           for (int kb = 0; kb < n_kb; ++kb) {
             mbar_wait(a_free + stage, phase ^ 1u);
             mbar_arrive_expect_tx(a_full + stage, a_bytes);
-            tma_load_2d(a_ring + (size_t)stage * a_bytes, &map_a, kb * kBlockK, tile * kBlockM, a_full + stage);
+            tma_load_2d(a_ring + (size_t)stage * a_bytes, &map_a, kb * kBlockK, item_row(tile), a_full + stage);
             if (++stage == p.a_stages) { stage = 0; phase ^= 1u; }
           }
+      }
     }
   } else if (warp == 3) {
     // ------------------------------------------------------------------ B producer (pre-split weights, L2-resident)
@@ -522,13 +533,13 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-        for (int half = 0; half < n_halves; ++half)
+        for (int half = 0, nh = item_nh(tile), h0 = item_half0(tile); half < nh; ++half)
           for (int kb = 0; kb < n_kb; ++kb) {
             mbar_wait(b_free + stage, phase ^ 1u);
             unsigned char* sb = b_ring + (size_t)stage * 2 * b_bytes;
             mbar_arrive_expect_tx(b_full + stage, (p.split ? 2u : 1u) * b_bytes);
-            tma_load_2d(sb, &map_b, kb * kBlockK, half * nmma, b_full + stage);
-            if (p.split) tma_load_2d(sb + b_bytes, &map_blo, kb * kBlockK, half * nmma, b_full + stage);
+            tma_load_2d(sb, &map_b, kb * kBlockK, (h0 + half) * nmma, b_full + stage);
+            if (p.split) tma_load_2d(sb + b_bytes, &map_blo, kb * kBlockK, (h0 + half) * nmma, b_full + stage);
             if (++stage == p.b_stages) { stage = 0; phase ^= 1u; }
           }
     }
@@ -545,6 +556,7 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       uint32_t a_cnt = 0;                // TMEM A stages consumed so far (stage = a_cnt % 4, parity = (a_cnt / 4) & 1)
       uint32_t job = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int n_halves = item_nh(tile);
         for (int half = 0; half < n_halves; ++half, ++job) {
           const uint32_t buf = job & 1u;
           mbar_wait(tmem_empty + buf, ((job >> 1) & 1u) ^ 1u);    // epilogue drained this accumulator
@@ -587,7 +599,7 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     int as = 0;
     uint32_t aph = 0, t_cnt = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-      for (int pass = 0; pass < n_a_pass; ++pass)
+      for (int pass = 0, n_a_pass = p.a_resident ? 1 : item_nh(tile); pass < n_a_pass; ++pass)
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(a_full + as, aph);
           const uint32_t row = a_ring_s + (uint32_t)as * a_bytes + (uint32_t)r * 128u;
@@ -651,7 +663,7 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     auto advance = [&](ChunkIt& it) {
       if (++it.c == nchunks) {
         it.c = 0;
-        if (++it.half == n_halves) { it.half = 0; it.tile += (int)gridDim.x; }
+        if (++it.half == item_nh(it.tile)) { it.half = 0; it.tile += (int)gridDim.x; }
       }
     };
     ChunkIt pf = {(int)blockIdx.x, 0, 0};
@@ -660,9 +672,9 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       if (pf.tile < n_tiles) {
         if (lane == 0) {
           const uint32_t slot = r_issued % (uint32_t)r_slots;
-          mbar_arrive_expect_tx(&r_full[e][slot], 4096u);
-          tma_load_2d(my_g + 4096 + slot * 4096u, &map_r, pf.half * nmma + chalf * ncol + pf.c * 32,
-                      pf.tile * kBlockM + quarter * 32, &r_full[e][slot]);
+          mbar_arrive_expect_tx(r_full + 2 * e + slot, 4096u);
+          tma_load_2d(my_g + 4096 + slot * 4096u, &map_r, (item_half0(pf.tile) + pf.half) * nmma + chalf * ncol + pf.c * 32,
+                      item_row(pf.tile) + quarter * 32, r_full + 2 * e + slot);
         }
         ++r_issued;
         advance(pf);
@@ -676,10 +688,11 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     uint32_t job = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int n_halves = item_nh(tile), h0 = item_half0(tile);
       for (int half = 0; half < n_halves; ++half, ++job) {
         const uint32_t buf = job & 1u;
-        const int row0 = tile * kBlockM + quarter * 32;
-        const int cbase = half * nmma + chalf * ncol;          // first global column of this warp's share
+        const int row0 = item_row(tile) + quarter * 32;
+        const int cbase = (h0 + half) * nmma + chalf * ncol;   // first global column of this warp's share
         const float* gb_row = p.gbias ? p.gbias + (int64_t)((row0 + lane < p.M ? row0 + lane : p.M - 1) / p.rows_per_group) * N : nullptr;
         mbar_wait(tmem_full + buf, (job >> 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -688,7 +701,7 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           uint32_t rslot_s = 0;
           if (p.R) {
             const uint32_t slot = r_used % (uint32_t)r_slots;
-            mbar_wait(&r_full[e][slot], (r_used / (uint32_t)r_slots) & 1u);
+            mbar_wait(r_full + 2 * e + slot, (r_used / (uint32_t)r_slots) & 1u);
             rslot_s = r_s + slot * 4096u;
           }
           // the previous bulk store(s) of this warp must have read the staging boxes before they are overwritten
@@ -701,16 +714,16 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = (uint32_t)(c0 + j);
             } else {
-              tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * nmma + (c0 - half * nmma) + h * 16), v);
+              tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * nmma + (c0 - (h0 + half) * nmma) + h * 16), v);
             }
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
               const int cidx = h * 4 + j4;                     // 16-byte chunk of the 128-byte box row
               const int col = c0 + cidx * 4;
               const uint32_t swz = row_off + (((uint32_t)cidx ^ sw) << 4);
-              float4 o = add4(make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]),
-                                          __uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])),
-                              *reinterpret_cast<const float4*>(s_bias + col));
+              float4 o = make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]),
+                                     __uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3]));
+              if (n_groups == 1) o = add4(o, *reinterpret_cast<const float4*>(s_bias + col));   // wide-N: no epilogue vectors
               if (p.gbias) o = add4(o, __ldg(reinterpret_cast<const float4*>(gb_row + col)));
               if (p.R) {
                 const float4 rr = lds_f4(rslot_s + swz);
@@ -852,14 +865,14 @@ namespace gemm {
 static int launch_gemm(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb, const float* bias,
                        const float* R, int64_t ldr, const float* rscale, const float* group_bias, int64_t rows_per_group,
                        float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int flags, cudaStream_t stream,
-                       float* C_act = nullptr, int64_t ldc_act = 0, float* stat_partial = nullptr) {
+                       float* C_act = nullptr, int64_t ldc_act = 0, float* stat_partial = nullptr, bool wide = false) {
   const bool split = B_lo != nullptr;
   int dev = 0, sms = 148, smem_optin = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   const int64_t tiles = ceil_div(M, kBlockM);
-  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
   const int l2_prefetch = (!(flags & SN_GEMM_NO_L2_PREFETCH) && R && N >= 256) ? 1 : 0;
   CUtensorMap map_a, map_b, map_blo;
   if (!make_map(&map_a, A, M, K, lda, kBlockM)) return SN_ERR_UNSUPPORTED;
@@ -896,8 +909,20 @@ static int launch_gemm(const float* A, int64_t lda, const float* B_hi, const flo
   p.gbias = group_bias; p.rows_per_group = group_bias ? (int)rows_per_group : 1;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
   p.nmma = N <= 128 ? (int)N : 128;
-  p.n_halves = (int)N / p.nmma;
-  p.a_resident = (p.n_halves > 1 && K / kBlockK <= kATmemStages) ? 1 : 0;
+  p.n_halves = (int)ceil_div(N, p.nmma);
+  p.n_groups = 1;
+  p.hpg = p.n_halves;
+  if (wide) {
+    // enough (row tile, column group) items for two rounds over the SMs, every group non-empty
+    int64_t g = ceil_div(2 * (int64_t)sms, tiles);
+    if (g > p.n_halves) g = p.n_halves;
+    if (g < 1) g = 1;
+    p.hpg = (int)ceil_div(p.n_halves, g);
+    p.n_groups = (int)ceil_div(p.n_halves, p.hpg);
+    const int64_t items = tiles * p.n_groups;
+    grid = (unsigned)(items < sms ? items : sms);
+  }
+  p.a_resident = (p.n_halves > 1 && ceil_div(K, kBlockK) <= kATmemStages) ? 1 : 0;
   p.split = split ? 1 : 0;
   p.l2_prefetch = l2_prefetch;
   p.elu_left = (flags & SN_GEMM_ELU_BWD_LEFT) ? 1 : 0;
@@ -1001,6 +1026,20 @@ SN_API int sn_gemm_tf32_presplit_f32(const float* A, int64_t lda, const float* B
   if (!B_lo || !aligned16(B_lo) || (flags & SN_GEMM_SINGLE_PASS)) return SN_ERR_ARG;
   return launch_gemm(A, lda, B_hi, B_lo, ldb, bias, R, ldr, rscale, group_bias, rows_per_group, C, ldc, M, N, K, flags,
                      (cudaStream_t)stream);
+}
+
+SN_API int sn_gemm_nt_wide_tf32_f32(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb, float* C,
+                                    int64_t ldc, int64_t M, int64_t N, int64_t K, sn_stream_t stream) {
+  using namespace sn;
+  using namespace sn::gemm;
+  if (M < 0 || N <= 0 || K <= 0) return SN_ERR_ARG;
+  if (M == 0) return SN_OK;
+  if (!A || !B_hi || !B_lo || !C || lda < K || ldb < K || ldc < N) return SN_ERR_ARG;
+  if (K % 4 || N % 4 || K > kATmemStages * kBlockK || lda % 4 || ldb % 4 || ldc % 4 || !aligned16(A) || !aligned16(B_hi) ||
+      !aligned16(B_lo) || !aligned16(C) || M >= 0x7fffffffLL - kBlockM || N >= 0x7fffffffLL - 128)
+    return SN_ERR_UNSUPPORTED;
+  return launch_gemm(A, lda, B_hi, B_lo, ldb, nullptr, nullptr, 0, nullptr, nullptr, 0, C, ldc, M, N, K, 0, (cudaStream_t)stream,
+                     nullptr, 0, nullptr, true);
 }
 
 SN_API size_t sn_gemm_act_ws_bytes(int64_t N) {

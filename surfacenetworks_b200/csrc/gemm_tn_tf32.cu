@@ -285,6 +285,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
       "r"(v[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::
+          "r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
 __device__ __forceinline__ float lds_f1(uint32_t saddr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
@@ -318,7 +326,10 @@ struct ParamsTS {
 // split warps sat on the `full` barrier of a two-stage ring).
 //
 // Roles: warp 0 = dY producer (TMA), warp 3 = Z producer (TMA), warp 1 = MMA issuer, warp 2 = TMEM allocation,
-// warps 4-7 = dY: shared memory -> column sums, hi / lo -> tensor memory; then the epilogue, warps 8-15 = Z lo tiles.
+// warps 4-11 = dY: shared memory -> column sums, hi / lo -> tensor memory (warps w and w + 4 share the TMEM lane quarter
+// (w - 4) % 4 and take the two 16-row halves of the 32-row k-block: the per-k-block latency chain LDS -> cvt ->
+// tcgen05.st -> wait::st of a single warp per quarter was the kernel's period, ~2600 clk against 1090 clk of MMA time);
+// warps 4-7 then run the epilogue; warps 12-15 = Z lo tiles.
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tn_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const ParamsTS p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -333,6 +344,7 @@ gemm_tn_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   __shared__ uint64_t a_full[kMaxAStages], a_free[kMaxAStages], a_ready[kATmemStages], a_tfree[kATmemStages];
   __shared__ uint64_t raw_full[kMaxRawStages], raw_free[kMaxRawStages], lo_ready[kMaxLoStages], lo_free[kMaxLoStages], done_bar;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_csum[kM];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb0 = blockIdx.x * p.kb_per_cta;
@@ -342,10 +354,10 @@ gemm_tn_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.a_stages; ++s) {
       mbar_init(a_full + s, 1);
-      mbar_init(a_free + s, 4);
+      mbar_init(a_free + s, 8);
     }
     for (int s = 0; s < kATmemStages; ++s) {
-      mbar_init(a_ready + s, 4);
+      mbar_init(a_ready + s, 8);
       mbar_init(a_tfree + s, 1);
     }
     for (int s = 0; s < p.raw_stages; ++s) {
@@ -353,7 +365,7 @@ gemm_tn_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       mbar_init(raw_free + s, 1);
     }
     for (int s = 0; s < p.lo_stages; ++s) {
-      mbar_init(lo_ready + s, 8);
+      mbar_init(lo_ready + s, 4);
       mbar_init(lo_free + s, 1);
     }
     mbar_init(&done_bar, 1);
@@ -427,20 +439,21 @@ gemm_tn_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         if (++ls == p.lo_stages) { ls = 0; lph ^= 1u; }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < 12) {
     // ------------------------------------------------------------------ dY: column m of the tile = row m of the A operand
-    const int m = threadIdx.x - 128;                           // 0..127 = TMEM lane
-    const uint32_t lane_base = (uint32_t)((warp - 4) * 32) << 16;
+    const int q = (warp - 4) & 3, kh = (warp - 4) >> 2;        // TMEM lane quarter, 16-row half of the k-block
+    const int m = q * 32 + lane;                               // 0..127 = TMEM lane
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const uint32_t a_ring_s = smem_u32(a_ring);
     float csum = 0.f;
     int as = 0;
     uint32_t aph = 0;
     for (int kb = 0; kb < my_kb; ++kb) {
       mbar_wait(a_full + as, aph);
-      const uint32_t col = a_ring_s + (uint32_t)as * a_bytes + (uint32_t)m * 4u;
-      uint32_t hi[32], lo[32];
+      const uint32_t col = a_ring_s + (uint32_t)as * a_bytes + (uint32_t)m * 4u + (uint32_t)(kh * 16) * (kM * 4);
+      uint32_t hi[16], lo[16];
 #pragma unroll
-      for (int k = 0; k < 32; ++k) {                           // lanes read consecutive words of one row: conflict-free
+      for (int k = 0; k < 16; ++k) {                           // lanes read consecutive words of one row: conflict-free
         const float x = lds_f1(col + (uint32_t)k * (kM * 4));
         csum += x;                                             // rows past R are zero-filled by TMA
         const float h = to_tf32(x);
@@ -452,15 +465,20 @@ gemm_tn_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const uint32_t at = (uint32_t)kb % kATmemStages;
       mbar_wait(a_tfree + at, (((uint32_t)kb / kATmemStages) & 1u) ^ 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t ta = tmem_base + lane_base + (uint32_t)(kATmemCol0 + at * 64);
-      tmem_st32(ta, hi);
-      if (p.split) tmem_st32(ta + 32, lo);
+      const uint32_t ta = tmem_base + lane_base + (uint32_t)(kATmemCol0 + at * 64 + kh * 16);
+      tmem_st16(ta, hi);
+      if (p.split) tmem_st16(ta + 32, lo);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready + at);
       if (++as == p.a_stages) { as = 0; aph ^= 1u; }
     }
+    // column sums: the two k-halves of a column are added in a fixed order (lower half first)
+    if (kh == 1) s_csum[m] = csum;
+    asm volatile("bar.sync 1, 256;" ::: "memory");             // the eight dY warps only
+    if (kh == 1) goto tn_done;
+    csum += s_csum[m];
     // ------------------------------------------------------------------ epilogue: this CTA's partial [128 x N] -> workspace
     p.csum_partial[(size_t)blockIdx.x * kM + m] = csum;
     float* out = p.partial + ((size_t)blockIdx.x * kM + m) * N;
@@ -478,9 +496,9 @@ gemm_tn_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     } else {
       for (int c0 = 0; c0 < N; c0 += 4) *reinterpret_cast<float4*>(out + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-  } else if (warp >= 8 && p.split) {
+  } else if (warp >= 12 && p.split) {
     // ------------------------------------------------------------------ Z: lo = tf32(x - trunc(x)) into the lo ring
-    const int t = threadIdx.x - 256;                           // 0..255
+    const int t = threadIdx.x - 384;                           // 0..127
     const uint32_t raw_s = smem_u32(raw_ring), lo_s = smem_u32(lo_ring);
     const int n_f4 = (int)(b_bytes / 16);
     int rs = 0, ls = 0;
@@ -489,18 +507,18 @@ gemm_tn_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       mbar_wait(raw_full + rs, rph);
       mbar_wait(lo_free + ls, lph ^ 1u);
       const uint32_t src = raw_s + (uint32_t)rs * b_bytes, dst = lo_s + (uint32_t)ls * b_bytes;
-      for (int i0 = t; i0 < n_f4; i0 += 4 * 256) {             // four independent 16-byte loads in flight per thread
+      for (int i0 = t; i0 < n_f4; i0 += 4 * 128) {             // four independent 16-byte loads in flight per thread
         float4 x[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-          if (i0 + u * 256 < n_f4) x[u] = lds_f4(src + (uint32_t)(i0 + u * 256) * 16u);
+          if (i0 + u * 128 < n_f4) x[u] = lds_f4(src + (uint32_t)(i0 + u * 128) * 16u);
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-          if (i0 + u * 256 < n_f4) {
+          if (i0 + u * 128 < n_f4) {
             float4 l;
             l.x = to_tf32(x[u].x - trunc_tf32(x[u].x)); l.y = to_tf32(x[u].y - trunc_tf32(x[u].y));
             l.z = to_tf32(x[u].z - trunc_tf32(x[u].z)); l.w = to_tf32(x[u].w - trunc_tf32(x[u].w));
-            sts_f4(dst + (uint32_t)(i0 + u * 256) * 16u, l);
+            sts_f4(dst + (uint32_t)(i0 + u * 128) * 16u, l);
           }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
@@ -511,6 +529,7 @@ gemm_tn_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
   }
 
+tn_done:
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 2) {

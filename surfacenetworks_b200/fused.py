@@ -30,6 +30,16 @@ __all__ = ["bn_linear", "gemm_tf32", "colstats", "fused_supported"]
 _GEMM_N = (64, 128, 256)
 
 
+def bn_momentum(bn):
+    """The exponential-average factor nn.BatchNorm uses for this call (evaluate AFTER num_batches_tracked was incremented):
+    ``momentum``, or -- for momentum=None, torch's cumulative moving average -- 1 / num_batches_tracked."""
+    if bn.momentum is not None:
+        return bn.momentum
+    if bn.num_batches_tracked is None:
+        return 0.0
+    return 1.0 / float(bn.num_batches_tracked)          # (reads the counter back: momentum=None is not graph-capturable)
+
+
 def _ws(nbytes, device):
     return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
 
@@ -275,6 +285,7 @@ class _BnLinear(torch.autograd.Function):
         return Y
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, dY):
         dZ, dgamma, dbeta, dW, db = bn_linear_backward(ctx.saved_tensors, dY, ctx.training,
                                                        ctx.elu_bwd_left and ctx.training)
@@ -351,6 +362,7 @@ class _AvgStage(torch.autograd.Function):
         return Y
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, dY):
         a, avg, W, stk, mean, maskw, inv_cnt = ctx.saved_tensors
         dY = dY.contiguous()
@@ -423,7 +435,7 @@ def avg_stage(x, mask, bn, fc, residual=None, in_cell=None, res_cell=None):
     training = bn.training or bn.running_mean is None
     if training and bn.num_batches_tracked is not None:
         bn.num_batches_tracked += 1
-    momentum = 0.1 if bn.momentum is None else bn.momentum
+    momentum = bn_momentum(bn)
     res2 = None if residual is None else residual.reshape(B * V, -1)
     return _AvgStage.apply(x2, maskw, inv_cnt, bn.weight, bn.bias, fc.weight, fc.bias, res2, bn.running_mean,
                            bn.running_var, training, momentum, bn.eps, B, V, in_cell, res_cell)
@@ -571,6 +583,49 @@ def masked_smooth_l1(outputs, targets, mask, scale):
     return _MaskedSmoothL1.apply(outputs, targets, maskw, scale)
 
 
+class _Correlation(torch.autograd.Function):
+    """out[b] = FA[b] @ FB[b]^T (dense_correspondence/models.py:199-203) on the tcgen05 3xTF32 kernel with the TMA-store
+    epilogue (sn_gemm_nt_wide_tf32_f32): the [Na, Nb] result is written exactly once, nothing is padded or copied.
+    Backward (dFA = G FB, dFB = G^T FA: contractions over thousands of vertices, plain library GEMM shapes) stays on
+    torch.bmm."""
+
+    @staticmethod
+    def forward(ctx, FA, FB):
+        B, Na, K = FA.shape
+        Nb = FB.shape[1]
+        FA, FB = FA.contiguous(), FB.contiguous()
+        out = torch.empty(B, Na, Nb, dtype=torch.float32, device=FA.device)
+        hi, lo = torch.empty_like(FB), torch.empty_like(FB)
+        with torch.cuda.device(FA.device):
+            for b in range(B):
+                N.call("sn_split_tf32_f32", _ptr(FB[b]), K, Nb, K, _ptr(hi[b]), _ptr(lo[b]), _stream())
+                if N.TIMER is not None:
+                    N.TIMER.annotate("correlation %dx%dx%d" % (Na, Nb, K), 4 * (Na * K + 2 * Nb * K + Na * Nb), 2 * Na * Nb * K)
+                N.call("sn_gemm_nt_wide_tf32_f32", _ptr(FA[b]), K, _ptr(hi[b]), _ptr(lo[b]), K, _ptr(out[b]), Nb, Na, Nb, K,
+                       _stream())
+        ctx.save_for_backward(FA, FB)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, G):
+        FA, FB = ctx.saved_tensors
+        dFA = torch.bmm(G, FB) if ctx.needs_input_grad[0] else None
+        dFB = torch.bmm(G.transpose(1, 2), FA) if ctx.needs_input_grad[1] else None
+        return dFA, dFB
+
+
+def correlation(FA, FB):
+    """``torch.bmm(FA, FB.transpose(1, 2))`` for [B, Na, K] x [B, Nb, K] feature matrices; the tensor-core kernel when the
+    layout allows it (fp32 CUDA, K <= 128, K % 4 == 0, Nb % 4 == 0), torch.bmm otherwise."""
+    ok = (FA.is_cuda and FA.dtype == torch.float32 and FB.dtype == torch.float32 and FA.dim() == 3 and FB.dim() == 3
+          and FA.shape[0] == FB.shape[0] and FA.shape[2] == FB.shape[2] and FA.shape[2] <= 128 and FA.shape[2] % 4 == 0
+          and FB.shape[1] % 4 == 0 and FA.shape[1] > 0 and FB.shape[1] > 0)
+    if ok:
+        return _Correlation.apply(FA, FB)
+    return torch.bmm(FA, FB.transpose(1, 2))
+
+
 def bn_linear_is_fused(rows_like, fc, residual_cols=None):
     """Will bn_linear take the fused path for a [rows, 2C] buffer made from ``rows_like`` [rows, C]?  (Same conditions as
     fused_supported, evaluated before the buffer exists.)"""
@@ -587,7 +642,7 @@ def bn_linear(z, bn, fc, residual=None, res_cell=None):
         training = bn.training or bn.running_mean is None
         if training and bn.num_batches_tracked is not None:
             bn.num_batches_tracked += 1
-        momentum = 0.1 if bn.momentum is None else bn.momentum
+        momentum = bn_momentum(bn)
         left = getattr(z, "_sn_left_stats", None) if training else None
         if left is not None and not (z.shape[1] - left[0].numel()) % 4 == 0:
             left = None
@@ -609,7 +664,7 @@ def bn_linear(z, bn, fc, residual=None, res_cell=None):
             training = bn.training or bn.running_mean is None
             if training and bn.num_batches_tracked is not None:
                 bn.num_batches_tracked += 1
-            momentum = 0.1 if bn.momentum is None else bn.momentum
+            momentum = bn_momentum(bn)
             y = _BnLinear.apply(z, bn.weight, bn.bias, w_pad, b_pad, None, bn.running_mean, bn.running_var, training,
                                 momentum, bn.eps, None)
             return _SliceCols.apply(y, n_out)

@@ -266,9 +266,9 @@ class SiameseModel(nn.Module):
     """dense_correspondence ``SiameseModel(model, layer)`` (models.py:184-203): one shared tower applied to both shapes,
     then the all-pairs feature correlation ``FA @ FB^T`` ([B, Na, 120] x [B, 120, Nb] -> [B, Na, Nb]).
 
-    The towers run on the libsurfnet_b200 kernels.  The correlation is a plain dense GEMM whose cost is writing the
-    Na x Nb result (196 MB per 7000-vertex pair, ~30 us of HBM time against 11.8 GFLOP): it stays on cuBLAS
-    (``torch.bmm``), like the reference (:203)."""
+    The towers run on the libsurfnet_b200 kernels.  The correlation's cost is writing the Na x Nb result (196 MB per
+    7000-vertex pair): it runs on the tcgen05 3xTF32 kernel with the TMA-store epilogue (``fused.correlation``,
+    sn_gemm_nt_wide_tf32_f32); its backward -- two contractions over the vertices -- on torch.bmm."""
 
     def __init__(self, model="dirac", layer=15):
         super().__init__()
@@ -282,4 +282,4 @@ class SiameseModel(nn.Module):
     def forward(self, OperationA, OperationB, inputA, inputB):
         FA = self.model(*OperationA, inputA)
         FB = self.model(*OperationB, inputB)
-        return torch.bmm(FA, FB.transpose(1, 2))
+        return fused.correlation(FA, FB)

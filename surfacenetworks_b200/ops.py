@@ -50,6 +50,7 @@ class _Spmm(torch.autograd.Function):
         return op.apply(X.contiguous())
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, gY):
         return ctx.op.T.apply(gY.contiguous()), None
 
@@ -99,6 +100,7 @@ class _StageConcat(torch.autograd.Function):
         return Z, stats[0], stats[1]
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, gZ, _gm=None, _gv=None):
         op, C = ctx.op, ctx.C
         gZ = gZ.contiguous()
@@ -172,18 +174,19 @@ class _DirBlock(torch.autograd.Function):
         stats_v, stats_f = (st[0], st[1], C), (st[2], st[3], C)
         D.apply(Zv[:, :C], out=Zf[:, C:])                       # faces <- vertices, gathers the activated rows in place
         f_out, saved0 = fused.bn_linear_forward(Zf, g0, b0, W0, c0, None, bn0.running_mean, bn0.running_var, True,
-                                                0.1 if bn0.momentum is None else bn0.momentum, bn0.eps, stats_f)
+                                                fused.bn_momentum(bn0), bn0.eps, stats_f)
         act_f = torch.empty_like(f_out)
         elu_into(f_out, act_f)
         DA.apply(act_f, out=Zv[:, C:])                          # vertices <- faces
         v_new, saved1 = fused.bn_linear_forward(Zv, g1, b1, W1, c1, v2, bn1.running_mean, bn1.running_var, True,
-                                                0.1 if bn1.momentum is None else bn1.momentum, bn1.eps, stats_v)
+                                                fused.bn_momentum(bn1), bn1.eps, stats_v)
         ctx.save_for_backward(act_f, *saved0, *saved1)
         ctx.D, ctx.DA, ctx.C = D, DA, C
         ctx.set_materialize_grads(False)
         return v_new, f_out
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, g_vnew, g_fdown):
         act_f, Zf, W0, stk0, mean0, Zv, W1, stk1, mean1 = ctx.saved_tensors
         C, D, DA = ctx.C, ctx.D, ctx.DA
@@ -225,6 +228,7 @@ class _FaceChainStart(torch.autograd.Function):
         return Zf, st
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, gZf, _gst=None):
         # the consuming block's dZ GEMM has already applied elu'(f) to the left half (SN_GEMM_ELU_BWD_LEFT)
         return None if gZf is None else gZf[:, :ctx.C]
@@ -263,11 +267,11 @@ class _DirBlockChained(torch.autograd.Function):
             act_f = Zf_next[:, :C]
             act = dict(act_out=act_f, mean=st_next[0, :C], var=st_next[1, :C], want_raw=False)
         _, saved0 = fused.bn_linear_forward(Zf, g0, b0, W0, c0, None, bn0.running_mean, bn0.running_var, True,
-                                            0.1 if bn0.momentum is None else bn0.momentum, bn0.eps, (stf[0], stf[1], 2 * C),
+                                            fused.bn_momentum(bn0), bn0.eps, (stf[0], stf[1], 2 * C),
                                             act=act)
         _spmm_with_stats(DA, act_f, Zv[:, C:], stv[0, C:], stv[1, C:])           # vertices <- faces
         v_new, saved1 = fused.bn_linear_forward(Zv, g1, b1, W1, c1, v2, bn1.running_mean, bn1.running_var, True,
-                                                0.1 if bn1.momentum is None else bn1.momentum, bn1.eps, (stv[0], stv[1], 2 * C))
+                                                fused.bn_momentum(bn1), bn1.eps, (stv[0], stv[1], 2 * C))
         ctx.save_for_backward(act_f, *saved0, *saved1)
         ctx.D, ctx.DA, ctx.C = D, DA, C
         ctx.set_materialize_grads(False)
@@ -278,6 +282,7 @@ class _DirBlockChained(torch.autograd.Function):
         return v_new, Zf_next, st_next
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, g_vnew, g_Zfnext, _gst=None):
         act_f, Zf, W0, stk0, mean0, Zv, W1, stk1, mean1 = ctx.saved_tensors
         C, D, DA = ctx.C, ctx.D, ctx.DA

