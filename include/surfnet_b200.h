@@ -375,7 +375,7 @@ int sn_masked_smooth_l1_bwd_f32(const float* Out, const float* T, const float* M
  *   backward  dZ [rows_out x 2C] (scratch and result: for the Dirac stage its LEFT half is the gradient of x_self),
  *             d_gather [rows_in x C] = gradient of x_gather (Laplacian: the full gradient of x) + g_extra (optional, e.g.
  *             a residual-path gradient), dgamma / dbeta [2C], dW [C x 2C], db [C].  t_* = the TRANSPOSED operator's arrays.
- * C in {64, 128}; workspaces from sn_stage_{fwd,bwd}_ws_bytes.
+ * C = 128 (the width of every reference model); workspaces from sn_stage_{fwd,bwd}_ws_bytes.
  * ---------------------------------------------------------------------------------------------- */
 size_t sn_stage_fwd_ws_bytes(int64_t C);
 size_t sn_stage_bwd_ws_bytes(int64_t rows_out, int64_t C);

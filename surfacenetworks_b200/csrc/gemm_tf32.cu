@@ -1035,7 +1035,7 @@ SN_API int sn_gemm_nt_wide_tf32_f32(const float* A, int64_t lda, const float* B_
   if (M < 0 || N <= 0 || K <= 0) return SN_ERR_ARG;
   if (M == 0) return SN_OK;
   if (!A || !B_hi || !B_lo || !C || lda < K || ldb < K || ldc < N) return SN_ERR_ARG;
-  if (K % 4 || N % 4 || K > kATmemStages * kBlockK || lda % 4 || ldb % 4 || ldc % 4 || !aligned16(A) || !aligned16(B_hi) ||
+  if (K % 4 || N % 4 || N < 128 || K < kBlockK || K > kATmemStages * kBlockK || lda % 4 || ldb % 4 || ldc % 4 || !aligned16(A) || !aligned16(B_hi) ||
       !aligned16(B_lo) || !aligned16(C) || M >= 0x7fffffffLL - kBlockM || N >= 0x7fffffffLL - 128)
     return SN_ERR_UNSUPPORTED;
   return launch_gemm(A, lda, B_hi, B_lo, ldb, nullptr, nullptr, 0, nullptr, nullptr, 0, C, ldc, M, N, K, 0, (cudaStream_t)stream,

@@ -182,22 +182,6 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
 #pragma unroll
     for (int p = 0; p < 4; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    // Epilogue operands of a row (up to 3 x C floats) are only needed when the row is stored, but fetching them then puts
-    // a DRAM round trip behind every row's gather.  Keeping them in registers from the row start costs 16 registers and a
-    // CTA per SM (measured slower, see below); a prefetch needs no registers: when a row starts, lanes 0..3 of its row
-    // group each pull one 128-byte line per operand (line p of G / A / G2 = quarter p of the row at C = 128; at other
-    // widths the same addresses simply cover part of the row) into L2, so the loads at the row end hit L2.
-    auto prefetch_row = [&](int rr) {
-      if (EPI && t < 4) {
-        const uint32_t grow = grow0 + (uint32_t)rr;
-        if (rr < RPG && grow < (uint32_t)n_rows) {
-          const uint32_t off = (uint32_t)t * kQuarterBytes;
-          if (epi.G != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr_mad(reinterpret_cast<const char*>(epi.G) + off, grow, epi.ldgb)));
-          if (epi.A != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr_mad(reinterpret_cast<const char*>(epi.A) + off, grow, epi.ldab)));
-          if (epi.G2 != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr_mad(reinterpret_cast<const char*>(epi.G2) + off, grow, epi.ldg2b)));
-        }
-      }
-    };
     // store every row that ends at entry k (the current one, then the empty rows behind it)
     auto flush = [&]() {
       while (r < RPG && k == next_end) {
@@ -211,7 +195,8 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
               acc[p] = add4(acc[p], __ldg(reinterpret_cast<const float4*>(grow_p + p * kQuarterBytes)));
           }
           // (fetching this operand when the row STARTS, 16 more registers and 3 CTAs/SM, was measured slower: 104 / 92 us
-          // against 96 / 89 us for D^T / (D*)^T at the cfg3 size)
+          // against 96 / 89 us for D^T / (D*)^T at the cfg3 size; a register-free prefetch.global.L2 of the three operand
+          // rows one row ahead changed nothing either -- 130.7 / 113.6 us against 130.5 / 107.0 us in the step, round 2)
           if (EPI && epi.A != nullptr) {        // ... times elu'(x) taken from the activated values a = elu(x): 1 or a + 1
             const char* arow_p = ptr_mad(reinterpret_cast<const char*>(epi.A) + t * 16, grow, epi.ldab);
 #pragma unroll
@@ -248,7 +233,6 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
         for (int p = 0; p < 4; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
         ++r;
         next_end = bp[rl0 + r + 1];
-        prefetch_row(r + 1);                    // the row after the one that starts now (one row of lead)
       }
     };
     // stage s <- entries kk .. kk + EPS - 1 of this group's run: X rows to registers; BSR4 values (64 bytes per
@@ -310,8 +294,6 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
       if (BLK == 4) __syncwarp();     // everyone has read stage s before its slot is refilled
     };
 
-    prefetch_row(0);
-    prefetch_row(1);
     flush();                                               // leading empty rows
 #pragma unroll
     for (int s = 0; s < PD; ++s) load(s, xs[s], wv[s], k + EPS * s);

@@ -16,8 +16,8 @@
 //         (dZ = dY W_s + p Z + q, elu'(x_self) applied to the left half) -> sn_{bsr4,csr}_spmm_epilogue_f32 on S^T
 //         ((S^T dZ_right [+ dZ_left]) .* elu'(x_gather))
 //
-// Supported: training-mode BatchNorm, C in {64, 128} (both GEMM shapes on the tensor-core kernel, the SpMM on the row-group
-// kernel), fp32, 16-byte aligned row-major operands.  Anything else: SN_ERR_UNSUPPORTED before the first launch.
+// Supported: training-mode BatchNorm, C = 128 (the width of every reference model; both GEMM shapes and the split-K
+// weight-gradient product on the tensor-core kernels, the SpMM on the row-group kernel), fp32, 16-byte aligned row-major operands.  Anything else: SN_ERR_UNSUPPORTED before the first launch.
 #include "common.cuh"
 
 namespace sn {
@@ -40,7 +40,7 @@ struct Op {
 
 int stage_shape_ok(int64_t rows_out, int64_t rows_in, int64_t C) {
   if (rows_out <= 0 || rows_in <= 0) return SN_ERR_ARG;
-  if (C != 64 && C != 128) return SN_ERR_UNSUPPORTED;
+  if (C != 128) return SN_ERR_UNSUPPORTED;     // the split-K weight-gradient kernel takes 128 output channels
   return SN_OK;
 }
 

@@ -617,10 +617,10 @@ class _Correlation(torch.autograd.Function):
 
 def correlation(FA, FB):
     """``torch.bmm(FA, FB.transpose(1, 2))`` for [B, Na, K] x [B, Nb, K] feature matrices; the tensor-core kernel when the
-    layout allows it (fp32 CUDA, K <= 128, K % 4 == 0, Nb % 4 == 0), torch.bmm otherwise."""
+    layout allows it (fp32 CUDA, 32 <= K <= 128, K % 4 == 0, Nb % 4 == 0, Nb >= 128), torch.bmm otherwise."""
     ok = (FA.is_cuda and FA.dtype == torch.float32 and FB.dtype == torch.float32 and FA.dim() == 3 and FB.dim() == 3
           and FA.shape[0] == FB.shape[0] and FA.shape[2] == FB.shape[2] and FA.shape[2] <= 128 and FA.shape[2] % 4 == 0
-          and FB.shape[1] % 4 == 0 and FA.shape[1] > 0 and FB.shape[1] > 0)
+          and FB.shape[1] % 4 == 0 and FA.shape[1] > 0 and FB.shape[1] >= 128 and FA.shape[2] >= 32)
     if ok:
         return _Correlation.apply(FA, FB)
     return torch.bmm(FA, FB.transpose(1, 2))
