@@ -51,7 +51,8 @@ def main():
         got = p.grad if p.grad is not None else torch.zeros_like(p)
         assert torch.equal(got, e), "rank %d: all-reduced gradient differs from the mean of the local gradients" % rank
     # (3) graph replay (NCCL inside the graph) == eager multi-rank steps
-    model_b.load_state_dict(model_a.state_dict())
+    model_b.load_state_dict(model_a.state_dict())        # (model_a's BatchNorm buffers moved in (1): both copies start from them)
+    model_c.load_state_dict(model_a.state_dict())
     sg = G.CapturedTrainStep(model_b, loss_fn, adam(model_b), t, o, warmup=1, capture=True)
     assert sg.mode == "cuda_graph_replay", sg.mode
     se = G.CapturedTrainStep(model_c, loss_fn, adam(model_c), t, o, warmup=1, capture=False)
