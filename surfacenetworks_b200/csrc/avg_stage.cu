@@ -97,7 +97,21 @@ avg_stats_kernel(const float* __restrict__ partial, int n_seg, int64_t rows, int
   double s = 0.0, q = 0.0, ma = 0.0;
   if (live) {
     const int n_part = n_seg * kSlices;
-    for (int i = g; i < n_part; i += 32) {
+    int i = g;
+    for (; i + 3 * 32 < n_part; i += 4 * 32) {   // eight independent loads in flight, same (fixed) order of additions
+      float a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a[u] = __ldg(partial + (size_t)(i + u * 32) * 3 * C + c);
+        b[u] = __ldg(partial + (size_t)(i + u * 32) * 3 * C + C + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s += (double)a[u];
+        q += (double)b[u];
+      }
+    }
+    for (; i < n_part; i += 32) {
       s += (double)__ldg(partial + (size_t)i * 3 * C + c);
       q += (double)__ldg(partial + (size_t)i * 3 * C + C + c);
     }
@@ -255,8 +269,8 @@ avg_fold_bwd_kernel(const float* __restrict__ GL, int64_t ldgl, const float* __r
   extern __shared__ __align__(16) float sm[];
   float* sdy_s = sm;                                    // [kMeshChunk][N]
   float* avg_s = sdy_s + kMeshChunk * N;                // [kMeshChunk][kCols]
-  float* ws_s = avg_s + kMeshChunk * kCols;             // [N][kCols]   W[n][k] s[k] of this slab
-  float* red = ws_s + N * kCols;                        // [2][kGroups][kCols]
+  float* ws_s = avg_s + kMeshChunk * kCols;             // [N][kCols + 1]   W[n][k] s[k] of this slab (padded: transposed reads)
+  float* red = ws_s + N * (kCols + 1);                        // [2][kGroups][kCols]
   float* pq = red + 2 * kGroups * kCols;                // [2][kCols]
   const int K = 2 * C;
   const int c = threadIdx.x % kCols, rg = threadIdx.x / kCols;
@@ -298,16 +312,20 @@ avg_fold_bwd_kernel(const float* __restrict__ GL, int64_t ldgl, const float* __r
     dW[(size_t)n * K + k] = fmaf(g[i], sk, d[i] * tk);
     dbeta_p = fmaf(w, d[i], dbeta_p);
     wg_p = fmaf(w, g[i], wg_p);
-    const float ws = w * sk;
-    ws_s[n * kCols + c] = ws;
-    const float h = tf32_rna(ws);
-    WsT_hi[(size_t)k * N + n] = h;
-    WsT_lo[(size_t)k * N + n] = tf32_rna(ws - h);
+    ws_s[n * (kCols + 1) + c] = w * sk;
     if (blockIdx.x == 0 && c == 0) db[n] = d[i];
   }
   red[(0 * kGroups + rg) * kCols + c] = dbeta_p;
   red[(1 * kGroups + rg) * kCols + c] = wg_p;
   __syncthreads();
+  // (W diag(s))^T rows of this slab, coalesced over n (a direct store strides N floats between the lanes of a warp)
+  for (int i = threadIdx.x; i < kCols * N; i += kCols * kGroups) {
+    const int kl = i / N, n = i - kl * N;
+    const float ws = ws_s[n * (kCols + 1) + kl];
+    const float h = tf32_rna(ws);
+    WsT_hi[(size_t)(blockIdx.x * kCols + kl) * N + n] = h;
+    WsT_lo[(size_t)(blockIdx.x * kCols + kl) * N + n] = tf32_rna(ws - h);
+  }
   if (rg == 0) {
     float dbeta_k = 0.f, wg = 0.f;
 #pragma unroll
@@ -343,8 +361,8 @@ avg_fold_bwd_kernel(const float* __restrict__ GL, int64_t ldgl, const float* __r
     for (int n = 0; n < N; n += 4) {
       const float4 sa = *reinterpret_cast<const float4*>(sdy_s + (bA < nb ? bA : 0) * N + n);
       const float4 sb = *reinterpret_cast<const float4*>(sdy_s + (bB < nb ? bB : 0) * N + n);
-      const float w0 = ws_s[(n + 0) * kCols + c], w1 = ws_s[(n + 1) * kCols + c], w2 = ws_s[(n + 2) * kCols + c],
-                  w3 = ws_s[(n + 3) * kCols + c];
+      const float w0 = ws_s[(n + 0) * (kCols + 1) + c], w1 = ws_s[(n + 1) * (kCols + 1) + c],
+                  w2 = ws_s[(n + 2) * (kCols + 1) + c], w3 = ws_s[(n + 3) * (kCols + 1) + c];
       hA = fmaf(sa.x, w0, hA); hA = fmaf(sa.y, w1, hA); hA = fmaf(sa.z, w2, hA); hA = fmaf(sa.w, w3, hA);
       hB = fmaf(sb.x, w0, hB); hB = fmaf(sb.y, w1, hB); hB = fmaf(sb.z, w2, hB); hB = fmaf(sb.w, w3, hB);
     }
@@ -418,7 +436,7 @@ SN_API int sn_avg_fold_bwd_f32(const float* GL, int64_t ldgl, const float* SdY, 
     return SN_ERR_ARG;
   if (C % 32 || (N != 128 && N != 256) || !aligned16(SdY)) return SN_ERR_UNSUPPORTED;
   const double rows = (double)n_seg * (double)rows_per_seg;
-  const size_t smem = (size_t)(kMeshChunk * N + kMeshChunk * kCols + N * kCols + 2 * kGroups * kCols + 2 * kCols) * sizeof(float);
+  const size_t smem = (size_t)(kMeshChunk * N + kMeshChunk * kCols + N * (kCols + 1) + 2 * kGroups * kCols + 2 * kCols) * sizeof(float);
   auto kern = N == 128 ? avg_fold_bwd_kernel<128> : avg_fold_bwd_kernel<256>;
   // > 48 KB of dynamic shared memory: opt in (cheap, idempotent)
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {

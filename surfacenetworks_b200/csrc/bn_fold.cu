@@ -33,6 +33,7 @@ bn_fold_fwd_kernel(const float* __restrict__ mean, const float* __restrict__ var
   const bool publish = blockIdx.x == 0 && threadIdx.x < 32;
   if (n >= N) return;
   float acc = 0.f;
+#pragma unroll 8
   for (int k = lane; k < K; k += 32) {
     const float m = mean[k], v = var[k];
     const float rstd = rsqrtf(v + eps);
@@ -62,6 +63,7 @@ bn_fold_fwd_kernel(const float* __restrict__ mean, const float* __restrict__ var
   if (lane == 0) bf[n] = b[n] + acc;
 }
 
+constexpr int kFoldMaxN = 256;     // rows of W a column slab stages for the transposed store
 __global__ void __launch_bounds__(kFoldCols * kFoldRowGroups)
 bn_fold_bwd_kernel(const float* __restrict__ G, const float* __restrict__ sdY, const float* __restrict__ W,
                    const float* __restrict__ s, const float* __restrict__ t, const float* __restrict__ rstd,
@@ -70,28 +72,39 @@ bn_fold_bwd_kernel(const float* __restrict__ G, const float* __restrict__ sdY, c
                    float* __restrict__ q_out, float* __restrict__ WsT, float* __restrict__ WsT_hi,
                    float* __restrict__ WsT_lo) {
   __shared__ float red[2][kFoldRowGroups][kFoldCols];
+  __shared__ float ws_s[kFoldMaxN][kFoldCols + 1];      // W[n][k] s[k] of this slab: written row-wise, stored transposed
   const int c = threadIdx.x % kFoldCols, rg = threadIdx.x / kFoldCols;
   const int k = blockIdx.x * kFoldCols + c;
   float dbeta_p = 0.f, wg_p = 0.f;
   if (k < K) {
     const float sk = s[k], tk = t[k];
+#pragma unroll 4
     for (int n = rg; n < N; n += kFoldRowGroups) {
       const float w = W[(size_t)n * K + k], g = G[(size_t)n * K + k], d = sdY[n];
       dW[(size_t)n * K + k] = fmaf(g, sk, d * tk);
       dbeta_p = fmaf(w, d, dbeta_p);
       wg_p = fmaf(w, g, wg_p);
-      const float ws = w * sk;
-      WsT[(size_t)k * N + n] = ws;
-      if (WsT_hi) {
-        const float h = tf32_round(ws);
-        WsT_hi[(size_t)k * N + n] = h;
-        WsT_lo[(size_t)k * N + n] = tf32_round(ws - h);
-      }
+      ws_s[n][c] = w * sk;
     }
   }
   red[0][rg][c] = dbeta_p;
   red[1][rg][c] = wg_p;
   __syncthreads();
+  // (W diag(s))^T [K x N]: consecutive threads write consecutive n of one row k (the direct store had a stride of N floats
+  // between the lanes of a warp: 32 sectors per instruction, three arrays)
+  const int k0 = blockIdx.x * kFoldCols;
+  for (int i = threadIdx.x; i < kFoldCols * N; i += kFoldCols * kFoldRowGroups) {
+    const int kl = i / N, n = i - kl * N;
+    if (k0 + kl < K) {
+      const float ws = ws_s[n][kl];
+      WsT[(size_t)(k0 + kl) * N + n] = ws;
+      if (WsT_hi) {
+        const float h = tf32_round(ws);
+        WsT_hi[(size_t)(k0 + kl) * N + n] = h;
+        WsT_lo[(size_t)(k0 + kl) * N + n] = tf32_round(ws - h);
+      }
+    }
+  }
   if (rg == 0 && k < K) {
     float dbeta_k = 0.f, wg = 0.f;
 #pragma unroll
@@ -136,6 +149,7 @@ SN_API int sn_bn_fold_bwd_f32(const float* G, const float* sdY, const float* W, 
   if (N <= 0 || K <= 0 || rows <= 0 || !G || !sdY || !W || !s || !t || !rstd || !mean || !dW || !db || !dgamma || !dbeta ||
       !p || !q || !WsT || (WsT_hi == nullptr) != (WsT_lo == nullptr))
     return SN_ERR_ARG;
+  if (N > kFoldMaxN) return SN_ERR_UNSUPPORTED;
   bn_fold_bwd_kernel<<<(unsigned)ceil_div(K, kFoldCols), kFoldCols * kFoldRowGroups, 0, (cudaStream_t)stream>>>(
       G, sdY, W, s, t, rstd, mean, (int)N, (int)K, (float)(1.0 / (double)rows), training, dW, db, dgamma, dbeta, p, q, WsT,
       WsT_hi, WsT_lo);

@@ -57,33 +57,34 @@ colstats_partial_kernel(const float* __restrict__ X, int64_t ldx, int64_t rows, 
   }
 }
 
-// fixed-order fp64 reduction of the per-CTA partials: CTA = 32 columns x 32 partial groups (1024 threads); group g
-// adds partials g, g + 32, ... (independent loads, short dependent chains) and the 32 group sums are added in order
-__global__ void __launch_bounds__(1024)
+// fixed-order fp64 reduction of the per-CTA partials: CTA = 8 columns x 128 partial groups (1024 threads), C / 8 CTAs; group g
+// adds partials g, g + 128, ... (at most 8 rows for the largest producer grid: all loads of a thread are independent and in
+// flight together -- the launch is pure latency; the first version, 32 columns x 32 groups on C / 32 CTAs, walked 28 rows
+// per thread in dependent batches and took 9-11 us) and the 128 group sums are added in order by the column's first thread.
+constexpr int kFinCols = 8, kFinGroups = 128;
+__global__ void __launch_bounds__(kFinCols * kFinGroups)
 colstats_final_kernel(const float* __restrict__ partial, int n_partials, int64_t rows, int C, const float* __restrict__ X,
                       float* __restrict__ mean, float* __restrict__ var) {
-  __shared__ double red[2][32][33];
-  const int lc = threadIdx.x & 31, g = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + lc;
+  __shared__ double red[2][kFinGroups][kFinCols + 1];
+  const int lc = threadIdx.x % kFinCols, g = threadIdx.x / kFinCols;
+  const int c = blockIdx.x * kFinCols + lc;
   double s = 0.0, q = 0.0;
   if (c < C) {
-    // 8 independent loads in flight per statistic, accumulated in the same fixed order as a plain loop (the launch is
-    // pure latency: ~28 dependent L2 round trips per thread otherwise, 14 us measured)
     int i = g;
-    for (; i + 7 * 32 < n_partials; i += 8 * 32) {
-      float a[8], b[8];
+    for (; i + 3 * kFinGroups < n_partials; i += 4 * kFinGroups) {
+      float a[4], b[4];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        a[u] = __ldg(partial + (size_t)(i + u * 32) * 2 * C + c);
-        b[u] = __ldg(partial + (size_t)(i + u * 32) * 2 * C + C + c);
+      for (int u = 0; u < 4; ++u) {
+        a[u] = __ldg(partial + (size_t)(i + u * kFinGroups) * 2 * C + c);
+        b[u] = __ldg(partial + (size_t)(i + u * kFinGroups) * 2 * C + C + c);
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < 4; ++u) {
         s += (double)a[u];
         q += (double)b[u];
       }
     }
-    for (; i < n_partials; i += 32) {
+    for (; i < n_partials; i += kFinGroups) {
       s += (double)__ldg(partial + (size_t)i * 2 * C + c);
       q += (double)__ldg(partial + (size_t)i * 2 * C + C + c);
     }
@@ -94,7 +95,7 @@ colstats_final_kernel(const float* __restrict__ partial, int n_partials, int64_t
   if (g == 0 && c < C) {
     s = 0.0;
     q = 0.0;
-    for (int k = 0; k < 32; ++k) {
+    for (int k = 0; k < kFinGroups; ++k) {
       s += red[0][k][lc];
       q += red[1][k][lc];
     }
@@ -155,7 +156,7 @@ elu_colstats_kernel(const float* __restrict__ X, int64_t ldx, float* __restrict_
 // statistics store path): partial [n_partials][2][C] (sum | sum of squares of x - shift), shift [C] or null.
 int launch_colstats_final(const float* partial, int n_partials, int64_t rows, int C, const float* shift, float* mean,
                           float* var, cudaStream_t st) {
-  colstats_final_kernel<<<(unsigned)ceil_div(C, 32), 1024, 0, st>>>(partial, n_partials, rows, C, shift, mean, var);
+  colstats_final_kernel<<<(unsigned)ceil_div(C, kFinCols), kFinCols * kFinGroups, 0, st>>>(partial, n_partials, rows, C, shift, mean, var);
   return launch_status();
 }
 
@@ -185,7 +186,7 @@ SN_API int sn_colstats_f32(const float* X, int64_t ldx, int64_t rows, int64_t C,
   const size_t smem = (size_t)RG * 2 * C * sizeof(float);
   if (smem > 48 * 1024) return SN_ERR_UNSUPPORTED;
   colstats_partial_kernel<<<grid, kStatThreads, smem, st>>>(X, ldx, rows, (int)C, (float*)ws);
-  colstats_final_kernel<<<(unsigned)ceil_div(C, 32), 1024, 0, st>>>((const float*)ws, grid, rows, (int)C, X, mean, var_biased);
+  colstats_final_kernel<<<(unsigned)ceil_div(C, kFinCols), kFinCols * kFinGroups, 0, st>>>((const float*)ws, grid, rows, (int)C, X, mean, var_biased);
   return launch_status();
 }
 
@@ -204,6 +205,6 @@ SN_API int sn_elu_colstats_f32(const float* X, int64_t ldx, float* Y, int64_t ld
   if (smem > 48 * 1024) return SN_ERR_UNSUPPORTED;
   elu_colstats_kernel<<<grid, kStatThreads, smem, st>>>(X, ldx, Y, ldy, rows, (int)C, (float*)ws);
   // the shift used by the partial sums is the activated row 0, which the kernel above has just written to Y
-  colstats_final_kernel<<<(unsigned)ceil_div(C, 32), 1024, 0, st>>>((const float*)ws, grid, rows, (int)C, Y, mean, var_biased);
+  colstats_final_kernel<<<(unsigned)ceil_div(C, kFinCols), kFinCols * kFinGroups, 0, st>>>((const float*)ws, grid, rows, (int)C, Y, mean, var_biased);
   return launch_status();
 }
