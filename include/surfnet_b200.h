@@ -238,6 +238,15 @@ int sn_gemm_tf32_presplit_act_f32(const float* A, int64_t lda, const float* B_hi
                                   const float* group_bias, int64_t rows_per_group, float* C, int64_t ldc, float* C_act,
                                   int64_t ldc_act, float* act_mean, float* act_var, int64_t M, int64_t N, int64_t K,
                                   int flags, void* ws, size_t ws_bytes, sn_stream_t stream);
+/* The dZ product of an AvgResNet2 stage backward with the ELU backward of utils_pt.py:231,237 in its epilogue (replaces
+ * sn_gemm_tf32_presplit_f32 + sn_elu_bwd_group_f32: the intermediate dZ is never written):
+ *   C = ((A * (B_hi + B_lo)^T + bias + row_scale[row] * group_bias[row / rows_per_group] + rscale .* R) .* elu'(R)) + R2
+ * R = the activated values a = elu(x) (elu' = 1 if a > 0 else a + 1), required; row_scale [M] (the mask weights) and
+ * R2 [M x N] (a gradient that bypasses the activation, e.g. the block residual's) may be NULL. */
+int sn_gemm_tf32_presplit_elubwd_f32(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb,
+                                     const float* bias, const float* R, int64_t ldr, const float* rscale,
+                                     const float* group_bias, int64_t rows_per_group, const float* row_scale, const float* R2,
+                                     int64_t ldr2, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, sn_stream_t stream);
 /* All-pairs feature correlation of the dense_correspondence SiameseModel (dense_correspondence/models.py:199-203,
  * torch.bmm(FA, FB^T) per shape pair): C[M x N] = A[M x K] * (B_hi + B_lo)[N x K]^T for WIDE N (thousands of columns),
  * K <= 128, K % 4 == 0, N % 4 == 0 (K and N tails are zero-filled / clipped by the tensor maps: no padding copies).

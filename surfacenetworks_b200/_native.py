@@ -82,6 +82,8 @@ SIGNATURES = {
                                     _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),
     "sn_lap_stage_bwd_f32": (_int, [_ptr, _ptr, _ptr, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64,
                                     _ptr, _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),
+    "sn_gemm_tf32_presplit_elubwd_f32": (_int, [_ptr, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _i64,
+                                                _ptr, _i64, _i64, _i64, _i64, _ptr]),
     "sn_split_tf32_f32": (_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr]),
     "sn_csr_spmm_epilogue_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64,
                                         _int, _ptr]),

@@ -428,6 +428,12 @@ struct ParamsTS {
   float* C2;
   int64_t ldc2;
   float* stat_partial;
+  // "+ elu-backward" epilogue of the AvgResNet2 stage backward (non-ACT kernel only):
+  //   C = ((acc + bias + row_scale[row] * gbias[row / rows_per_group] + rscale .* R) .* elu'(R)) + R2
+  // row_scale [M] (the mask weights), elu_all: the derivative applies to every column, R2 (optional second residual, e.g.
+  // the block-residual gradient) arrives through map_c2 into its own slots.
+  const float* row_scale;
+  int elu_all, has_r2;
   int r_slots;           // residual boxes in flight per epilogue warp (1 or 2)
   int epi_slots;         // 4 KB staging boxes per epilogue warp: output (+ residual slots / activated copy)
   int debug;             // timing experiments only (SN_GEMM_DEBUG_*, tools/gemm_stage_bench.py): results are garbage
@@ -459,6 +465,7 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   __shared__ uint64_t r_full[kEpiWarps * 2];                  // [epilogue warp][residual slot]
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float s_bias[256], s_rscale[256];   // epilogue vectors: LDS instead of an L1-missing __ldg per chunk
+  __shared__ __align__(16) float s_gb[kEpiWarps][64];          // per-warp copy of the job's group-bias row (when one mesh covers the slab)
   __shared__ __align__(16) float s_stat[ACT ? kEpiWarps : 1][2][128];   // ACT: per-epilogue-warp column sums / sums of squares
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -656,6 +663,7 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const uint32_t out_s = my_s;                               // output box
     const int r_slots = p.r_slots;                             // residual slots (ACT: the last box stages the activated copy)
     const uint32_t r_s = my_s + 4096;
+    const uint32_t r2_s = r_s + (uint32_t)r_slots * 4096;      // second residual: same slot count, behind the first
     const uint32_t act_s = my_s + (uint32_t)(p.epi_slots - 1) * 4096;
     const uint32_t row_off = (uint32_t)lane * 128u;
     const uint32_t sw = (uint32_t)(lane & 7);
@@ -672,9 +680,13 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       if (pf.tile < n_tiles) {
         if (lane == 0) {
           const uint32_t slot = r_issued % (uint32_t)r_slots;
-          mbar_arrive_expect_tx(r_full + 2 * e + slot, 4096u);
+          mbar_arrive_expect_tx(r_full + 2 * e + slot, (!ACT && p.has_r2) ? 8192u : 4096u);
           tma_load_2d(my_g + 4096 + slot * 4096u, &map_r, (item_half0(pf.tile) + pf.half) * nmma + chalf * ncol + pf.c * 32,
                       item_row(pf.tile) + quarter * 32, r_full + 2 * e + slot);
+          if (!ACT && p.has_r2)
+            tma_load_2d(my_g + 4096 + ((uint32_t)r_slots + slot) * 4096u, &map_c2,
+                        (item_half0(pf.tile) + pf.half) * nmma + chalf * ncol + pf.c * 32, item_row(pf.tile) + quarter * 32,
+                        r_full + 2 * e + slot);
         }
         ++r_issued;
         advance(pf);
@@ -693,16 +705,33 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const uint32_t buf = job & 1u;
         const int row0 = item_row(tile) + quarter * 32;
         const int cbase = (h0 + half) * nmma + chalf * ncol;   // first global column of this warp's share
-        const float* gb_row = p.gbias ? p.gbias + (int64_t)((row0 + lane < p.M ? row0 + lane : p.M - 1) / p.rows_per_group) * N : nullptr;
+        const int row_c = row0 + lane < p.M ? row0 + lane : p.M - 1;
+        const float* gb_row = p.gbias ? p.gbias + (int64_t)(row_c / p.rows_per_group) * N : nullptr;
+        const float gb_w = (!ACT && p.row_scale) ? __ldg(p.row_scale + row_c) : 1.f;
+        // group bias: the 32 rows of this slab almost always belong to one group (a mesh is thousands of rows): stage that
+        // row's 64 columns once per job and read them as shared-memory broadcasts; slabs that straddle a boundary load per lane
+        bool gb_uniform = false;
+        if (p.gbias) {
+          const int last = row0 + 31 < p.M ? row0 + 31 : p.M - 1;
+          gb_uniform = row0 < p.M && row0 / p.rows_per_group == last / p.rows_per_group;
+          if (gb_uniform) {
+            __syncwarp();
+            if (lane * 4 < ncol)
+              *reinterpret_cast<float4*>(&s_gb[e][lane * 4]) =
+                  __ldg(reinterpret_cast<const float4*>(p.gbias + (int64_t)(row0 / p.rows_per_group) * N + cbase + lane * 4));
+            __syncwarp();
+          }
+        }
         mbar_wait(tmem_full + buf, (job >> 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int ci = 0; ci < nchunks && !(p.debug & 1); ++ci) {
           const int c0 = cbase + ci * 32;
-          uint32_t rslot_s = 0;
+          uint32_t rslot_s = 0, r2slot_s = 0;
           if (p.R) {
             const uint32_t slot = r_used % (uint32_t)r_slots;
             mbar_wait(r_full + 2 * e + slot, (r_used / (uint32_t)r_slots) & 1u);
             rslot_s = r_s + slot * 4096u;
+            r2slot_s = r2_s + slot * 4096u;
           }
           // the previous bulk store(s) of this warp must have read the staging boxes before they are overwritten
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -724,16 +753,19 @@ gemm_tf32_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               float4 o = make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]),
                                      __uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3]));
               if (n_groups == 1) o = add4(o, *reinterpret_cast<const float4*>(s_bias + col));   // wide-N: no epilogue vectors
-              if (p.gbias) o = add4(o, __ldg(reinterpret_cast<const float4*>(gb_row + col)));
+              if (p.gbias)
+                o = fma4(gb_w, gb_uniform ? *reinterpret_cast<const float4*>(&s_gb[e][col - cbase])
+                                          : __ldg(reinterpret_cast<const float4*>(gb_row + col)), o);
               if (p.R) {
                 const float4 rr = lds_f4(rslot_s + swz);
                 const float4 rs = *reinterpret_cast<const float4*>(s_rscale + col);
                 o.x = fmaf(rs.x, rr.x, o.x); o.y = fmaf(rs.y, rr.y, o.y);
                 o.z = fmaf(rs.z, rr.z, o.z); o.w = fmaf(rs.w, rr.w, o.w);
-                if (!ACT && p.elu_left && c0 < (N >> 1)) {     // chunk-uniform: 32-column chunks never straddle N/2
+                if (!ACT && ((p.elu_left && c0 < (N >> 1)) || p.elu_all)) {   // chunk-uniform: 32-column chunks never straddle N/2
                   o.x *= rr.x > 0.f ? 1.f : rr.x + 1.f; o.y *= rr.y > 0.f ? 1.f : rr.y + 1.f;
                   o.z *= rr.z > 0.f ? 1.f : rr.z + 1.f; o.w *= rr.w > 0.f ? 1.f : rr.w + 1.f;
                 }
+                if (!ACT && p.has_r2) o = add4(o, lds_f4(r2slot_s + swz));
               }
               if (!ACT || p.C)
                 asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(out_s + swz), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
@@ -865,7 +897,8 @@ namespace gemm {
 static int launch_gemm(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb, const float* bias,
                        const float* R, int64_t ldr, const float* rscale, const float* group_bias, int64_t rows_per_group,
                        float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int flags, cudaStream_t stream,
-                       float* C_act = nullptr, int64_t ldc_act = 0, float* stat_partial = nullptr, bool wide = false) {
+                       float* C_act = nullptr, int64_t ldc_act = 0, float* stat_partial = nullptr, bool wide = false,
+                       const float* row_scale = nullptr, const float* R2 = nullptr, int64_t ldr2 = 0, bool elu_all = false) {
   const bool split = B_lo != nullptr;
   int dev = 0, sms = 148, smem_optin = 0;
   cudaGetDevice(&dev);
@@ -940,6 +973,12 @@ static int launch_gemm(const float* A, int64_t lda, const float* B_hi, const flo
   if (C_act && !make_map(&map_c2, C_act, M, N, ldc_act, 32)) return SN_ERR_UNSUPPORTED;
   if (!C) map_c = map_c2;
   if (!C_act) map_c2 = map_c;
+  if (R2) {                              // non-ACT kernel: map_c2 carries the second residual
+    if (C_act || !R || !make_map(&map_c2, R2, M, N, ldr2, 32)) return SN_ERR_UNSUPPORTED;
+  }
+  p.row_scale = row_scale;
+  p.elu_all = elu_all ? 1 : 0;
+  p.has_r2 = R2 ? 1 : 0;
   if (R) {
     if (!make_map(&map_r, R, M, N, ldr, 32)) return SN_ERR_UNSUPPORTED;
   } else {
@@ -950,12 +989,12 @@ static int launch_gemm(const float* A, int64_t lda, const float* B_hi, const flo
   static const int env_rslots = [] { const char* v = getenv("SN_GEMM_RSLOTS"); return v ? atoi(v) : 0; }();
   static const int env_bstages = [] { const char* v = getenv("SN_GEMM_BSTAGES"); return v ? atoi(v) : 0; }();
   p.r_slots = R ? ((env_rslots == 1 || env_rslots == 2) ? env_rslots : (C_act ? 1 : 2)) : 0;
-  if (C_act && p.r_slots > 1) p.r_slots = 1;
-  p.epi_slots = 1 + p.r_slots + (C_act ? 1 : 0);
+  if ((C_act || R2) && p.r_slots > 1) p.r_slots = 1;
+  p.epi_slots = 1 + p.r_slots * (R2 ? 2 : 1) + (C_act ? 1 : 0);
   const size_t a_bytes = (size_t)kBlockM * kBlockK * 4, b_stage = 2 * (size_t)p.nmma * kBlockK * 4;
   const size_t epi_bytes = (size_t)kEpiWarps * p.epi_slots * 4096;
   // static: epilogue vectors, barriers (+ 8 KB of statistics accumulators in the ACT kernel); 1 KB alignment
-  const size_t budget = (size_t)smem_optin - (C_act ? 12 : 4) * 1024 - 1024;
+  const size_t budget = (size_t)smem_optin - (C_act ? 14 : 6) * 1024 - 1024;
   p.b_stages = (env_bstages >= 2 && env_bstages <= kMaxBStages) ? env_bstages : (epi_bytes <= 64 * 1024 ? 3 : 2);
   int a_stages = (int)((budget - p.b_stages * b_stage - epi_bytes) / a_bytes);
   if (a_stages > kMaxAStages) a_stages = kMaxAStages;
@@ -1026,6 +1065,21 @@ SN_API int sn_gemm_tf32_presplit_f32(const float* A, int64_t lda, const float* B
   if (!B_lo || !aligned16(B_lo) || (flags & SN_GEMM_SINGLE_PASS)) return SN_ERR_ARG;
   return launch_gemm(A, lda, B_hi, B_lo, ldb, bias, R, ldr, rscale, group_bias, rows_per_group, C, ldc, M, N, K, flags,
                      (cudaStream_t)stream);
+}
+
+SN_API int sn_gemm_tf32_presplit_elubwd_f32(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb,
+                                            const float* bias, const float* R, int64_t ldr, const float* rscale,
+                                            const float* group_bias, int64_t rows_per_group, const float* row_scale,
+                                            const float* R2, int64_t ldr2, float* C, int64_t ldc, int64_t M, int64_t N,
+                                            int64_t K, sn_stream_t stream) {
+  using namespace sn;
+  using namespace sn::gemm;
+  const int rc = check_gemm_args(A, lda, B_hi, ldb, bias, R, ldr, rscale, group_bias, rows_per_group, C, ldc, M, N, K, 0);
+  if (rc != SN_OK || M == 0) return rc;
+  if (!B_lo || !aligned16(B_lo) || !R) return SN_ERR_ARG;
+  if (R2 && (ldr2 < N || ldr2 % 4 || !aligned16(R2))) return SN_ERR_UNSUPPORTED;
+  return launch_gemm(A, lda, B_hi, B_lo, ldb, bias, R, ldr, rscale, group_bias, rows_per_group, C, ldc, M, N, K, 0,
+                     (cudaStream_t)stream, nullptr, 0, nullptr, false, row_scale, R2, ldr2, true);
 }
 
 SN_API int sn_gemm_nt_wide_tf32_f32(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb, float* C,

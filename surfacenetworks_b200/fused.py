@@ -384,12 +384,19 @@ class _AvgStage(torch.autograd.Function):
                    _ptr(db), _ptr(vec[0]), _ptr(vec[1]), _ptr(vec[2]), _ptr(vec[3]), _ptr(WsT[0]), _ptr(WsT[1]), _ptr(gb),
                    _stream())
         p, q = vec[2], vec[3]
-        dZl = gemm_tf32(dY, WsT[0][:C], bias=q[:C], R=a, rscale=p[:C], B_lo=WsT[1][:C])
         dx = torch.empty_like(a)
         g3 = ctx.in_cell.pop("residual_grad", None) if ctx.in_cell is not None else None
+        if g3 is not None and (g3.stride(1) != 1 or g3.stride(0) % 4 or g3.data_ptr() % 16):
+            g3 = g3.contiguous()
+        # dx = ((dY (W_L diag(s_L)) + p a + q + mask * gb[mesh]) .* elu'(a)) + g3: the dZ GEMM with the ELU backward, the
+        # per-mesh gradient of the averages and the block-residual gradient in its epilogue (dZ_L is never written)
+        if N.TIMER is not None:
+            N.TIMER.annotate("gemm+elu' %dx%dx%d%s" % (rows, C, Nn, "" if g3 is None else " +R2"),
+                             4 * (rows * Nn + rows * C * (2 if g3 is None else 3) + 2 * C * Nn), 2 * rows * C * Nn)
         with torch.cuda.device(dev):
-            N.call("sn_elu_bwd_group_f32", _ptr(a), a.stride(0), _ptr(dZl), dZl.stride(0), _ptr(gb), _ptr(maskw), ctx.rps,
-                   _ptr(g3), 0 if g3 is None else g3.stride(0), _ptr(dx), dx.stride(0), rows, C, _stream())
+            N.call("sn_gemm_tf32_presplit_elubwd_f32", _ptr(dY), dY.stride(0), _ptr(WsT[0]), _ptr(WsT[1]), Nn, _ptr(q), _ptr(a),
+                   a.stride(0), _ptr(p), _ptr(gb), ctx.rps, _ptr(maskw), _ptr(g3), 0 if g3 is None else g3.stride(0), _ptr(dx),
+                   dx.stride(0), rows, C, Nn, _stream())
         g_res = dY if ctx.has_res else None
         if g_res is not None and ctx.res_cell is not None:
             ctx.res_cell["residual_grad"] = dY           # picked up by the block's first stage (runs later in backward)

@@ -230,3 +230,37 @@ def test_avg_block_fused_stage_vs_oracle(C, B, nv):
     gscale = max(float(P[k].grad.abs().max()) for k, _ in blk.named_parameters())
     for k, p in blk.named_parameters():
         close(p.grad, P[k].grad, "grad " + k, 1e-3, floor=1e-2 * gscale)
+
+
+@pytest.mark.parametrize("with_r2", [False, True])
+@pytest.mark.parametrize("rows_per_seg,n_seg,C,K", [(700, 3, 128, 128), (2000, 8, 128, 128), (333, 5, 256, 256)])
+def test_gemm_elu_backward_epilogue(rows_per_seg, n_seg, C, K, with_r2):
+    """sn_gemm_tf32_presplit_elubwd_f32 (AvgResNet2 stage backward, utils_pt.py:231-243 through autograd) against the two
+    launches it replaces: sn_gemm_tf32_presplit_f32 (dZ = dY W + q + p .* a) then sn_elu_bwd_group_f32
+    ((dZ + mask * gb[mesh]) .* elu'(a) + g3).  Same arithmetic per element up to one fused multiply-add: 4 ulps of the
+    summed magnitudes."""
+    from surfacenetworks_b200 import _native as Nv, fused
+    M = rows_per_seg * n_seg
+    g = torch.Generator(device=DEV).manual_seed(M + C + K)
+    dY = torch.randn(M, K, device=DEV, generator=g)
+    W = torch.randn(C, K, device=DEV, generator=g) / K ** 0.5
+    hi, lo = torch.empty_like(W), torch.empty_like(W)
+    st = torch.cuda.current_stream().cuda_stream
+    Nv.call("sn_split_tf32_f32", W.data_ptr(), K, C, K, hi.data_ptr(), lo.data_ptr(), st)
+    a = torch.nn.functional.elu(torch.randn(M, C, device=DEV, generator=g))
+    p, q = torch.randn(C, device=DEV, generator=g) * 0.1, torch.randn(C, device=DEV, generator=g)
+    gb = torch.randn(n_seg, C, device=DEV, generator=g)
+    maskw = (torch.rand(M, device=DEV, generator=g) > 0.1).float()
+    g3 = torch.randn(M, C, device=DEV, generator=g) if with_r2 else None
+    dZ = fused.gemm_tf32(dY, hi, bias=q, R=a, rscale=p, B_lo=lo)
+    ref = torch.empty_like(a)
+    Nv.call("sn_elu_bwd_group_f32", a.data_ptr(), C, dZ.data_ptr(), C, gb.data_ptr(), maskw.data_ptr(), rows_per_seg,
+            0 if g3 is None else g3.data_ptr(), C, ref.data_ptr(), C, M, C, st)
+    out = torch.empty_like(a)
+    Nv.call("sn_gemm_tf32_presplit_elubwd_f32", dY.data_ptr(), K, hi.data_ptr(), lo.data_ptr(), K, q.data_ptr(), a.data_ptr(), C,
+            p.data_ptr(), gb.data_ptr(), rows_per_seg, maskw.data_ptr(), 0 if g3 is None else g3.data_ptr(), C, out.data_ptr(), C,
+            M, C, K, st)
+    # magnitude of the summed terms (the two paths add them in different orders)
+    mag = ((dZ - q - p * a).abs() + q.abs() + (p * a).abs() + gb.abs()[torch.arange(M, device=DEV) // rows_per_seg]
+           + (0 if g3 is None else g3.abs()) + 1e-6)
+    assert torch.all((out - ref).abs() <= 5e-7 * mag), float(((out - ref).abs() / mag).max())
