@@ -133,6 +133,10 @@ int launch_bsr4_rowgroup(const int32_t* browptr, const int32_t* bcolind, const f
                          const float* G, int64_t ldg, const float* A, int64_t lda, const float* G2, int64_t ldg2, cudaStream_t st,
                          float* stat_partial = nullptr, int* grid_out = nullptr);
 int64_t rowgroup_max_grid();
+// spmm_rowdirect.cu: small operators (one or two waves of threads)
+bool rowdirect_applies(int64_t n_rows, int64_t C, bool three_in_flight);
+int launch_bsr4_rowdirect(const int32_t* browptr, const int32_t* bcolind, const float* bval, const float* X, int64_t ldx,
+                          float* Y, int64_t ldy, int64_t n_brows, int64_t n_blocks, int64_t C, cudaStream_t st);
 
 }  // namespace sn
 
@@ -161,8 +165,16 @@ SN_API int sn_bsr4_spmm_f32(const int32_t* browptr, const int32_t* bcolind, cons
   if (flags & SN_SPMM_SMEM_STREAM) {       // cp.async streaming kernel: C = 128 / 256 / 512
     const int rc = launch_bsr4_stream(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C, elu, st);
     if (rc != SN_ERR_UNSUPPORTED) return rc;
-  } else if (!(flags & SN_SPMM_DIRECT_GATHER)) {  // row-group kernel: C = 16 ... 512 (powers of two)
-    const int rc = launch_bsr4_rowgroup(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C, elu, (flags >> 8) & 15, nullptr, 0,
+  } else if (!(flags & SN_SPMM_DIRECT_GATHER)) {
+    const int variant = (flags >> 8) & 15, hint = (flags >> 12) & 15;
+    // small operators (a single mesh, a mesh_mnist batch): the latency-oriented kernel, bit-identical results
+    if (!elu && variant != 7 && (variant == 6 || (variant == 0 && rowdirect_applies(n_brows, C, hint >= 1 && hint <= 3)))) {
+      const int rc = launch_bsr4_rowdirect(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows,
+                                           hint >= 1 && hint <= 3 ? 3 * n_brows : -1, C, st);
+      if (rc != SN_ERR_UNSUPPORTED) return rc;
+    }
+    // row-group kernel: C = 32 ... 512 (powers of two)
+    const int rc = launch_bsr4_rowgroup(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C, elu, variant >= 6 ? 0 : variant, nullptr, 0,
                                         nullptr, 0, nullptr, 0, st);
     if (rc != SN_ERR_UNSUPPORTED) return rc;
   }

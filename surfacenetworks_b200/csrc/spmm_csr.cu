@@ -124,6 +124,10 @@ int launch_csr_rowgroup(const int32_t* rowptr, const int32_t* colind, const floa
                         int64_t ldg, const float* A, int64_t lda, const float* G2, int64_t ldg2, cudaStream_t st,
                         float* stat_partial = nullptr, int* grid_out = nullptr);
 int64_t rowgroup_max_grid();
+// spmm_rowdirect.cu: small operators (one or two waves of threads)
+bool rowdirect_applies(int64_t n_rows, int64_t C, bool three_in_flight);
+int launch_csr_rowdirect(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X, int64_t ldx,
+                         float* Y, int64_t ldy, int64_t n_rows, int64_t nnz, int64_t C, cudaStream_t st);
 
 }  // namespace sn
 
@@ -147,9 +151,17 @@ SN_API int sn_csr_spmm_f32(const int32_t* rowptr, const int32_t* colind, const f
       csr_spmm_scalar_kernel<false><<<(unsigned)grid, 256, 0, st>>>(rowptr, colind, val, X, ldx, Y, ldy, n_rows, (int)C);
     return launch_status();
   }
-  if (!(flags & SN_SPMM_DIRECT_GATHER)) {  // row-group kernel: C = 16 ... 512
-    const int rc = launch_csr_rowgroup(rowptr, colind, val, X, ldx, Y, ldy, n_rows, C, elu, (flags >> 8) & 15, nullptr, 0, nullptr,
-                                       0, nullptr, 0, st);
+  if (!(flags & SN_SPMM_DIRECT_GATHER)) {
+    const int variant = (flags >> 8) & 15, hint = (flags >> 12) & 15;
+    // small operators (a mesh_mnist batch, a single mesh): the latency-oriented kernel, bit-identical results
+    if (!elu && aligned16(val) && variant != 7 && (variant == 6 || (variant == 0 && rowdirect_applies(n_rows, C, hint >= 1 && hint <= 3)))) {
+      const int rc = launch_csr_rowdirect(rowptr, colind, val, X, ldx, Y, ldy, n_rows, hint >= 1 && hint <= 3 ? 3 * n_rows : -1,
+                                          C, st);
+      if (rc != SN_ERR_UNSUPPORTED) return rc;
+    }
+    // row-group kernel: C = 32 ... 512
+    const int rc = launch_csr_rowgroup(rowptr, colind, val, X, ldx, Y, ldy, n_rows, C, elu, variant >= 6 ? 0 : variant, nullptr, 0,
+                                       nullptr, 0, nullptr, 0, st);
     if (rc != SN_ERR_UNSUPPORTED) return rc;
   }
   const int64_t v = C / 4;  // float4 columns

@@ -394,7 +394,7 @@ class Bsr4Operator:
         if N.TIMER is not None:
             N.TIMER.annotate("bsr4 %dx%d C=%d" % (self.n_brows, self.n_bcols, C), self.algorithmic_bytes(C), self.flops(C))
         with torch.cuda.device(X.device):
-            flags = N.spmm_flags(elu_input, direct_gather, smem_stream, variant)
+            flags = N.spmm_flags(elu_input, direct_gather, smem_stream, variant, row_entries=self.max_row_blocks)
             N.call("sn_bsr4_spmm_f32", _ptr(self.browptr), _ptr(self.bcolind), _ptr(self.bval),
                    _ptr(X), X.stride(0), _ptr(out), out.stride(0), self.n_brows, C, flags, _stream())
         return out

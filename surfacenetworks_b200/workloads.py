@@ -34,8 +34,17 @@ class MeshOps:
         return self.F.shape[0]
 
 
-def make_mesh_ops(num_vertices, seeds):
-    return [MeshOps(*geometry.synth_mesh(num_vertices, s)) for s in seeds]
+def make_mesh_ops(num_vertices, seeds, order=None):
+    """Synthetic meshes with their operators; ``order`` ("bisect", "morton", "rcm", "morton_xy") renumbers each mesh with
+    ``geometry.locality_order`` first (a preprocessing choice: same meshes, same per-vertex results, renumbered)."""
+    out = []
+    for s in seeds:
+        V, F = geometry.synth_mesh(num_vertices, s)
+        if order and order != "none":
+            kw = {"method": "morton", "axes": (0, 1)} if order == "morton_xy" else {"method": order}
+            V, F = geometry.reorder_mesh(V, F, *geometry.locality_order(V, F, **kw))
+        out.append(MeshOps(V, F))
+    return out
 
 
 def block_diag_coo(mats, size0, size1):

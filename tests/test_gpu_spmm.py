@@ -214,8 +214,12 @@ def test_bsr4_feature_widths_and_strides(golden, C):
     y64, bound = c_oracle.dirac_view_mm_f64(idx[0], idx[1], val, 2 * nf, x)
     y = Di.apply(xg)
     within_bound(y.cpu().numpy(), y64, bound, "contiguous")
-    for variant in (1, 2, 3, 4, 5):        # tuning variants of the row-group kernel share its summation order
+    # tuning variants of the row-group kernel and the small-operator kernel (6; 7 = persistent kernel forced) share one
+    # summation order; below C = 32 the persistent kernel does not exist and 1-5 / 7 fall back to the direct-gather kernel
+    for variant in (1, 2, 3, 4, 5, 6, 7) if C >= 32 else (6,):
         assert torch.equal(y, Di.apply(xg, variant=variant)), "row-group variant %d" % variant
+    if C == 16:
+        within_bound(Di.apply(xg, variant=7).cpu().numpy(), y64, bound, "C = 16 without the small-operator kernel")
     # cp.async streaming kernel (C = 128/256/512) and direct-gather kernel use the same summation order: bit-identical
     yd = Di.apply(xg, direct_gather=True)
     within_bound(yd.cpu().numpy(), y64, bound, "direct-gather kernel")
@@ -255,7 +259,7 @@ def test_rowgroup_long_rows_and_empty_runs(C):
     y64, bound = c_oracle.coo_mm_f64(row, col, val, n_rows, x)
     y = op.apply(xg)
     within_bound(y.cpu().numpy(), y64, bound, "csr rowgroup")
-    for variant in (1, 2, 3, 4, 5):
+    for variant in (1, 2, 3, 4, 5, 6, 7):     # 6 / 7: small-operator kernel (spmm_rowdirect.cu) / persistent kernel forced
         assert torch.equal(y, op.apply(xg, variant=variant)), "csr variant %d" % variant
     # the same pattern as 4x4 blocks (dense random blocks): block row r has lens[r] blocks
     blk = rng.standard_normal((row.size, 4, 4)).astype(np.float32)
@@ -268,8 +272,11 @@ def test_rowgroup_long_rows_and_empty_runs(C):
     y = opb.apply(xg)
     within_bound(y.cpu().numpy(), y64, bound, "bsr4 rowgroup")
     within_bound(opb.apply(xg, direct_gather=True).cpu().numpy(), y64, bound, "bsr4 direct")
-    for variant in (1, 2, 3, 4, 5):
+    for variant in (1, 2, 3, 4, 5, 6, 7) if C >= 32 else (6,):      # C = 16: see test_bsr4_feature_widths_and_strides
         assert torch.equal(y, opb.apply(xg, variant=variant)), "bsr4 variant %d" % variant
+    # the row-length hint only changes how many gathers are in flight (here it is wrong on purpose: rows hold up to 150)
+    opb.max_row_blocks = 3
+    assert torch.equal(y, opb.apply(xg, variant=6)), "bsr4 small-operator kernel, three entries in flight"
 
 
 @pytest.mark.parametrize("C,n_rows", [(16, 480_000), (64, 200_000), (128, 150_001), (512, 40_000)])
@@ -289,7 +296,7 @@ def test_rowgroup_persistent_warps(C, n_rows):
     yd = op.apply(xg, direct_gather=True)
     mag = O.CsrOperator(op.rowptr, op.colind, op.val.abs(), op.n_rows, op.n_cols).apply(xg.abs(), direct_gather=True)
     assert torch.all((y - yd).abs() <= 64 * EPS32 * mag + 1e-30)
-    for variant in (1, 3):
+    for variant in (1, 3, 6):                  # 6: the small-operator kernel forced onto a large operator
         assert torch.equal(y, op.apply(xg, variant=variant)), "variant %d" % variant
     # oracle check on a row sample (full fp64 product of 480k x 16 ... 150k x 128 stays cheap on the CPU)
     y64, bound = c_oracle.coo_mm_f64(row, col, val, n_rows, x)

@@ -28,14 +28,15 @@ def main():
     ap.add_argument("--variants", default="rg,rg1,rg2,rg3,rg4,rg5,smem,direct",
                     help="rg[N] = row-group kernel (tuning variant N), smem = cp.async streaming kernel (BSR4 only), "
                          "direct = first-generation direct-gather kernel; +elu = ELU on load")
+    ap.add_argument("--order", default="none", help="none | bisect | morton | morton_xy | rcm: renumber every mesh with geometry.locality_order")
     args = ap.parse_args()
-    from surfacenetworks_b200 import operators as OP, workloads as W
+    from surfacenetworks_b200 import geometry, operators as OP, workloads as W
     dev = torch.device("cuda", 0)
     peak = 6558.1
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         peak = float(json.load(open(p))["hbm_gbs"])
-    base = W.make_mesh_ops(args.vertices, range(args.distinct))
+    base = W.make_mesh_ops(args.vertices, range(args.distinct), order=args.order)
     meshes = [base[i % args.distinct] for i in range(args.meshes)]
     C = args.features
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -69,6 +70,10 @@ def main():
     c = torch.empty_like(a)
     ms, best = time_it(lambda: c.copy_(a))
     print(json.dumps({"op": "copy 256MB", "us": ms * 1e3, "GBps": 2 * a.numel() * 4 / ms / 1e6}))
+    eye = torch.sparse_coo_tensor(torch.arange(32).repeat(2, 1), torch.ones(32), (32, 32)).coalesce()
+    tiny, xt = OP.as_csr(eye.to(dev)), torch.randn(32, 16, device=dev)
+    ms, best = time_it(lambda: tiny.apply(xt))
+    print(json.dumps({"op": "launch floor (32-row operator)", "us": ms * 1e3, "us_best": best * 1e3}))
     for name in args.ops.split(","):
         op = ops[name]
         ncols = op.n_bcols if op.kind == "bsr4" else op.n_cols
@@ -83,7 +88,7 @@ def main():
                 kw["variant"] = int(v[2])
             ms, best = time_it(lambda: op.apply(X, out=Y, **kw))
             gb = op.algorithmic_bytes(C) / 1e9
-            print(json.dumps({"op": name, "variant": v, "rows": op.n_brows if op.kind == "bsr4" else op.n_rows,
+            print(json.dumps({"op": name, "variant": v, "order": args.order, "rows": op.n_brows if op.kind == "bsr4" else op.n_rows,
                               "C": C, "us": ms * 1e3, "us_best": best * 1e3, "alg_MB": gb * 1e3,
                               "GBps": gb / (ms / 1e3), "frac_of_measured_peak": gb / (ms / 1e3) / peak,
                               "GFLOPs": op.flops(C) / ms / 1e6}), flush=True)
