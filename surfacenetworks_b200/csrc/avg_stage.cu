@@ -163,87 +163,115 @@ avg_stats_kernel(const float* __restrict__ partial, int n_seg, int64_t rows, int
   }
 }
 
-// bn_fold_fwd_kernel (bn_fold.cu) for K = 2C plus the per-mesh bias: one warp per output row n.
+// bn_fold_fwd_kernel (bn_fold.cu) for K = 2C plus the per-mesh bias:
 //   s = gamma rstd, t = beta - mean s, W' = W diag(s) (tf32 hi / lo split), b'[n] = b[n] + sum_k W[n,k] t[k],
 //   u[b][n] = b'[n] + sum_c avg[b][c] W'[n][C + c]
-// The averages are staged in shared memory in chunks of kMeshChunk meshes (every warp of the CTA reads all of them).
+// A launch of this kernel sits between two full-device kernels with nothing to overlap it: its cost is its critical path.
+// (The first version -- one warp per output row, shuffle reductions, averages staged by a rolled load/store loop --
+// took 21 us for 1 M multiply-adds: 8 dependent L2 round trips of staging and 16 rounds of five dependent shuffles.)
+// Now: one CTA per kFoldRows output rows; EVERY global read of the CTA is issued up front (the per-mesh averages by
+// cp.async, no registers held), thread k folds column k of the CTA's rows, one block reduction gives b', and thread
+// (mesh, row) computes one u[mesh][row] as a shared-memory dot product with four independent accumulators.
 constexpr int kMeshChunk = 64;
-__global__ void __launch_bounds__(256)
+constexpr int kFoldRows = 4;
+constexpr int kFoldThreads = 256;
+__global__ void __launch_bounds__(kFoldThreads)
 avg_fold_fwd_kernel(const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ W, const float* __restrict__ b, int N, int C,
                     float eps, float* __restrict__ Wf_hi, float* __restrict__ Wf_lo, float* __restrict__ s_out,
-                    float* __restrict__ t_out, float* __restrict__ rstd_out, float* running_mean, float* running_var,
-                    float momentum, float unbias, const float* __restrict__ avg, int n_seg, float* __restrict__ u) {
-  extern __shared__ __align__(16) float avg_s[];          // [kMeshChunk][C]
-  const int K = 2 * C;
-  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  const bool publish = blockIdx.x == 0 && threadIdx.x < 32;
-  const bool live = n < N;                               // dead warps still take part in the staging barriers
-  float acc = 0.f;
-  float wr[8];                                           // W'[n][C + lane + 32 j]   (C <= 256)
+                    float* __restrict__ t_out, float* __restrict__ rstd_out, float* __restrict__ running_mean,
+                    float* __restrict__ running_var, float momentum, float unbias, const float* __restrict__ avg, int n_seg,
+                    float* __restrict__ u) {
+  extern __shared__ __align__(16) float fold_sm[];
+  const int AS = C + 16, WS = C + 4;                      // row strides: conflict-free 16-byte reads (see the dot loop)
+  float* avg_s = fold_sm;                                 // [kMeshChunk][AS]
+  float* w_s = avg_s + kMeshChunk * AS;                   // [kFoldRows][WS]   W'[n][C + c] of this CTA's rows
+  float* red = w_s + kFoldRows * WS;                      // [8 warps][kFoldRows]
+  float* bf_s = red + 8 * kFoldRows;                      // [kFoldRows]
+  const int K = 2 * C, CV = C / 4;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n0 = blockIdx.x * kFoldRows;
+  const bool publish = blockIdx.x == 0;
+  const bool running = publish && running_mean != nullptr;
+  auto stage_avg = [&](int b0, int nb) {                  // meshes b0 .. b0 + nb - 1 -> avg_s, 16 bytes per cp.async
+    for (int i = tid; i < nb * CV; i += kFoldThreads) {
+      const int bl = i / CV, cv = i - bl * CV;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(avg_s + bl * AS + 4 * cv)),
+                   "l"(avg + (size_t)(b0 + bl) * C + 4 * cv) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage_avg(0, min(kMeshChunk, n_seg));
+  float acc[kFoldRows];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) wr[j] = 0.f;
-  if (live) {
-#pragma unroll 4
-    for (int k = lane; k < K; k += 32) {
-      const float m = mean[k], v = var[k];
-      const float rstd = rsqrtf(v + eps);
-      const float s = gamma[k] * rstd;
-      const float t = beta[k] - m * s;
-      const float w = W[(size_t)n * K + k];
-      const float ws = w * s;
-      const float h = tf32_rna(ws);
-      Wf_hi[(size_t)n * K + k] = h;
-      Wf_lo[(size_t)n * K + k] = tf32_rna(ws - h);
-      acc = fmaf(w, t, acc);
-      if (k >= C) {
-        const int j = (k - C) >> 5;
+  for (int j = 0; j < kFoldRows; ++j) acc[j] = 0.f;
+#pragma unroll 2
+  for (int k = tid; k < K; k += kFoldThreads) {           // K <= 512: at most two columns per thread, all loads in flight
+    const float m = mean[k], v = var[k], ga = gamma[k], be = beta[k];
+    float w[kFoldRows];
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj)
-          if (jj == j) wr[jj] = ws;
+    for (int j = 0; j < kFoldRows; ++j) w[j] = n0 + j < N ? W[(size_t)(n0 + j) * K + k] : 0.f;
+    const float rm = running ? running_mean[k] : 0.f, rv = running ? running_var[k] : 0.f;
+    const float rstd = rsqrtf(v + eps);
+    const float sk = ga * rstd;
+    const float tk = be - m * sk;
+#pragma unroll
+    for (int j = 0; j < kFoldRows; ++j) {
+      const float ws = w[j] * sk;
+      if (n0 + j < N) {
+        const float h = tf32_rna(ws);
+        Wf_hi[(size_t)(n0 + j) * K + k] = h;
+        Wf_lo[(size_t)(n0 + j) * K + k] = tf32_rna(ws - h);
       }
-      if (publish) {
-        s_out[k] = s;
-        t_out[k] = t;
-        rstd_out[k] = rstd;
-        if (running_mean) {
-          running_mean[k] = (1.f - momentum) * running_mean[k] + momentum * m;
-          running_var[k] = (1.f - momentum) * running_var[k] + momentum * v * unbias;
-        }
+      acc[j] = fmaf(w[j], tk, acc[j]);
+      if (k >= C) w_s[j * WS + (k - C)] = ws;
+    }
+    if (publish) {
+      s_out[k] = sk;
+      t_out[k] = tk;
+      rstd_out[k] = rstd;
+      if (running) {
+        running_mean[k] = (1.f - momentum) * rm + momentum * m;
+        running_var[k] = (1.f - momentum) * rv + momentum * v * unbias;
       }
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  const float bf = live ? b[n] + acc : 0.f;
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int j = 0; j < kFoldRows; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < kFoldRows; ++j) red[warp * kFoldRows + j] = acc[j];
+  }
+  __syncthreads();
+  if (tid < kFoldRows) {
+    float a = 0.f;
+    for (int w8 = 0; w8 < kFoldThreads / 32; ++w8) a += red[w8 * kFoldRows + tid];      // fixed order
+    bf_s[tid] = (n0 + tid < N ? b[n0 + tid] : 0.f) + a;
+  }
+  // thread (bl, j): u[b0 + bl][n0 + j].  A quarter-warp is 2 meshes x 4 rows: its 16-byte reads of avg_s touch two rows
+  // AS floats apart (AS mod 32 = 16: disjoint banks), those of w_s four rows WS floats apart (WS mod 32 = 4: disjoint)
+  const int bl = tid >> 2, j = tid & 3;
   for (int b0 = 0; b0 < n_seg; b0 += kMeshChunk) {
     const int nb = min(kMeshChunk, n_seg - b0);
-    __syncthreads();
-    for (int i = threadIdx.x * 4; i < nb * C; i += blockDim.x * 4)
-      *reinterpret_cast<float4*>(avg_s + i) = __ldg(reinterpret_cast<const float4*>(avg + (size_t)b0 * C + i));
-    __syncthreads();
-    if (live) {
-      for (int sg = 0; sg < nb; sg += 4) {               // four meshes per round: independent shuffle trees
-        float d[4];
-#pragma unroll
-        for (int x = 0; x < 4; ++x) {
-          d[x] = 0.f;
-          if (sg + x < nb) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (lane + 32 * j < C) d[x] = fmaf(avg_s[(sg + x) * C + lane + 32 * j], wr[j], d[x]);
-          }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-          for (int x = 0; x < 4; ++x) d[x] += __shfl_xor_sync(0xffffffffu, d[x], o);
-        }
-        if (lane < 4 && sg + lane < nb) {
-          const float dv = lane == 0 ? d[0] : lane == 1 ? d[1] : lane == 2 ? d[2] : d[3];
-          u[(size_t)(b0 + sg + lane) * N + n] = bf + dv;
-        }
+    if (b0 > 0) {
+      __syncthreads();                                    // previous chunk consumed
+      stage_avg(b0, nb);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                      // averages, w_s and bf_s visible
+    if (bl < nb && n0 + j < N) {
+      const float4* ap = reinterpret_cast<const float4*>(avg_s + bl * AS);
+      const float4* wp = reinterpret_cast<const float4*>(w_s + j * WS);
+      float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+      for (int c4 = 0; c4 < CV; ++c4) {
+        const float4 a = ap[c4], ww = wp[c4];
+        d.x = fmaf(a.x, ww.x, d.x); d.y = fmaf(a.y, ww.y, d.y); d.z = fmaf(a.z, ww.z, d.z); d.w = fmaf(a.w, ww.w, d.w);
       }
+      u[(size_t)(b0 + bl) * N + n0 + j] = bf_s[j] + ((d.x + d.y) + (d.z + d.w));
     }
   }
 }
@@ -413,13 +441,13 @@ SN_API int sn_avg_fold_fwd_f32(const float* mean, const float* var, const float*
   if (C > 256) return SN_ERR_UNSUPPORTED;
   const float unbias = rows > 1 ? (float)((double)rows / (double)(rows - 1)) : 1.f;
   if (C % 4 || !aligned16(avg)) return SN_ERR_UNSUPPORTED;
-  const size_t smem = (size_t)kMeshChunk * C * sizeof(float);
+  const size_t smem = (size_t)(kMeshChunk * (C + 16) + kFoldRows * (C + 4) + 8 * kFoldRows + kFoldRows) * sizeof(float);
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(avg_fold_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
     cudaGetLastError();
     return SN_ERR_UNSUPPORTED;
   }
-  avg_fold_fwd_kernel<<<(unsigned)ceil_div(N, 8), 256, smem, (cudaStream_t)stream>>>(
+  avg_fold_fwd_kernel<<<(unsigned)ceil_div(N, kFoldRows), kFoldThreads, smem, (cudaStream_t)stream>>>(
       mean, var, gamma, beta, W, b, (int)N, (int)C, eps, Wf_hi, Wf_lo, s, t, rstd, running_mean, running_var, momentum, unbias,
       avg, (int)n_seg, u);
   return launch_status();

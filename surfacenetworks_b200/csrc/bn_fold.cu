@@ -18,49 +18,79 @@ __device__ __forceinline__ float tf32_round(float x) {
 constexpr int kFoldCols = 32;      // columns per CTA
 constexpr int kFoldRowGroups = 32; // row groups per CTA of the backward kernel (1024 threads: 4 rows per thread at N = 128)
 
-// ONE launch for the forward fold: one warp per output row n (8 rows per CTA).  Every warp recomputes s_k / t_k for its
-// lanes' columns from the statistics (a few flops) instead of waiting for a first kernel to publish them, writes its row
-// of W' = W diag(s) and reduces b'[n] = b[n] + sum_k W[n,k] t[k] (fixed-order lane partials + shuffle tree).  Warp 0 of
-// CTA 0 also publishes s, t, rstd and updates the running statistics.  (Was two dependent launches, 22 us; the work is
-// O(N K) = 32 k elements.)
-__global__ void __launch_bounds__(256)
+// ONE launch for the forward fold.  The launch sits between two full-device kernels, so what matters is its critical
+// path, not its throughput: one CTA per kFwdRows output rows, thread k owns column k (and k + 256, ...) of those rows, so
+// every global read of a thread -- statistics, affine parameters, running statistics, its kFwdRows weights -- is issued
+// before the first dependent instruction; b'[n] = b[n] + sum_k W[n,k] t[k] is one block reduction (fixed order).  Every
+// CTA recomputes s_k / t_k (a few flops) instead of waiting for a first kernel to publish them; CTA 0 publishes s, t,
+// rstd and updates the running statistics.  (History: two dependent launches, 22 us; one warp per row, 11 us -- the
+// publishing warp walked its eight columns as eight dependent load -> store round trips; now ~5 us.)
+constexpr int kFwdRows = 4;
+constexpr int kFwdThreads = 256;
+__global__ void __launch_bounds__(kFwdThreads)
 bn_fold_fwd_kernel(const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ gamma,
                    const float* __restrict__ beta, const float* __restrict__ W, const float* __restrict__ b, int N, int K,
                    float eps, float* __restrict__ Wf, float* __restrict__ bf, float* __restrict__ s_out,
-                   float* __restrict__ t_out, float* __restrict__ rstd_out, float* running_mean, float* running_var,
-                   float momentum, float unbias, float* __restrict__ Wf_hi, float* __restrict__ Wf_lo) {
-  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  const bool publish = blockIdx.x == 0 && threadIdx.x < 32;
-  if (n >= N) return;
-  float acc = 0.f;
-#pragma unroll 8
-  for (int k = lane; k < K; k += 32) {
-    const float m = mean[k], v = var[k];
+                   float* __restrict__ t_out, float* __restrict__ rstd_out, float* __restrict__ running_mean,
+                   float* __restrict__ running_var, float momentum, float unbias, float* __restrict__ Wf_hi,
+                   float* __restrict__ Wf_lo) {
+  __shared__ float red[kFwdThreads / 32][kFwdRows];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n0 = blockIdx.x * kFwdRows;
+  const bool publish = blockIdx.x == 0;
+  const bool running = publish && running_mean != nullptr;
+  float acc[kFwdRows];
+#pragma unroll
+  for (int j = 0; j < kFwdRows; ++j) acc[j] = 0.f;
+#pragma unroll 2
+  for (int k = tid; k < K; k += kFwdThreads) {
+    const float m = mean[k], v = var[k], ga = gamma[k], be = beta[k];
+    float w[kFwdRows];
+#pragma unroll
+    for (int j = 0; j < kFwdRows; ++j) w[j] = n0 + j < N ? W[(size_t)(n0 + j) * K + k] : 0.f;
+    const float rm = running ? running_mean[k] : 0.f, rv = running ? running_var[k] : 0.f;
     const float rstd = rsqrtf(v + eps);
-    const float s = gamma[k] * rstd;
-    const float t = beta[k] - m * s;
-    const float w = W[(size_t)n * K + k];
-    const float ws = w * s;
-    Wf[(size_t)n * K + k] = ws;
-    if (Wf_hi) {                         // the 3xTF32 GEMM's pre-split B operand (sn_gemm_tf32_presplit_f32)
-      const float h = tf32_round(ws);
-      Wf_hi[(size_t)n * K + k] = h;
-      Wf_lo[(size_t)n * K + k] = tf32_round(ws - h);
+    const float sk = ga * rstd;
+    const float tk = be - m * sk;
+#pragma unroll
+    for (int j = 0; j < kFwdRows; ++j) {
+      if (n0 + j < N) {
+        const float ws = w[j] * sk;
+        Wf[(size_t)(n0 + j) * K + k] = ws;
+        if (Wf_hi) {                       // the 3xTF32 GEMM's pre-split B operand (sn_gemm_tf32_presplit_f32)
+          const float h = tf32_round(ws);
+          Wf_hi[(size_t)(n0 + j) * K + k] = h;
+          Wf_lo[(size_t)(n0 + j) * K + k] = tf32_round(ws - h);
+        }
+      }
+      acc[j] = fmaf(w[j], tk, acc[j]);
     }
-    acc = fmaf(w, t, acc);
     if (publish) {
-      s_out[k] = s;
-      t_out[k] = t;
+      s_out[k] = sk;
+      t_out[k] = tk;
       rstd_out[k] = rstd;
-      if (running_mean) {
-        running_mean[k] = (1.f - momentum) * running_mean[k] + momentum * m;
-        running_var[k] = (1.f - momentum) * running_var[k] + momentum * v * unbias;
+      if (running) {
+        running_mean[k] = (1.f - momentum) * rm + momentum * m;
+        running_var[k] = (1.f - momentum) * rv + momentum * v * unbias;
       }
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) bf[n] = b[n] + acc;
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int j = 0; j < kFwdRows; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < kFwdRows; ++j) red[warp][j] = acc[j];
+  }
+  __syncthreads();
+  if (tid < kFwdRows && n0 + tid < N) {
+    float a = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < kFwdThreads / 32; ++w8) a += red[w8][tid];       // fixed order
+    bf[n0 + tid] = b[n0 + tid] + a;
+  }
 }
 
 constexpr int kFoldMaxN = 256;     // rows of W a column slab stages for the transposed store
@@ -135,9 +165,9 @@ SN_API int sn_bn_fold_fwd_f32(const float* mean, const float* var, const float* 
   if ((Wf_hi == nullptr) != (Wf_lo == nullptr)) return SN_ERR_ARG;
   const float unbias = rows > 1 ? (float)((double)rows / (double)(rows - 1)) : 1.f;
   cudaStream_t st = (cudaStream_t)stream;
-  bn_fold_fwd_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(mean, var, gamma, beta, W, b, (int)N, (int)K, eps, Wf, bf, s, t,
-                                                              rstd, running_mean, running_var, momentum, unbias, Wf_hi,
-                                                              Wf_lo);
+  bn_fold_fwd_kernel<<<(unsigned)ceil_div(N, kFwdRows), kFwdThreads, 0, st>>>(mean, var, gamma, beta, W, b, (int)N, (int)K, eps,
+                                                                              Wf, bf, s, t, rstd, running_mean, running_var,
+                                                                              momentum, unbias, Wf_hi, Wf_lo);
   return launch_status();
 }
 

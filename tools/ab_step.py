@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""In-process A/B of a module-level switch on the captured training step (cfg3 size).  Box-to-box and run-to-run
+clock differences (power capping: 1867 ... 1957 MHz between bench runs) are +-2 % -- larger than most single changes --
+so both variants are captured in ONE process and replayed alternately, round after round.
+
+    python tools/ab_step.py --toggle module.SWITCH [--rounds 12] [--steps 10]
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--toggle", required=True, help="module.ATTRIBUTE inside surfacenetworks_b200 (A: True, B: False)")
+    ap.add_argument("--meshes", type=int, default=64)
+    ap.add_argument("--vertices", type=int, default=2000)
+    ap.add_argument("--rounds", type=int, default=12)
+    ap.add_argument("--steps", type=int, default=10)
+    args = ap.parse_args()
+    from surfacenetworks_b200 import graph as G, models as M, operators as OP, workloads as W
+    modname, attr = args.toggle.rsplit(".", 1)
+    mod = importlib.import_module("surfacenetworks_b200." + modname)
+    dev = torch.device("cuda")
+    meshes = W.make_mesh_ops(args.vertices, range(args.meshes))
+    host = W.arap_batch(meshes, seed=0)
+    t = {k: host[k].to(dev) for k in ("inputs", "targets", "mask")}
+    o = {"Di": OP.Bsr4Operator.from_torch_coo(host["Di"].to(dev)), "DiA": OP.Bsr4Operator.from_torch_coo(host["DiA"].to(dev))}
+    B = args.meshes
+
+    def loss_fn(m, t, o):
+        return M.arap_loss(m(o["Di"], o["DiA"], t["mask"], t["inputs"]), t["targets"], t["mask"], B)
+
+    steps = {}
+    for name, val in (("A", True), ("B", False)):
+        setattr(mod, attr, val)
+        torch.manual_seed(0)
+        model = M.ArapDirModel().to(dev).train()
+        opt = torch.optim.Adam(model.parameters(), 1e-3, weight_decay=1e-5, fused=True, capturable=True)
+        steps[name] = G.CapturedTrainStep(model, loss_fn, opt, t, o, warmup=2)
+        assert steps[name].graph is not None, steps[name].mode
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms = {"A": [], "B": []}
+    for r in range(args.rounds):
+        for name in (("A", "B") if r % 2 == 0 else ("B", "A")):
+            st = steps[name]
+            st.replay()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(args.steps):
+                st.replay()
+            e1.record()
+            e1.synchronize()
+            ms[name].append(e0.elapsed_time(e1) / args.steps)
+    out = {"toggle": args.toggle}
+    for name in ("A", "B"):
+        v = sorted(ms[name])
+        out[name] = {"median_ms": round(v[len(v) // 2], 4), "min_ms": round(v[0], 4), "max_ms": round(v[-1], 4),
+                     "loss": float(steps[name].loss)}
+    out["A_minus_B_ms"] = round(out["A"]["median_ms"] - out["B"]["median_ms"], 4)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
