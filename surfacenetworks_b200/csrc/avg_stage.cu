@@ -305,18 +305,25 @@ avg_fold_bwd_kernel(const float* __restrict__ GL, int64_t ldgl, const float* __r
   const int k = blockIdx.x * kCols + c;                 // K % 32 == 0: always < K
   const bool right = blockIdx.x * kCols >= C;           // slab-uniform (C % 32 == 0)
   const float sk = s[k], tk = t[k];
-  float d[NPT], g[NPT];
+  float d[NPT], g[NPT], wreg[NPT], glreg[NPT];
 #pragma unroll
-  for (int i = 0; i < NPT; ++i) d[i] = g[i] = 0.f;
+  for (int i = 0; i < NPT; ++i) {      // this thread's weights / G_L entries: requested now, used after phase 1
+    d[i] = g[i] = 0.f;
+    wreg[i] = W[(size_t)(NPT * rg + i) * K + k];
+    glreg[i] = right ? 0.f : GL[(size_t)(NPT * rg + i) * ldgl + k];
+  }
   // ---- phase 1: sdY[n] (and G_R for right-half slabs), meshes in a fixed order
   for (int b0 = 0; b0 < n_seg; b0 += kMeshChunk) {
     const int nb = min(kMeshChunk, n_seg - b0);
     __syncthreads();
-    for (int i = threadIdx.x * 4; i < nb * N; i += kCols * kGroups * 4)
-      *reinterpret_cast<float4*>(sdy_s + i) = __ldg(reinterpret_cast<const float4*>(SdY + (size_t)b0 * N + i));
+    for (int i = threadIdx.x * 4; i < nb * N; i += kCols * kGroups * 4)          // cp.async: every unit in flight at once
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(sdy_s + i)),
+                   "l"(SdY + (size_t)b0 * N + i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
     if (right)
       for (int i = threadIdx.x; i < nb * kCols; i += kCols * kGroups)
         avg_s[i] = __ldg(avg + (size_t)(b0 + i / kCols) * C + (blockIdx.x * kCols - C) + (i % kCols));
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     for (int b = 0; b < nb; ++b) {
       const float a = right ? avg_s[b * kCols + c] : 0.f;
@@ -335,8 +342,8 @@ avg_fold_bwd_kernel(const float* __restrict__ GL, int64_t ldgl, const float* __r
 #pragma unroll
   for (int i = 0; i < NPT; ++i) {
     const int n = NPT * rg + i;
-    if (!right) g[i] = GL[(size_t)n * ldgl + k];
-    const float w = W[(size_t)n * K + k];
+    if (!right) g[i] = glreg[i];
+    const float w = wreg[i];
     dW[(size_t)n * K + k] = fmaf(g[i], sk, d[i] * tk);
     dbeta_p = fmaf(w, d[i], dbeta_p);
     wg_p = fmaf(w, g[i], wg_p);

@@ -140,6 +140,13 @@ def within_reference_noise(ours, ref32, ref64, what, k=10.0):
     ours, ref32, ref64 = [np.asarray(a, dtype=np.float64) for a in (ours, ref32, ref64)]
     noise = np.abs(ref32 - ref64).max()
     err = np.abs(ours - ref64).max()
+    assert np.isfinite(ours).all(), what
+    if noise >= 0.5 * np.abs(ref64).max():
+        # The reference's own fp32 result carries no significant digit here (the first layers' gradients of the 2-mesh
+        # fixture: |ref32 - ref64| ~ |ref64|).  Any change of summation order moves such a tensor by a large random
+        # factor of that noise -- parity is undefined; only the order of magnitude is checked.  Systematic errors are
+        # bounded by test_arap_models_eval_mode_vs_oracle (no statistics amplification, 1e-4).
+        k = 100.0
     assert err <= k * noise + 1e-5 * np.abs(ref64).max(), "%s: err %g vs reference fp32 noise %g" % (what, err, noise)
 
 
@@ -205,6 +212,48 @@ def test_arap_models_vs_oracle_wide_batch(kind):
     within_reference_noise(loss.item(), l32, l64, kind + " loss")
     for k, p in gm.named_parameters():
         within_reference_noise(p.grad.cpu().numpy(), g32[k], g64[k], kind + " grad " + k)
+
+
+@pytest.mark.parametrize("kind", ["dir", "lap"])
+def test_arap_models_eval_mode_vs_oracle(kind):
+    """The same 15-block stacks with BatchNorm in eval mode (running statistics: no batch-statistics feedback, so
+    rounding is not amplified): outputs and loss against the fp64 oracle at 1e-4 of the tensor's scale, every parameter
+    gradient at 3e-4 (fifteen blocks of 3xTF32 products back to back; measured worst element 1.0e-3 of its own value at
+    1e-4 of the scale) -- a bound on any SYSTEMATIC (non-rounding) error of the stack, which the noise-relative
+    criterion of the training-mode tests above cannot give."""
+    from oracle import layers as O
+    from surfacenetworks_b200 import models as M, workloads as W
+    meshes = W.make_mesh_ops(300, [0, 1]) + W.make_mesh_ops(280, [2, 3])
+    host = W.arap_batch(meshes, 0, dirac=(kind == "dir"))
+    model = det_fill(M.ArapDirModel() if kind == "dir" else M.ArapLapModel(15), 23, gain=0.25)
+    ops_host = (host["Di"], host["DiA"]) if kind == "dir" else (host["L"],)
+    P = {}
+    for k, v in model.state_dict().items():
+        v = v.clone().to(torch.float64) if v.is_floating_point() else v.clone()
+        if v.is_floating_point() and not k.endswith(("running_mean", "running_var")):
+            v.requires_grad_(True)
+        P[k] = v
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        args = [o.to(torch.float64) for o in ops_host] + [host["mask"].double(), host["inputs"].double()]
+        o64 = (O.arap_dir_model if kind == "dir" else O.arap_lap_model)(P, *args, training=False)
+        l64 = O.arap_loss(o64, host["targets"].double(), host["mask"].double(), 4)
+        l64.backward()
+    finally:
+        torch.set_default_dtype(old)
+    gm = model.to(DEV).eval()
+    args = [o.to(DEV) for o in ops_host] + [host["mask"].to(DEV), host["inputs"].to(DEV)]
+    out = gm(*args)
+    loss = M.arap_loss(out, host["targets"].to(DEV), host["mask"].to(DEV), 4)
+    loss.backward()
+    close(out.detach().cpu().numpy(), o64.detach().numpy(), kind + " eval out", rtol=1e-4)
+    close(loss.item(), float(l64.detach()), kind + " eval loss", rtol=1e-4)
+    gscale = max(float(v.grad.abs().max()) for v in P.values() if v.requires_grad and v.grad is not None)
+    for k, p in gm.named_parameters():
+        if P[k].grad is None:
+            continue
+        close(p.grad.cpu().numpy(), P[k].grad.numpy(), kind + " eval grad " + k, rtol=3e-4, floor=1e-3 * gscale)
 
 
 def test_state_dict_roundtrip_and_cpu_refusal(golden, batch):
