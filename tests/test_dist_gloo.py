@@ -63,6 +63,65 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+class _Stack(nn.Module):
+    def __init__(self):
+        super().__init__()
+        for i in range(6):
+            setattr(self, "rn%d" % i, nn.Sequential(nn.Linear(8, 8), nn.Tanh()))
+
+    def forward(self, x):
+        for i in range(6):
+            x = x + getattr(self, "rn%d" % i)(x)
+        return x
+
+
+def _step_worker(rank, world, port, out):
+    """graph.CapturedTrainStep's N > 1 path on CPU tensors (eager; gloo): after a step every rank's gradients are the
+    mean of the ranks' local gradients."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import copy
+    from surfacenetworks_b200 import dist as D, graph as G
+    D.init_from_env(backend="gloo")
+    torch.manual_seed(3 + rank)
+    x, y = torch.randn(32, 8), torch.randn(32, 8)
+    torch.manual_seed(0)
+    model = _Stack()
+    D.broadcast_module(model)
+    ref = copy.deepcopy(model)
+    ((ref(x) - y) ** 2).mean().backward()
+    expect = []
+    for p in ref.parameters():
+        parts = [torch.zeros_like(p.grad) for _ in range(world)]
+        dist.all_gather(parts, p.grad)
+        expect.append(sum(parts[1:], parts[0]) * (1.0 / world))
+    opt = torch.optim.SGD(model.parameters(), lr=0.0)            # lr 0: parameters stay put, gradients are inspected
+    step = G.CapturedTrainStep(model, lambda m, t, o: ((m(t["x"]) - t["y"]) ** 2).mean(), opt, {"x": x, "y": y},
+                               warmup=0, capture=False)
+    for _ in range(2):
+        step.eager_step()
+        for p, e in zip(model.parameters(), expect):
+            assert torch.allclose(p.grad, e, rtol=1e-6, atol=1e-7)
+    if rank == 0:
+        out.put(step.grad_bytes)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_captured_step_world2():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_step_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(150)
+        assert p.exitcode == 0, "rank failed"
+    assert out.get(timeout=5) == 6 * (8 * 8 + 8) * 4
+
+
 def _offsets(params):
     off = 0
     for p in params:
