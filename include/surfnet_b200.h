@@ -307,13 +307,15 @@ int sn_csr_spmm_stats_f32(const int32_t* rowptr, const int32_t* colind, const fl
 
 /* O(C^2) glue of the fused dense stage, one launch each way.
  * forward : s = gamma*rstd, t = beta - mean*s, Wf = W diag(s) [N x K], bf = b + W t, rstd = 1/sqrt(var+eps); when
- *           running_mean/var are given they are updated with `momentum` (unbiased variance, rows/(rows-1)).
+ *           running_mean/var are given they are updated with `momentum` (unbiased variance, rows/(rows-1));
+ *           num_batches_tracked (device int64, NULL = none) is incremented by one -- nn.BatchNorm's counter, kept by
+ *           the kernel so that a training step launches no separate increment per layer.
  * backward: from G = dY^T Z [N x K] and sdY = colsum(dY) [N]:  dW, db, dgamma, dbeta, the coefficients p, q of
  *           dZ = dY (W diag(s)) + p .* Z + q (training-mode BatchNorm backward folded), and WsT = (W diag(s))^T [K x N]. */
 int sn_bn_fold_fwd_f32(const float* mean, const float* var, const float* gamma, const float* beta, const float* W,
                        const float* b, int64_t N, int64_t K, float eps, float* Wf, float* bf, float* s, float* t,
                        float* rstd, float* running_mean, float* running_var, float momentum, int64_t rows,
-                       float* Wf_hi, float* Wf_lo, sn_stream_t stream);
+                       float* Wf_hi, float* Wf_lo, int64_t* num_batches_tracked, sn_stream_t stream);
 int sn_bn_fold_bwd_f32(const float* G, const float* sdY, const float* W, const float* s, const float* t,
                        const float* rstd, const float* mean, int64_t N, int64_t K, int64_t rows, int training,
                        float* dW, float* db, float* dgamma, float* dbeta, float* p, float* q, float* WsT,
@@ -340,7 +342,7 @@ int sn_avg_stage_pre_f32(const float* X, int64_t ldx, const float* w, const floa
 int sn_avg_fold_fwd_f32(const float* mean, const float* var, const float* gamma, const float* beta, const float* W,
                         const float* b, int64_t N, int64_t C, float eps, float* Wf_hi, float* Wf_lo, float* s, float* t,
                         float* rstd, float* running_mean, float* running_var, float momentum, int64_t rows,
-                        const float* avg, int64_t n_seg, float* u, sn_stream_t stream);
+                        const float* avg, int64_t n_seg, float* u, int64_t* num_batches_tracked, sn_stream_t stream);
 int sn_avg_fold_bwd_f32(const float* GL, int64_t ldgl, const float* SdY, const float* avg, const float* W, const float* s,
                         const float* t, const float* rstd, const float* mean, const float* inv_cnt, int64_t N, int64_t C,
                         int64_t n_seg, int64_t rows_per_seg, int training, float* dW, float* db, float* dgamma,

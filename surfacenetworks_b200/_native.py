@@ -40,7 +40,7 @@ SIGNATURES = {
     "sn_gemm_tn_tf32_f32": (_int, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _int, _ptr, _sz, _ptr]),
     "sn_gemm_tn_colsum_tf32_f32": (_int, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _int, _ptr, _sz, _ptr]),
     "sn_bn_fold_fwd_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _f32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
-                                  _f32, _i64, _ptr, _ptr, _ptr]),
+                                  _f32, _i64, _ptr, _ptr, _ptr, _ptr]),
     "sn_bn_fold_bwd_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _int, _ptr, _ptr, _ptr, _ptr,
                                   _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "sn_colstats_ws_bytes": (_sz, [_i64]),
@@ -60,7 +60,7 @@ SIGNATURES = {
     "sn_avg_stage_ws_bytes": (_sz, [_i64, _i64]),
     "sn_avg_stage_pre_f32": (_int, [_ptr, _i64, _ptr, _ptr, _i64, _i64, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),
     "sn_avg_fold_fwd_f32": (_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _f32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
-                                   _f32, _i64, _ptr, _i64, _ptr, _ptr]),
+                                   _f32, _i64, _ptr, _i64, _ptr, _ptr, _ptr]),
     "sn_avg_fold_bwd_f32": (_int, [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _int,
                                    _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "sn_linear_smallk_fwd_f32": (_int, [_ptr, _i64, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr]),

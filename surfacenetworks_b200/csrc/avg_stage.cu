@@ -181,7 +181,7 @@ avg_fold_fwd_kernel(const float* __restrict__ mean, const float* __restrict__ va
                     float eps, float* __restrict__ Wf_hi, float* __restrict__ Wf_lo, float* __restrict__ s_out,
                     float* __restrict__ t_out, float* __restrict__ rstd_out, float* __restrict__ running_mean,
                     float* __restrict__ running_var, float momentum, float unbias, const float* __restrict__ avg, int n_seg,
-                    float* __restrict__ u) {
+                    float* __restrict__ u, long long* __restrict__ batches_tracked) {
   extern __shared__ __align__(16) float fold_sm[];
   const int AS = C + 16, WS = C + 4;                      // row strides: conflict-free 16-byte reads (see the dot loop)
   float* avg_s = fold_sm;                                 // [kMeshChunk][AS]
@@ -193,6 +193,7 @@ avg_fold_fwd_kernel(const float* __restrict__ mean, const float* __restrict__ va
   const int n0 = blockIdx.x * kFoldRows;
   const bool publish = blockIdx.x == 0;
   const bool running = publish && running_mean != nullptr;
+  if (publish && threadIdx.x == 0 && batches_tracked) *batches_tracked += 1;   // nn.BatchNorm's num_batches_tracked
   auto stage_avg = [&](int b0, int nb) {                  // meshes b0 .. b0 + nb - 1 -> avg_s, 16 bytes per cp.async
     for (int i = tid; i < nb * CV; i += kFoldThreads) {
       const int bl = i / CV, cv = i - bl * CV;
@@ -440,7 +441,7 @@ SN_API int sn_avg_stage_pre_f32(const float* X, int64_t ldx, const float* w, con
 SN_API int sn_avg_fold_fwd_f32(const float* mean, const float* var, const float* gamma, const float* beta, const float* W,
                                const float* b, int64_t N, int64_t C, float eps, float* Wf_hi, float* Wf_lo, float* s,
                                float* t, float* rstd, float* running_mean, float* running_var, float momentum, int64_t rows,
-                               const float* avg, int64_t n_seg, float* u, sn_stream_t stream) {
+                               const float* avg, int64_t n_seg, float* u, int64_t* num_batches_tracked, sn_stream_t stream) {
   using namespace sn;
   if (N <= 0 || C <= 0 || n_seg <= 0 || !mean || !var || !gamma || !beta || !W || !b || !Wf_hi || !Wf_lo || !s || !t ||
       !rstd || !avg || !u)
@@ -456,7 +457,7 @@ SN_API int sn_avg_fold_fwd_f32(const float* mean, const float* var, const float*
   }
   avg_fold_fwd_kernel<<<(unsigned)ceil_div(N, kFoldRows), kFoldThreads, smem, (cudaStream_t)stream>>>(
       mean, var, gamma, beta, W, b, (int)N, (int)C, eps, Wf_hi, Wf_lo, s, t, rstd, running_mean, running_var, momentum, unbias,
-      avg, (int)n_seg, u);
+      avg, (int)n_seg, u, reinterpret_cast<long long*>(num_batches_tracked));
   return launch_status();
 }
 

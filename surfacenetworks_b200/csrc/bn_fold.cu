@@ -33,12 +33,13 @@ bn_fold_fwd_kernel(const float* __restrict__ mean, const float* __restrict__ var
                    float eps, float* __restrict__ Wf, float* __restrict__ bf, float* __restrict__ s_out,
                    float* __restrict__ t_out, float* __restrict__ rstd_out, float* __restrict__ running_mean,
                    float* __restrict__ running_var, float momentum, float unbias, float* __restrict__ Wf_hi,
-                   float* __restrict__ Wf_lo) {
+                   float* __restrict__ Wf_lo, long long* __restrict__ batches_tracked) {
   __shared__ float red[kFwdThreads / 32][kFwdRows];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n0 = blockIdx.x * kFwdRows;
   const bool publish = blockIdx.x == 0;
   const bool running = publish && running_mean != nullptr;
+  if (publish && threadIdx.x == 0 && batches_tracked) *batches_tracked += 1;   // nn.BatchNorm's num_batches_tracked
   float acc[kFwdRows];
 #pragma unroll
   for (int j = 0; j < kFwdRows; ++j) acc[j] = 0.f;
@@ -159,7 +160,7 @@ bn_fold_bwd_kernel(const float* __restrict__ G, const float* __restrict__ sdY, c
 SN_API int sn_bn_fold_fwd_f32(const float* mean, const float* var, const float* gamma, const float* beta, const float* W,
                               const float* b, int64_t N, int64_t K, float eps, float* Wf, float* bf, float* s, float* t,
                               float* rstd, float* running_mean, float* running_var, float momentum, int64_t rows,
-                              float* Wf_hi, float* Wf_lo, sn_stream_t stream) {
+                              float* Wf_hi, float* Wf_lo, int64_t* num_batches_tracked, sn_stream_t stream) {
   using namespace sn;
   if (N <= 0 || K <= 0 || !mean || !var || !gamma || !beta || !W || !b || !Wf || !bf || !s || !t || !rstd) return SN_ERR_ARG;
   if ((Wf_hi == nullptr) != (Wf_lo == nullptr)) return SN_ERR_ARG;
@@ -167,7 +168,8 @@ SN_API int sn_bn_fold_fwd_f32(const float* mean, const float* var, const float* 
   cudaStream_t st = (cudaStream_t)stream;
   bn_fold_fwd_kernel<<<(unsigned)ceil_div(N, kFwdRows), kFwdThreads, 0, st>>>(mean, var, gamma, beta, W, b, (int)N, (int)K, eps,
                                                                               Wf, bf, s, t, rstd, running_mean, running_var,
-                                                                              momentum, unbias, Wf_hi, Wf_lo);
+                                                                              momentum, unbias, Wf_hi, Wf_lo,
+                                                                              reinterpret_cast<long long*>(num_batches_tracked));
   return launch_status();
 }
 

@@ -87,7 +87,7 @@ int stage_fwd(const Op& S, int64_t rows_out, int64_t rows_in, const float* x_sel
   }
   if (rc != SN_OK) return rc;
   rc = sn_bn_fold_fwd_f32(mean, var, gamma, beta, W, b, C, K, eps, Wf, bf, stk, stk + K, stk + 2 * K, running_mean, running_var,
-                          momentum, rows_out, Wf_hi, Wf_lo, stream);
+                          momentum, rows_out, Wf_hi, Wf_lo, nullptr, stream);
   if (rc != SN_OK) return rc;
   return sn_gemm_tf32_presplit_f32(Z, K, Wf_hi, Wf_lo, K, bf, residual, ldr, nullptr, nullptr, 0, Y, ldy, rows_out, C, K, 0, stream);
 }

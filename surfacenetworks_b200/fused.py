@@ -40,6 +40,18 @@ def bn_momentum(bn):
     return 1.0 / float(bn.num_batches_tracked)          # (reads the counter back: momentum=None is not graph-capturable)
 
 
+def bn_count_batch(bn, training):
+    """nn.BatchNorm's ``num_batches_tracked += 1`` for one training-mode call.  Returns the counter tensor when the fold
+    kernel should do the increment (sn_*_fold_fwd_f32: no separate launch per layer), None when it was done here (the
+    cumulative-average mode momentum=None needs the new value on the host) or when there is nothing to count."""
+    if not training or bn.num_batches_tracked is None:
+        return None
+    if bn.momentum is None or not bn.num_batches_tracked.is_cuda or bn.num_batches_tracked.dtype != torch.int64:
+        bn.num_batches_tracked += 1
+        return None
+    return bn.num_batches_tracked
+
+
 def _ws(nbytes, device):
     return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
 
@@ -200,7 +212,7 @@ def gemm_tn_tf32(A, B, single_pass=False, colsum=False):
 
 
 def bn_linear_forward(Z, gamma, beta, W, b, residual, running_mean, running_var, training, momentum, eps, left_stats,
-                      act=None):
+                      act=None, counter=None):
     """Forward of GraphConv1x1(batch_norm="pre") on rows (no autograd): statistics pass, BN folded into the weights,
     tcgen05 GEMM with the residual in its epilogue.  Returns (Y, saved) with ``saved`` = what bn_linear_backward needs.
     ``act``: dict(act_out=, mean=, var=, want_raw=) -- the GEMM also emits elu(Y) (and its column statistics) for the next
@@ -232,7 +244,8 @@ def bn_linear_forward(Z, gamma, beta, W, b, residual, running_mean, running_var,
     with torch.cuda.device(dev):
         N.call("sn_bn_fold_fwd_f32", _ptr(mean), _ptr(var), _ptr(gamma), _ptr(beta), _ptr(W), _ptr(b), Nn, K, float(eps),
                _ptr(Wf[0]), _ptr(bf), _ptr(stk[0]), _ptr(stk[1]), _ptr(stk[2]), _ptr(running_mean) if update else 0,
-               _ptr(running_var) if update else 0, float(momentum), rows, _ptr(Wf[1]), _ptr(Wf[2]), _stream())
+               _ptr(running_var) if update else 0, float(momentum), rows, _ptr(Wf[1]), _ptr(Wf[2]),
+               _ptr(counter) if training else 0, _stream())
     res = None if residual is None else residual.contiguous()
     if act is not None:
         Y, _ = gemm_tf32_act(Z, Wf[1], Wf[2], bias=bf, R=res, act_out=act["act_out"], mean=act.get("mean"), var=act.get("var"),
@@ -276,9 +289,9 @@ def bn_linear_backward(saved, dY, training, elu_bwd_left=False):
 class _BnLinear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, Z, gamma, beta, W, b, residual, running_mean, running_var, training, momentum, eps, left_stats,
-                elu_bwd_left=False, res_cell=None):
+                elu_bwd_left=False, res_cell=None, counter=None):
         Y, saved = bn_linear_forward(Z, gamma, beta, W, b, residual, running_mean, running_var, training, momentum, eps,
-                                     left_stats)
+                                     left_stats, counter=counter)
         ctx.save_for_backward(*saved)
         ctx.training, ctx.has_res, ctx.elu_bwd_left = training, residual is not None, elu_bwd_left
         ctx.res_cell = res_cell           # see ops.stage_concat(in_cell=...): where the residual's gradient goes instead
@@ -295,7 +308,7 @@ class _BnLinear(torch.autograd.Function):
                 g_res = g_res.contiguous()
             ctx.res_cell["residual_grad"] = g_res
             g_res = None
-        return dZ, dgamma, dbeta, dW, db, g_res, None, None, None, None, None, None, None, None
+        return dZ, dgamma, dbeta, dW, db, g_res, None, None, None, None, None, None, None, None, None
 
 
 def segment_sum(X, rows_per_seg, n_seg, weight=None, out=None, ws=None):
@@ -327,7 +340,7 @@ class _AvgStage(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, maskw, inv_cnt, gamma, beta, W, b, residual, running_mean, running_var, training, momentum, eps,
-                n_seg, rows_per_seg, in_cell=None, res_cell=None):
+                n_seg, rows_per_seg, in_cell=None, res_cell=None, counter=None):
         rows, C = x.shape
         Nn = W.shape[0]
         dev = x.device
@@ -352,7 +365,8 @@ class _AvgStage(torch.autograd.Function):
         with torch.cuda.device(dev):
             N.call("sn_avg_fold_fwd_f32", _ptr(mean), _ptr(var), _ptr(gamma), _ptr(beta), _ptr(W), _ptr(b), Nn, C, float(eps),
                    _ptr(Wf[0]), _ptr(Wf[1]), _ptr(stk[0]), _ptr(stk[1]), _ptr(stk[2]), _ptr(running_mean) if update else 0,
-                   _ptr(running_var) if update else 0, float(momentum), rows, _ptr(avg), n_seg, _ptr(u), _stream())
+                   _ptr(running_var) if update else 0, float(momentum), rows, _ptr(avg), n_seg, _ptr(u),
+                   _ptr(counter) if training else 0, _stream())
         res = None if residual is None else residual.contiguous()
         Y = gemm_tf32(a, Wf[0][:, :C], R=res, group_bias=u, rows_per_group=rows_per_seg, B_lo=Wf[1][:, :C])
         ctx.save_for_backward(a, avg, W, stk, mean, maskw, inv_cnt)
@@ -405,7 +419,7 @@ class _AvgStage(torch.autograd.Function):
         if g_res is not None and ctx.res_cell is not None:
             ctx.res_cell["residual_grad"] = dY           # picked up by the block's first stage (runs later in backward)
             g_res = None
-        return (dx, None, None, vec[0], vec[1], dW, db, g_res, None, None, None, None, None, None, None, None, None)
+        return (dx, None, None, vec[0], vec[1], dW, db, g_res, None, None, None, None, None, None, None, None, None, None)
 
 
 def avg_stage_supported(x, weight):
@@ -444,12 +458,11 @@ def avg_stage(x, mask, bn, fc, residual=None, in_cell=None, res_cell=None):
         return None
     maskw, inv_cnt = mask_info(mask, B, V)
     training = bn.training or bn.running_mean is None
-    if training and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked += 1
+    counter = bn_count_batch(bn, training)
     momentum = bn_momentum(bn)
     res2 = None if residual is None else residual.reshape(B * V, -1)
     return _AvgStage.apply(x2, maskw, inv_cnt, bn.weight, bn.bias, fc.weight, fc.bias, res2, bn.running_mean,
-                           bn.running_var, training, momentum, bn.eps, B, V, in_cell, res_cell)
+                           bn.running_var, training, momentum, bn.eps, B, V, in_cell, res_cell, counter)
 
 
 class _SmallKLinear(torch.autograd.Function):
@@ -651,8 +664,7 @@ def bn_linear(z, bn, fc, residual=None, res_cell=None):
     ``res_cell``: honoured by the fused path only -- callers must check ``bn_linear_is_fused`` before handing one over."""
     if fused_supported(z, fc.weight) and (residual is None or (residual.shape == (z.shape[0], fc.weight.shape[0]))):
         training = bn.training or bn.running_mean is None
-        if training and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked += 1
+        counter = bn_count_batch(bn, training)
         momentum = bn_momentum(bn)
         left = getattr(z, "_sn_left_stats", None) if training else None
         if left is not None and not (z.shape[1] - left[0].numel()) % 4 == 0:
@@ -662,7 +674,7 @@ def bn_linear(z, bn, fc, residual=None, res_cell=None):
         if fold:
             cell["left_premultiplied"] = True
         return _BnLinear.apply(z, bn.weight, bn.bias, fc.weight, fc.bias, residual, bn.running_mean, bn.running_var,
-                               training, momentum, bn.eps, left, fold, res_cell)
+                               training, momentum, bn.eps, left, fold, res_cell, counter)
     # Output widths between the tensor-core shapes (the 128 -> 120 head of the ARAP / dense_correspondence models,
     # conv2 at as_rigid_as_possible/models.py:121): zero-pad the Linear to the next supported width and slice -- the
     # cuBLAS fp32 SIMT GEMMs it replaces were 0.6 ms of the 19 ms step (profiles/r1b_launches_bench_summary.json)
@@ -673,11 +685,10 @@ def bn_linear(z, bn, fc, residual=None, res_cell=None):
         if fused_supported(z, w_pad):
             b_pad = torch.cat([fc.bias, fc.bias.new_zeros(n_pad - n_out)])
             training = bn.training or bn.running_mean is None
-            if training and bn.num_batches_tracked is not None:
-                bn.num_batches_tracked += 1
+            counter = bn_count_batch(bn, training)
             momentum = bn_momentum(bn)
             y = _BnLinear.apply(z, bn.weight, bn.bias, w_pad, b_pad, None, bn.running_mean, bn.running_var, training,
-                                momentum, bn.eps, None)
+                                momentum, bn.eps, None, False, None, counter)
             return _SliceCols.apply(y, n_out)
     y = fc(bn(z))
     return y if residual is None else y + residual

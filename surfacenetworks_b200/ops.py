@@ -173,13 +173,14 @@ class _DirBlock(torch.autograd.Function):
         fused.elu_colstats(f2, Zf[:, :C], st[2, :C], st[3, :C])
         stats_v, stats_f = (st[0], st[1], C), (st[2], st[3], C)
         D.apply(Zv[:, :C], out=Zf[:, C:])                       # faces <- vertices, gathers the activated rows in place
+        cnt0, cnt1 = fused.bn_count_batch(bn0, True), fused.bn_count_batch(bn1, True)
         f_out, saved0 = fused.bn_linear_forward(Zf, g0, b0, W0, c0, None, bn0.running_mean, bn0.running_var, True,
-                                                fused.bn_momentum(bn0), bn0.eps, stats_f)
+                                                fused.bn_momentum(bn0), bn0.eps, stats_f, counter=cnt0)
         act_f = torch.empty_like(f_out)
         elu_into(f_out, act_f)
         DA.apply(act_f, out=Zv[:, C:])                          # vertices <- faces
         v_new, saved1 = fused.bn_linear_forward(Zv, g1, b1, W1, c1, v2, bn1.running_mean, bn1.running_var, True,
-                                                fused.bn_momentum(bn1), bn1.eps, stats_v)
+                                                fused.bn_momentum(bn1), bn1.eps, stats_v, counter=cnt1)
         ctx.save_for_backward(act_f, *saved0, *saved1)
         ctx.D, ctx.DA, ctx.C = D, DA, C
         ctx.set_materialize_grads(False)
@@ -266,12 +267,13 @@ class _DirBlockChained(torch.autograd.Function):
             st_next = torch.empty_like(stf)
             act_f = Zf_next[:, :C]
             act = dict(act_out=act_f, mean=st_next[0, :C], var=st_next[1, :C], want_raw=False)
+        cnt0, cnt1 = fused.bn_count_batch(bn0, True), fused.bn_count_batch(bn1, True)
         _, saved0 = fused.bn_linear_forward(Zf, g0, b0, W0, c0, None, bn0.running_mean, bn0.running_var, True,
                                             fused.bn_momentum(bn0), bn0.eps, (stf[0], stf[1], 2 * C),
-                                            act=act)
+                                            act=act, counter=cnt0)
         _spmm_with_stats(DA, act_f, Zv[:, C:], stv[0, C:], stv[1, C:])           # vertices <- faces
         v_new, saved1 = fused.bn_linear_forward(Zv, g1, b1, W1, c1, v2, bn1.running_mean, bn1.running_var, True,
-                                                fused.bn_momentum(bn1), bn1.eps, (stv[0], stv[1], 2 * C))
+                                                fused.bn_momentum(bn1), bn1.eps, (stv[0], stv[1], 2 * C), counter=cnt1)
         ctx.save_for_backward(act_f, *saved0, *saved1)
         ctx.D, ctx.DA, ctx.C = D, DA, C
         ctx.set_materialize_grads(False)
@@ -341,17 +343,12 @@ def face_chain_start(f2):
 def dir_block_chained(D, DA, v2, Zf, stf, conv0, conv1, last):
     """One DirResNet2 block inside a chain: returns (v_new, Zf_next, st_next); ``last`` = no Dirac block follows (the
     activated faces then go to a plain buffer, Zf_next / st_next come back empty)."""
-    for conv in (conv0, conv1):
-        if conv.bn.num_batches_tracked is not None:
-            conv.bn.num_batches_tracked += 1
+    # num_batches_tracked: incremented by the fold kernels (fused.bn_count_batch), here for momentum=None
     return _DirBlockChained.apply(v2, Zf, stf, conv0.bn.weight, conv0.bn.bias, conv0.fc.weight, conv0.fc.bias, conv1.bn.weight,
                                   conv1.bn.bias, conv1.fc.weight, conv1.fc.bias, D, DA, conv0.bn, conv1.bn, bool(last))
 
 
 def dir_block(D, DA, v2, f2, conv0, conv1):
     """(v_new, f_out) of one DirResNet2 block on rows; conv0 / conv1 are its two GraphConv1x1(2C -> C, "pre")."""
-    for conv in (conv0, conv1):
-        if conv.bn.num_batches_tracked is not None:
-            conv.bn.num_batches_tracked += 1
     return _DirBlock.apply(v2, f2, conv0.bn.weight, conv0.bn.bias, conv0.fc.weight, conv0.fc.bias, conv1.bn.weight,
                            conv1.bn.bias, conv1.fc.weight, conv1.fc.bias, D, DA, conv0.bn, conv1.bn)
