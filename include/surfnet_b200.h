@@ -55,7 +55,8 @@ typedef void* sn_stream_t; /* cudaStream_t */
 #define SN_SPMM_DIRECT_GATHER 2 /* force the first-generation direct-gather kernel (one row per lane group)       */
 #define SN_SPMM_SMEM_STREAM 4   /* sn_bsr4_spmm_f32: force the cp.async shared-memory streaming kernel (C=128/256/512) */
 #define SN_SPMM_VARIANT(v) (((v) & 15) << 8) /* tuning variant of the row-group kernel (benchmarks only; 0 = default;
-                                                6 = force the small-operator kernel, 7 = force the persistent one) */
+                                                6 = force the small-operator kernel, 7 = force the persistent one;
+                                                sn_*_spmm_epilogue_f32: 8 = operand loads at the row's end) */
 #define SN_SPMM_ROW_ENTRIES(n) (((n) & 15) << 12) /* caller's hint: no row holds more than n entries (0 = unknown); the
                                                      small-operator kernel keeps that many gathers in flight (D: 3) */
 

@@ -60,7 +60,12 @@ struct Geo {
   static constexpr size_t kSmem = (size_t)kWarps * WARP_WORDS * 4;
   // MODE 3 (statistics in the store path): one [2][C] accumulator per (warp, row group) behind the per-warp regions
   static constexpr size_t kStatSmem = (size_t)kWarps * G * 2 * (16 * LPR) * 4;
-  static constexpr size_t smem_bytes(int mode) { return kSmem + (mode == 3 ? kStatSmem : 0); }
+  // MODE 4 (epilogue operands staged): per lane 3 operands x 4 quarters x 16 bytes, laid out [operand][quarter][lane]
+  // (mode 4 + n: n = 1 ... 3 operands present -- the zone is sized by what the launch uses: 16 KB per operand and CTA)
+  static constexpr size_t kOperandSmem = (size_t)kWarps * 4 * 32 * 16;
+  static constexpr size_t smem_bytes(int mode) {
+    return kSmem + (mode == 3 ? kStatSmem : 0) + (mode >= 5 ? (size_t)(mode - 4) * kOperandSmem : 0);
+  }
 };
 
 // Optional output epilogue Y = (S X + G) .* elu'(A) + G2 (backward of "elu, then gather": the activation derivative and the
@@ -88,7 +93,11 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
                      float* __restrict__ Y, uint32_t ldyb, int n_rows, int n_wtiles, const Epilogue epi) {
   using Gm = Geo<LPR, RPG, BLK, PD, EPS>;
   constexpr bool ELU = MODE == 1;      // ELU on the gathered operand
-  constexpr bool EPI = MODE == 2;      // output epilogue (G, elu')
+  constexpr bool EPI = MODE == 2 || MODE == 4;   // output epilogue (G, elu', G2)
+  // MODE 4: the epilogue operands of a row are requested when the row STARTS -- cp.async into a per-lane landing zone in
+  // shared memory (no registers held; every lane copies exactly the 16-byte pieces it will read, so no synchronisation) --
+  // instead of by loads at the row's end, where their latency sat behind the whole gather chain of the row
+  constexpr bool STAGED = MODE == 4;
   constexpr bool STATS = MODE == 3;    // column statistics of the output in the store path
   constexpr int C = 16 * LPR;
   constexpr int kQuarterBytes = C;             // (C/4 floats) * 4 bytes
@@ -112,6 +121,29 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
   if (!STATS && wt >= n_wtiles) return;          // warps never synchronise with each other (STATS: once, at the very end)
   // STATS: this (warp, row group)'s accumulator; lane t owns columns q C/4 + 4t .. +3 (q = 0..3) of both statistics
   float* wstat = reinterpret_cast<float*>(smem_i + kWarps * Gm::WARP_WORDS) + (warp * G + g) * 2 * C + 4 * t;
+  // STAGED: this lane's landing zone; piece (operand o, quarter q) at ops_s + ((4 o + q) * 32) float4s (conflict-free)
+  const int n_ops = (epi.G != nullptr) + (epi.A != nullptr) + (epi.G2 != nullptr);
+  float4* ops_s = reinterpret_cast<float4*>(smem_i + kWarps * Gm::WARP_WORDS) + warp * (n_ops * 4 * 32) + lane;
+  const int slot_a = epi.G != nullptr ? 4 * 32 : 0, slot_g2 = slot_a + (epi.A != nullptr ? 4 * 32 : 0);   // G: slot 0
+  auto stage_operands = [&](uint32_t grow) {
+    if (grow < (uint32_t)n_rows) {
+      const char* src[3] = {reinterpret_cast<const char*>(epi.G), reinterpret_cast<const char*>(epi.A),
+                            reinterpret_cast<const char*>(epi.G2)};
+      const uint32_t ld[3] = {epi.ldgb, epi.ldab, epi.ldg2b};
+      const int slot[3] = {0, slot_a, slot_g2};
+#pragma unroll
+      for (int o = 0; o < 3; ++o) {
+        if (src[o] != nullptr) {
+          const char* rp = ptr_mad(src[o] + t * 16, grow, ld[o]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(ops_s + slot[o] + q * 32)),
+                         "l"(rp + q * kQuarterBytes) : "memory");
+        }
+      }
+    }
+    cp_async_commit();
+  };
   if (STATS) {
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
@@ -188,11 +220,12 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
         const uint32_t grow = grow0 + r;
         if (grow < (uint32_t)n_rows) {
           char* yrow = const_cast<char*>(ptr_mad(Yl, grow, ldyb));
+          if (STAGED) cp_async_wait<0>();       // this lane's operand pieces (requested at the row's start) have landed
           if (EPI && epi.G != nullptr) {        // Y = S X + G
             const char* grow_p = ptr_mad(reinterpret_cast<const char*>(epi.G) + t * 16, grow, epi.ldgb);
 #pragma unroll
             for (int p = 0; p < 4; ++p)
-              acc[p] = add4(acc[p], __ldg(reinterpret_cast<const float4*>(grow_p + p * kQuarterBytes)));
+              acc[p] = add4(acc[p], STAGED ? ops_s[p * 32] : __ldg(reinterpret_cast<const float4*>(grow_p + p * kQuarterBytes)));
           }
           // (fetching this operand when the row STARTS, 16 more registers and 3 CTAs/SM, was measured slower: 104 / 92 us
           // against 96 / 89 us for D^T / (D*)^T at the cfg3 size; a register-free prefetch.global.L2 of the three operand
@@ -201,7 +234,7 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
             const char* arow_p = ptr_mad(reinterpret_cast<const char*>(epi.A) + t * 16, grow, epi.ldab);
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
-              const float4 a = __ldg(reinterpret_cast<const float4*>(arow_p + p * kQuarterBytes));
+              const float4 a = STAGED ? ops_s[slot_a + p * 32] : __ldg(reinterpret_cast<const float4*>(arow_p + p * kQuarterBytes));
               acc[p].x *= a.x > 0.f ? 1.f : a.x + 1.f;
               acc[p].y *= a.y > 0.f ? 1.f : a.y + 1.f;
               acc[p].z *= a.z > 0.f ? 1.f : a.z + 1.f;
@@ -212,7 +245,7 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
             const char* g2row_p = ptr_mad(reinterpret_cast<const char*>(epi.G2) + t * 16, grow, epi.ldg2b);
 #pragma unroll
             for (int p = 0; p < 4; ++p)
-              acc[p] = add4(acc[p], __ldg(reinterpret_cast<const float4*>(g2row_p + p * kQuarterBytes)));
+              acc[p] = add4(acc[p], STAGED ? ops_s[slot_g2 + p * 32] : __ldg(reinterpret_cast<const float4*>(g2row_p + p * kQuarterBytes)));
           }
 #pragma unroll
           for (int p = 0; p < 4; ++p) st_stream_f4(reinterpret_cast<float*>(yrow + p * kQuarterBytes), acc[p]);
@@ -233,6 +266,7 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
         for (int p = 0; p < 4; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
         ++r;
         next_end = bp[rl0 + r + 1];
+        if (STAGED && r < RPG) stage_operands(grow0 + r);   // the next row of this group: its operands travel with its gathers
       }
     };
     // stage s <- entries kk .. kk + EPS - 1 of this group's run: X rows to registers; BSR4 values (64 bytes per
@@ -294,6 +328,7 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
       if (BLK == 4) __syncwarp();     // everyone has read stage s before its slot is refilled
     };
 
+    if (STAGED) stage_operands(grow0);
     flush();                                               // leading empty rows
 #pragma unroll
     for (int s = 0; s < PD; ++s) load(s, xs[s], wv[s], k + EPS * s);
@@ -340,7 +375,7 @@ struct Launcher {
   static int64_t resident_warps(int mode, int sms) {
     // occupancy is a property of (kernel, device model): queried once per process and device ordinal (a benign race:
     // concurrent first calls compute the same value)
-    static int64_t cached[4][32] = {};
+    static int64_t cached[8][32] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     const bool cacheable = dev >= 0 && dev < 32;
@@ -353,6 +388,7 @@ struct Launcher {
     auto kern = mode == 1 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 1, PD, EPS, MINB>
                 : mode == 2 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 2, PD, EPS, MINB>
                 : mode == 3 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 3, PD, EPS, MINB>
+                : mode >= 5 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 4, PD, EPS, MINB>
                             : rowgroup_spmm_kernel<LPR, RPG, BLK, 0, PD, EPS, MINB>;
     const size_t smem = Gm::smem_bytes(mode);
     if (smem > 48 * 1024 &&
@@ -381,6 +417,7 @@ struct Launcher {
     auto kern = mode == 1 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 1, PD, EPS, MINB>
                 : mode == 2 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 2, PD, EPS, MINB>
                 : mode == 3 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 3, PD, EPS, MINB>
+                : mode >= 5 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 4, PD, EPS, MINB>
                             : rowgroup_spmm_kernel<LPR, RPG, BLK, 0, PD, EPS, MINB>;
     const int64_t n_wtiles = ceil_div(n_rows, Gm::WR);
     const int64_t ctas = ceil_div(n_wtiles, kWarps);
@@ -433,9 +470,13 @@ template <int BLK>
 int launch_family(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X, int64_t ldx,
                   float* Y, int64_t ldy, int64_t n_rows, int64_t C, bool elu, int variant, const Epilogue& epi,
                   cudaStream_t st) {
-  const int mode = (epi.G || epi.A || epi.G2) ? 2 : (epi.stat_partial ? 3 : (elu ? 1 : 0));
-  if (mode >= 2 && (elu || variant >= 4)) return SN_ERR_UNSUPPORTED;   // the epilogues exist for the default shape only
-  if (mode == 2 && epi.stat_partial) return SN_ERR_UNSUPPORTED;
+  // epilogue: operands staged through shared memory (4) unless variant 8 asks for the loads at the row's end (2, A/B runs)
+  const bool has_epi = epi.G || epi.A || epi.G2;
+  const int n_ops = (epi.G != nullptr) + (epi.A != nullptr) + (epi.G2 != nullptr);
+  const int mode0 = has_epi ? (variant == 8 ? 2 : 4 + n_ops) : (epi.stat_partial ? 3 : (elu ? 1 : 0));   // 5 .. 7: staged
+  if (has_epi && variant == 8) variant = 0;
+  if (mode0 >= 2 && (elu || variant >= 4)) return SN_ERR_UNSUPPORTED;   // the epilogues exist for the default shape only
+  if (has_epi && epi.stat_partial) return SN_ERR_UNSUPPORTED;
   // ldx / ldy in bytes and entry offsets (64 B per block) must fit 32 bits
   if (n_rows >= 0x7fffff00LL || ldx >= (1LL << 30) || ldy >= (1LL << 30)) return SN_ERR_UNSUPPORTED;
   // tuning variants (tools/spmm_bench.py --variants rgN): 1 / 2 / 3 force short / medium / long warp-tiles;
@@ -451,14 +492,19 @@ int launch_family(const int32_t* rowptr, const int32_t* colind, const float* val
     case 5: return SN_RG(LPR, 2, 1, 3);          \
     default: return SN_RG(LPR, 1, 1, 4);         \
   }
-  switch (C) {
-    case 32: return SN_RG(2, 1, 1, 4);
-    case 64: return SN_RG(4, 1, 1, 4);
-    case 128: SN_RG_TUNE(8)
-    case 256: SN_RG_TUNE(16)
-    case 512: return SN_RG(32, 1, 1, 4);
-    default: return SN_ERR_UNSUPPORTED;
-  }
+  auto run = [&](const int mode) -> int {
+    switch (C) {
+      case 32: return SN_RG(2, 1, 1, 4);
+      case 64: return SN_RG(4, 1, 1, 4);
+      case 128: SN_RG_TUNE(8)
+      case 256: SN_RG_TUNE(16)
+      case 512: return SN_RG(32, 1, 1, 4);
+      default: return SN_ERR_UNSUPPORTED;
+    }
+  };
+  const int rc = run(mode0);
+  // (the staged epilogue needs 16 KB more shared memory per operand and CTA: where that does not fit, the loads at the row's end)
+  return (rc == SN_ERR_UNSUPPORTED && mode0 >= 5) ? run(2) : rc;
 #undef SN_RG_TUNE
 #undef SN_RG
 }

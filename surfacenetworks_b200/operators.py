@@ -249,6 +249,11 @@ def _apply_stats(op, entry, n_rows, n_cols, ptrs, X, out, mean, var):
     return None if rc == N.SN_ERR_UNSUPPORTED else out
 
 
+# The store-path epilogue reads its operand rows through a shared-memory landing zone filled when the row starts; False
+# selects the loads at the row's end (SN_SPMM_VARIANT(8); A/B timings, tools/ab_step.py --toggle operators.EPILOGUE_STAGED)
+EPILOGUE_STAGED = True
+
+
 def _apply_epilogue(op, entry, n_rows, n_cols, ptrs, X, G, A, out, G2=None):
     """``out = (op @ X + G) * elu'(A) + G2`` in one launch (sn_*_spmm_epilogue_f32); returns None when the row-group kernel
     does not cover the shape, so that the caller can run the separate passes."""
@@ -269,7 +274,7 @@ def _apply_epilogue(op, entry, n_rows, n_cols, ptrs, X, G, A, out, G2=None):
     with torch.cuda.device(X.device):
         rc = N.call(entry, *ptrs, _ptr(X), X.stride(0), _ptr(out), out.stride(0), n_rows, C, _ptr(G),
                     0 if G is None else G.stride(0), _ptr(A), 0 if A is None else A.stride(0), _ptr(G2),
-                    0 if G2 is None else G2.stride(0), 0, _stream(), soft_unsupported=True)
+                    0 if G2 is None else G2.stride(0), 0 if EPILOGUE_STAGED else (8 << 8), _stream(), soft_unsupported=True)
     return None if rc == N.SN_ERR_UNSUPPORTED else out
 
 
