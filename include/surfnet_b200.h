@@ -56,9 +56,12 @@ typedef void* sn_stream_t; /* cudaStream_t */
 #define SN_SPMM_SMEM_STREAM 4   /* sn_bsr4_spmm_f32: force the cp.async shared-memory streaming kernel (C=128/256/512) */
 #define SN_SPMM_VARIANT(v) (((v) & 15) << 8) /* tuning variant of the row-group kernel (benchmarks only; 0 = default;
                                                 6 = force the small-operator kernel, 7 = force the persistent one;
-                                                sn_*_spmm_epilogue_f32: 8 = operand loads at the row's end) */
-#define SN_SPMM_ROW_ENTRIES(n) (((n) & 15) << 12) /* caller's hint: no row holds more than n entries (0 = unknown); the
-                                                     small-operator kernel keeps that many gathers in flight (D: 3) */
+                                                sn_*_spmm_epilogue_f32: 8 = operand loads at the row's end;
+                                                9 / 10 = two / three gathers in flight through shared memory) */
+#define SN_SPMM_ROW_ENTRIES(n) (((n) & 15) << 12) /* caller's hint: typical (mean, rounded up) entries per row, 0 = unknown.
+                                                     Picks the pipeline shape only, never the result: <= 3 (D) -> the
+                                                     small-operator kernel keeps three gathers in flight; >= 5 (D*) -> the
+                                                     BSR4 row-group kernel keeps two, landing in shared memory */
 
 int sn_version(void);
 const char* sn_status_string(int status);

@@ -114,7 +114,7 @@ SN_SPMM_SMEM_STREAM = 4
 
 def spmm_flags(elu_input=False, direct_gather=False, smem_stream=False, variant=0, row_entries=0):
     """flags word of sn_csr_spmm_f32 / sn_bsr4_spmm_f32 (include/surfnet_b200.h).  ``row_entries``: SN_SPMM_ROW_ENTRIES
-    hint (no row holds more than that many entries; 0 = unknown)."""
+    hint (typical entries per row; 0 = unknown)."""
     return ((SN_SPMM_ELU_INPUT if elu_input else 0) | (SN_SPMM_DIRECT_GATHER if direct_gather else 0)
             | (SN_SPMM_SMEM_STREAM if smem_stream else 0) | ((int(variant) & 15) << 8)
             | ((int(row_entries) if 0 < int(row_entries) < 16 else 0) << 12))

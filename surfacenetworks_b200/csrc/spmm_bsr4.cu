@@ -173,8 +173,11 @@ SN_API int sn_bsr4_spmm_f32(const int32_t* browptr, const int32_t* bcolind, cons
                                            hint >= 1 && hint <= 3 ? 3 * n_brows : -1, C, st);
       if (rc != SN_ERR_UNSUPPORTED) return rc;
     }
-    // row-group kernel: C = 32 ... 512 (powers of two)
-    const int rc = launch_bsr4_rowgroup(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C, elu, variant >= 6 ? 0 : variant, nullptr, 0,
+    // row-group kernel: C = 32 ... 512 (powers of two).  Long rows (D*: one block per incident face, ~6) keep two gathers
+    // in flight per row group, landing in shared memory (variant 9: D* 69.4 -> 63.5 us at the cfg3 size, C = 128;
+    // 111.5 -> 100.7 us at C = 256); for rows of three blocks (D) the extra shared-memory traffic loses (58 -> 64 us)
+    const int rg_variant = (variant == 6 || variant == 7) ? 0 : (variant == 0 && hint >= 5 ? 9 : variant);
+    const int rc = launch_bsr4_rowgroup(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C, elu, rg_variant, nullptr, 0,
                                         nullptr, 0, nullptr, 0, st);
     if (rc != SN_ERR_UNSUPPORTED) return rc;
   }
@@ -223,7 +226,9 @@ SN_API int sn_bsr4_spmm_stats_f32(const int32_t* browptr, const int32_t* bcolind
   if (C % 16 || ldx % 4 || ldy % 4 || !aligned16(X) || !aligned16(Y) || !aligned16(bval)) return SN_ERR_UNSUPPORTED;
   if (!ws || ws_bytes < sn_spmm_stats_ws_bytes(C) || !aligned16(ws)) return SN_ERR_WORKSPACE;
   int grid = 0;
-  const int rc = launch_bsr4_rowgroup(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C, false, (flags >> 8) & 3, nullptr, 0,
+  const int variant = (flags >> 8) & 15, hint = (flags >> 12) & 15;
+  const int rc = launch_bsr4_rowgroup(browptr, bcolind, bval, X, ldx, Y, ldy, n_brows, C, false,
+                                      variant == 0 && hint >= 5 ? 9 : variant, nullptr, 0,
                                       nullptr, 0, nullptr, 0, (cudaStream_t)stream, reinterpret_cast<float*>(ws), &grid);
   if (rc != SN_OK) return rc;
   return launch_colstats_final(reinterpret_cast<const float*>(ws), grid, n_brows, (int)C, nullptr, mean, var_biased,

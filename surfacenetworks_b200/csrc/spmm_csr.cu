@@ -160,7 +160,7 @@ SN_API int sn_csr_spmm_f32(const int32_t* rowptr, const int32_t* colind, const f
       if (rc != SN_ERR_UNSUPPORTED) return rc;
     }
     // row-group kernel: C = 32 ... 512
-    const int rc = launch_csr_rowgroup(rowptr, colind, val, X, ldx, Y, ldy, n_rows, C, elu, variant >= 6 ? 0 : variant, nullptr, 0,
+    const int rc = launch_csr_rowgroup(rowptr, colind, val, X, ldx, Y, ldy, n_rows, C, elu, (variant == 6 || variant == 7) ? 0 : variant, nullptr, 0,
                                        nullptr, 0, nullptr, 0, st);
     if (rc != SN_ERR_UNSUPPORTED) return rc;
   }
@@ -202,7 +202,7 @@ SN_API int sn_csr_spmm_stats_f32(const int32_t* rowptr, const int32_t* colind, c
   if (C % 16 || ldx % 4 || ldy % 4 || !aligned16(X) || !aligned16(Y)) return SN_ERR_UNSUPPORTED;
   if (!ws || ws_bytes < (size_t)rowgroup_max_grid() * 2 * (size_t)C * sizeof(float) || !aligned16(ws)) return SN_ERR_WORKSPACE;
   int grid = 0;
-  const int rc = launch_csr_rowgroup(rowptr, colind, val, X, ldx, Y, ldy, n_rows, C, false, (flags >> 8) & 3, nullptr, 0, nullptr,
+  const int rc = launch_csr_rowgroup(rowptr, colind, val, X, ldx, Y, ldy, n_rows, C, false, (flags >> 8) & 15, nullptr, 0, nullptr,
                                      0, nullptr, 0, (cudaStream_t)stream, reinterpret_cast<float*>(ws), &grid);
   if (rc != SN_OK) return rc;
   return launch_colstats_final(reinterpret_cast<const float*>(ws), grid, n_rows, (int)C, nullptr, mean, var_biased,

@@ -49,14 +49,17 @@ __device__ __forceinline__ const char* ptr_mad(const char* base, uint32_t a, uin
   return reinterpret_cast<const char*>(r);
 }
 
-template <int LPR, int RPG, int BLK, int PD, int EPS>
+template <int LPR, int RPG, int BLK, int PD, int EPS, bool XS = false>
 struct Geo {
   static constexpr int G = 32 / LPR;        // row groups per warp
   static constexpr int WR = G * RPG;        // rows per warp-tile
   static constexpr int CAP = WR * 10;       // staged column indices (and CSR values) per warp-tile (excess: global loads)
   static constexpr int BPS = WR + 4;        // ints per row-pointer buffer (WR + 1 used, +1 read past the end)
   static constexpr int WRING = BLK == 4 ? PD * G * 16 * EPS : 0;   // floats: PD stages x G groups x EPS blocks
-  static constexpr int WARP_WORDS = ((WRING + 3 * BPS + 2 * CAP + (BLK == 1 ? 2 * CAP : 0)) + 3) / 4 * 4;
+  // XS: the gathered rows of the PD stages in flight land in shared memory ([stage][entry][quarter][lane] x 16 bytes, every
+  // lane reads back exactly the pieces it requested) instead of registers
+  static constexpr int XZONE = XS ? PD * EPS * 4 * 32 * 4 : 0;
+  static constexpr int WARP_WORDS = ((XZONE + WRING + 3 * BPS + 2 * CAP + (BLK == 1 ? 2 * CAP : 0)) + 3) / 4 * 4;
   static constexpr size_t kSmem = (size_t)kWarps * WARP_WORDS * 4;
   // MODE 3 (statistics in the store path): one [2][C] accumulator per (warp, row group) behind the per-warp regions
   static constexpr size_t kStatSmem = (size_t)kWarps * G * 2 * (16 * LPR) * 4;
@@ -86,12 +89,12 @@ struct Epilogue {
 // LPR lanes per row (C = 16 LPR); RPG rows per row group per warp-tile; BLK = 4: BSR4 (16 values per entry, rotated
 // column-major, see sn_csr32_to_bsr4_fill), BLK = 1: CSR (one value per entry); PD = pipeline depth in stages of EPS
 // consecutive entries per row group; MINB = CTAs per SM the register allocation is tuned for.
-template <int LPR, int RPG, int BLK, int MODE, int PD, int EPS, int MINB>
+template <int LPR, int RPG, int BLK, int MODE, int PD, int EPS, int MINB, bool XS = false>
 __global__ void __launch_bounds__(kThreads, MINB)
 rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
                      const float* __restrict__ val, const float* __restrict__ X, uint32_t ldxb,
                      float* __restrict__ Y, uint32_t ldyb, int n_rows, int n_wtiles, const Epilogue epi) {
-  using Gm = Geo<LPR, RPG, BLK, PD, EPS>;
+  using Gm = Geo<LPR, RPG, BLK, PD, EPS, XS>;
   constexpr bool ELU = MODE == 1;      // ELU on the gathered operand
   constexpr bool EPI = MODE == 2 || MODE == 4;   // output epilogue (G, elu', G2)
   // MODE 4: the epilogue operands of a row are requested when the row STARTS -- cp.async into a per-lane landing zone in
@@ -106,8 +109,9 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* wbase = smem_i + warp * Gm::WARP_WORDS;
-  float* wring = reinterpret_cast<float*>(wbase);        // [PD][G][16 EPS]   (BSR4 only; 16-byte aligned)
-  int* bp_buf = wbase + Gm::WRING;                       // [3][BPS]
+  float4* xzone = reinterpret_cast<float4*>(wbase) + lane;         // XS: [PD][EPS][4][32] float4, this lane's column
+  float* wring = reinterpret_cast<float*>(wbase + Gm::XZONE);      // [PD][G][16 EPS]   (BSR4 only; 16-byte aligned)
+  int* bp_buf = wbase + Gm::XZONE + Gm::WRING;           // [3][BPS]
   int* bc_buf = bp_buf + 3 * BPS;                        // [2][CAP]
   float* bv_buf = reinterpret_cast<float*>(bc_buf + 2 * CAP);   // [2][CAP]  (CSR only)
   const int g = lane / LPR, t = lane % LPR;
@@ -279,7 +283,13 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
           const int j = rel < CAP ? bc[rel] : __ldg(colind + kk + e);
           const char* xp = ptr_mad(Xl, (uint32_t)j, ldxb);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) x[4 * e + q] = __ldg(reinterpret_cast<const float4*>(xp + q * kQuarterBytes));
+          for (int q = 0; q < 4; ++q) {
+            if (XS)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(xzone + ((s * EPS + e) * 4 + q) * 32)),
+                           "l"(xp + q * kQuarterBytes) : "memory");
+            else
+              x[4 * e + q] = __ldg(reinterpret_cast<const float4*>(xp + q * kQuarterBytes));
+          }
           if (BLK == 1) w[e] = rel < CAP ? bv[rel] : __ldg(val + kk + e);
         }
       }
@@ -294,6 +304,8 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
                          : "memory");
         }
         cp_async_commit();                                  // every lane, every call: uniform group counting
+      } else if (XS) {
+        cp_async_commit();
       }
     };
     auto fma_entry = [&](const float4* x, const float* wsm, float wscalar) {
@@ -313,13 +325,15 @@ rowgroup_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
     };
     auto compute = [&](const int s, float4 (&x)[4 * EPS], const float (&w)[EPS]) {
       const float* wsm = wslot0 + s * kSlot;
-      if (BLK == 4) {
-        cp_async_wait<PD - 1>();      // this lane's share of stage s has landed ...
-        __syncwarp();                 // ... and the other lanes' shares
-      }
+      if (BLK == 4 || XS) cp_async_wait<PD - 1>();      // this lane's share of stage s has landed ...
+      if (BLK == 4) __syncwarp();                       // ... and the other lanes' shares (the blocks' values)
 #pragma unroll
       for (int e = 0; e < EPS; ++e) {
         if (k < kend) {               // a run that ends inside the stage skips the remaining entries
+          if (XS) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) x[4 * e + q] = xzone[((s * EPS + e) * 4 + q) * 32];
+          }
           fma_entry(x + 4 * e, wsm + 16 * e, w[e]);
           ++k;
           flush();
@@ -368,9 +382,9 @@ inline DeviceInfo device_info() {
   return {sms};
 }
 
-template <int LPR, int RPG, int BLK, int PD, int EPS, int MINB>
+template <int LPR, int RPG, int BLK, int PD, int EPS, int MINB, bool XS = false>
 struct Launcher {
-  using Gm = Geo<LPR, RPG, BLK, PD, EPS>;
+  using Gm = Geo<LPR, RPG, BLK, PD, EPS, XS>;
   // persistent warps resident on the device for this instantiation (0: kernel cannot run)
   static int64_t resident_warps(int mode, int sms) {
     // occupancy is a property of (kernel, device model): queried once per process and device ordinal (a benign race:
@@ -385,11 +399,11 @@ struct Launcher {
     return w;
   }
   static int64_t query_resident_warps(int mode, int sms) {
-    auto kern = mode == 1 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 1, PD, EPS, MINB>
-                : mode == 2 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 2, PD, EPS, MINB>
-                : mode == 3 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 3, PD, EPS, MINB>
-                : mode >= 5 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 4, PD, EPS, MINB>
-                            : rowgroup_spmm_kernel<LPR, RPG, BLK, 0, PD, EPS, MINB>;
+    auto kern = mode == 1 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 1, PD, EPS, MINB, XS>
+                : mode == 2 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 2, PD, EPS, MINB, XS>
+                : mode == 3 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 3, PD, EPS, MINB, XS>
+                : mode >= 5 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 4, PD, EPS, MINB, XS>
+                            : rowgroup_spmm_kernel<LPR, RPG, BLK, 0, PD, EPS, MINB, XS>;
     const size_t smem = Gm::smem_bytes(mode);
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -414,11 +428,11 @@ struct Launcher {
                     float* Y, int64_t ldy, int64_t n_rows, int mode, int64_t warps, const Epilogue& epi,
                     cudaStream_t st) {
     if (warps <= 0) return SN_ERR_UNSUPPORTED;
-    auto kern = mode == 1 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 1, PD, EPS, MINB>
-                : mode == 2 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 2, PD, EPS, MINB>
-                : mode == 3 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 3, PD, EPS, MINB>
-                : mode >= 5 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 4, PD, EPS, MINB>
-                            : rowgroup_spmm_kernel<LPR, RPG, BLK, 0, PD, EPS, MINB>;
+    auto kern = mode == 1 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 1, PD, EPS, MINB, XS>
+                : mode == 2 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 2, PD, EPS, MINB, XS>
+                : mode == 3 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 3, PD, EPS, MINB, XS>
+                : mode >= 5 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 4, PD, EPS, MINB, XS>
+                            : rowgroup_spmm_kernel<LPR, RPG, BLK, 0, PD, EPS, MINB, XS>;
     const int64_t n_wtiles = ceil_div(n_rows, Gm::WR);
     const int64_t ctas = ceil_div(n_wtiles, kWarps);
     const int64_t grid = ctas < warps / kWarps ? ctas : warps / kWarps;
@@ -433,21 +447,21 @@ struct Launcher {
 // persistent warp busy on small operators and shrink the last-wave quantisation (each warp walks an integer number of
 // tiles).  Pick the longest of {4 RS, 2 RS, RS} rows per group whose quantisation efficiency is >= 0.93, else the
 // most efficient one.  tile_mode 1 / 2 / 3 force short / medium / long (benchmarks).
-template <int LPR, int BLK, int PD, int EPS, int MINB>
+template <int LPR, int BLK, int PD, int EPS, int MINB, bool XS = false>
 int launch_lpr(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X, int64_t ldx, float* Y,
                int64_t ldy, int64_t n_rows, int mode, int tile_mode, const Epilogue& epi, cudaStream_t st) {
   constexpr int G = 32 / LPR;
   constexpr int RS = G >= 4 ? 1 : 4 / G;      // short tile: >= 4 rows per warp
-  using LS = Launcher<LPR, RS, BLK, PD, EPS, MINB>;
-  using LM = Launcher<LPR, 2 * RS, BLK, PD, EPS, MINB>;
-  using LL = Launcher<LPR, 4 * RS, BLK, PD, EPS, MINB>;
+  using LS = Launcher<LPR, RS, BLK, PD, EPS, MINB, XS>;
+  using LM = Launcher<LPR, 2 * RS, BLK, PD, EPS, MINB, XS>;
+  using LL = Launcher<LPR, 4 * RS, BLK, PD, EPS, MINB, XS>;
   const int sms = device_info().sms;
   const int64_t ws = LS::resident_warps(mode, sms), wm = LM::resident_warps(mode, sms), wl = LL::resident_warps(mode, sms);
   int pick = tile_mode;
   // small operators at C >= 256 (one mesh of a few thousand rows, BASELINE cfg5): a single row per row group, so the
   // serial chain of a warp is one row's entries instead of RS rows'
   if ((pick < 1 || pick > 3) && RS > 1 && ceil_div(n_rows, G * RS) < ws) {
-    using LT = Launcher<LPR, 1, BLK, PD, EPS, MINB>;
+    using LT = Launcher<LPR, 1, BLK, PD, EPS, MINB, XS>;
     return LT::launch(rowptr, colind, val, X, ldx, Y, ldy, n_rows, mode, LT::resident_warps(mode, sms), epi, st);
   }
   if ((pick < 1 || pick > 3) && LPR == 32) pick = 1;   // C = 512: one row per warp pass; short tiles measured fastest
@@ -475,7 +489,8 @@ int launch_family(const int32_t* rowptr, const int32_t* colind, const float* val
   const int n_ops = (epi.G != nullptr) + (epi.A != nullptr) + (epi.G2 != nullptr);
   const int mode0 = has_epi ? (variant == 8 ? 2 : 4 + n_ops) : (epi.stat_partial ? 3 : (elu ? 1 : 0));   // 5 .. 7: staged
   if (has_epi && variant == 8) variant = 0;
-  if (mode0 >= 2 && (elu || variant >= 4)) return SN_ERR_UNSUPPORTED;   // the epilogues exist for the default shape only
+  // the epilogues exist for the default pipeline shape only; 9 / 10 (rows through shared memory) also carry the statistics
+  if (mode0 >= 2 && (elu || (variant >= 4 && !(mode0 == 3 && variant >= 9)))) return SN_ERR_UNSUPPORTED;
   if (has_epi && epi.stat_partial) return SN_ERR_UNSUPPORTED;
   // ldx / ldy in bytes and entry offsets (64 B per block) must fit 32 bits
   if (n_rows >= 0x7fffff00LL || ldx >= (1LL << 30) || ldy >= (1LL << 30)) return SN_ERR_UNSUPPORTED;
@@ -486,10 +501,14 @@ int launch_family(const int32_t* rowptr, const int32_t* colind, const float* val
   const int tile_mode = variant >= 1 && variant <= 3 ? variant : 0;
 #define SN_RG(LPR, PD, EPS, MINB) \
   launch_lpr<LPR, BLK, PD, EPS, MINB>(rowptr, colind, val, X, ldx, Y, ldy, n_rows, mode, tile_mode, epi, st)
+#define SN_RGX(LPR, PD, EPS, MINB) \
+  launch_lpr<LPR, BLK, PD, EPS, MINB, true>(rowptr, colind, val, X, ldx, Y, ldy, n_rows, mode, tile_mode, epi, st)
 #define SN_RG_TUNE(LPR)                          \
   switch (variant) {                             \
     case 4: return SN_RG(LPR, 1, 2, 3);          \
     case 5: return SN_RG(LPR, 2, 1, 3);          \
+    case 9: return mode >= 5 ? SN_ERR_UNSUPPORTED : SN_RGX(LPR, 2, 1, 4);  /* two / three gathers in flight per row */ \
+    case 10: return mode >= 5 ? SN_ERR_UNSUPPORTED : SN_RGX(LPR, 3, 1, 4); /* group, landing in shared memory */       \
     default: return SN_RG(LPR, 1, 1, 4);         \
   }
   auto run = [&](const int mode) -> int {
@@ -506,6 +525,7 @@ int launch_family(const int32_t* rowptr, const int32_t* colind, const float* val
   // (the staged epilogue needs 16 KB more shared memory per operand and CTA: where that does not fit, the loads at the row's end)
   return (rc == SN_ERR_UNSUPPORTED && mode0 >= 5) ? run(2) : rc;
 #undef SN_RG_TUNE
+#undef SN_RGX
 #undef SN_RG
 }
 

@@ -215,6 +215,9 @@ class CsrOperator:
                    _stream())
         return out
 
+    def row_entries_hint(self):
+        return 0          # (the CSR kernels take no hint: the shared-memory variant loses on the Laplacian, 47 -> 50 us)
+
     def apply_stats(self, X, out, mean, var):
         """``out = S @ X`` and the column statistics of ``out`` (mean, biased variance over all rows) in one launch, or
         None if unsupported for this shape (then run ``apply`` + ``fused.colstats``)."""
@@ -244,8 +247,8 @@ def _apply_stats(op, entry, n_rows, n_cols, ptrs, X, out, mean, var):
     if N.TIMER is not None:
         N.TIMER.annotate("%s %dx%d C=%d +stats" % (op.kind, n_rows, n_cols, C), op.algorithmic_bytes(C), op.flops(C))
     with torch.cuda.device(X.device):
-        rc = N.call(entry, *ptrs, _ptr(X), X.stride(0), _ptr(out), out.stride(0), n_rows, C, _ptr(mean), _ptr(var), 0,
-                    _ptr(ws), nb, _stream(), soft_unsupported=True)
+        rc = N.call(entry, *ptrs, _ptr(X), X.stride(0), _ptr(out), out.stride(0), n_rows, C, _ptr(mean), _ptr(var),
+                    N.spmm_flags(row_entries=op.row_entries_hint()), _ptr(ws), nb, _stream(), soft_unsupported=True)
     return None if rc == N.SN_ERR_UNSUPPORTED else out
 
 
@@ -399,10 +402,14 @@ class Bsr4Operator:
         if N.TIMER is not None:
             N.TIMER.annotate("bsr4 %dx%d C=%d" % (self.n_brows, self.n_bcols, C), self.algorithmic_bytes(C), self.flops(C))
         with torch.cuda.device(X.device):
-            flags = N.spmm_flags(elu_input, direct_gather, smem_stream, variant, row_entries=self.max_row_blocks)
+            flags = N.spmm_flags(elu_input, direct_gather, smem_stream, variant, row_entries=self.row_entries_hint())
             N.call("sn_bsr4_spmm_f32", _ptr(self.browptr), _ptr(self.bcolind), _ptr(self.bval),
                    _ptr(X), X.stride(0), _ptr(out), out.stride(0), self.n_brows, C, flags, _stream())
         return out
+
+    def row_entries_hint(self):
+        """Mean blocks per block-row, rounded up (D: 3, D*: the mean vertex valence, ~6): the SN_SPMM_ROW_ENTRIES hint."""
+        return min(15, -(-self.n_blocks // max(self.n_brows, 1))) if self.n_blocks > 0 else 0
 
     def apply_stats(self, X, out, mean, var):
         """``out = S @ X`` and the column statistics of ``out`` in one launch (see CsrOperator.apply_stats)."""

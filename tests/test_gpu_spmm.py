@@ -259,7 +259,8 @@ def test_rowgroup_long_rows_and_empty_runs(C):
     y64, bound = c_oracle.coo_mm_f64(row, col, val, n_rows, x)
     y = op.apply(xg)
     within_bound(y.cpu().numpy(), y64, bound, "csr rowgroup")
-    for variant in (1, 2, 3, 4, 5, 6, 7):     # 6 / 7: small-operator kernel (spmm_rowdirect.cu) / persistent kernel forced
+    # 6 / 7: small-operator kernel (spmm_rowdirect.cu) / persistent kernel forced; 9 / 10: gathers through shared memory
+    for variant in (1, 2, 3, 4, 5, 6, 7, 9, 10):
         assert torch.equal(y, op.apply(xg, variant=variant)), "csr variant %d" % variant
     # the same pattern as 4x4 blocks (dense random blocks): block row r has lens[r] blocks
     blk = rng.standard_normal((row.size, 4, 4)).astype(np.float32)
@@ -272,7 +273,7 @@ def test_rowgroup_long_rows_and_empty_runs(C):
     y = opb.apply(xg)
     within_bound(y.cpu().numpy(), y64, bound, "bsr4 rowgroup")
     within_bound(opb.apply(xg, direct_gather=True).cpu().numpy(), y64, bound, "bsr4 direct")
-    for variant in (1, 2, 3, 4, 5, 6, 7) if C >= 32 else (6,):      # C = 16: see test_bsr4_feature_widths_and_strides
+    for variant in (1, 2, 3, 4, 5, 6, 7, 9, 10) if C >= 32 else (6,):      # C = 16: see test_bsr4_feature_widths_and_strides
         assert torch.equal(y, opb.apply(xg, variant=variant)), "bsr4 variant %d" % variant
     # the row-length hint only changes how many gathers are in flight (here it is wrong on purpose: rows hold up to 150)
     opb.max_row_blocks = 3
@@ -296,7 +297,7 @@ def test_rowgroup_persistent_warps(C, n_rows):
     yd = op.apply(xg, direct_gather=True)
     mag = O.CsrOperator(op.rowptr, op.colind, op.val.abs(), op.n_rows, op.n_cols).apply(xg.abs(), direct_gather=True)
     assert torch.all((y - yd).abs() <= 64 * EPS32 * mag + 1e-30)
-    for variant in (1, 3, 6):                  # 6: the small-operator kernel forced onto a large operator
+    for variant in (1, 3, 6, 9, 10):           # 6: the small-operator kernel forced onto a large operator
         assert torch.equal(y, op.apply(xg, variant=variant)), "variant %d" % variant
     # oracle check on a row sample (full fp64 product of 480k x 16 ... 150k x 128 stays cheap on the CPU)
     y64, bound = c_oracle.coo_mm_f64(row, col, val, n_rows, x)

@@ -84,8 +84,8 @@ def main():
             kw = {"elu_input": "elu" in v, "direct_gather": v.startswith("direct")}
             if op.kind == "bsr4":
                 kw["smem_stream"] = v.startswith("smem")
-            if v.startswith("rg") and v[2:3].isdigit():
-                kw["variant"] = int(v[2])
+            if v.startswith("rg") and v[2:].replace("+elu", "").isdigit():
+                kw["variant"] = int(v[2:].replace("+elu", ""))
             ms, best = time_it(lambda: op.apply(X, out=Y, **kw))
             gb = op.algorithmic_bytes(C) / 1e9
             print(json.dumps({"op": name, "variant": v, "order": args.order, "rows": op.n_brows if op.kind == "bsr4" else op.n_rows,
