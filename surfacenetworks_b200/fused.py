@@ -255,9 +255,10 @@ def bn_linear_forward(Z, gamma, beta, W, b, residual, running_mean, running_var,
     return Y, (Z, W, stk, mean)
 
 
-def bn_linear_backward(saved, dY, training, elu_bwd_left=False):
+def bn_linear_backward(saved, dY, training, elu_bwd_left=False, elu_bwd_all=False):
     """Backward of bn_linear_forward: returns (dZ, dgamma, dbeta, dW, db).  ``elu_bwd_left``: the left half of Z holds
-    activated values elu(x); its gradient leaves the dZ GEMM epilogue already multiplied by elu'(x)."""
+    activated values elu(x); its gradient leaves the dZ GEMM epilogue already multiplied by elu'(x).  ``elu_bwd_all``: ALL
+    of Z holds activated values (the models' heads, conv2(elu(v))): the whole dZ is multiplied by elu'."""
     Z, W, stk, mean = saved
     if dY.stride(1) != 1 or dY.stride(0) % 4 or dY.data_ptr() % 16:     # row-strided views (halves of a dZ) are fine
         dY = dY.contiguous()
@@ -279,7 +280,16 @@ def bn_linear_backward(saved, dY, training, elu_bwd_left=False):
         N.call("sn_bn_fold_bwd_f32", _ptr(G), _ptr(sdY), _ptr(W), _ptr(stk[0]), _ptr(stk[1]), _ptr(stk[2]), _ptr(mean),
                Nn, K, rows, 1 if training else 0, _ptr(dW), _ptr(db), _ptr(vec[0]), _ptr(vec[1]), _ptr(vec[2]),
                _ptr(vec[3]), _ptr(WsT[0]), _ptr(WsT[1]), _ptr(WsT[2]), _stream())
-    if training:
+    if elu_bwd_all:
+        # (dY Ws + p Z + q) .* elu'(Z): the elu-backward epilogue of the AvgResNet2 stage without its per-mesh terms
+        # (p = q = 0 in eval mode, written by the fold kernel)
+        dZ = torch.empty(rows, K, dtype=torch.float32, device=dev)
+        if N.TIMER is not None:
+            N.TIMER.annotate("gemm+elu' %dx%dx%d" % (rows, K, Nn), 4 * (rows * Nn + 2 * rows * K + 2 * K * Nn), 2 * rows * K * Nn)
+        with torch.cuda.device(dev):
+            N.call("sn_gemm_tf32_presplit_elubwd_f32", _ptr(dY), dY.stride(0), _ptr(WsT[1]), _ptr(WsT[2]), Nn, _ptr(vec[3]),
+                   _ptr(Z), Z.stride(0), _ptr(vec[2]), 0, 0, 0, 0, 0, _ptr(dZ), dZ.stride(0), rows, K, Nn, _stream())
+    elif training:
         dZ = gemm_tf32(dY, WsT[1], bias=vec[3], R=Z, rscale=vec[2], elu_bwd_left=elu_bwd_left, B_lo=WsT[2])
     else:
         dZ = gemm_tf32(dY, WsT[1], B_lo=WsT[2])
@@ -322,6 +332,60 @@ def segment_sum(X, rows_per_seg, n_seg, weight=None, out=None, ws=None):
         N.call("sn_segment_sum_f32", _ptr(X), X.stride(0), _ptr(weight), rows_per_seg, n_seg, X.shape[1], _ptr(out),
                _ptr(ws), nb, _stream())
     return out
+
+
+class _EluBnLinear(torch.autograd.Function):
+    """GraphConv1x1("pre")(elu(x)) -- the heads of the model stacks (as_rigid_as_possible/models.py:121,151 and twins) -- as
+    one node: activation + BatchNorm statistics in one pass (sn_elu_colstats_f32), and elu' applied by the dZ GEMM's
+    epilogue in backward (no separate activation / derivative passes over the [rows, C] features)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, W, b, running_mean, running_var, training, momentum, eps, counter):
+        rows, K = x.shape
+        a = torch.empty(rows, K, dtype=torch.float32, device=x.device)
+        if training:
+            st = torch.empty(2, K, dtype=torch.float32, device=x.device)
+            elu_colstats(x, a, st[0], st[1])
+            left = (st[0], st[1], K)
+        else:
+            from .ops import elu_into
+            elu_into(x, a)
+            left = None
+        Y, saved = bn_linear_forward(a, gamma, beta, W, b, None, running_mean, running_var, training, momentum, eps, left,
+                                     counter=counter)
+        ctx.save_for_backward(*saved)
+        ctx.training = training
+        return Y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dY):
+        dx, dgamma, dbeta, dW, db = bn_linear_backward(ctx.saved_tensors, dY, ctx.training, elu_bwd_all=True)
+        return dx, dgamma, dbeta, dW, db, None, None, None, None, None, None
+
+
+def elu_bn_linear(x, bn, fc):
+    """fc(bn(elu(x))) on rows [rows, K]: fused (see _EluBnLinear) when the widths allow it -- output widths between the
+    tensor-core shapes are zero-padded and sliced like ``bn_linear`` -- else the composition."""
+    n_out, k = fc.weight.shape
+    n_pad = next((n for n in _GEMM_N if n >= n_out), None)
+    x = x if (x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0) else x.contiguous()
+    ok = (n_pad is not None and (n_pad == n_out or (n_out >= 64 and fc.bias is not None)) and x.is_cuda and
+          x.dtype == torch.float32 and fc.bias is not None and elu_colstats_supported(x, x) and k in _GEMM_N and
+          gemm_tn_supported(n_pad, k))
+    if ok:
+        W, b = fc.weight, fc.bias
+        if n_pad != n_out:
+            W = torch.cat([W, W.new_zeros(n_pad - n_out, k)], 0)
+            b = torch.cat([b, b.new_zeros(n_pad - n_out)])
+        ok = fused_supported(x, W)
+    if not ok:
+        return bn_linear(F.elu(x), bn, fc)
+    training = bn.training or bn.running_mean is None
+    counter = bn_count_batch(bn, training)
+    y = _EluBnLinear.apply(x, bn.weight, bn.bias, W, b, bn.running_mean, bn.running_var, training, bn_momentum(bn), bn.eps,
+                           counter)
+    return y if n_pad == n_out else _SliceCols.apply(y, n_out)
 
 
 class _AvgStage(torch.autograd.Function):

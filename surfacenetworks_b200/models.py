@@ -83,7 +83,7 @@ class ArapLapModel(nn.Module):
         x = self.conv1(inputs)
         for i in range(self.layer):
             x = self._modules["rn{}".format(i)](L, mask, x)
-        return _add_last3_tiled(self.conv2(F.elu(x)), inputs, 40)
+        return _add_last3_tiled(self.conv2.forward_elu(x), inputs, 40)
 
 
 class ArapAvgModel(nn.Module):
@@ -97,7 +97,7 @@ class ArapAvgModel(nn.Module):
         x = self.conv1(inputs)
         for i in range(15):
             x = self._modules["rn{}".format(i)](L, mask, x)
-        return _add_last3_tiled(self.conv2(F.elu(x)), inputs, 40)
+        return _add_last3_tiled(self.conv2.forward_elu(x), inputs, 40)
 
 
 class ArapMlpModel(nn.Module):
@@ -131,7 +131,7 @@ class ArapDirModel(nn.Module):
         v = self.conv1(inputs)
         f = v.new_zeros(batch_size, _num_faces(Di, DiA, batch_size), 128)
         v = _dirac_stack(self, 15, D, DA, mask, v, f)
-        return _add_last3_tiled(self.conv2(F.elu(v)), inputs, 40)
+        return _add_last3_tiled(self.conv2.forward_elu(v), inputs, 40)
 
 
 def arap_loss(outputs, targets, mask, batch_size):
@@ -159,7 +159,7 @@ class LapEncoder(nn.Module):
         x = self.conv1(inputs)
         for i in range(self.num_layers):
             x = self._modules["rn{}".format(i)](L, mask, x)
-        x = F.elu(self.bn_conv2(F.elu(x)))
+        x = F.elu(self.bn_conv2.forward_elu(x))
         x = utils.global_average(x, mask).squeeze()
         return self.fc_mu(x), self.fc_logvar(x)
 
@@ -237,7 +237,7 @@ class DcLapModel(nn.Module):
         x = self.conv1(inputs)
         for i in range(self.layer):
             x = self._modules["rn{}".format(i)](Lop, mask, x)
-        return _add_last3_tiled(self.conv2(F.elu(x)), inputs, 40)
+        return _add_last3_tiled(self.conv2.forward_elu(x), inputs, 40)
 
 
 class DcDirModel(nn.Module):
@@ -259,7 +259,7 @@ class DcDirModel(nn.Module):
         v = self.conv1(inputs)
         f = v.new_zeros(batch_size, DA.n_bcols // batch_size, 128)
         v = _dirac_stack(self, self.layer, D, DA, mask, v, f)
-        return _add_last3_tiled(self.conv2(F.elu(v)), inputs, 40)
+        return _add_last3_tiled(self.conv2.forward_elu(v), inputs, 40)
 
 
 class SiameseModel(nn.Module):

@@ -126,6 +126,15 @@ class GraphConv1x1(nn.Module):
         assert num_inputs == self.num_inputs
         return self.forward_rows(x.reshape(-1, num_inputs)).view(batch_size, num_nodes, self.num_outputs)
 
+    def forward_elu(self, x):
+        """``self(F.elu(x))`` -- how every model stack of the reference ends (as_rigid_as_possible/models.py:121,151) -- with
+        the activation inside the fused stage: one pass for elu + BatchNorm statistics, elu' in the dZ GEMM epilogue."""
+        if self.batch_norm != "pre" or not x.is_cuda:
+            return self(F.elu(x))
+        batch_size, num_nodes, num_inputs = x.size()
+        assert num_inputs == self.num_inputs
+        return fused.elu_bn_linear(x.reshape(-1, num_inputs), self.bn, self.fc).view(batch_size, num_nodes, self.num_outputs)
+
 
 class GraphBatchNorm(nn.Module):
     """BatchNorm over [B*N, C] that always uses batch statistics (utils_pt.py:107-118)."""
