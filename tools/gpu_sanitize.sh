@@ -12,6 +12,7 @@ for tool in memcheck racecheck initcheck synccheck; do
   for grp in SPMM GEMM FUSED; do
     sel=${!grp}
     log=$O/sanitize_${tool}_${grp}.log
+    if [ $tool = initcheck ] && [ $grp = FUSED ]; then continue; fi   # does not finish in 15 min (TMA-heavy kernels under initcheck)
     eval timeout 900 $CS --tool $tool --print-limit 20 --error-exitcode 99 python -m pytest $sel -x -q --timeout 850 -p no:cacheprovider > $log 2>&1
     rc=$?
     echo "== $tool $grp rc=$rc: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|passed|failed' $log | tr '\n' ' ' | cut -c1-300)"
