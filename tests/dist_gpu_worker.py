@@ -14,6 +14,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 
 
+def _mark(rank, what):
+    if rank == 0:
+        print("[dist_gpu_worker] " + what, flush=True)
+
+
 def main():
     from surfacenetworks_b200 import dist as D, graph as G, models as M, operators as OP, workloads as W
     rank, local_rank, world = D.init_from_env()
@@ -35,6 +40,7 @@ def main():
     def adam(m):
         return torch.optim.Adam(m.parameters(), 1e-3, weight_decay=1e-5, fused=True, capturable=True)
 
+    _mark(rank, "setup done")
     # (1) local gradients, averaged by hand
     loss_fn(model_a, t, o).backward()
     expected = []
@@ -45,16 +51,19 @@ def main():
         expected.append(sum(parts[1:], parts[0]) * (1.0 / world))
     # (2) captured step, first replay happens on the SAME initial parameters? No: warm-up steps move them.  Use
     #     warmup=0 and capture=False for the gradient check, then the captured variant for (3).
+    _mark(rank, "expected gradients gathered")
     sb = G.CapturedTrainStep(model_b, loss_fn, adam(model_b), t, o, warmup=0, capture=False)
     sb.eager_step()
     for p, e in zip(model_b.parameters(), expected):
         got = p.grad if p.grad is not None else torch.zeros_like(p)
         assert torch.equal(got, e), "rank %d: all-reduced gradient differs from the mean of the local gradients" % rank
+    _mark(rank, "all-reduced gradients == mean of the local gradients")
     # (3) graph replay (NCCL inside the graph) == eager multi-rank steps
     model_b.load_state_dict(model_a.state_dict())        # (model_a's BatchNorm buffers moved in (1): both copies start from them)
     model_c.load_state_dict(model_a.state_dict())
     sg = G.CapturedTrainStep(model_b, loss_fn, adam(model_b), t, o, warmup=1, capture=True)
     assert sg.mode == "cuda_graph_replay", sg.mode
+    _mark(rank, "step captured")
     se = G.CapturedTrainStep(model_c, loss_fn, adam(model_c), t, o, warmup=1, capture=False)
     for _ in range(2):
         se.eager_step()
@@ -63,11 +72,15 @@ def main():
         assert lg == le, (lg, le)
     for (k, pa), (_, pb) in zip(model_b.state_dict().items(), model_c.state_dict().items()):
         assert torch.equal(pa, pb), k
+    _mark(rank, "three replays == three eager steps")
     # every rank holds the same parameters after the averaged steps
     for p in model_b.parameters():
         ref = p.detach().clone()
         dist.broadcast(ref, 0)
         assert torch.equal(ref, p.detach())
+    # captured graphs hold NCCL kernels: release them before the process group goes away
+    del sg, se, sb
+    torch.cuda.synchronize()
     dist.barrier()
     if rank == 0:
         print("DIST_GPU_OK", flush=True)

@@ -4,7 +4,7 @@ set -u
 mkdir -p gpurun_out
 O=gpurun_out
 T=${1:-r2dist}
-timeout 300 python -m pytest tests/test_gpu_graph.py -x -q --timeout 240 > $O/${T}_pytest_graph.log 2>&1
+timeout 200 python -m pytest tests/test_gpu_graph.py -x -q --timeout 170 > $O/${T}_pytest_graph.log 2>&1
 echo "pytest graph exit $?"; tail -n 5 $O/${T}_pytest_graph.log | cut -c1-300
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 10 --warmup 3 > $O/${T}_bench_n2.json 2> $O/${T}_bench_n2.err
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu-baseline --no-spmm-sweep > $O/${T}_bench_n2.json 2> $O/${T}_bench_n2.err
 echo "bench n2 exit $?"; tail -n 1 $O/${T}_bench_n2.json | cut -c1-400; tail -n 3 $O/${T}_bench_n2.err | cut -c1-200
