@@ -16,3 +16,5 @@ echo "reference exit $?"; cut -c1-300 $O/${T}_bench_reference.json
 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${T}_launches_raw.csv python tools/step_once.py > $O/${T}_step_once.log 2>&1
 echo "ncu exit $?"
 python tools/launch_list.py $O/${T}_launches_raw.csv $O/${T}_launches_step | head -32
+timeout 300 ncu --set full --clock-control none --import-source on -f -k regex:rowgroup_spmm_kernel -s 4 -c 4 -o $O/${T}_rowgroup_block python tools/block_step.py > $O/${T}_ncu_block.log 2>&1
+echo "ncu block $?"
