@@ -57,7 +57,8 @@ typedef void* sn_stream_t; /* cudaStream_t */
 #define SN_SPMM_VARIANT(v) (((v) & 15) << 8) /* tuning variant of the row-group kernel (benchmarks only; 0 = default;
                                                 6 = force the small-operator kernel, 7 = force the persistent one;
                                                 sn_*_spmm_epilogue_f32: 8 = operand loads at the row's end;
-                                                9 / 10 = two / three gathers in flight through shared memory) */
+                                                5 / 9 = two gathers in flight per row group, in registers /
+                                                through shared memory) */
 #define SN_SPMM_ROW_ENTRIES(n) (((n) & 15) << 12) /* caller's hint: typical (mean, rounded up) entries per row, 0 = unknown.
                                                      Picks the pipeline shape only, never the result: <= 3 (D) -> the
                                                      small-operator kernel keeps three gathers in flight; >= 5 (D*) -> the

@@ -385,6 +385,24 @@ inline DeviceInfo device_info() {
 template <int LPR, int RPG, int BLK, int PD, int EPS, int MINB, bool XS = false>
 struct Launcher {
   using Gm = Geo<LPR, RPG, BLK, PD, EPS, XS>;
+  using Kernel = void (*)(const int32_t*, const int32_t*, const float*, const float*, uint32_t, float*, uint32_t, int, int,
+                          const Epilogue);
+  // Which (pipeline shape, store-path mode) pairs exist.  The store-path modes (epilogue, statistics) are built for the
+  // default shape -- one stage of one entry, four CTAs per SM -- only; the tuning shapes exist for the plain product,
+  // the shared-memory gather variant also with the statistics.  (Everything else would be ~300 more kernels to compile.)
+  template <int MODE>
+  static constexpr bool exists() {
+    return (PD == 1 && EPS == 1 && !XS) || MODE <= 1 || (XS && MODE == 3);
+  }
+  template <int MODE>
+  static Kernel kernel_or_null() {
+    if constexpr (exists<MODE>()) return rowgroup_spmm_kernel<LPR, RPG, BLK, MODE, PD, EPS, MINB, XS>;
+    else return nullptr;
+  }
+  static Kernel pick(int mode) {      // runtime mode: 0 .. 3 as the template's, 5 .. 7 = staged epilogue with 1 .. 3 operands
+    return mode == 1 ? kernel_or_null<1>() : mode == 2 ? kernel_or_null<2>() : mode == 3 ? kernel_or_null<3>()
+           : mode >= 5 ? kernel_or_null<4>() : kernel_or_null<0>();
+  }
   // persistent warps resident on the device for this instantiation (0: kernel cannot run)
   static int64_t resident_warps(int mode, int sms) {
     // occupancy is a property of (kernel, device model): queried once per process and device ordinal (a benign race:
@@ -399,11 +417,8 @@ struct Launcher {
     return w;
   }
   static int64_t query_resident_warps(int mode, int sms) {
-    auto kern = mode == 1 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 1, PD, EPS, MINB, XS>
-                : mode == 2 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 2, PD, EPS, MINB, XS>
-                : mode == 3 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 3, PD, EPS, MINB, XS>
-                : mode >= 5 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 4, PD, EPS, MINB, XS>
-                            : rowgroup_spmm_kernel<LPR, RPG, BLK, 0, PD, EPS, MINB, XS>;
+    const Kernel kern = pick(mode);
+    if (kern == nullptr) return 0;
     const size_t smem = Gm::smem_bytes(mode);
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -428,11 +443,8 @@ struct Launcher {
                     float* Y, int64_t ldy, int64_t n_rows, int mode, int64_t warps, const Epilogue& epi,
                     cudaStream_t st) {
     if (warps <= 0) return SN_ERR_UNSUPPORTED;
-    auto kern = mode == 1 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 1, PD, EPS, MINB, XS>
-                : mode == 2 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 2, PD, EPS, MINB, XS>
-                : mode == 3 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 3, PD, EPS, MINB, XS>
-                : mode >= 5 ? rowgroup_spmm_kernel<LPR, RPG, BLK, 4, PD, EPS, MINB, XS>
-                            : rowgroup_spmm_kernel<LPR, RPG, BLK, 0, PD, EPS, MINB, XS>;
+    const Kernel kern = pick(mode);
+    if (kern == nullptr) return SN_ERR_UNSUPPORTED;
     const int64_t n_wtiles = ceil_div(n_rows, Gm::WR);
     const int64_t ctas = ceil_div(n_wtiles, kWarps);
     const int64_t grid = ctas < warps / kWarps ? ctas : warps / kWarps;
@@ -480,6 +492,18 @@ int launch_lpr(const int32_t* rowptr, const int32_t* colind, const float* val, c
   return LS::launch(rowptr, colind, val, X, ldx, Y, ldy, n_rows, mode, ws, epi, st);
 }
 
+// Variant 9: two gathers in flight per row group, landing in shared memory -- built for the block operators (the scalar
+// Laplacian was measured slower with it: 47.3 -> 49.9 us) and for the plain product and the statistics mode.
+template <int LPR, int BLK>
+int launch_xs(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X, int64_t ldx, float* Y,
+              int64_t ldy, int64_t n_rows, int mode, int tile_mode, const Epilogue& epi, cudaStream_t st) {
+  if constexpr (BLK == 4) {
+    if (mode <= 1 || mode == 3)
+      return launch_lpr<LPR, BLK, 2, 1, 4, true>(rowptr, colind, val, X, ldx, Y, ldy, n_rows, mode, tile_mode, epi, st);
+  }
+  return launch_lpr<LPR, BLK, 1, 1, 4>(rowptr, colind, val, X, ldx, Y, ldy, n_rows, mode, tile_mode, epi, st);
+}
+
 template <int BLK>
 int launch_family(const int32_t* rowptr, const int32_t* colind, const float* val, const float* X, int64_t ldx,
                   float* Y, int64_t ldy, int64_t n_rows, int64_t C, bool elu, int variant, const Epilogue& epi,
@@ -489,26 +513,23 @@ int launch_family(const int32_t* rowptr, const int32_t* colind, const float* val
   const int n_ops = (epi.G != nullptr) + (epi.A != nullptr) + (epi.G2 != nullptr);
   const int mode0 = has_epi ? (variant == 8 ? 2 : 4 + n_ops) : (epi.stat_partial ? 3 : (elu ? 1 : 0));   // 5 .. 7: staged
   if (has_epi && variant == 8) variant = 0;
-  // the epilogues exist for the default pipeline shape only; 9 / 10 (rows through shared memory) also carry the statistics
-  if (mode0 >= 2 && (elu || (variant >= 4 && !(mode0 == 3 && variant >= 9)))) return SN_ERR_UNSUPPORTED;
+  // the epilogues exist for the default pipeline shape only; 9 (rows through shared memory) also carries the statistics
+  if (mode0 >= 2 && (elu || (variant >= 4 && !(mode0 == 3 && variant == 9)))) return SN_ERR_UNSUPPORTED;
   if (has_epi && epi.stat_partial) return SN_ERR_UNSUPPORTED;
   // ldx / ldy in bytes and entry offsets (64 B per block) must fit 32 bits
   if (n_rows >= 0x7fffff00LL || ldx >= (1LL << 30) || ldy >= (1LL << 30)) return SN_ERR_UNSUPPORTED;
   // tuning variants (tools/spmm_bench.py --variants rgN): 1 / 2 / 3 force short / medium / long warp-tiles;
-  // 4 / 5 (C = 128 / 256 only) change the pipeline shape (stages in flight, entries per stage, CTAs per SM).
+  // 5 / 9 (C = 128 / 256 only) change the pipeline shape (two gathers in flight: in registers at 3 CTAs per SM / through
+  // shared memory at 4).  (Two entries per stage and three stages through shared memory were measured too and removed.)
   // Measured on B200 at 64 x 2000 V (profiles/r1_spmm_rowgroup_notes.md): occupancy beats per-warp prefetch depth --
   // (1, 1, 4) = 32 warps per SM with one entry in flight per row group is the fastest shape at every width.
   const int tile_mode = variant >= 1 && variant <= 3 ? variant : 0;
 #define SN_RG(LPR, PD, EPS, MINB) \
   launch_lpr<LPR, BLK, PD, EPS, MINB>(rowptr, colind, val, X, ldx, Y, ldy, n_rows, mode, tile_mode, epi, st)
-#define SN_RGX(LPR, PD, EPS, MINB) \
-  launch_lpr<LPR, BLK, PD, EPS, MINB, true>(rowptr, colind, val, X, ldx, Y, ldy, n_rows, mode, tile_mode, epi, st)
 #define SN_RG_TUNE(LPR)                          \
   switch (variant) {                             \
-    case 4: return SN_RG(LPR, 1, 2, 3);          \
-    case 5: return SN_RG(LPR, 2, 1, 3);          \
-    case 9: return mode >= 5 ? SN_ERR_UNSUPPORTED : SN_RGX(LPR, 2, 1, 4);  /* two / three gathers in flight per row */ \
-    case 10: return mode >= 5 ? SN_ERR_UNSUPPORTED : SN_RGX(LPR, 3, 1, 4); /* group, landing in shared memory */       \
+    case 5: return SN_RG(LPR, 2, 1, 3);          /* two gathers in flight per row group, registers */ \
+    case 9: return launch_xs<LPR, BLK>(rowptr, colind, val, X, ldx, Y, ldy, n_rows, mode, tile_mode, epi, st); \
     default: return SN_RG(LPR, 1, 1, 4);         \
   }
   auto run = [&](const int mode) -> int {
@@ -525,7 +546,6 @@ int launch_family(const int32_t* rowptr, const int32_t* colind, const float* val
   // (the staged epilogue needs 16 KB more shared memory per operand and CTA: where that does not fit, the loads at the row's end)
   return (rc == SN_ERR_UNSUPPORTED && mode0 >= 5) ? run(2) : rc;
 #undef SN_RG_TUNE
-#undef SN_RGX
 #undef SN_RG
 }
 

@@ -25,7 +25,7 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--distinct", type=int, default=8, help="distinct meshes (repeated to fill the batch)")
     ap.add_argument("--ops", default="D,Dstar,L")
-    ap.add_argument("--variants", default="rg,rg1,rg2,rg3,rg4,rg5,smem,direct",
+    ap.add_argument("--variants", default="rg,rg1,rg2,rg3,rg5,rg9,smem,direct",
                     help="rg[N] = row-group kernel (tuning variant N), smem = cp.async streaming kernel (BSR4 only), "
                          "direct = first-generation direct-gather kernel; +elu = ELU on load")
     ap.add_argument("--order", default="none", help="none | bisect | morton | morton_xy | rcm: renumber every mesh with geometry.locality_order")
