@@ -74,3 +74,29 @@ def test_ply_reader(tmp_path):
     p.write_text("\n".join(lines) + "\n")
     V2, F2 = geometry.read_ply_ascii(str(p))
     assert np.array_equal(V, V2) and np.array_equal(F, F2)
+
+
+@pytest.mark.parametrize("method", ["bisect", "morton", "rcm"])
+def test_locality_order_renumbers_the_same_mesh(method):
+    """geometry.locality_order / reorder_mesh: both orders are permutations, the renumbered mesh is the same mesh, and
+    its operators are the original ones with rows / columns permuted (D' = P_f D P_v^T blockwise, L' = P_v L P_v^T up to
+    the summation order of duplicate contributions)."""
+    V, F = geometry.synth_mesh(120, 3)
+    vorder, forder = geometry.locality_order(V, F, method)
+    assert sorted(vorder.tolist()) == list(range(V.shape[0])) and sorted(forder.tolist()) == list(range(F.shape[0]))
+    V2, F2 = geometry.reorder_mesh(V, F, vorder, forder)
+    assert np.array_equal(V2[F2], V[F[forder]])                     # every face keeps its corner positions, in order
+    D, DA = geometry.build_dirac(V, F)
+    D2, DA2 = geometry.build_dirac(V2, F2)
+    rows = (4 * forder[:, None] + np.arange(4)).ravel()
+    cols = (4 * vorder[:, None] + np.arange(4)).ravel()
+    assert np.array_equal(D2.toarray(), D.toarray()[np.ix_(rows, cols)])
+    # D* divides by vertex areas accumulated over the incident faces: their order changes, the value by a rounding
+    np.testing.assert_allclose(DA2.toarray(), DA.toarray()[np.ix_(cols, rows)], rtol=1e-6, atol=0)
+    L, L2 = geometry.build_laplacian(V, F), geometry.build_laplacian(V2, F2)
+    ref = L.toarray()[np.ix_(vorder, vorder)]
+    np.testing.assert_allclose(L2.toarray(), ref, rtol=2e-5, atol=2e-5 * np.abs(ref).max())
+    if method == "bisect":                                           # consecutive faces form patches: fewer distinct corners
+        def span(Fx):
+            return np.mean([len(np.unique(Fx[i:i + 32])) for i in range(0, len(Fx) - 32, 32)])
+        assert span(F2) < span(F)

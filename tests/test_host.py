@@ -225,3 +225,32 @@ def test_arena_replays_allocations_and_structure_source_expands_blocks():
                              torch.tensor([1.0, 2.0, 3.0]), 3, 4, 3)
     r, c_, v = csr._coo()
     assert r.tolist() == [0, 0, 2] and c_.tolist() == [1, 3, 0] and v.tolist() == [1.0, 2.0, 3.0]
+
+
+def test_spmm_flag_word_and_row_length_hint():
+    """The flags word of the SpMM entry points (include/surfnet_b200.h): variant in bits 8-11, row-length hint in 12-15;
+    the hint of a block operator is its mean block count per row, rounded up."""
+    from surfacenetworks_b200 import _native as N, operators as OP
+    assert N.spmm_flags() == 0
+    assert N.spmm_flags(elu_input=True, variant=9, row_entries=6) == (1 | (9 << 8) | (6 << 12))
+    assert N.spmm_flags(row_entries=40) == 0 and N.spmm_flags(row_entries=-1) == 0          # out of range: no hint
+    t = torch.zeros(0)
+    assert OP.Bsr4Operator(t, t, t, 100, 50, n_blocks=300).row_entries_hint() == 3           # D: three blocks per face
+    assert OP.Bsr4Operator(t, t, t, 100, 200, n_blocks=590).row_entries_hint() == 6          # D*: mean valence ~5.9
+    assert OP.Bsr4Operator(t, t, t, 100, 200, n_blocks=0).row_entries_hint() == 0
+    assert OP.Bsr4Operator(t, t, t, 2, 200, n_blocks=400).row_entries_hint() == 15           # capped to the 4-bit field
+
+
+def test_bn_count_batch_host_side():
+    """fused.bn_count_batch: the counter is handed to the fold kernel only when it lives on the GPU and a fixed momentum is
+    set; otherwise (cumulative average, CPU buffers) it is incremented on the host like nn.BatchNorm does."""
+    import torch.nn as nn
+    from surfacenetworks_b200 import fused
+    bn = nn.BatchNorm1d(4)
+    assert fused.bn_count_batch(bn, training=False) is None and int(bn.num_batches_tracked) == 0
+    assert fused.bn_count_batch(bn, training=True) is None and int(bn.num_batches_tracked) == 1     # CPU buffer: host add
+    bn = nn.BatchNorm1d(4, momentum=None)
+    assert fused.bn_count_batch(bn, training=True) is None and int(bn.num_batches_tracked) == 1
+    assert fused.bn_momentum(bn) == 1.0
+    bn = nn.BatchNorm1d(4, track_running_stats=False)
+    assert fused.bn_count_batch(bn, training=True) is None
