@@ -32,7 +32,7 @@ def main():
     args = ap.parse_args()
     from surfacenetworks_b200 import geometry, operators as OP, workloads as W
     dev = torch.device("cuda", 0)
-    peak = 6558.1
+    peak = 6551.0
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         peak = float(json.load(open(p))["hbm_gbs"])
