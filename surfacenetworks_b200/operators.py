@@ -654,8 +654,9 @@ class MeshOperatorCache:
     def _n_cols(op):
         return op.n_cols if op.kind == "csr" else op.n_bcols
 
-    def _assemble_one(self, parts, kind, rows_pad, cols_pad, out):
-        dev = self.device
+    def _table(self, parts, kind, rows_pad, cols_pad):
+        """(device table [n, 6] int64 of (rowptr, colind, val, n_rows, n_entries, entry offset), total entries, largest
+        row length) of one block-diagonal assembly: the host-side half of ``_assemble_one``."""
         table, off = [], 0
         for op in parts:
             rp, ci, va, n_rows, n_ent = self._arrays(op)
@@ -665,8 +666,24 @@ class MeshOperatorCache:
                 raise ValueError("mesh operator has %d columns, more than the padded size %d" % (self._n_cols(op), cols_pad))
             table += [rp.data_ptr(), ci.data_ptr(), va.data_ptr(), n_rows, n_ent, off]
             off += n_ent
-        table = torch.tensor(table, dtype=torch.int64).to(dev, non_blocking=True)
-        n = len(parts)
+        table = torch.tensor(table, dtype=torch.int64).to(self.device, non_blocking=True)
+        mrb = 0 if kind == "csr" else max(op.max_row_blocks for op in parts)
+        return table, off, mrb
+
+    def plan(self, keys, kind, rows_pad, cols_pad):
+        """The host-side half of ``assemble`` for the meshes ``keys`` -- validation, the two pointer tables (operator and
+        transpose) and their upload on the CURRENT stream -- so that a data loader can prepare the next batch while the
+        GPU is busy; ``assemble(..., plan=p)`` then only launches the assembly kernels.  The plan stays valid as long as
+        the cached operators it points to."""
+        parts = [self._ops[(k, kind)] for k in keys]
+        return {"kind": kind, "n": len(parts), "rows_pad": rows_pad, "cols_pad": cols_pad,
+                "fwd": self._table(parts, kind, rows_pad, cols_pad),
+                "bwd": self._table([p.T for p in parts], kind, cols_pad, rows_pad)}
+
+    def _assemble_one(self, tab, n, kind, rows_pad, cols_pad, out):
+        dev = self.device
+        table, off, mrb = tab
+        table.record_stream(torch.cuda.current_stream(dev))      # (a plan may have been uploaded on another stream)
         vpe = 1 if kind == "csr" else 16
         if out is None:
             rowptr = torch.empty(n * rows_pad + 1, dtype=torch.int32, device=dev)
@@ -684,20 +701,25 @@ class MeshOperatorCache:
                 out._nnz = off
             else:
                 out._n_blocks = off
-                out.max_row_blocks = max(op.max_row_blocks for op in parts)
+                out.max_row_blocks = mrb
             return out
         if kind == "csr":
             return CsrOperator(rowptr, colind[:off] if off else colind, val[:off] if off else val, n * rows_pad,
                                n * cols_pad, None, off)
         return Bsr4Operator(rowptr, colind[:off] if off else colind, val[:16 * off] if off else val, n * rows_pad,
-                            n * cols_pad, None, off, max(op.max_row_blocks for op in parts))
+                            n * cols_pad, None, off, mrb)
 
-    def assemble(self, keys, kind, rows_pad, cols_pad, out=None):
+    def assemble(self, keys, kind, rows_pad, cols_pad, out=None, plan=None):
         """Block-diagonal batch operator of the meshes ``keys`` (in order), each padded to ``rows_pad x cols_pad``
         (block rows / columns for "bsr4", scalar for "csr"), with its transpose attached.  ``out``: an operator of
-        the same batch shape whose buffers (and whose transpose's) are overwritten in place."""
-        parts = [self._ops[(k, kind)] for k in keys]
-        fwd = self._assemble_one(parts, kind, rows_pad, cols_pad, out)
-        bwd = self._assemble_one([p.T for p in parts], kind, cols_pad, rows_pad, None if out is None else out.T)
+        the same batch shape whose buffers (and whose transpose's) are overwritten in place.  ``plan``: the result of
+        ``plan(keys, kind, rows_pad, cols_pad)`` prepared earlier (``keys`` is then ignored)."""
+        if plan is None:
+            plan = self.plan(keys, kind, rows_pad, cols_pad)
+        elif (plan["kind"], plan["rows_pad"], plan["cols_pad"]) != (kind, rows_pad, cols_pad):
+            raise ValueError("assembly plan was made for another operator kind / padded size")
+        n = plan["n"]
+        fwd = self._assemble_one(plan["fwd"], n, kind, rows_pad, cols_pad, out)
+        bwd = self._assemble_one(plan["bwd"], n, kind, cols_pad, rows_pad, None if out is None else out.T)
         fwd._T, bwd._T = bwd, fwd
         return fwd

@@ -508,6 +508,16 @@ def test_gpu_batch_assembly_matches_host_assembly():
         assert torch.equal(slot.bval, ref2.bval) and torch.equal(slot.T.bval, ref2.T.bval)
         x = torch.randn(slot.n_bcols, 128, device=DEV)
         assert torch.equal(slot.apply(x), ref2.apply(x))
+        # the same through a plan prepared ahead of time on another stream (what a data loader does while the GPU is busy)
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            plan = cache.plan([(name, i) for i in order], "bsr4", rows_pad, cols_pad)
+        torch.cuda.current_stream().wait_stream(side)
+        cache.assemble(None, "bsr4", rows_pad, cols_pad, out=slot, plan=plan)
+        assert torch.equal(slot.browptr, ref.browptr) and torch.equal(slot.bcolind, ref.bcolind)
+        assert torch.equal(slot.bval, ref.bval) and torch.equal(slot.T.bval, ref.T.bval) and slot.n_blocks == ref.n_blocks
+        with pytest.raises(ValueError):
+            cache.assemble(None, "bsr4", rows_pad + 1, cols_pad, out=slot, plan=plan)
     refL = O.CsrOperator.from_torch_coo(W.lap_batch(sel)["L"].to(DEV))
     gotL = cache.assemble([("L", i) for i in order], "csr", nv, nv)
     for a, b in ((gotL, refL), (gotL.T, refL.T)):
