@@ -16,10 +16,14 @@
 //   * the column indices of the NEXT E entries are requested while the current gathers fly.
 //
 // A row of n entries costs 2 + ceil(n / E) round trips: 3 for D (exactly three blocks per face), 4 for D* / L at valence
-// <= 8.  Registers are spent freely (the launch is a single wave anyway).
+// <= 8.  Registers are spent freely (96 / 114 per thread), so the kernel is used only while ALL row groups of the launch
+// are resident at once (rowdirect_applies below); beyond one wave the persistent kernel is as fast or faster.
 //
-// Bound: latency (the roofline fraction of a 4 - 50 MB problem is reported for what it is); algorithmic bytes as in
-// spmm_rowgroup.cu.
+// Measured on B200, one 7000-vertex mesh, L2 flushed (profiles/r2_small_operator_spmm.jsonl): D* 16.5 -> 12.2 us at
+// C <= 128, D 10.6 -> 9.3 us at C <= 64.  The timing method itself reports 7.1 us for a 32-row operator, so these
+// launches sit 2 - 5 us above the floor of "launch + first cold misses"; the rest is not the kernel's to win.
+//
+// Bound: latency; algorithmic bytes as in spmm_rowgroup.cu.
 #include "common.cuh"
 
 namespace sn {
